@@ -1,0 +1,246 @@
+"""complexity_tokenizer -- drop-in `Tokenizer` for the batched encode/decode hot path, running on a B200.
+
+Mirrors the Python surface of the reference's PyO3 class for this path
+(/root/reference/src/bindings/tokenizer.rs:19-23, 203-238, 271-289, 655-663 and the re-export in
+python/complexity_tokenizer/__init__.py:16-18): same method names, argument meaning, defaults and
+error behaviour (`from_file` raises IOError/OSError; encode/decode never raise for valid input).
+All compute happens in libctk.so (CUDA, sm_100a) through the C ABI of include/ctk.h.  There is no
+CPU fallback: importing works without a GPU, but constructing a Tokenizer raises if the library or
+a device is missing.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+__version__ = '0.3.3+b200'
+__all__ = ['Tokenizer', 'Trainer', '__version__']
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+CTK_OK, CTK_ERR_IO, CTK_ERR_INVALID_DATA, CTK_ERR_UNSUPPORTED, CTK_ERR_CUDA, CTK_ERR_ARG = range(6)
+
+
+class UnsupportedTokenizerError(IOError):
+    """tokenizer.json uses a pipeline outside the ByteLevel-BPE hot path (ctk code 3)."""
+
+
+def _lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, 'libctk.so')
+    if not os.path.exists(path):
+        raise ImportError('libctk.so is not built (run `python complexity-tokenizer_b200/build.py`); '
+                          'this package has no CPU fallback')
+    lib = ctypes.CDLL(path)
+    P, S, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    U64 = ctypes.c_uint64
+    sig = {
+        'ctk_from_file': (I, [ctypes.c_char_p, I, ctypes.POINTER(P)]),
+        'ctk_from_json': (I, [P, S, I, ctypes.POINTER(P)]),
+        'ctk_free': (None, [P]),
+        'ctk_vocab_size': (S, [P]),
+        'ctk_token_to_id': (I, [P, ctypes.c_char_p, S, ctypes.POINTER(ctypes.c_uint32)]),
+        'ctk_id_to_token': (P, [P, ctypes.c_uint32, ctypes.POINTER(S)]),
+        'ctk_n_special_tokens': (S, [P]),
+        'ctk_special_token': (P, [P, S, ctypes.POINTER(S), ctypes.POINTER(ctypes.c_uint32)]),
+        'ctk_device': (I, [P]),
+        'ctk_encode_batch': (I, [P, P, P, S, ctypes.POINTER(P)]),
+        'ctk_decode_batch': (I, [P, P, P, S, I, I, ctypes.POINTER(P)]),
+        'ctk_result_ids': (P, [P]),
+        'ctk_result_offsets': (P, [P]),
+        'ctk_result_bytes': (P, [P]),
+        'ctk_result_count': (S, [P]),
+        'ctk_result_free': (None, [P]),
+        'ctk_encode_batch_device': (I, [P, P, P, S, U64, P, U64, P, ctypes.POINTER(U64), P]),
+        'ctk_decode_batch_device': (I, [P, P, P, S, U64, I, I, P, U64, P, ctypes.POINTER(U64), P]),
+        'ctk_decode_max_bytes': (S, [P]),
+        'ctk_last_error': (ctypes.c_char_p, []),
+        'ctk_kernel_launches': (U64, []),
+        'ctk_set_cache_persistent': (None, [P, I]),
+        'ctk_debug_starts_host': (I, [P, U64, P, S, P]),
+        'ctk_debug_load_only': (I, [P, S, ctypes.POINTER(U64), ctypes.POINTER(U64), ctypes.POINTER(I), ctypes.POINTER(I)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _raise(rc):
+    msg = (_lib().ctk_last_error() or b'').decode('utf-8', 'replace')
+    if rc == CTK_ERR_IO:
+        raise IOError(msg)                              # PyIOError in the reference
+    if rc == CTK_ERR_INVALID_DATA:
+        raise IOError(msg)                              # io::ErrorKind::InvalidData -> PyIOError
+    if rc == CTK_ERR_UNSUPPORTED:
+        raise UnsupportedTokenizerError(msg)
+    if rc == CTK_ERR_ARG:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def _pack_texts(texts):
+    blobs = [t.encode('utf-8') for t in texts]          # str.encode raises on lone surrogates, like PyO3's &str
+    off = np.zeros(len(blobs) + 1, dtype=np.uint64)
+    if blobs:
+        np.cumsum([len(b) for b in blobs], out=off[1:])
+    buf = np.frombuffer(b''.join(blobs), dtype=np.uint8) if blobs else np.zeros(0, dtype=np.uint8)
+    return buf, off
+
+
+class Tokenizer:
+    """HuggingFace tokenizer.json byte-level BPE tokenizer; encode/decode run on the GPU."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    # ---- constructors
+    @staticmethod
+    def from_file(path, device=None):
+        lib = _lib()
+        h = ctypes.c_void_p()
+        dev = int(os.environ.get('CTK_DEVICE', '0')) if device is None else int(device)
+        rc = lib.ctk_from_file(os.fsencode(path), dev, ctypes.byref(h))
+        if rc != CTK_OK:
+            _raise(rc)
+        return Tokenizer(h)
+
+    @staticmethod
+    def from_str(json_text, device=None):
+        lib = _lib()
+        data = json_text.encode('utf-8') if isinstance(json_text, str) else bytes(json_text)
+        buf = ctypes.create_string_buffer(data, len(data))
+        h = ctypes.c_void_p()
+        dev = int(os.environ.get('CTK_DEVICE', '0')) if device is None else int(device)
+        rc = lib.ctk_from_json(ctypes.addressof(buf), len(data), dev, ctypes.byref(h))
+        if rc != CTK_OK:
+            _raise(rc)
+        return Tokenizer(h)
+
+    from_buffer = from_str
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h and _LIB is not None:
+            try:
+                _LIB.ctk_free(h)
+            except Exception:
+                pass
+
+    # ---- packed (zero-object) API: numpy in, numpy out
+    def encode_packed(self, text, offsets):
+        """text: uint8 array (packed UTF-8), offsets: uint64[n+1] -> (ids uint32, ids_off uint64[n+1])"""
+        lib = _lib()
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        res = ctypes.c_void_p()
+        rc = lib.ctk_encode_batch(self._h, text.ctypes.data if text.size else None, offsets.ctypes.data, n, ctypes.byref(res))
+        if rc != CTK_OK:
+            _raise(rc)
+        try:
+            off = np.ctypeslib.as_array(ctypes.cast(lib.ctk_result_offsets(res), ctypes.POINTER(ctypes.c_uint64)), (n + 1,)).copy()
+            tot = int(off[-1])
+            ids = np.ctypeslib.as_array(ctypes.cast(lib.ctk_result_ids(res), ctypes.POINTER(ctypes.c_uint32)), (max(tot, 1),))[:tot].copy()
+        finally:
+            lib.ctk_result_free(res)
+        return ids, off
+
+    def decode_packed(self, ids, offsets, skip_special_tokens=False, clean_up_tokenization_spaces=True):
+        """ids uint32 (packed), offsets uint64[n+1] -> (bytes uint8, byte_off uint64[n+1])"""
+        lib = _lib()
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        res = ctypes.c_void_p()
+        rc = lib.ctk_decode_batch(self._h, ids.ctypes.data if ids.size else None, offsets.ctypes.data, n,
+                                  int(bool(skip_special_tokens)), int(bool(clean_up_tokenization_spaces)), ctypes.byref(res))
+        if rc != CTK_OK:
+            _raise(rc)
+        try:
+            off = np.ctypeslib.as_array(ctypes.cast(lib.ctk_result_offsets(res), ctypes.POINTER(ctypes.c_uint64)), (n + 1,)).copy()
+            tot = int(off[-1])
+            b = np.ctypeslib.as_array(ctypes.cast(lib.ctk_result_bytes(res), ctypes.POINTER(ctypes.c_uint8)), (max(tot, 1),))[:tot].copy()
+        finally:
+            lib.ctk_result_free(res)
+        return b, off
+
+    # ---- reference API (bindings/tokenizer.rs:203-238, 655-663)
+    def encode(self, text):
+        return self.encode_batch([text])[0]
+
+    def encode_batch(self, texts):
+        if isinstance(texts, str):
+            raise TypeError("argument 'texts': Can't extract `str` to `Vec`")
+        buf, off = _pack_texts(list(texts))
+        ids, ioff = self.encode_packed(buf, off)
+        lst = ids.tolist()
+        o = ioff.tolist()
+        return [lst[o[i]:o[i + 1]] for i in range(len(o) - 1)]
+
+    def decode(self, ids):
+        return self.decode_batch_with_options([ids], False, True)[0]
+
+    def decode_with_options(self, ids, skip_special_tokens=False, clean_up_tokenization_spaces=True):
+        return self.decode_batch_with_options([ids], skip_special_tokens, clean_up_tokenization_spaces)[0]
+
+    def decode_batch(self, batch):
+        return self.decode_batch_with_options(batch, False, True)
+
+    def decode_batch_with_options(self, batch, skip_special_tokens=False, clean_up_tokenization_spaces=True):
+        batch = [list(b) for b in batch]
+        off = np.zeros(len(batch) + 1, dtype=np.uint64)
+        if batch:
+            np.cumsum([len(b) for b in batch], out=off[1:])
+        flat = np.fromiter((i for b in batch for i in b), dtype=np.uint32, count=int(off[-1]))   # OverflowError like PyO3's u32
+        b, boff = self.decode_packed(flat, off, skip_special_tokens, clean_up_tokenization_spaces)
+        raw = b.tobytes()
+        o = boff.tolist()
+        return [raw[o[i]:o[i + 1]].decode('utf-8') for i in range(len(o) - 1)]
+
+    def batch_decode(self, sequences, skip_special_tokens=False, clean_up_tokenization_spaces=True):
+        return self.decode_batch_with_options(sequences, skip_special_tokens, clean_up_tokenization_spaces)
+
+    # ---- getters (bindings/tokenizer.rs:271-289)
+    @property
+    def vocab_size(self):
+        return int(_lib().ctk_vocab_size(self._h))
+
+    def token_to_id(self, token):
+        out = ctypes.c_uint32()
+        b = token.encode('utf-8')
+        return int(out.value) if _lib().ctk_token_to_id(self._h, b, len(b), ctypes.byref(out)) else None
+
+    def id_to_token(self, id):
+        n = ctypes.c_size_t()
+        p = _lib().ctk_id_to_token(self._h, int(id), ctypes.byref(n))
+        return ctypes.string_at(p, n.value).decode('utf-8') if p else None
+
+    @property
+    def special_tokens(self):
+        lib = _lib()
+        out = {}
+        for i in range(lib.ctk_n_special_tokens(self._h)):
+            n, tid = ctypes.c_size_t(), ctypes.c_uint32()
+            p = lib.ctk_special_token(self._h, i, ctypes.byref(n), ctypes.byref(tid))
+            out[ctypes.string_at(p, n.value).decode('utf-8')] = int(tid.value)
+        return out
+
+    @property
+    def device(self):
+        return int(_lib().ctk_device(self._h))
+
+    def set_cache_persistent(self, flag):
+        _lib().ctk_set_cache_persistent(self._h, int(bool(flag)))
+
+
+class Trainer:
+    """Present for import compatibility only: BPE training is outside the accelerated hot path."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError('Trainer is outside the B200 encode/decode hot path (SURVEY.md section 2, rows 13-15)')

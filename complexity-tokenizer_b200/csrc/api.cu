@@ -1,0 +1,331 @@
+// C ABI (include/ctk.h): engine life cycle, table upload, host-buffer entry points.
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <new>
+#include <vector>
+
+#include "engine.hpp"
+#include "unicode_trie_gen.h"
+
+namespace ctk {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+std::atomic<uint64_t> g_kernel_launches{0};
+
+int Engine::finish(const uint32_t* d_err, const uint64_t* d_off_out, size_t n, uint64_t* total_host, cudaStream_t st) {
+    if (!total_host) return CTK_OK;                       // asynchronous use: flags are checked by the next synchronous call
+    cudaError_t e = cudaMemcpyAsync(h_flags, d_err, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_flags + 2, d_off_out + n, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "finish");
+    uint32_t f = h_flags[0];
+    if (f & ERRF_OFFSETS) return fail(CTK_ERR_ARG, "offsets must start at 0, be non-decreasing and end at the buffer length");
+    if (f & ERRF_UTF8) return fail(CTK_ERR_INVALID_DATA, "input text is not valid UTF-8");
+    if (f & ERRF_CAPACITY) return fail(CTK_ERR_ARG, "output capacity too small");
+    if (f & ERRF_POOL) return fail(CTK_ERR_CUDA, "internal scratch pool exhausted");
+    memcpy(total_host, h_flags + 2, 8);
+    return CTK_OK;
+}
+
+struct Result {
+    size_t n = 0;
+    uint32_t* ids = nullptr;      // pinned
+    uint64_t* off = nullptr;      // pinned
+    uint8_t* bytes = nullptr;     // pinned
+};
+
+static int upload(Engine& eng) {
+    cudaError_t e;
+#define UP(slot, dst, src, bytes)                                                                     \
+    do {                                                                                              \
+        size_t b_ = (bytes);                                                                          \
+        e = cudaMalloc(&eng.d_table_mem[slot], b_ ? b_ : 16);                                         \
+        if (e != cudaSuccess) return eng.cuda_fail(e, "cudaMalloc(tables)");                          \
+        if (b_) { e = cudaMemcpy(eng.d_table_mem[slot], (src), b_, cudaMemcpyHostToDevice);           \
+                  if (e != cudaSuccess) return eng.cuda_fail(e, "cudaMemcpy(tables)"); }              \
+        dst = reinterpret_cast<decltype(dst)>(eng.d_table_mem[slot]);                                 \
+    } while (0)
+    const HostModel& m = eng.model;
+    // pair table: linear probing, power-of-two capacity >= 4 * entries
+    uint64_t cap = 64;
+    while (cap < m.pairs.size() * 4) cap <<= 1;
+    std::vector<PairSlot> slots(cap, PairSlot{kNone, kNone, kNone, 0});
+    for (const PairEntry& p : m.pairs) {
+        uint32_t h = pair_hash(p.a, p.b) & (uint32_t)(cap - 1);
+        while (slots[h].a != kNone) h = (h + 1) & (uint32_t)(cap - 1);
+        slots[h] = PairSlot{p.a, p.b, p.rank, p.new_id};
+    }
+    eng.tables.pair_mask = (uint32_t)(cap - 1);
+    UP(0, eng.tables.pairs, slots.data(), cap * sizeof(PairSlot));
+    UP(1, eng.tables.byte_init, m.byte_init_id, 256 * 4);
+    UP(2, eng.tables.trie_index, CTK_TRIE_INDEX, sizeof(CTK_TRIE_INDEX));
+    UP(3, eng.tables.trie_blocks, CTK_TRIE_BLOCKS, sizeof(CTK_TRIE_BLOCKS));
+    eng.dec.n_ids = (uint32_t)m.id_present.size();
+    UP(4, eng.dec.blob, m.dec_blob.data(), m.dec_blob.size());
+    UP(5, eng.dec.off, m.dec_off.data(), m.dec_off.size() * 4);
+    UP(6, eng.dec.special, m.dec_special.data(), m.dec_special.size());
+    eng.nfc.nd = CTK_N_DECOMP; eng.nfc.nc = CTK_N_COMP; eng.nfc.nq = CTK_N_CCC;
+    UP(7, eng.nfc.dkey, CTK_DECOMP_KEY, sizeof(CTK_DECOMP_KEY));
+    UP(8, eng.nfc.da, CTK_DECOMP_A, sizeof(CTK_DECOMP_A));
+    UP(9, eng.nfc.db, CTK_DECOMP_B, sizeof(CTK_DECOMP_B));
+    UP(10, eng.nfc.ckey, CTK_COMP_KEY, sizeof(CTK_COMP_KEY));
+    UP(11, eng.nfc.cval, CTK_COMP_VAL, sizeof(CTK_COMP_VAL));
+    UP(12, eng.nfc.qkey, CTK_CCC_KEY, sizeof(CTK_CCC_KEY));
+    UP(13, eng.nfc.qval, CTK_CCC_VAL, sizeof(CTK_CCC_VAL));
+    eng.nfc.trie_index = eng.tables.trie_index; eng.nfc.trie_blocks = eng.tables.trie_blocks;
+#undef UP
+    e = cudaHostAlloc((void**)&eng.h_flags, 64, cudaHostAllocDefault);
+    if (e != cudaSuccess) return eng.cuda_fail(e, "cudaHostAlloc");
+    return CTK_OK;
+}
+
+// normaliser -> pre-tokenise -> BPE -> emit, all on the device (mod.rs:551-613 for every document)
+static int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n, uint64_t n_bytes, uint32_t* d_ids,
+                         uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st) {
+    if (n_bytes && (reinterpret_cast<uintptr_t>(d_text) & 15)) return eng.fail(CTK_ERR_ARG, "device text buffer must be 16-byte aligned");
+    const uint8_t* t2; const uint64_t* o2; uint64_t b2;
+    int rc = nfc_stage(eng, d_text, d_off, n, n_bytes, &t2, &o2, &b2, st);
+    if (rc != CTK_OK) return rc;
+    return encode_general(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st);
+}
+
+static int create(const uint8_t* json, size_t len, int device, ctk_tokenizer** out) {
+    if (!out) { set_last_error("out is NULL"); return CTK_ERR_ARG; }
+    *out = nullptr;
+    Engine* eng = new (std::nothrow) Engine();
+    if (!eng) { set_last_error("out of memory"); return CTK_ERR_CUDA; }
+    std::string err;
+    int rc = load_model(json, len, eng->model, err);
+    if (rc != CTK_OK) { set_last_error(err); delete eng; return rc; }
+    if (eng->model.any_added_may_match) {
+        set_last_error("an added token can occur inside a single pre-token; in-word added-token matching is not supported yet");
+        delete eng;
+        return CTK_ERR_UNSUPPORTED;
+    }
+    if (eng->model.add_prefix_space) {
+        set_last_error("ByteLevel add_prefix_space=true is not supported yet");
+        delete eng;
+        return CTK_ERR_UNSUPPORTED;
+    }
+    if (eng->model.pairs.size() >= (1u << 26)) { set_last_error("too many merges"); delete eng; return CTK_ERR_UNSUPPORTED; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_last_error(std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+        delete eng;
+        return CTK_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_last_error("bad device index"); delete eng; return CTK_ERR_ARG; }
+    eng->device = device;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { rc = eng->cuda_fail(e, "cudaSetDevice"); delete eng; return rc; }
+    rc = upload(*eng);
+    if (rc != CTK_OK) { delete eng; return rc; }
+    *out = reinterpret_cast<ctk_tokenizer*>(eng);
+    return CTK_OK;
+}
+
+}  // namespace ctk
+
+using namespace ctk;
+
+extern "C" {
+
+int ctk_from_json(const uint8_t* json, size_t len, int device, ctk_tokenizer** out) {
+    if (!json) { set_last_error("json is NULL"); return CTK_ERR_ARG; }
+    return create(json, len, device, out);
+}
+
+int ctk_from_file(const char* path, int device, ctk_tokenizer** out) {
+    if (!path) { set_last_error("path is NULL"); return CTK_ERR_ARG; }
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { set_last_error(std::string("cannot open ") + path + ": No such file or directory (os error 2)"); return CTK_ERR_IO; }
+    std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (f.bad()) { set_last_error(std::string("read error on ") + path); return CTK_ERR_IO; }
+    return create((const uint8_t*)data.data(), data.size(), device, out);
+}
+
+void ctk_free(ctk_tokenizer* tok) {
+    if (!tok) return;
+    Engine* eng = reinterpret_cast<Engine*>(tok);
+    cudaSetDevice(eng->device);
+    cudaDeviceSynchronize();
+    eng->ws.release();
+    for (void* p : eng->d_table_mem) if (p) cudaFree(p);
+    if (eng->h_flags) cudaFreeHost(eng->h_flags);
+    delete eng;
+}
+
+size_t ctk_vocab_size(const ctk_tokenizer* tok) { return reinterpret_cast<const Engine*>(tok)->model.vocab.size(); }
+
+int ctk_token_to_id(const ctk_tokenizer* tok, const uint8_t* token, size_t len, uint32_t* id) {
+    const HostModel& m = reinterpret_cast<const Engine*>(tok)->model;
+    auto it = m.vocab.find(std::string((const char*)token, len));
+    if (it == m.vocab.end()) return 0;
+    if (id) *id = it->second;
+    return 1;
+}
+
+const uint8_t* ctk_id_to_token(const ctk_tokenizer* tok, uint32_t id, size_t* len) {
+    const HostModel& m = reinterpret_cast<const Engine*>(tok)->model;
+    if (id >= m.id_present.size() || !m.id_present[id]) return nullptr;
+    if (len) *len = m.id_to_token[id].size();
+    return (const uint8_t*)m.id_to_token[id].data();
+}
+
+size_t ctk_n_special_tokens(const ctk_tokenizer* tok) { return reinterpret_cast<const Engine*>(tok)->model.specials.size(); }
+
+const uint8_t* ctk_special_token(const ctk_tokenizer* tok, size_t i, size_t* len, uint32_t* id) {
+    const HostModel& m = reinterpret_cast<const Engine*>(tok)->model;
+    if (i >= m.specials.size()) return nullptr;
+    if (len) *len = m.specials[i].first.size();
+    if (id) *id = m.specials[i].second;
+    return (const uint8_t*)m.specials[i].first.data();
+}
+
+int ctk_device(const ctk_tokenizer* tok) { return reinterpret_cast<const Engine*>(tok)->device; }
+size_t ctk_decode_max_bytes(const ctk_tokenizer* tok) { return reinterpret_cast<const Engine*>(tok)->model.dec_max_bytes; }
+const char* ctk_last_error(void) { return g_last_error.c_str(); }
+uint64_t ctk_kernel_launches(void) { return g_kernel_launches.load(); }
+void ctk_set_cache_persistent(ctk_tokenizer* tok, int persistent) { reinterpret_cast<Engine*>(tok)->cache_persistent = persistent != 0; }
+
+int ctk_encode_batch_device(const ctk_tokenizer* tok, const uint8_t* d_text, const uint64_t* d_text_off, size_t n,
+                            uint64_t total_bytes, uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off,
+                            uint64_t* n_ids_host, void* stream) {
+    if (!tok || !d_text_off || !d_ids_off || (total_bytes && (!d_text || !d_ids))) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
+    Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
+    std::lock_guard<std::mutex> lk(eng->mu);
+    cudaError_t e = cudaSetDevice(eng->device);
+    if (e != cudaSuccess) return eng->cuda_fail(e, "cudaSetDevice");
+    return encode_device(*eng, d_text, d_text_off, n, total_bytes, d_ids, ids_cap, d_ids_off, n_ids_host, (cudaStream_t)stream);
+}
+
+int ctk_decode_batch_device(const ctk_tokenizer* tok, const uint32_t* d_ids, const uint64_t* d_ids_off, size_t n,
+                            uint64_t total_ids, int skip_special_tokens, int clean_up_tokenization_spaces,
+                            uint8_t* d_text_out, uint64_t text_cap, uint64_t* d_text_off_out, uint64_t* n_bytes_host,
+                            void* stream) {
+    if (!tok || !d_ids_off || !d_text_off_out || !d_text_out || (total_ids && !d_ids)) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
+    Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
+    std::lock_guard<std::mutex> lk(eng->mu);
+    cudaError_t e = cudaSetDevice(eng->device);
+    if (e != cudaSuccess) return eng->cuda_fail(e, "cudaSetDevice");
+    return decode_device(*eng, d_ids, d_ids_off, n, total_ids, skip_special_tokens, clean_up_tokenization_spaces, d_text_out,
+                         text_cap, d_text_off_out, n_bytes_host, (cudaStream_t)stream);
+}
+
+#define CKE(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = eng->cuda_fail(e_, #x); goto done; } } while (0)
+
+int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64_t* text_off, size_t n, ctk_result** res) {
+    if (!tok || !text_off || !res) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
+    *res = nullptr;
+    Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
+    if (text_off[0] != 0) { set_last_error("text_off[0] must be 0"); return CTK_ERR_ARG; }
+    uint64_t B = text_off[n];
+    if (B && !text) { set_last_error("NULL text"); return CTK_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(eng->mu);
+    int rc = CTK_OK;
+    Result* r = new Result();
+    r->n = n;
+    uint8_t* d_text; uint64_t *d_off, *d_ids_off; uint32_t* d_ids;
+    uint64_t total = 0;
+    cudaStream_t st = 0;
+    CKE(cudaSetDevice(eng->device));
+    CKE(eng->ws.get(20, B + 64, (void**)&d_text));
+    CKE(eng->ws.get(21, (n + 1) * 8, (void**)&d_off));
+    CKE(eng->ws.get(22, (n + 1) * 8, (void**)&d_ids_off));
+    CKE(eng->ws.get(23, (3 * B + n + 16) * 4, (void**)&d_ids));   // NFC can grow text up to 3x
+    if (B) CKE(cudaMemcpyAsync(d_text, text, B, cudaMemcpyHostToDevice, st));
+    CKE(cudaMemcpyAsync(d_off, text_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CKE(cudaMemsetAsync(d_text + B, 0, 64, st));
+    rc = encode_device(*eng, d_text, d_off, n, B, d_ids, 3 * B + n + 16, d_ids_off, &total, st);
+    if (rc != CTK_OK) goto done;
+    CKE(cudaHostAlloc((void**)&r->off, (n + 1) * 8, cudaHostAllocDefault));
+    CKE(cudaHostAlloc((void**)&r->ids, (total + 1) * 4, cudaHostAllocDefault));
+    CKE(cudaMemcpyAsync(r->off, d_ids_off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (total) CKE(cudaMemcpyAsync(r->ids, d_ids, total * 4, cudaMemcpyDeviceToHost, st));
+    CKE(cudaStreamSynchronize(st));
+done:
+    if (rc != CTK_OK) { ctk_result_free(reinterpret_cast<ctk_result*>(r)); return rc; }
+    *res = reinterpret_cast<ctk_result*>(r);
+    return CTK_OK;
+}
+
+int ctk_decode_batch(const ctk_tokenizer* tok, const uint32_t* ids, const uint64_t* ids_off, size_t n, int skip_special_tokens,
+                     int clean_up_tokenization_spaces, ctk_result** res) {
+    if (!tok || !ids_off || !res) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
+    *res = nullptr;
+    Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
+    if (ids_off[0] != 0) { set_last_error("ids_off[0] must be 0"); return CTK_ERR_ARG; }
+    for (size_t i = 0; i < n; ++i) if (ids_off[i + 1] < ids_off[i]) { set_last_error("ids_off must be non-decreasing"); return CTK_ERR_ARG; }
+    uint64_t T = ids_off[n];
+    if (T && !ids) { set_last_error("NULL ids"); return CTK_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(eng->mu);
+    int rc = CTK_OK;
+    Result* r = new Result();
+    r->n = n;
+    uint32_t* d_ids; uint64_t *d_off, *d_out_off; uint8_t* d_out;
+    uint64_t total = 0;
+    cudaStream_t st = 0;
+    CKE(cudaSetDevice(eng->device));
+    CKE(eng->ws.get(24, (T + 1) * 4, (void**)&d_ids));
+    CKE(eng->ws.get(21, (n + 1) * 8, (void**)&d_off));
+    CKE(eng->ws.get(22, (n + 1) * 8, (void**)&d_out_off));
+    if (T) CKE(cudaMemcpyAsync(d_ids, ids, T * 4, cudaMemcpyHostToDevice, st));
+    CKE(cudaMemcpyAsync(d_off, ids_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    rc = decode_device(*eng, d_ids, d_off, n, T, skip_special_tokens, clean_up_tokenization_spaces, nullptr, 0, d_out_off, &total, st);
+    if (rc != CTK_OK) goto done;
+    d_out = eng->last_decode_out;
+    CKE(cudaHostAlloc((void**)&r->off, (n + 1) * 8, cudaHostAllocDefault));
+    CKE(cudaHostAlloc((void**)&r->bytes, total + 1, cudaHostAllocDefault));
+    CKE(cudaMemcpyAsync(r->off, d_out_off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (total) CKE(cudaMemcpyAsync(r->bytes, d_out, total, cudaMemcpyDeviceToHost, st));
+    CKE(cudaStreamSynchronize(st));
+done:
+    if (rc != CTK_OK) { ctk_result_free(reinterpret_cast<ctk_result*>(r)); return rc; }
+    *res = reinterpret_cast<ctk_result*>(r);
+    return CTK_OK;
+}
+
+const uint32_t* ctk_result_ids(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->ids; }
+const uint64_t* ctk_result_offsets(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->off; }
+const uint8_t* ctk_result_bytes(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->bytes; }
+size_t ctk_result_count(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->n; }
+
+void ctk_result_free(ctk_result* res) {
+    if (!res) return;
+    Result* r = reinterpret_cast<Result*>(res);
+    if (r->ids) cudaFreeHost(r->ids);
+    if (r->off) cudaFreeHost(r->off);
+    if (r->bytes) cudaFreeHost(r->bytes);
+    delete r;
+}
+
+// ---- debug/test hooks (host only, no GPU needed): the scalar start predicate on host memory ----------
+// out_bits: one bit per byte position, set where a pre-token starts.  Used by the CPU test-suite to
+// check the device predicate's logic against the oracle's regex restatement.
+int ctk_debug_starts_host(const uint8_t* text, uint64_t n, const uint64_t* off, size_t n_docs, uint32_t* out_bits) {
+    uint64_t n_words = (n + 31) / 32 + 1;
+    std::vector<uint32_t> ds(n_words, 0);
+    for (size_t d = 0; d <= n_docs; ++d) if (off[d] < n) ds[off[d] >> 5] |= 1u << (off[d] & 31);
+    TextView tv{text, n, ds.data(), CTK_TRIE_INDEX, CTK_TRIE_BLOCKS};
+    for (uint64_t w = 0; w < n_words; ++w) out_bits[w] = 0;
+    for (uint64_t i = 0; i < n; ++i) if (tv.is_start(i)) out_bits[i >> 5] |= 1u << (i & 31);
+    return CTK_OK;
+}
+
+// model-only load (no device): returns the CTK_* code the loader gives, for CPU tests of the load rules
+int ctk_debug_load_only(const uint8_t* json, size_t len, uint64_t* n_pairs, uint64_t* vocab_size, int* nfc, int* may_match) {
+    HostModel m;
+    std::string err;
+    int rc = load_model(json, len, m, err);
+    if (rc != CTK_OK) { set_last_error(err); return rc; }
+    if (n_pairs) *n_pairs = m.pairs.size();
+    if (vocab_size) *vocab_size = m.vocab.size();
+    if (nfc) *nfc = m.nfc;
+    if (may_match) *may_match = m.any_added_may_match;
+    return CTK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+// decode_batch on the GPU.
+//
+//   k_dec_len / scan / k_dec_gather   ids -> token byte strings -> concatenation per document
+//                                      (mod.rs:717-735 filter + lookup, decoders.rs:94-116 with the
+//                                      char->byte map folded into the per-token blob at load)
+//   k_dec_valid                       is every document's byte string valid UTF-8?  (fast path: the
+//                                      gather output already IS String::from_utf8_lossy's result)
+//   k_dec_post                        per document: from_utf8_lossy (decoders.rs:118) and
+//                                      clean_up_tokenization_spaces (mod.rs:749-769), exact sequential
+//                                      semantics (15 ordered str::replace, split_whitespace().join(" "))
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "engine.hpp"
+
+namespace ctk {
+
+struct ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return v; } };
+
+__global__ void k_dec_len(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
+                          uint32_t* __restrict__ len) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j > n) return;
+    uint32_t L = 0;
+    if (j < n) {
+        uint32_t id = ids[j];
+        if (id < t.n_ids && !(skip_special && t.special[id])) L = t.off[id + 1] - t.off[id];
+    }
+    len[j] = L;
+}
+
+__global__ void k_dec_gather(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
+                             const uint64_t* __restrict__ boff, uint8_t* __restrict__ raw) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t id = ids[j];
+    if (id >= t.n_ids || (skip_special && t.special[id])) return;
+    uint32_t s = t.off[id], e = t.off[id + 1];
+    uint8_t* dst = raw + boff[j];
+    for (uint32_t k = s; k < e; ++k) dst[k - s] = t.blob[k];
+}
+
+__global__ void k_dec_doc_off(const uint64_t* __restrict__ ids_off, uint64_t n_docs, const uint64_t* __restrict__ boff,
+                              uint64_t* __restrict__ raw_off) {
+    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d <= n_docs) raw_off[d] = boff[ids_off[d]];
+}
+
+// length of a well-formed UTF-8 sequence at p[i] (maximal-subpart rules), 0 if ill-formed;
+// *bad = number of bytes from_utf8_lossy replaces by one U+FFFD when ill-formed
+__device__ __forceinline__ int utf8_seq(const uint8_t* p, uint64_t i, uint64_t n, int* bad) {
+    uint8_t c = p[i];
+    if (c < 0x80) return 1;
+    int need = 0; uint8_t lo = 0x80, hi = 0xBF;
+    if (c >= 0xC2 && c <= 0xDF) need = 1;
+    else if (c == 0xE0) { need = 2; lo = 0xA0; }
+    else if (c >= 0xE1 && c <= 0xEC) need = 2;
+    else if (c == 0xED) { need = 2; hi = 0x9F; }
+    else if (c >= 0xEE && c <= 0xEF) need = 2;
+    else if (c == 0xF0) { need = 3; lo = 0x90; }
+    else if (c >= 0xF1 && c <= 0xF3) need = 3;
+    else if (c == 0xF4) { need = 3; hi = 0x8F; }
+    if (!need) { *bad = 1; return 0; }
+    for (int k = 1; k <= need; ++k) {
+        if (i + k >= n) { *bad = k; return 0; }
+        uint8_t d = p[i + k], l = k == 1 ? lo : 0x80, h = k == 1 ? hi : 0xBF;
+        if (d < l || d > h) { *bad = k; return 0; }
+    }
+    return need + 1;
+}
+
+__global__ void k_dec_valid(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off, uint64_t n_docs,
+                            uint32_t* __restrict__ any_invalid) {
+    // one thread per 64-byte chunk of a document would be the fast version; documents are checked
+    // independently because a sequence may not straddle two documents.
+    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const uint8_t* p = raw + raw_off[d];
+    uint64_t n = raw_off[d + 1] - raw_off[d];
+    for (uint64_t i = 0; i < n;) {
+        int bad, L = utf8_seq(p, i, n, &bad);
+        if (!L) { atomicOr(any_invalid, 1u); return; }
+        i += L;
+    }
+}
+
+// White_Space (Rust char::is_whitespace) at p[i] in valid UTF-8: byte length or 0
+__device__ __forceinline__ int ws_at(const uint8_t* p, uint64_t i, uint64_t n) {
+    uint8_t c = p[i];
+    if (c == 0x20 || (c >= 9 && c <= 13)) return 1;
+    if (c == 0xC2 && i + 1 < n && (p[i + 1] == 0x85 || p[i + 1] == 0xA0)) return 2;
+    if (i + 2 < n) {
+        uint8_t d = p[i + 1], e = p[i + 2];
+        if (c == 0xE1 && d == 0x9A && e == 0x80) return 3;
+        if (c == 0xE2 && d == 0x80 && ((e >= 0x80 && e <= 0x8A) || e == 0xA8 || e == 0xA9 || e == 0xAF)) return 3;
+        if (c == 0xE2 && d == 0x81 && e == 0x9F) return 3;
+        if (c == 0xE3 && d == 0x80 && e == 0x80) return 3;
+    }
+    return 0;
+}
+
+__device__ uint64_t replace_pass(const uint8_t* src, uint64_t n, uint8_t* dst, const char* pat, int pl, char rep) {
+    uint64_t i = 0, o = 0;
+    while (i < n) {
+        bool m = i + pl <= n;
+        for (int k = 0; m && k < pl; ++k) m = src[i + k] == (uint8_t)pat[k];
+        if (m) { dst[o++] = (uint8_t)rep; i += pl; }
+        else dst[o++] = src[i++];
+    }
+    return o;
+}
+
+// one thread per document; scratch A/B hold 3*raw_len+4 bytes per document each
+__global__ void k_dec_post(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off, uint64_t n_docs,
+                           int cleanup, uint8_t* bufA, uint8_t* bufB, uint64_t* __restrict__ out_len,
+                           uint8_t* __restrict__ which) {
+    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const uint8_t* p = raw + raw_off[d];
+    uint64_t n = raw_off[d + 1] - raw_off[d];
+    uint64_t so = 3 * raw_off[d] + 4 * d;
+    uint8_t *a = bufA + so, *b = bufB + so;
+    // String::from_utf8_lossy
+    uint64_t m = 0;
+    for (uint64_t i = 0; i < n;) {
+        int bad = 0, L = utf8_seq(p, i, n, &bad);
+        if (L) { for (int k = 0; k < L; ++k) a[m++] = p[i + k]; i += L; }
+        else { a[m++] = 0xEF; a[m++] = 0xBF; a[m++] = 0xBD; i += bad; }
+    }
+    int cur = 0;
+    if (cleanup) {
+        const char* pats[15] = {" .", " ,", " !", " ?", " :", " ;", "\" ", " \"", "' ", " '", "( ", " )", "[ ", " ]", " - "};
+        const char reps[15] = {'.', ',', '!', '?', ':', ';', '"', '"', '\'', '\'', '(', ')', '[', ']', '-'};
+        const int lens[15] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3};
+        for (int k = 0; k < 15; ++k) {
+            m = replace_pass(cur ? b : a, m, cur ? a : b, pats[k], lens[k], reps[k]);
+            cur ^= 1;
+        }
+        // split_whitespace().join(" ")
+        const uint8_t* s = cur ? b : a;
+        uint8_t* o = cur ? a : b;
+        uint64_t w = 0;
+        bool pending = false, any = false;
+        for (uint64_t i = 0; i < m;) {
+            int wl = ws_at(s, i, m);
+            if (wl) { pending = true; i += wl; continue; }
+            if (pending && any) o[w++] = ' ';
+            pending = false; any = true;
+            o[w++] = s[i++];
+        }
+        m = w;
+        cur ^= 1;
+    }
+    out_len[d] = m;
+    which[d] = (uint8_t)cur;
+}
+
+__global__ void k_dec_copy_out(const uint8_t* __restrict__ bufA, const uint8_t* __restrict__ bufB,
+                               const uint64_t* __restrict__ raw_off, const uint8_t* __restrict__ which,
+                               const uint64_t* __restrict__ out_off, uint64_t n_docs, uint8_t* __restrict__ out,
+                               uint64_t out_cap, uint32_t* __restrict__ err) {
+    // one warp per document
+    uint64_t d = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_docs) return;
+    int lane = threadIdx.x & 31;
+    uint64_t so = 3 * raw_off[d] + 4 * d;
+    const uint8_t* s = (which[d] ? bufB : bufA) + so;
+    uint64_t o = out_off[d], n = out_off[d + 1] - o;
+    if (o + n > out_cap) { if (lane == 0) atomicOr(err, ERRF_CAPACITY); return; }
+    for (uint64_t i = lane; i < n; i += 32) out[o + i] = s[i];
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
+
+int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off, size_t n_docs, uint64_t T,
+                  int skip_special, int cleanup, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off,
+                  uint64_t* n_bytes_host, cudaStream_t st) {
+    Workspace& ws = eng.ws;
+    uint32_t *len, *err;
+    uint64_t *boff, *raw_off;
+    CK(ws.get(4, 256, (void**)&err));
+    CK(cudaMemsetAsync(err, 0, 256, st));
+    CK(ws.get(10, (T + 2) * 4, (void**)&len));
+    CK(ws.get(11, (T + 2) * 8, (void**)&boff));
+    CK(ws.get(12, (n_docs + 2) * 8, (void**)&raw_off));
+    k_dec_len<<<(unsigned)((T + 1 + 255) / 256), 256, 0, st>>>(eng.dec, d_ids, T, skip_special, len);
+    eng.launched(1);
+    cub::TransformInputIterator<uint64_t, ToU64, const uint32_t*> it(len, ToU64());
+    size_t cub_bytes = 0;
+    void* cub_tmp;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, boff, T + 1, st));
+    CK(ws.get(5, cub_bytes + 16, &cub_tmp));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, it, boff, T + 1, st));
+    eng.launched(1);
+    uint64_t raw_total = 0;
+    CK(cudaMemcpyAsync(&raw_total, boff + T, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint8_t* raw;
+    CK(ws.get(13, raw_total + 16, (void**)&raw));
+    if (T) { k_dec_gather<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(eng.dec, d_ids, T, skip_special, boff, raw); eng.launched(1); }
+    k_dec_doc_off<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_ids_off, n_docs, boff, raw_off);
+    eng.launched(1);
+    bool need_post = cleanup != 0;
+    if (!need_post && n_docs) {
+        k_dec_valid<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(raw, raw_off, n_docs, err + 1);
+        eng.launched(1);
+        uint32_t inv = 0;
+        CK(cudaMemcpyAsync(&inv, err + 1, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        need_post = inv != 0;
+    }
+    if (!d_out) {                                          // host-buffer entry point: output lives in the workspace
+        out_cap = need_post ? 3 * raw_total + 16 : raw_total + 16;
+        CK(ws.get(25, out_cap, (void**)&d_out));
+        eng.last_decode_out = d_out;
+    }
+    if (!need_post) {
+        if (raw_total > out_cap) return eng.fail(CTK_ERR_ARG, "decode output capacity too small");
+        if (raw_total) CK(cudaMemcpyAsync(d_out, raw, raw_total, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(d_out_off, raw_off, (n_docs + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+        uint8_t *bufA, *bufB, *which;
+        uint64_t *out_len;
+        uint64_t sz = 3 * raw_total + 4 * (n_docs + 1) + 16;
+        CK(ws.get(14, sz, (void**)&bufA));
+        CK(ws.get(15, sz, (void**)&bufB));
+        CK(ws.get(16, (n_docs + 2) * 8, (void**)&out_len));
+        CK(ws.get(17, n_docs + 16, (void**)&which));
+        if (n_docs) {
+            k_dec_post<<<(unsigned)((n_docs + 127) / 128), 128, 0, st>>>(raw, raw_off, n_docs, cleanup, bufA, bufB, out_len, which);
+            eng.launched(1);
+        }
+        CK(cudaMemsetAsync(out_len + n_docs, 0, 8, st));
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, out_len, d_out_off, n_docs + 1, st));
+        CK(ws.get(5, cub_bytes + 16, &cub_tmp));
+        CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, out_len, d_out_off, n_docs + 1, st));
+        eng.launched(1);
+        if (n_docs) {
+            k_dec_copy_out<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, st>>>(bufA, bufB, raw_off, which, d_out_off, n_docs,
+                                                                                  d_out, out_cap, err);
+            eng.launched(1);
+        }
+    }
+    CK(cudaGetLastError());
+    return eng.finish(err, d_out_off, n_docs, n_bytes_host, st);
+}
+
+}  // namespace ctk

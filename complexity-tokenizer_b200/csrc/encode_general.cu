@@ -1,0 +1,236 @@
+// General (multi-kernel) encode pipeline.  Handles every input the hot path supports, including
+// pre-tokens of any length; the fused single-pass kernel in encode_fused.cu is the fast path for
+// pre-tokens up to 32 bytes and hands anything longer to the routines here.
+//
+//   k_docstart   scatter one bit per document start                      (mod.rs:694-696: docs are independent)
+//   k_starts     pre-token boundaries, 1 bit per byte + per-block counts (pretokenizers.rs:13, :158-185)
+//   k_list       compaction: bit map -> sorted list of pre-token starts
+//   k_bpe        one warp per pre-token: byte -> initial id, merge loop   (bpe.rs:88-153)
+//   k_emit       prefix-sum offsets -> packed ids + per-document offsets  (mod.rs:562-612 `result.extend`)
+#include <cub/device/device_scan.cuh>
+
+#include "device_common.cuh"
+#include "engine.hpp"
+
+namespace ctk {
+
+__global__ void k_docstart(const uint64_t* __restrict__ off, uint64_t n_docs, uint64_t n_bytes,
+                           uint32_t* __restrict__ ds, uint32_t* __restrict__ err) {
+    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d > n_docs) return;
+    uint64_t p = off[d];
+    if (d == 0 && p != 0) atomicOr(err, ERRF_OFFSETS);
+    if (d == n_docs && p != n_bytes) atomicOr(err, ERRF_OFFSETS);
+    if (d < n_docs && off[d + 1] < p) atomicOr(err, ERRF_OFFSETS);
+    if (p < n_bytes) atomicOr(&ds[p >> 5], 1u << (p & 31));
+}
+
+// one thread per 32 byte positions -> one word of the start bitmap
+__global__ void __launch_bounds__(256) k_starts(TextView tv, uint32_t* __restrict__ start_bits,
+                                                uint32_t* __restrict__ block_counts) {
+    uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t base = w * 32;
+    uint32_t bits = 0;
+    if (base < tv.n) {
+        for (int k = 0; k < 32; ++k) {
+            uint64_t i = base + k;
+            if (i < tv.n && tv.is_start(i)) bits |= 1u << k;
+        }
+        start_bits[w] = bits;
+    }
+    int c = __popc(bits);
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    __shared__ int s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < 8; ++k) t += s[k];
+        block_counts[blockIdx.x] = (uint32_t)t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_list(const uint32_t* __restrict__ start_bits, uint64_t n_words,
+                                              const uint32_t* __restrict__ block_base, uint32_t* __restrict__ starts) {
+    uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint32_t bits = w < n_words ? start_bits[w] : 0u;
+    int c = __popc(bits), lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+    __shared__ int s[8];
+    if (lane == 31) s[wid] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int k = 0; k < wid; ++k) wbase += s[k];
+    uint32_t o = block_base[blockIdx.x] + (uint32_t)(wbase + incl - c);
+    while (bits) {
+        int k = __ffs(bits) - 1;
+        bits &= bits - 1;
+        starts[o++] = (uint32_t)(w * 32 + k);
+    }
+}
+
+// Pre-tokens longer than 32 symbols: same one-merge-per-iteration order, symbols kept compacted in
+// global memory (the tmp_ids slice of this pre-token), every pair re-probed each iteration.
+// O(n^2/32) probes per lane: exact but slow; long pre-tokens are rare outside config 4.
+__device__ int bpe_warp_long(const DevTables& t, uint32_t* sym, int n) {
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    while (n > 1) {
+        uint32_t best = kNone, best_new = 0;
+        uint32_t best_pos = 0;
+        for (int i = lane; i + 1 < n; i += 32) {
+            uint2 r = pair_lookup(t, sym[i], sym[i + 1]);
+            if (r.x < best) { best = r.x; best_new = r.y; best_pos = (uint32_t)i; }   // strict <: leftmost within the lane
+        }
+        // lowest rank, then leftmost position, across lanes
+        unsigned long long key = best == kNone ? ~0ull : ((unsigned long long)best << 32) | best_pos;
+        unsigned long long k2 = key;
+        for (int o = 16; o; o >>= 1) { unsigned long long v = __shfl_xor_sync(full, k2, o); k2 = v < k2 ? v : k2; }
+        if (k2 == ~0ull) break;
+        int idx = (int)(uint32_t)k2;
+        int owner = __ffs(__ballot_sync(full, key == k2)) - 1;
+        uint32_t new_id = __shfl_sync(full, best_new, owner);
+        __syncwarp();
+        // shift left by one beyond idx, in rounds of 32 so reads happen before writes
+        for (int base = idx + 1; base < n - 1; base += 32) {
+            int i = base + lane;
+            uint32_t v = (i < n - 1) ? sym[i + 1] : 0u;
+            __syncwarp();
+            if (i < n - 1) sym[i] = v;
+            __syncwarp();
+        }
+        if (lane == 0) sym[idx] = new_id;
+        __syncwarp();
+        --n;
+    }
+    return n;
+}
+
+// one warp per pre-token
+__global__ void __launch_bounds__(256) k_bpe(DevTables t, const uint8_t* __restrict__ text, uint64_t n_bytes,
+                                             const uint32_t* __restrict__ starts, uint32_t n_pre,
+                                             uint32_t* __restrict__ tmp_ids, uint32_t* __restrict__ ntok) {
+    const unsigned full = 0xFFFFFFFFu;
+    uint64_t k = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_pre) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t s = starts[k];
+    uint32_t e = (k + 1 < n_pre) ? starts[k + 1] : (uint32_t)n_bytes;
+    int len = (int)(e - s);
+    int m;
+    if (len <= 32) {
+        uint32_t sym = kNone;
+        if (lane < len) sym = __ldg(t.byte_init + text[s + lane]);
+        unsigned have = __ballot_sync(full, sym != kNone);       // bpe.rs:94-97: unknown chars are dropped
+        int n = __popc(have);
+        if (have != (len == 32 ? full : ((1u << len) - 1u))) {   // compact
+            int dst = __popc(have & ((1u << lane) - 1u));
+            uint32_t out = kNone;
+            for (int src = 0; src < 32; ++src) {
+                uint32_t v = __shfl_sync(full, sym, src);
+                int d = __shfl_sync(full, dst, src);
+                if (((have >> src) & 1u) && d == lane) out = v;
+            }
+            sym = out;
+        }
+        m = n ? bpe_warp32(t, sym, n) : 0;
+        if (lane < m) tmp_ids[s + lane] = sym;
+    } else {
+        uint32_t* sym = tmp_ids + s;
+        int n = 0;
+        for (int base = 0; base < len; base += 32) {
+            int i = base + lane;
+            uint32_t v = i < len ? __ldg(t.byte_init + text[s + i]) : kNone;
+            unsigned have = __ballot_sync(full, v != kNone);
+            if (v != kNone) sym[n + __popc(have & ((1u << lane) - 1u))] = v;
+            n += __popc(have);
+        }
+        __syncwarp();
+        m = bpe_warp_long(t, sym, n);
+    }
+    if (lane == 0) ntok[k] = (uint32_t)m;
+}
+
+__global__ void __launch_bounds__(256) k_emit(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ tok_off,
+                                              uint32_t n_pre, const uint32_t* __restrict__ tmp_ids,
+                                              uint32_t* __restrict__ out, uint64_t out_cap, uint32_t* __restrict__ err) {
+    uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (k >= n_pre) return;
+    uint32_t o = tok_off[k], c = tok_off[k + 1] - o, s = starts[k];
+    if ((uint64_t)o + c > out_cap) { atomicOr(err, ERRF_CAPACITY); return; }
+    for (uint32_t i = 0; i < c; ++i) out[o + i] = tmp_ids[s + i];
+}
+
+// ids_off[d] = number of ids produced by pre-tokens that start before text_off[d]
+__global__ void k_doc_offsets(const uint64_t* __restrict__ text_off, uint64_t n_docs, const uint32_t* __restrict__ starts,
+                              uint32_t n_pre, const uint32_t* __restrict__ tok_off, uint64_t* __restrict__ ids_off) {
+    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d > n_docs) return;
+    uint64_t p = text_off[d];
+    uint32_t lo = 0, hi = n_pre;                 // lower_bound(starts, p)
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (starts[mid] < p) lo = mid + 1; else hi = mid;
+    }
+    ids_off[d] = tok_off[lo];
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
+
+int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
+                   uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st) {
+    if (n_bytes >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_ARG, "one device call handles less than 4 GiB of text");
+    if (n_bytes == 0) {
+        CK(cudaMemsetAsync(d_ids_off, 0, (n_docs + 1) * 8, st));
+        if (n_ids_host) { CK(cudaStreamSynchronize(st)); *n_ids_host = 0; }
+        return CTK_OK;
+    }
+    uint64_t n_words = (n_bytes + 31) / 32;
+    uint32_t n_blocks = (uint32_t)((n_words + 255) / 256);
+    Workspace& ws = eng.ws;
+    uint32_t *ds, *sb, *bc, *bb, *err;
+    CK(ws.get(0, (n_words + 1) * 4, (void**)&ds));
+    CK(ws.get(1, (n_words + 1) * 4, (void**)&sb));
+    CK(ws.get(2, ((uint64_t)n_blocks + 1) * 4, (void**)&bc));
+    CK(ws.get(3, ((uint64_t)n_blocks + 1) * 4, (void**)&bb));
+    CK(ws.get(4, 256, (void**)&err));
+    CK(cudaMemsetAsync(ds, 0, (n_words + 1) * 4, st));
+    CK(cudaMemsetAsync(err, 0, 256, st));
+    k_docstart<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_off, n_docs, n_bytes, ds, err);
+    eng.launched(1);
+    TextView tv{d_text, n_bytes, ds, eng.tables.trie_index, eng.tables.trie_blocks};
+    k_starts<<<n_blocks, 256, 0, st>>>(tv, sb, bc);
+    eng.launched(1);
+    size_t cub_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, bc, bb, n_blocks + 1, st));
+    void* cub_tmp;
+    CK(ws.get(5, cub_bytes + 16, &cub_tmp));
+    CK(cudaMemsetAsync(bc + n_blocks, 0, 4, st));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, bc, bb, n_blocks + 1, st));
+    eng.launched(1);
+    uint32_t n_pre = 0;
+    CK(cudaMemcpyAsync(&n_pre, bb + n_blocks, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t *starts, *tmp_ids, *ntok, *tok_off;
+    CK(ws.get(6, ((uint64_t)n_pre + 2) * 4, (void**)&starts));
+    CK(ws.get(7, (n_bytes + 64) * 4, (void**)&tmp_ids));
+    CK(ws.get(8, ((uint64_t)n_pre + 2) * 4, (void**)&ntok));
+    CK(ws.get(9, ((uint64_t)n_pre + 2) * 4, (void**)&tok_off));
+    k_list<<<n_blocks, 256, 0, st>>>(sb, n_words, bb, starts);
+    eng.launched(1);
+    k_bpe<<<(unsigned)(((uint64_t)n_pre * 32 + 255) / 256), 256, 0, st>>>(eng.tables, d_text, n_bytes, starts, n_pre, tmp_ids, ntok);
+    eng.launched(1);
+    CK(cudaMemsetAsync(ntok + n_pre, 0, 4, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, ntok, tok_off, n_pre + 1, st));
+    CK(ws.get(5, cub_bytes + 16, &cub_tmp));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntok, tok_off, n_pre + 1, st));
+    eng.launched(1);
+    k_emit<<<(n_pre + 255) / 256, 256, 0, st>>>(starts, tok_off, n_pre, tmp_ids, d_ids, ids_cap, err);
+    k_doc_offsets<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_off, n_docs, starts, n_pre, tok_off, d_ids_off);
+    eng.launched(2);
+    CK(cudaGetLastError());
+    return eng.finish(err, d_ids_off, n_docs, n_ids_host, st);
+}
+
+}  // namespace ctk

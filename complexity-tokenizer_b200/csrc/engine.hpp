@@ -1,0 +1,89 @@
+// Engine: one loaded tokenizer bound to one GPU (device tables, scratch workspace, stream-ordered calls).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "../../include/ctk.h"
+#include "device_common.cuh"
+#include "model.hpp"
+
+namespace ctk {
+
+// device-side error flags (OR-ed into a word the host reads back)
+enum : uint32_t { ERRF_OFFSETS = 1, ERRF_CAPACITY = 2, ERRF_UTF8 = 4, ERRF_POOL = 8, ERRF_NFC_LONG = 16 };
+
+void set_last_error(const std::string& s);
+extern std::atomic<uint64_t> g_kernel_launches;
+
+// Grow-only device scratch, one buffer per slot.  Growing frees the old buffer (cudaFree
+// synchronises the device, so nothing in flight can still be using it).
+struct Workspace {
+    static constexpr int kSlots = 32;
+    void* p[kSlots] = {};
+    size_t cap[kSlots] = {};
+    cudaError_t get(int slot, size_t bytes, void** out) {
+        if (bytes > cap[slot]) {
+            if (p[slot]) cudaFree(p[slot]);
+            p[slot] = nullptr; cap[slot] = 0;
+            size_t want = bytes + bytes / 8 + 256;
+            cudaError_t e = cudaMalloc(&p[slot], want);
+            if (e != cudaSuccess) return e;
+            cap[slot] = want;
+        }
+        *out = p[slot];
+        return cudaSuccess;
+    }
+    void release() { for (int i = 0; i < kSlots; ++i) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; } }
+};
+
+struct DecodeTables {
+    const uint8_t* blob = nullptr;
+    const uint32_t* off = nullptr;      // n_ids + 1
+    const uint8_t* special = nullptr;   // n_ids
+    uint32_t n_ids = 0;
+};
+
+struct NfcTables {                      // canonical decomposition / composition / ccc, sorted for binary search
+    const uint32_t *dkey, *da, *db; int nd;
+    const uint64_t* ckey; const uint32_t* cval; int nc;
+    const uint32_t* qkey; const uint8_t* qval; int nq;
+    const uint8_t *trie_index, *trie_blocks;
+};
+
+struct Engine {
+    HostModel model;
+    int device = 0;
+    DevTables tables{};
+    DecodeTables dec{};
+    NfcTables nfc{};
+    void* d_table_mem[16] = {};
+    Workspace ws;
+    std::mutex mu;                      // serialises device work issued through this tokenizer
+    bool cache_persistent = false;
+    // pinned staging for error flags / counters
+    uint32_t* h_flags = nullptr;
+    uint8_t* last_decode_out = nullptr;   // decode_device(d_out = NULL) leaves its output here
+
+    int fail(int code, const std::string& msg) { set_last_error(msg); return code; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        set_last_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what);
+        return CTK_ERR_CUDA;
+    }
+    void launched(int n) { g_kernel_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+    // common tail of an encode/decode device call: optionally synchronise, check the error flags,
+    // return the total (last entry of the n+1 offsets array)
+    int finish(const uint32_t* d_err, const uint64_t* d_off_out, size_t n, uint64_t* total_host, cudaStream_t st);
+};
+
+int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
+              const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st);
+int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
+                   uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
+int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off, size_t n, uint64_t total_ids,
+                  int skip_special, int cleanup, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off,
+                  uint64_t* n_bytes_host, cudaStream_t st);
+
+}  // namespace ctk

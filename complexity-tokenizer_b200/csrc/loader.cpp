@@ -1,0 +1,326 @@
+// tokenizer.json -> HostModel, following the reference's load rules:
+//   schema / merges forms        src/huggingface/mod.rs:31-116
+//   from_tokenizer_json_*        src/huggingface/mod.rs:247-334
+//   BpeTokenizer::new            src/bpe.rs:52-79   (rank = original index, merges vector compacted;
+//                                                     new_id read back as merges[rank] at bpe.rs:141)
+//   Vocab::new                   src/vocab.rs:47-51
+//   component defaults           src/huggingface/parsing.rs:10-90, 93-190, 272-364
+#include "model.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+#include "../../include/ctk.h"
+#include "json.hpp"
+
+namespace ctk {
+
+void byte_map(uint32_t byte_to_cp[256]) {
+    int n = 0;
+    for (int b = 0; b < 256; ++b) {
+        bool keep = (b >= '!' && b <= '~') || (b >= 0xA1 && b <= 0xAC) || (b >= 0xAE);
+        byte_to_cp[b] = keep ? (uint32_t)b : (uint32_t)(256 + n++);
+    }
+}
+
+namespace {
+
+void put_utf8(std::string& s, uint32_t cp) {
+    if (cp < 0x80) s += (char)cp;
+    else if (cp < 0x800) { s += (char)(0xC0 | (cp >> 6)); s += (char)(0x80 | (cp & 63)); }
+    else if (cp < 0x10000) { s += (char)(0xE0 | (cp >> 12)); s += (char)(0x80 | ((cp >> 6) & 63)); s += (char)(0x80 | (cp & 63)); }
+    else { s += (char)(0xF0 | (cp >> 18)); s += (char)(0x80 | ((cp >> 12) & 63)); s += (char)(0x80 | ((cp >> 6) & 63)); s += (char)(0x80 | (cp & 63)); }
+}
+
+// decode one code point of a valid UTF-8 std::string
+uint32_t next_cp(const std::string& s, size_t& i) {
+    unsigned char c = (unsigned char)s[i];
+    if (c < 0x80) { ++i; return c; }
+    if (c < 0xE0) { uint32_t r = ((c & 0x1Fu) << 6) | ((unsigned char)s[i + 1] & 63u); i += 2; return r; }
+    if (c < 0xF0) { uint32_t r = ((c & 0x0Fu) << 12) | (((unsigned char)s[i + 1] & 63u) << 6) | ((unsigned char)s[i + 2] & 63u); i += 3; return r; }
+    uint32_t r = ((c & 7u) << 18) | (((unsigned char)s[i + 1] & 63u) << 12) | (((unsigned char)s[i + 2] & 63u) << 6) | ((unsigned char)s[i + 3] & 63u);
+    i += 4;
+    return r;
+}
+
+bool rust_regex_would_compile(const std::string& p) {
+    // Rust `regex` has no look-around and no back-references: Regex::new fails and
+    // regex_split_with_behavior returns the text unchanged (pretokenizers.rs:299-302).
+    static const char* bad[] = {"(?=", "(?!", "(?<=", "(?<!"};
+    for (const char* b : bad) if (p.find(b) != std::string::npos) return false;
+    for (char d = '1'; d <= '9'; ++d) { char pat[3] = {'\\', d, 0}; if (p.find(pat) != std::string::npos) return false; }
+    return true;
+}
+
+const char* type_of(const JValue* v) {
+    if (!v || !v->is_obj()) return nullptr;
+    const JValue* t = v->get("type");
+    if (!t) return nullptr;
+    return t->is_str() ? t->s.c_str() : "";
+}
+
+// parsing.rs:10-90.  ok=false => unsupported
+bool parse_normalizer(const JValue* v, bool& nfc, std::string& err) {
+    const char* t = type_of(v);
+    if (!t) { nfc = true; return true; }                       // missing/null/malformed => NFC (:89)
+    std::string ty = t;
+    if (ty == "NFC") { nfc = true; return true; }
+    if (ty == "Sequence") {
+        const JValue* seq = v->get("normalizers");
+        nfc = false;
+        if (!seq || !seq->is_arr()) return true;                // => None
+        for (auto& x : seq->arr) {
+            bool sub = false;
+            JValue tmp = x;
+            if (!parse_normalizer(x.t == JValue::Null ? nullptr : &x, sub, err)) return false;
+            nfc = nfc || sub;                                   // NFC is idempotent
+        }
+        return true;
+    }
+    static const char* out_of_scope[] = {"NFD", "NFKC", "NFKD", "Lowercase", "Strip", "StripAccents", "Replace",
+                                         "Prepend", "BertNormalizer", "Precompiled"};
+    for (const char* o : out_of_scope)
+        if (ty == o) { err = "normalizer '" + ty + "' is outside the ByteLevel-BPE hot path"; return false; }
+    nfc = false;                                                // unknown type => None
+    return true;
+}
+
+// parsing.rs:93-190.  Collects ByteLevel stages; returns 0 ok, 1 = "None", 2 = unsupported
+int parse_pre(const JValue* v, std::vector<bool>& stages, std::string& err) {
+    const char* t = type_of(v);
+    if (!t) { stages.push_back(false); return 0; }              // default ByteLevel{false} (:187-189)
+    std::string ty = t;
+    if (ty == "ByteLevel") {
+        const JValue* a = v->get("add_prefix_space");
+        stages.push_back(a && a->t == JValue::Bool ? a->b : false);   // use_regex / trim_offsets ignored (:99-107)
+        return 0;
+    }
+    if (ty == "Split") {
+        const JValue* pat = v->get("pattern");
+        const JValue* rx = pat ? pat->get("Regex") : nullptr;
+        std::string p = (rx && rx->is_str()) ? rx->s : "";
+        if (rust_regex_would_compile(p)) { err = "Split pre-tokenizer with a compilable regex is outside the hot path"; return 2; }
+        return 0;                                               // passes text through
+    }
+    if (ty == "Sequence") {
+        const JValue* seq = v->get("pretokenizers");
+        if (!seq || !seq->is_arr()) return 1;
+        bool any = false;
+        for (auto& x : seq->arr) {
+            int r = parse_pre(x.t == JValue::Null ? nullptr : &x, stages, err);
+            if (r == 2) return 2;
+            if (r == 0) any = true;
+        }
+        return any ? 0 : 1;
+    }
+    static const char* out_of_scope[] = {"Metaspace", "Whitespace", "WhitespaceSplit", "Punctuation", "BertPreTokenizer",
+                                         "CharDelimiterSplit", "UnicodeScripts", "Digits"};
+    for (const char* o : out_of_scope)
+        if (ty == o) { err = "pre_tokenizer '" + ty + "' is outside the ByteLevel-BPE hot path"; return 2; }
+    return 1;                                                   // unknown type => None
+}
+
+int klass_ascii(uint8_t c) {   // 0 other, 1 letter, 2 number, 3 whitespace
+    if ((c | 0x20) >= 'a' && (c | 0x20) <= 'z') return 1;
+    if (c >= '0' && c <= '9') return 2;
+    if (c == ' ' || (c >= 9 && c <= 13)) return 3;
+    return 0;
+}
+
+// Can this added token ever occur inside ONE byte-mapped pre-token (mod.rs:566-610 searches words,
+// not raw text)?  Conservative: "false" only when provably impossible.  A pre-token is a
+// contraction, a whitespace run, or [one leading 0x20] + a run of a single class.
+void analyse_added(AddedTok& a, const std::unordered_map<uint32_t, uint8_t>& cp_to_byte) {
+    a.may_match = false;
+    a.bytes.clear();
+    for (size_t i = 0; i < a.content.size();) {
+        uint32_t cp = next_cp(a.content, i);
+        auto it = cp_to_byte.find(cp);
+        if (it == cp_to_byte.end()) return;                     // char outside the mapped alphabet
+        a.bytes.push_back(it->second);
+    }
+    if (a.bytes.empty()) return;
+    std::string s((const char*)a.bytes.data(), a.bytes.size());
+    static const char* contr[] = {"'s", "'t", "'re", "'ve", "'m", "'ll", "'d"};
+    for (const char* c : contr) if (std::string(c).find(s) != std::string::npos) { a.may_match = true; return; }
+    int seen = -1;
+    for (size_t i = 0; i < a.bytes.size(); ++i) {
+        uint8_t b = a.bytes[i];
+        if (b >= 0x80) continue;                                // part of a multi-byte char: class unknown here
+        int k = klass_ascii(b);
+        if (i == 0 && b == 0x20) continue;                      // glued leading space, or first char of a \s+ run
+        if (seen < 0) seen = k;
+        else if (seen != k) return;                             // two classes in one pre-token: impossible
+    }
+    if (a.bytes[0] == 0x20 && a.bytes.size() > 1 && seen == 3) { a.may_match = true; return; }
+    a.may_match = true;
+}
+
+}  // namespace
+
+int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err) {
+    JValue root;
+    {
+        JParser p((const char*)json, len);
+        if (!p.parse(root, err)) return CTK_ERR_INVALID_DATA;
+    }
+    if (!root.is_obj()) { err = "invalid type: expected struct TokenizerJson"; return CTK_ERR_INVALID_DATA; }
+    const JValue* ver = root.get("version");
+    if (ver && ver->t != JValue::Null && !ver->is_str()) { err = "version: expected a string"; return CTK_ERR_INVALID_DATA; }
+    const JValue* model = root.get("model");
+    if (!model || !model->is_obj()) { err = "missing field `model`"; return CTK_ERR_INVALID_DATA; }
+    const JValue* mt = model->get("type");
+    if (mt && mt->t != JValue::Null && !mt->is_str()) { err = "model.type: expected a string"; return CTK_ERR_INVALID_DATA; }
+    const JValue* vocab = model->get("vocab");
+    if (!vocab || !vocab->is_obj()) { err = "missing field `vocab`"; return CTK_ERR_INVALID_DATA; }
+    uint32_t max_id = 0;
+    for (auto& kv : vocab->obj) {
+        const JValue& v = kv.second;
+        if (v.t != JValue::Num || !v.is_uint || v.u > 0xFFFFFFFFull) { err = "vocab id is not a u32"; return CTK_ERR_INVALID_DATA; }
+        m.vocab[kv.first] = (uint32_t)v.u;                      // duplicate keys: last wins
+    }
+    for (auto& kv : m.vocab) max_id = std::max(max_id, kv.second);
+    if (!m.vocab.empty() && max_id > (1u << 24)) { err = "vocab ids above 2^24 are not supported"; return CTK_ERR_UNSUPPORTED; }
+
+    // ---- merges (mod.rs:56-101 then :252-264)
+    std::vector<std::pair<std::string, std::string>> merges;
+    const JValue* mj = model->get("merges");
+    if (mj) {
+        if (!mj->is_arr()) { err = "merges: expected a sequence"; return CTK_ERR_INVALID_DATA; }
+        for (auto& it : mj->arr) {
+            std::string line;
+            if (it.is_str()) line = it.s;
+            else if (it.is_arr()) {
+                if (it.arr.size() == 2 && it.arr[0].is_str() && it.arr[1].is_str()) line = it.arr[0].s + " " + it.arr[1].s;
+                else continue;
+            } else continue;
+            size_t sp = line.find(' ');
+            if (sp == std::string::npos) continue;
+            if (line.find(' ', sp + 1) != std::string::npos) continue;      // split(' ') must give exactly 2 parts
+            merges.emplace_back(line.substr(0, sp), line.substr(sp + 1));
+        }
+    }
+    // ---- BpeTokenizer::new (bpe.rs:52-79)
+    std::unordered_map<uint64_t, uint32_t> rank_of;
+    std::vector<uint32_t> ops_new_id;
+    for (size_t rank = 0; rank < merges.size(); ++rank) {
+        auto ia = m.vocab.find(merges[rank].first);
+        auto ib = m.vocab.find(merges[rank].second);
+        if (ia == m.vocab.end() || ib == m.vocab.end()) continue;
+        auto im = m.vocab.find(merges[rank].first + merges[rank].second);
+        if (im == m.vocab.end()) continue;
+        rank_of[((uint64_t)ia->second << 32) | ib->second] = (uint32_t)rank;    // insert: later overwrites
+        ops_new_id.push_back(im->second);
+    }
+    m.pairs.reserve(rank_of.size());
+    for (auto& kv : rank_of) {
+        if (kv.second >= ops_new_id.size()) {
+            err = "merges table would make the reference panic (bpe.rs:141: rank beyond the compacted merges vector)";
+            return CTK_ERR_UNSUPPORTED;
+        }
+        m.pairs.push_back({(uint32_t)(kv.first >> 32), (uint32_t)kv.first, kv.second, ops_new_id[kv.second]});
+    }
+    std::sort(m.pairs.begin(), m.pairs.end(), [](const PairEntry& x, const PairEntry& y) { return x.rank < y.rank; });
+
+    // ---- added tokens (mod.rs:274-305)
+    const JValue* aj = root.get("added_tokens");
+    std::unordered_map<std::string, size_t> added_idx;
+    std::unordered_map<std::string, uint32_t> special_map;
+    if (aj) {
+        if (!aj->is_arr()) { err = "added_tokens: expected a sequence"; return CTK_ERR_INVALID_DATA; }
+        for (auto& t : aj->arr) {
+            const JValue *id = t.get("id"), *content = t.get("content"), *special = t.get("special");
+            if (!t.is_obj() || !id || id->t != JValue::Num || !id->is_uint || id->u > 0xFFFFFFFFull || !content ||
+                !content->is_str() || !special || special->t != JValue::Bool) {
+                err = "added_tokens: missing or mistyped id/content/special";
+                return CTK_ERR_INVALID_DATA;
+            }
+            AddedTok a;
+            a.content = content->s;
+            a.id = (uint32_t)id->u;
+            a.special = special->b;
+            auto flag = [&](const char* k, bool& dst) -> bool {
+                const JValue* f = t.get(k);
+                if (!f) { dst = false; return true; }
+                if (f->t != JValue::Bool) return false;
+                dst = f->b;
+                return true;
+            };
+            bool normalized;
+            if (!flag("single_word", a.single_word) || !flag("lstrip", a.lstrip) || !flag("rstrip", a.rstrip) ||
+                !flag("normalized", normalized)) { err = "added_tokens: flag is not a bool"; return CTK_ERR_INVALID_DATA; }
+            auto f = added_idx.find(a.content);
+            if (f == added_idx.end()) { added_idx[a.content] = m.added.size(); m.added.push_back(a); }
+            else m.added[f->second] = a;
+            if (a.special) special_map[a.content] = a.id;
+        }
+    }
+    for (auto& kv : special_map) m.specials.emplace_back(kv.first, kv.second);
+    std::sort(m.specials.begin(), m.specials.end());
+
+    // ---- components
+    const JValue* nj = root.get("normalizer");
+    if (!parse_normalizer(nj && nj->t != JValue::Null ? nj : nullptr, m.nfc, err)) return CTK_ERR_UNSUPPORTED;
+    std::vector<bool> stages;
+    const JValue* pj = root.get("pre_tokenizer");
+    int pr = parse_pre(pj && pj->t != JValue::Null ? pj : nullptr, stages, err);
+    if (pr == 2) return CTK_ERR_UNSUPPORTED;
+    if (pr == 1 || stages.size() != 1) {
+        err = "pre_tokenizer must resolve to exactly one ByteLevel stage for the hot path";
+        return CTK_ERR_UNSUPPORTED;
+    }
+    m.add_prefix_space = stages[0];
+    const JValue* dj = root.get("decoder");
+    const char* dt = type_of(dj && dj->t != JValue::Null ? dj : nullptr);
+    if (dt && std::string(dt) != "ByteLevel") { err = std::string("decoder '") + dt + "' is outside the ByteLevel-BPE hot path"; return CTK_ERR_UNSUPPORTED; }
+
+    // ---- derived tables
+    uint32_t b2c[256];
+    byte_map(b2c);
+    std::unordered_map<uint32_t, uint8_t> c2b;
+    for (int b = 0; b < 256; ++b) {
+        c2b[b2c[b]] = (uint8_t)b;
+        std::string s;
+        put_utf8(s, b2c[b]);
+        auto it = m.vocab.find(s);
+        m.byte_init_id[b] = it == m.vocab.end() ? kNoId : it->second;
+    }
+    m.any_added_may_match = false;
+    for (auto& a : m.added) {
+        if (a.content.empty()) { err = "empty added token (the reference loops forever on it)"; return CTK_ERR_UNSUPPORTED; }
+        analyse_added(a, c2b);
+        m.any_added_may_match = m.any_added_may_match || a.may_match;
+    }
+    // Vocab::new (vocab.rs:48-51): id -> token.  Two tokens with one id: the reference keeps an
+    // arbitrary one (hash iteration order); we keep the lexicographically largest, deterministically.
+    size_t nid = m.vocab.empty() ? 0 : (size_t)max_id + 1;
+    m.id_to_token.assign(nid, std::string());
+    m.id_present.assign(nid, 0);
+    for (auto& kv : m.vocab) {
+        if (!m.id_present[kv.second] || m.id_to_token[kv.second] < kv.first) m.id_to_token[kv.second] = kv.first;
+        m.id_present[kv.second] = 1;
+    }
+    m.dec_off.assign(nid + 1, 0);
+    m.dec_special.assign(nid, 0);
+    m.dec_blob.clear();
+    m.dec_max_bytes = 0;
+    for (size_t id = 0; id < nid; ++id) {
+        m.dec_off[id] = (uint32_t)m.dec_blob.size();
+        if (!m.id_present[id]) continue;
+        const std::string& tok = m.id_to_token[id];
+        size_t before = m.dec_blob.size();
+        for (size_t i = 0; i < tok.size();) {                   // decoders.rs:100-116
+            uint32_t cp = next_cp(tok, i);
+            if (cp == 0x120) { m.dec_blob.push_back(0x20); continue; }
+            auto it = c2b.find(cp);
+            if (it != c2b.end()) m.dec_blob.push_back(it->second);
+            else if (cp < 0x80) m.dec_blob.push_back((uint8_t)cp);
+        }
+        m.dec_max_bytes = std::max(m.dec_max_bytes, m.dec_blob.size() - before);
+        if (special_map.count(tok)) m.dec_special[id] = 1;
+    }
+    m.dec_off[nid] = (uint32_t)m.dec_blob.size();
+    return CTK_OK;
+}
+
+}  // namespace ctk

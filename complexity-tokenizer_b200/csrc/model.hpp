@@ -1,0 +1,47 @@
+// Host-side model: what HuggingFaceTokenizer::from_tokenizer_json_with_config builds
+// (reference src/huggingface/mod.rs:247-334), reduced to the tables the hot path needs.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace ctk {
+
+constexpr uint32_t kNoId = 0xFFFFFFFFu;
+
+struct AddedTok {
+    std::string content;        // as written in tokenizer.json (compared against byte-MAPPED words)
+    std::vector<uint8_t> bytes; // content translated back through the byte map (only if may_match)
+    uint32_t id = 0;
+    bool special = false, single_word = false, lstrip = false, rstrip = false;
+    bool may_match = false;     // can occur inside one pre-token (see loader.cpp: analyse_added)
+};
+
+struct PairEntry { uint32_t a, b, rank, new_id; };
+
+struct HostModel {
+    std::unordered_map<std::string, uint32_t> vocab;      // model.vocab
+    std::vector<std::string> id_to_token;                  // dense, index = id
+    std::vector<uint8_t> id_present;
+    std::vector<PairEntry> pairs;                          // merge_ranks with new_id resolved (bpe.rs:52-79,:141)
+    std::vector<AddedTok> added;                           // de-duplicated by content (HashMap semantics)
+    std::vector<std::pair<std::string, uint32_t>> specials;// special_tokens map (mod.rs:290-291)
+    bool nfc = true;                                       // parsing.rs:89
+    bool add_prefix_space = false;                         // parsing.rs:99-107
+    uint32_t byte_init_id[256];                            // byte -> id of its mapped char, kNoId if absent (bpe.rs:94-97)
+    // decode side (vocab.rs:47-51 + decoders.rs:94-116 folded per token at load)
+    std::vector<uint8_t> dec_blob;
+    std::vector<uint32_t> dec_off;                         // max_id+2 entries; absent ids have empty ranges
+    std::vector<uint8_t> dec_special;                      // 1 if the token string is in special_tokens
+    size_t dec_max_bytes = 0;
+    bool any_added_may_match = false;
+};
+
+// Returns a CTK_* code; on failure `err` holds the message.
+int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err);
+
+// GPT-2 byte <-> code point map (pretokenizers.rs:130-153 / decoders.rs:70-91)
+void byte_map(uint32_t byte_to_cp[256]);
+
+}  // namespace ctk

@@ -1,0 +1,230 @@
+// Unicode NFC on the GPU (reference: Normalizer::NFC, src/normalizers.rs:45-47, the default
+// normalizer per src/huggingface/parsing.rs:89).
+//
+// Almost all text is already NFC.  k_nfc_flag scans every byte once (vectorised) and marks the
+// documents that contain an "NFC-suspect" code point (NFC_QC != Yes or ccc != 0; none exist below
+// U+0300, i.e. below lead byte 0xCC).  If no document is marked the stage is a no-op.  Otherwise
+// marked documents are normalised by a streaming decompose / canonical-reorder / compose pass
+// (UAX #15) and every other document is copied, into a fresh packed buffer with new offsets.
+#include <cub/device/device_scan.cuh>
+
+#include "engine.hpp"
+
+namespace ctk {
+
+__device__ __forceinline__ int nfc_ccc(const NfcTables& t, uint32_t cp) {
+    if (cp < 0x300) return 0;
+    int lo = 0, hi = t.nq - 1;
+    while (lo <= hi) { int mid = (lo + hi) >> 1; uint32_t k = t.qkey[mid]; if (cp < k) hi = mid - 1; else if (cp > k) lo = mid + 1; else return t.qval[mid]; }
+    return 0;
+}
+__device__ __forceinline__ int nfc_decomp_idx(const NfcTables& t, uint32_t cp) {
+    if (cp < 0xC0) return -1;
+    int lo = 0, hi = t.nd - 1;
+    while (lo <= hi) { int mid = (lo + hi) >> 1; uint32_t k = t.dkey[mid]; if (cp < k) hi = mid - 1; else if (cp > k) lo = mid + 1; else return mid; }
+    return -1;
+}
+__device__ __forceinline__ uint32_t nfc_compose(const NfcTables& t, uint32_t a, uint32_t b) {
+    if (a >= 0x1100 && a < 0x1113 && b >= 0x1161 && b < 0x1176) return 0xAC00 + ((a - 0x1100) * 21 + (b - 0x1161)) * 28;
+    if (a >= 0xAC00 && a < 0xD7A4 && (a - 0xAC00) % 28 == 0 && b > 0x11A7 && b < 0x11C3) return a + (b - 0x11A7);
+    uint64_t key = ((uint64_t)a << 21) | b;
+    int lo = 0, hi = t.nc - 1;
+    while (lo <= hi) { int mid = (lo + hi) >> 1; uint64_t k = t.ckey[mid]; if (key < k) hi = mid - 1; else if (key > k) lo = mid + 1; else return t.cval[mid]; }
+    return 0;
+}
+
+constexpr int kSegMax = 48;      // code points buffered between two stable starters
+
+struct NfcSink {                 // counts, and writes when out != nullptr
+    uint8_t* out; uint64_t n;
+    __device__ void put(uint32_t cp) {
+        if (out) {
+            if (cp < 0x80) out[n] = (uint8_t)cp;
+            else if (cp < 0x800) { out[n] = 0xC0 | (cp >> 6); out[n + 1] = 0x80 | (cp & 63); }
+            else if (cp < 0x10000) { out[n] = 0xE0 | (cp >> 12); out[n + 1] = 0x80 | ((cp >> 6) & 63); out[n + 2] = 0x80 | (cp & 63); }
+            else { out[n] = 0xF0 | (cp >> 18); out[n + 1] = 0x80 | ((cp >> 12) & 63); out[n + 2] = 0x80 | ((cp >> 6) & 63); out[n + 3] = 0x80 | (cp & 63); }
+        }
+        n += cp < 0x80 ? 1 : cp < 0x800 ? 2 : cp < 0x10000 ? 3 : 4;
+    }
+};
+
+struct NfcStream {
+    const NfcTables& t;
+    NfcSink& sink;
+    uint32_t buf[kSegMax];
+    uint8_t cc[kSegMax];
+    int n = 0;
+    bool overflow = false;
+    __device__ NfcStream(const NfcTables& t_, NfcSink& s_) : t(t_), sink(s_) {}
+
+    // compose buf[0..n) in place (it is canonically ordered), return new length
+    __device__ void compose_buf() {
+        if (n < 2) return;
+        int w = 0, starter = -1, prev_cc = 0;
+        for (int k = 0; k < n; ++k) {
+            uint32_t c = buf[k]; int c_cc = cc[k];
+            if (starter >= 0 && (prev_cc == 0 || prev_cc < c_cc)) {
+                uint32_t comp = nfc_compose(t, buf[starter], c);
+                if (comp) { buf[starter] = comp; continue; }
+            }
+            if (c_cc == 0) starter = w;
+            prev_cc = c_cc;
+            buf[w] = c; cc[w] = (uint8_t)c_cc; ++w;
+        }
+        n = w;
+    }
+    __device__ void flush() { compose_buf(); for (int k = 0; k < n; ++k) sink.put(buf[k]); n = 0; }
+    // one fully decomposed code point
+    __device__ void push_decomposed(uint32_t cp) {
+        int c = nfc_ccc(t, cp);
+        if (c == 0) {
+            // a starter closes the segment unless it can still combine with a lone preceding starter
+            compose_buf();
+            if (n == 1 && cc[0] == 0) {
+                uint32_t comp = nfc_compose(t, buf[0], cp);
+                if (comp) { buf[0] = comp; return; }
+            }
+            for (int k = 0; k < n; ++k) sink.put(buf[k]);
+            n = 0;
+            buf[0] = cp; cc[0] = 0; n = 1;
+            return;
+        }
+        if (n >= kSegMax) { overflow = true; flush(); }
+        // canonical ordering: insert after the last mark with ccc <= c
+        int j = n;
+        while (j > 0 && cc[j - 1] > c) { buf[j] = buf[j - 1]; cc[j] = cc[j - 1]; --j; }
+        buf[j] = cp; cc[j] = (uint8_t)c; ++n;
+    }
+    __device__ void push(uint32_t cp) {
+        if (cp >= 0xAC00 && cp < 0xD7A4) {
+            uint32_t s = cp - 0xAC00;
+            push_decomposed(0x1100 + s / 588);
+            push_decomposed(0x1161 + (s % 588) / 28);
+            if (s % 28) push_decomposed(0x11A7 + s % 28);
+            return;
+        }
+        // iterative full canonical decomposition (depth <= 4): expand the first element repeatedly
+        uint32_t stack[8]; int sp = 0;
+        stack[sp++] = cp;
+        while (sp) {
+            uint32_t c = stack[--sp];
+            int di = nfc_decomp_idx(t, c);
+            if (di < 0) { push_decomposed(c); continue; }
+            uint32_t a = t.da[di], b = t.db[di];
+            if (b && sp < 7) stack[sp++] = b;
+            if (sp < 8) stack[sp++] = a;
+        }
+    }
+};
+
+__device__ __forceinline__ uint32_t dec_cp(const uint8_t* s, uint64_t n, uint64_t& i) {
+    uint32_t c = s[i];
+    if (c < 0x80) { ++i; return c; }
+    if (c < 0xE0) { uint32_t r = ((c & 0x1F) << 6) | ((i + 1 < n ? s[i + 1] : 0) & 63); i += 2; return r; }
+    if (c < 0xF0) { uint32_t r = ((c & 0x0F) << 12) | (((i + 1 < n ? s[i + 1] : 0) & 63) << 6) | ((i + 2 < n ? s[i + 2] : 0) & 63); i += 3; return r; }
+    uint32_t r = ((c & 7) << 18) | (((i + 1 < n ? s[i + 1] : 0) & 63) << 12) | (((i + 2 < n ? s[i + 2] : 0) & 63) << 6) | ((i + 3 < n ? s[i + 3] : 0) & 63);
+    i += 4;
+    return r;
+}
+
+// one thread per 16 bytes: any suspect code point -> mark its document
+__global__ void __launch_bounds__(256) k_nfc_flag(NfcTables t, const uint8_t* __restrict__ text, uint64_t n,
+                                                  const uint64_t* __restrict__ off, uint64_t n_docs,
+                                                  uint8_t* __restrict__ doc_flag, uint32_t* __restrict__ any) {
+    uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
+    if (base >= n) return;
+    uint4 v = *reinterpret_cast<const uint4*>(text + base);          // text buffers are 16-byte aligned and padded
+    // quick reject: no byte >= 0xCC (SWAR: (x & 0x80) && ((x & 0x7F) + 0x34) & 0x80)
+    auto hi = [](uint32_t x) { return (x & 0x80808080u) & (((x & 0x7F7F7F7Fu) + 0x34343434u)); };
+    if (!(hi(v.x) | hi(v.y) | hi(v.z) | hi(v.w))) return;
+    const uint8_t* p = text;
+    for (int k = 0; k < 16; ++k) {
+        uint64_t i = base + k;
+        if (i >= n) break;
+        uint32_t c = p[i];
+        if (c < 0xCC) continue;
+        uint64_t j = i;
+        uint32_t cp = dec_cp(p, n, j);
+        if (trie_nibble(t.trie_index, t.trie_blocks, cp) & 4u) {
+            uint64_t lo = 0, hi2 = n_docs;                            // last doc with off[d] <= i
+            while (lo + 1 < hi2) { uint64_t mid = (lo + hi2) >> 1; if (off[mid] <= i) lo = mid; else hi2 = mid; }
+            doc_flag[lo] = 1;
+            *any = 1;
+        }
+    }
+}
+
+// one warp per document: flagged -> lane 0 normalises (count or write); else length / coalesced copy
+__global__ void __launch_bounds__(256) k_nfc_doc(NfcTables t, const uint8_t* __restrict__ text, const uint64_t* __restrict__ off,
+                                                 uint64_t n_docs, const uint8_t* __restrict__ doc_flag,
+                                                 const uint64_t* __restrict__ new_off, uint8_t* out, uint64_t* __restrict__ new_len,
+                                                 uint32_t* __restrict__ err) {
+    uint64_t d = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_docs) return;
+    int lane = threadIdx.x & 31;
+    const uint8_t* s = text + off[d];
+    uint64_t n = off[d + 1] - off[d];
+    if (!doc_flag[d]) {
+        if (!out) { if (lane == 0) new_len[d] = n; return; }
+        uint8_t* o = out + new_off[d];
+        for (uint64_t i = lane; i < n; i += 32) o[i] = s[i];
+        return;
+    }
+    if (lane) return;
+    NfcSink sink{out ? out + new_off[d] : nullptr, 0};
+    NfcStream st(t, sink);
+    for (uint64_t i = 0; i < n;) st.push(dec_cp(s, n, i));
+    st.flush();
+    if (st.overflow) atomicOr(err, ERRF_NFC_LONG);
+    if (!out) new_len[d] = sink.n;
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
+
+// In: d_text/d_off.  Out: *o_text/*o_off/*o_bytes = the normalised batch (the inputs themselves when
+// nothing had to change).
+int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
+              const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st) {
+    *o_text = d_text; *o_off = d_off; *o_bytes = n_bytes;
+    if (!eng.model.nfc || n_bytes == 0 || n_docs == 0) return CTK_OK;
+    Workspace& ws = eng.ws;
+    uint8_t* flag; uint32_t* any;
+    CK(ws.get(26, n_docs + 16, (void**)&flag));
+    CK(ws.get(27, 64, (void**)&any));
+    CK(cudaMemsetAsync(flag, 0, n_docs + 16, st));
+    CK(cudaMemsetAsync(any, 0, 64, st));
+    NfcTables t = eng.nfc;
+    k_nfc_flag<<<(unsigned)(((n_bytes + 15) / 16 + 255) / 256), 256, 0, st>>>(t, d_text, n_bytes, d_off, n_docs, flag, any);
+    eng.launched(1);
+    CK(cudaMemcpyAsync(eng.h_flags + 8, any, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!eng.h_flags[8]) return CTK_OK;
+    uint64_t *new_len, *new_off;
+    CK(ws.get(28, (n_docs + 2) * 8, (void**)&new_len));
+    CK(ws.get(29, (n_docs + 2) * 8, (void**)&new_off));
+    unsigned grid = (unsigned)((n_docs * 32 + 255) / 256);
+    k_nfc_doc<<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, nullptr, nullptr, new_len, any + 1);
+    eng.launched(1);
+    CK(cudaMemsetAsync(new_len + n_docs, 0, 8, st));
+    size_t cub_bytes = 0; void* cub_tmp;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, new_len, new_off, n_docs + 1, st));
+    CK(ws.get(5, cub_bytes + 16, &cub_tmp));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, new_len, new_off, n_docs + 1, st));
+    eng.launched(1);
+    uint64_t total = 0;
+    CK(cudaMemcpyAsync(&total, new_off + n_docs, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint8_t* out;
+    CK(ws.get(30, total + 64, (void**)&out));
+    CK(cudaMemsetAsync(out + total, 0, 64, st));
+    k_nfc_doc<<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, new_off, out, nullptr, any + 1);
+    eng.launched(1);
+    CK(cudaMemcpyAsync(eng.h_flags + 8, any + 1, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (eng.h_flags[8] & ERRF_NFC_LONG)
+        return eng.fail(CTK_ERR_UNSUPPORTED, "a combining sequence longer than 48 code points needs NFC; not supported");
+    *o_text = out; *o_off = new_off; *o_bytes = total;
+    return CTK_OK;
+}
+
+}  // namespace ctk

@@ -1,0 +1,111 @@
+/* ctk.h -- C ABI of the B200-native batched encode/decode path for complexity-tokenizer.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its
+ * boundary is the PyO3 class `Tokenizer` (src/bindings/tokenizer.rs:11-14) whose hot-path methods
+ * forward to `HuggingFaceTokenizer` (src/huggingface/mod.rs).  Each entry point below names the
+ * reference function it replaces; INTEGRATION.md shows the Rust `extern "C"` block and the
+ * three-line bodies a maintainer would put in src/bindings/tokenizer.rs.
+ *
+ * Conventions
+ *   - Batches are PACKED: one contiguous byte (or id) buffer plus n+1 uint64 offsets; item i is
+ *     [off[i], off[i+1]).  No per-string pointers cross the boundary.
+ *   - Text is UTF-8 and must be valid (the reference takes &str, which guarantees it).
+ *   - A ctk_tokenizer is immutable after creation and may be used from several host threads.
+ *   - All compute runs on the GPU.  There is no CPU fallback: if no usable device or the CUDA
+ *     library is missing the call fails with CTK_ERR_CUDA.
+ *   - Return value: 0 ok, else one of CTK_ERR_*; ctk_last_error() gives a thread-local message.
+ */
+#ifndef CTK_H
+#define CTK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTK_OK 0
+#define CTK_ERR_IO 1            /* file could not be read            (io::Error -> PyIOError)          */
+#define CTK_ERR_INVALID_DATA 2  /* not a tokenizer.json / bad UTF-8  (io::ErrorKind::InvalidData)      */
+#define CTK_ERR_UNSUPPORTED 3   /* pipeline outside the hot path (non-ByteLevel, NFKC, ...)            */
+#define CTK_ERR_CUDA 4          /* CUDA failure, no device, out of memory                              */
+#define CTK_ERR_ARG 5           /* bad argument (null pointer, unaligned device buffer, ...)           */
+
+typedef struct ctk_tokenizer ctk_tokenizer;   /* opaque */
+typedef struct ctk_result ctk_result;         /* opaque, owns host (pinned) result buffers */
+
+/* ---- load ---------------------------------------------------------------------------------
+ * Replaces HuggingFaceTokenizer::from_file (src/huggingface/mod.rs:159-166) and ::from_str /
+ * ::from_buffer (:169-180): parses tokenizer.json with the reference's rules (mod.rs:31-116,
+ * :247-334; bpe.rs:52-79; parsing.rs defaults) and uploads the tables to `device`. */
+int ctk_from_file(const char* path, int device, ctk_tokenizer** out);
+int ctk_from_json(const uint8_t* json, size_t len, int device, ctk_tokenizer** out);
+void ctk_free(ctk_tokenizer* tok);
+
+/* ---- cheap getters (src/bindings/tokenizer.rs:271-289) ------------------------------------- */
+size_t ctk_vocab_size(const ctk_tokenizer* tok);                               /* mod.rs:856-858 */
+/* mod.rs:860-862: returns 1 and sets *id if present, 0 if absent */
+int ctk_token_to_id(const ctk_tokenizer* tok, const uint8_t* token, size_t len, uint32_t* id);
+/* mod.rs:864-866: returns pointer to the token's UTF-8 bytes (owned by tok) or NULL */
+const uint8_t* ctk_id_to_token(const ctk_tokenizer* tok, uint32_t id, size_t* len);
+/* mod.rs:868-870: number of special tokens; i-th content/id */
+size_t ctk_n_special_tokens(const ctk_tokenizer* tok);
+const uint8_t* ctk_special_token(const ctk_tokenizer* tok, size_t i, size_t* len, uint32_t* id);
+int ctk_device(const ctk_tokenizer* tok);
+
+/* ---- encode_batch, host buffers ------------------------------------------------------------
+ * Replaces HuggingFaceTokenizer::encode_batch (src/huggingface/mod.rs:694-696) and, with n = 1,
+ * ::encode (:551-613).  text/text_off are host memory (pinned memory is copied by DMA directly).
+ * On success *res owns: ids (uint32, packed) and ids_off (uint64[n+1]).  Bit-exact with the
+ * reference's Vec<Vec<u32>>. */
+int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64_t* text_off, size_t n,
+                     ctk_result** res);
+const uint32_t* ctk_result_ids(const ctk_result* res);
+const uint64_t* ctk_result_offsets(const ctk_result* res);   /* n+1 entries */
+size_t ctk_result_count(const ctk_result* res);              /* n */
+
+/* ---- decode_batch, host buffers ------------------------------------------------------------
+ * Replaces HuggingFaceTokenizer::decode_batch_with_options (src/huggingface/mod.rs:775-785);
+ * decode_batch (:771-773) is skip_special_tokens=0, clean_up_tokenization_spaces=1; decode /
+ * decode_with_options (:698-709) are n = 1.  Result: UTF-8 bytes (packed) + uint64[n+1] offsets. */
+int ctk_decode_batch(const ctk_tokenizer* tok, const uint32_t* ids, const uint64_t* ids_off, size_t n,
+                     int skip_special_tokens, int clean_up_tokenization_spaces, ctk_result** res);
+const uint8_t* ctk_result_bytes(const ctk_result* res);
+
+void ctk_result_free(ctk_result* res);
+
+/* ---- device-resident variants (inputs already in HBM, outputs left in HBM) -------------------
+ * Same semantics; every pointer is a device pointer on ctk_device(tok).  Used for the roofline
+ * measurement and by callers that keep corpora on the GPU.
+ *   d_text        16-byte aligned, total_bytes = text_off[n]; d_text_off uint64[n+1]
+ *   d_ids         capacity ids_cap uint32 (total_bytes + n always suffices: at most 1 id per byte)
+ *   d_ids_off     uint64[n+1]; d_ids_off[n] = total ids
+ * `stream` is a cudaStream_t (NULL = legacy default stream).  The call enqueues work and returns;
+ * *n_ids_host, if not NULL, makes the call synchronise and receive the total id count.
+ * Scratch memory is owned by the tokenizer and grown on demand (one concurrent device call per
+ * tokenizer; the host-buffer entry points above serialise internally). */
+int ctk_encode_batch_device(const ctk_tokenizer* tok, const uint8_t* d_text, const uint64_t* d_text_off,
+                            size_t n, uint64_t total_bytes, uint32_t* d_ids, uint64_t ids_cap,
+                            uint64_t* d_ids_off, uint64_t* n_ids_host, void* stream);
+/*   d_text_out    capacity text_cap bytes; d_text_off_out uint64[n+1].  Required capacity is at
+ *                 most ctk_decode_max_bytes(tok) * total_ids (3x that if ids decode to invalid
+ *                 UTF-8 that must be replaced by U+FFFD). */
+int ctk_decode_batch_device(const ctk_tokenizer* tok, const uint32_t* d_ids, const uint64_t* d_ids_off,
+                            size_t n, uint64_t total_ids, int skip_special_tokens,
+                            int clean_up_tokenization_spaces, uint8_t* d_text_out, uint64_t text_cap,
+                            uint64_t* d_text_off_out, uint64_t* n_bytes_host, void* stream);
+size_t ctk_decode_max_bytes(const ctk_tokenizer* tok);   /* longest decoded token, in bytes */
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+const char* ctk_last_error(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t ctk_kernel_launches(void);
+/* Reset the per-batch pre-token cache policy: 0 = clear at the start of every encode call
+ * (default; every call does all of its own work), 1 = keep entries across calls. */
+void ctk_set_cache_persistent(ctk_tokenizer* tok, int persistent);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTK_H */
