@@ -60,6 +60,8 @@ def _lib():
         'ctk_last_error': (ctypes.c_char_p, []),
         'ctk_kernel_launches': (U64, []),
         'ctk_set_cache_persistent': (None, [P, I]),
+        'ctk_profile_enable': (None, [P, I]),
+        'ctk_profile_report': (S, [P, ctypes.c_char_p, S]),
         'ctk_debug_starts_host': (I, [P, U64, P, S, P]),
         'ctk_debug_load_only': (I, [P, S, ctypes.POINTER(U64), ctypes.POINTER(U64), ctypes.POINTER(I), ctypes.POINTER(I)]),
     }
@@ -234,6 +236,40 @@ class Tokenizer:
     @property
     def device(self):
         return int(_lib().ctk_device(self._h))
+
+    def profile_enable(self, on=True):
+        _lib().ctk_profile_enable(self._h, int(bool(on)))
+
+    def profile_report(self):
+        """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream"""
+        buf = ctypes.create_string_buffer(1 << 16)
+        _lib().ctk_profile_report(self._h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.split('\t')
+            out[name] = (float(ms), int(cnt))
+        return out
+
+    # ---- device-resident API (pointers are device pointers on self.device; see include/ctk.h)
+    def encode_device(self, d_text, d_text_off, n_docs, total_bytes, d_ids, ids_cap, d_ids_off, stream=0, sync=True):
+        lib = _lib()
+        tot = ctypes.c_uint64(0)
+        rc = lib.ctk_encode_batch_device(self._h, d_text, d_text_off, n_docs, total_bytes, d_ids, ids_cap, d_ids_off,
+                                         ctypes.byref(tot) if sync else None, stream or None)
+        if rc != CTK_OK:
+            _raise(rc)
+        return int(tot.value) if sync else None
+
+    def decode_device(self, d_ids, d_ids_off, n_docs, total_ids, d_out, out_cap, d_out_off, skip_special_tokens=False,
+                      clean_up_tokenization_spaces=True, stream=0, sync=True):
+        lib = _lib()
+        tot = ctypes.c_uint64(0)
+        rc = lib.ctk_decode_batch_device(self._h, d_ids, d_ids_off, n_docs, total_ids, int(bool(skip_special_tokens)),
+                                         int(bool(clean_up_tokenization_spaces)), d_out, out_cap, d_out_off,
+                                         ctypes.byref(tot) if sync else None, stream or None)
+        if rc != CTK_OK:
+            _raise(rc)
+        return int(tot.value) if sync else None
 
     def set_cache_persistent(self, flag):
         _lib().ctk_set_cache_persistent(self._h, int(bool(flag)))

@@ -20,6 +20,7 @@ int Engine::finish(const uint32_t* d_err, const uint64_t* d_off_out, size_t n, u
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_flags + 2, d_off_out + n, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "finish");
+    collect_marks();
     uint32_t f = h_flags[0];
     if (f & ERRF_OFFSETS) return fail(CTK_ERR_ARG, "offsets must start at 0, be non-decreasing and end at the buffer length");
     if (f & ERRF_UTF8) return fail(CTK_ERR_INVALID_DATA, "input text is not valid UTF-8");
@@ -189,6 +190,24 @@ int ctk_device(const ctk_tokenizer* tok) { return reinterpret_cast<const Engine*
 size_t ctk_decode_max_bytes(const ctk_tokenizer* tok) { return reinterpret_cast<const Engine*>(tok)->model.dec_max_bytes; }
 const char* ctk_last_error(void) { return g_last_error.c_str(); }
 uint64_t ctk_kernel_launches(void) { return g_kernel_launches.load(); }
+void ctk_profile_enable(ctk_tokenizer* tok, int on) {
+    Engine* eng = reinterpret_cast<Engine*>(tok);
+    std::lock_guard<std::mutex> lk(eng->mu);
+    eng->profile = on != 0;
+    eng->prof.clear();
+}
+size_t ctk_profile_report(ctk_tokenizer* tok, char* buf, size_t cap) {
+    Engine* eng = reinterpret_cast<Engine*>(tok);
+    std::lock_guard<std::mutex> lk(eng->mu);
+    std::string s;
+    for (auto& kv : eng->prof) {
+        char line[256];
+        snprintf(line, sizeof line, "%s\t%.6f\t%llu\n", kv.first.c_str(), kv.second.first, (unsigned long long)kv.second.second);
+        s += line;
+    }
+    if (buf && cap) { size_t n = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(buf, s.data(), n); buf[n] = 0; }
+    return s.size();
+}
 void ctk_set_cache_persistent(ctk_tokenizer* tok, int persistent) { reinterpret_cast<Engine*>(tok)->cache_persistent = persistent != 0; }
 
 int ctk_encode_batch_device(const ctk_tokenizer* tok, const uint8_t* d_text, const uint64_t* d_text_off, size_t n,

@@ -197,18 +197,19 @@ int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, si
     CK(ws.get(4, 256, (void**)&err));
     CK(cudaMemsetAsync(ds, 0, (n_words + 1) * 4, st));
     CK(cudaMemsetAsync(err, 0, 256, st));
+    eng.mark(nullptr, st);
     k_docstart<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_off, n_docs, n_bytes, ds, err);
-    eng.launched(1);
+    eng.launched(1); eng.mark("k_docstart", st);
     TextView tv{d_text, n_bytes, ds, eng.tables.trie_index, eng.tables.trie_blocks};
     k_starts<<<n_blocks, 256, 0, st>>>(tv, sb, bc);
-    eng.launched(1);
+    eng.launched(1); eng.mark("k_starts", st);
     size_t cub_bytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, bc, bb, n_blocks + 1, st));
     void* cub_tmp;
     CK(ws.get(5, cub_bytes + 16, &cub_tmp));
     CK(cudaMemsetAsync(bc + n_blocks, 0, 4, st));
     CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, bc, bb, n_blocks + 1, st));
-    eng.launched(1);
+    eng.launched(1); eng.mark("scan_blocks", st);
     uint32_t n_pre = 0;
     CK(cudaMemcpyAsync(&n_pre, bb + n_blocks, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -217,18 +218,19 @@ int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, si
     CK(ws.get(7, (n_bytes + 64) * 4, (void**)&tmp_ids));
     CK(ws.get(8, ((uint64_t)n_pre + 2) * 4, (void**)&ntok));
     CK(ws.get(9, ((uint64_t)n_pre + 2) * 4, (void**)&tok_off));
+    eng.mark(nullptr, st);
     k_list<<<n_blocks, 256, 0, st>>>(sb, n_words, bb, starts);
-    eng.launched(1);
+    eng.launched(1); eng.mark("k_list", st);
     k_bpe<<<(unsigned)(((uint64_t)n_pre * 32 + 255) / 256), 256, 0, st>>>(eng.tables, d_text, n_bytes, starts, n_pre, tmp_ids, ntok);
-    eng.launched(1);
+    eng.launched(1); eng.mark("k_bpe", st);
     CK(cudaMemsetAsync(ntok + n_pre, 0, 4, st));
     CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, ntok, tok_off, n_pre + 1, st));
     CK(ws.get(5, cub_bytes + 16, &cub_tmp));
     CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntok, tok_off, n_pre + 1, st));
-    eng.launched(1);
+    eng.launched(1); eng.mark("scan_ntok", st);
     k_emit<<<(n_pre + 255) / 256, 256, 0, st>>>(starts, tok_off, n_pre, tmp_ids, d_ids, ids_cap, err);
     k_doc_offsets<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_off, n_docs, starts, n_pre, tok_off, d_ids_off);
-    eng.launched(2);
+    eng.launched(2); eng.mark("k_emit+doc_offsets", st);
     CK(cudaGetLastError());
     return eng.finish(err, d_ids_off, n_docs, n_ids_host, st);
 }

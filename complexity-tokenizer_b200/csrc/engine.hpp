@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/ctk.h"
 #include "device_common.cuh"
@@ -66,6 +68,33 @@ struct Engine {
     // pinned staging for error flags / counters
     uint32_t* h_flags = nullptr;
     uint8_t* last_decode_out = nullptr;   // decode_device(d_out = NULL) leaves its output here
+
+    // optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
+    bool profile = false;
+    struct Mark { const char* name; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    std::vector<cudaEvent_t> ev_pool;
+    std::map<std::string, std::pair<double, uint64_t>> prof;      // name -> (total ms, launches)
+    void mark(const char* name, cudaStream_t st) {                // call once before the first kernel (name = nullptr) and after each kernel
+        if (!profile) return;
+        cudaEvent_t ev;
+        if (!ev_pool.empty()) { ev = ev_pool.back(); ev_pool.pop_back(); }
+        else if (cudaEventCreate(&ev) != cudaSuccess) return;
+        cudaEventRecord(ev, st);
+        marks.push_back({name, ev});
+    }
+    void collect_marks() {                                        // after a synchronise
+        for (size_t i = 0; i < marks.size(); ++i) {
+            if (i > 0 && marks[i].name) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, marks[i - 1].ev, marks[i].ev) == cudaSuccess) {
+                    auto& e = prof[marks[i].name]; e.first += ms; e.second += 1;
+                }
+            }
+        }
+        for (auto& m : marks) ev_pool.push_back(m.ev);
+        marks.clear();
+    }
 
     int fail(int code, const std::string& msg) { set_last_error(msg); return code; }
     int cuda_fail(cudaError_t e, const char* what) {

@@ -101,6 +101,10 @@ size_t ctk_decode_max_bytes(const ctk_tokenizer* tok);   /* longest decoded toke
 const char* ctk_last_error(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t ctk_kernel_launches(void);
+/* Per-kernel timing with CUDA events on the launching stream (off by default).  The report is text,
+ * one line per kernel: name <TAB> total milliseconds <TAB> launches; returns the full length. */
+void ctk_profile_enable(ctk_tokenizer* tok, int on);
+size_t ctk_profile_report(ctk_tokenizer* tok, char* buf, size_t cap);
 /* Reset the per-batch pre-token cache policy: 0 = clear at the start of every encode call
  * (default; every call does all of its own work), 1 = keep entries across calls. */
 void ctk_set_cache_persistent(ctk_tokenizer* tok, int persistent);

@@ -1,0 +1,145 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads and exports every symbol that
+include/ctk.h declares, the tokenizer.json loader follows the reference's rules, and the device
+start-predicate (compiled for the host through a debug hook) agrees with the oracle's regex
+restatement.  No compute call is made on a GPU here."""
+import ctypes
+import json
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import py_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, 'include', 'ctk.h')).read()
+    names = sorted(set(re.findall(r'\b(ctk_[a-z_0-9]+)\s*\(', hdr)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(built_lib, n), 'libctk.so does not export ' + n
+
+
+def test_no_cpu_fallback_without_device(built_lib, small_tok_json):
+    """Without a GPU, constructing a tokenizer must fail loudly (CTK_ERR_CUDA), not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    import complexity_tokenizer as ct
+    with pytest.raises(RuntimeError, match='no CUDA device|CUDA'):
+        ct.Tokenizer.from_str(small_tok_json)
+
+
+def _load_only(lib, tj):
+    data = json.dumps(tj, ensure_ascii=False).encode() if not isinstance(tj, (bytes, str)) else (tj.encode() if isinstance(tj, str) else tj)
+    buf = ctypes.create_string_buffer(data, len(data))
+    npairs, vs, nfc, mm = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.ctk_debug_load_only(ctypes.addressof(buf), len(data), ctypes.byref(npairs), ctypes.byref(vs), ctypes.byref(nfc), ctypes.byref(mm))
+    return rc, npairs.value, vs.value, nfc.value, mm.value, (lib.ctk_last_error() or b'').decode()
+
+
+BASE = {'model': {'type': 'BPE', 'vocab': {'a': 0, 'b': 1, 'c': 2, 'ab': 3, 'bc': 4}, 'merges': ['a b', 'b c']}}
+
+
+def test_loader_rules(built_lib):
+    lib = built_lib
+    rc, npairs, vs, nfc, mm, _ = _load_only(lib, BASE)
+    assert (rc, npairs, vs, nfc, mm) == (0, 2, 5, 1, 0)                       # missing normalizer => NFC (parsing.rs:89)
+    # array-form merges (mod.rs:85-91), lines that do not split into exactly two parts are dropped (:252-264)
+    tj = json.loads(json.dumps(BASE)); tj['model']['merges'] = [['a', 'b'], 'b c', 'a b c', 'nospace', ['x'], 7]
+    assert _load_only(lib, tj)[:2] == (0, 2)
+    # "normalizer": null => NFC ; unknown type => none ; NFKC => unsupported (3)
+    for norm, want_rc, want_nfc in ((None, 0, 1), ({'type': 'NFC'}, 0, 1), ({'type': 'Whatever'}, 0, 0),
+                                    ({'type': 'Sequence', 'normalizers': [{'type': 'NFC'}]}, 0, 1), ({'type': 'NFKC'}, 3, None),
+                                    ({'type': 'Sequence', 'normalizers': [{'type': 'Lowercase'}]}, 3, None)):
+        tj = dict(BASE, normalizer=norm)
+        r = _load_only(lib, tj)
+        assert r[0] == want_rc, (norm, r)
+        if want_nfc is not None:
+            assert r[3] == want_nfc
+    # pre-tokenizers: ByteLevel, Llama-3 style Sequence[Split(look-ahead), ByteLevel] ok; Whitespace etc. unsupported
+    llama3 = {'type': 'Sequence', 'pretokenizers': [
+        {'type': 'Split', 'pattern': {'Regex': r"(?i:'s|'t)|\s+(?!\S)|\s+"}, 'behavior': 'Isolated', 'invert': False},
+        {'type': 'ByteLevel', 'add_prefix_space': False, 'trim_offsets': True, 'use_regex': False}]}
+    assert _load_only(lib, dict(BASE, pre_tokenizer=llama3))[0] == 0
+    assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'ByteLevel', 'add_prefix_space': False, 'use_regex': True}))[0] == 0
+    assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Whitespace'}))[0] == 3
+    assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Metaspace'}))[0] == 3
+    assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Unknown'}))[0] == 3
+    compilable = {'type': 'Sequence', 'pretokenizers': [{'type': 'Split', 'pattern': {'Regex': r'\d'}, 'behavior': 'Isolated'},
+                                                        {'type': 'ByteLevel'}]}
+    assert _load_only(lib, dict(BASE, pre_tokenizer=compilable))[0] == 3
+    assert _load_only(lib, dict(BASE, decoder={'type': 'ByteLevel'}))[0] == 0
+    assert _load_only(lib, dict(BASE, decoder={'type': 'WordPiece'}))[0] == 3
+    # invalid data (2): not JSON, no model, vocab id not a u32, added token without `special` (mod.rs:107)
+    assert _load_only(lib, b'{"model": ')[0] == 2
+    assert _load_only(lib, {'version': '1.0'})[0] == 2
+    assert _load_only(lib, {'model': {'vocab': {'a': -1}}})[0] == 2
+    assert _load_only(lib, {'model': {'vocab': {'a': 1.5}}})[0] == 2
+    assert _load_only(lib, dict(BASE, added_tokens=[{'id': 0, 'content': 'a'}]))[0] == 2
+    # a merges table that would make the reference panic (bpe.rs:141) is rejected
+    tj = json.loads(json.dumps(BASE)); tj['model']['merges'] = ['x y', 'a b']
+    rc, *_, msg = _load_only(lib, tj)
+    assert rc == 3 and 'panic' in msg
+    # duplicate keys: last wins, like a HashMap insert
+    assert _load_only(lib, b'{"model": {"vocab": {"a": 0, "a": 7, "b": 1}, "merges": []}}')[:3] == (0, 0, 2)
+    # escapes
+    assert _load_only(lib, b'{"model": {"vocab": {"\\u0120a": 0, "\\ud83d\\ude00": 1}, "merges": []}}')[:3] == (0, 0, 2)
+    assert _load_only(lib, b'{"model": {"vocab": {"\\ud83d": 0}}}')[0] == 2
+
+
+def test_added_token_may_match_analysis(built_lib):
+    lib = built_lib
+    for content, want in (('<s>', 0), ('</s>', 0), ('<|endoftext|>', 0), ('<pad>', 0), ('[MASK]', 0), ('hello', 1), ('Ġhello', 1),
+                          (' hello', 0), ("'s", 1), ('...', 1), ('Ġ...', 1), ('a1', 0), ('Ġ', 1), ('日本', 0)):
+        tj = dict(BASE, added_tokens=[{'id': 9, 'content': content, 'special': True}])
+        rc, _, _, _, mm, _ = _load_only(lib, tj)
+        assert rc == 0 and mm == want, content
+
+
+def _starts_product(lib, docs):
+    import synth
+    text, offs = synth.pack(docs)
+    n = text.size
+    out = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+    lib.ctk_debug_starts_host(text.ctypes.data if n else None, n, offs.ctypes.data, len(docs), out.ctypes.data)
+    bits = np.unpackbits(out.view(np.uint8), bitorder='little')[:n]
+    return set(np.nonzero(bits)[0].tolist())
+
+
+def _starts_oracle(docs):
+    s, base = set(), 0
+    for d in docs:
+        t = d.decode()
+        bidx = [0]
+        for ch in t:
+            bidx.append(bidx[-1] + len(ch.encode()))
+        for a, _ in py_oracle.gpt2_find_iter(t):
+            s.add(base + bidx[a])
+        base += len(d)
+    return s
+
+
+def test_start_predicate_differential(built_lib):
+    """The bounded-window local rule used on the device == leftmost-first regex matching (pretokenizers.rs:13)."""
+    random.seed(7)
+    alpha = ["a", "b", "s", "t", "r", "e", "v", "l", "m", "d", "'", " ", " ", "\n", "\t", "1", "9", ".", "!", "-", "é", "ü",
+             "中", "あ", "　", " ", "\U0001F600", "́", "x", "'s", "'ll", "  ", "Ⅷ", "²", "_", " ", "٣", "ß"]
+    bad = 0
+    for _ in range(20000):
+        docs = [''.join(random.choice(alpha) for _ in range(random.randint(0, 12))).encode() for _ in range(random.randint(1, 3))]
+        if _starts_product(built_lib, docs) != _starts_oracle(docs):
+            bad += 1
+    assert bad == 0
+
+
+def test_start_predicate_on_corpora(built_lib):
+    import synth
+    for kind, seed in (('english', 11), ('mixed', 12)):
+        text, offs = synth.gen_corpus(kind, seed, 96 << 10, doc_median=700)
+        docs = synth.split_docs(text, offs)
+        assert _starts_product(built_lib, docs) == _starts_oracle(docs)
