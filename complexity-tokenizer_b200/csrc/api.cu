@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "start_window.cuh"
 #include "unicode_trie_gen.h"
 
 namespace ctk {
@@ -331,6 +332,37 @@ int ctk_debug_starts_host(const uint8_t* text, uint64_t n, const uint64_t* off, 
     TextView tv{text, n, ds.data(), CTK_TRIE_INDEX, CTK_TRIE_BLOCKS};
     for (uint64_t w = 0; w < n_words; ++w) out_bits[w] = 0;
     for (uint64_t i = 0; i < n; ++i) if (tv.is_start(i)) out_bits[i >> 5] |= 1u << (i & 31);
+    return CTK_OK;
+}
+
+// Same, through the bit-parallel window logic the fused kernel uses (classify16 + start_window), with the
+// 16-byte groups / neighbour windows emulated on the host.
+int ctk_debug_starts_window_host(const uint8_t* text, uint64_t n, const uint64_t* off, size_t n_docs, uint32_t* out_bits) {
+    uint64_t n_groups = (n + 15) / 16 + 2;                       // one group of padding on each side
+    std::vector<uint8_t> buf((n_groups + 2) * 16, 0);
+    uint8_t* chunk = buf.data() + 16;                            // chunk[0] = first padding group
+    if (n) memcpy(chunk + 16, text, n);
+    std::vector<uint32_t> ds(n_groups, 0);
+    for (size_t d = 0; d <= n_docs; ++d) { uint64_t p = off[d] + 16; if (off[d] <= n) ds[p >> 4] |= 1u << (p & 15); }
+    std::vector<Masks16> m(n_groups);
+    for (uint64_t g = 0; g < n_groups; ++g) {
+        uint32_t w[4];
+        memcpy(w, chunk + g * 16, 16);
+        m[g] = classify16(chunk, (int)(g * 16), w[0], w[1], w[2], w[3], CTK_TRIE_INDEX, CTK_TRIE_BLOCKS);
+    }
+    uint64_t n_words = (n + 31) / 32 + 1;
+    for (uint64_t w = 0; w < n_words; ++w) out_bits[w] = 0;
+    Masks16 z{};
+    for (uint64_t g = 1; g + 1 < n_groups; ++g) {
+        const Masks16 &a = m[g - 1], &b = m[g], &c = (g + 1 < n_groups) ? m[g + 1] : z;
+        uint32_t S = start_window(window(a.L, b.L, c.L), window(a.N, b.N, c.N), window(a.W, b.W, c.W), window(a.SP, b.SP, c.SP),
+                                  window(a.AP, b.AP, c.AP), window(a.CONT, b.CONT, c.CONT), window(ds[g - 1], ds[g], ds[g + 1]),
+                                  chunk + g * 16 - 8);
+        for (int k = 0; k < 16; ++k) {
+            uint64_t pos = (g - 1) * 16 + k;
+            if (pos < n && ((S >> (8 + k)) & 1u)) out_bits[pos >> 5] |= 1u << (pos & 31);
+        }
+    }
     return CTK_OK;
 }
 
