@@ -62,6 +62,7 @@ def _lib():
         'ctk_set_cache_persistent': (None, [P, I]),
         'ctk_profile_enable': (None, [P, I]),
         'ctk_profile_report': (S, [P, ctypes.c_char_p, S]),
+        'ctk_debug_use_general': (None, [P, I]),
         'ctk_debug_starts_host': (I, [P, U64, P, S, P]),
         'ctk_debug_starts_window_host': (I, [P, U64, P, S, P]),
         'ctk_debug_load_only': (I, [P, S, ctypes.POINTER(U64), ctypes.POINTER(U64), ctypes.POINTER(I), ctypes.POINTER(I)]),

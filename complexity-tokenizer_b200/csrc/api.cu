@@ -90,7 +90,8 @@ static int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_o
     const uint8_t* t2; const uint64_t* o2; uint64_t b2;
     int rc = nfc_stage(eng, d_text, d_off, n, n_bytes, &t2, &o2, &b2, st);
     if (rc != CTK_OK) return rc;
-    return encode_general(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st);
+    if (eng.use_general) return encode_general(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st);
+    return encode_fused(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st);
 }
 
 static int create(const uint8_t* json, size_t len, int device, ctk_tokenizer** out) {
@@ -321,6 +322,9 @@ void ctk_result_free(ctk_result* res) {
     if (r->bytes) cudaFreeHost(r->bytes);
     delete r;
 }
+
+// debug: select the multi-kernel general pipeline (1) or the fused kernel (0, default)
+void ctk_debug_use_general(ctk_tokenizer* tok, int on) { reinterpret_cast<Engine*>(tok)->use_general = on != 0; }
 
 // ---- debug/test hooks (host only, no GPU needed): the scalar start predicate on host memory ----------
 // out_bits: one bit per byte position, set where a pre-token starts.  Used by the CPU test-suite to

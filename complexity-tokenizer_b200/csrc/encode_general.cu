@@ -70,43 +70,6 @@ __global__ void __launch_bounds__(256) k_list(const uint32_t* __restrict__ start
     }
 }
 
-// Pre-tokens longer than 32 symbols: same one-merge-per-iteration order, symbols kept compacted in
-// global memory (the tmp_ids slice of this pre-token), every pair re-probed each iteration.
-// O(n^2/32) probes per lane: exact but slow; long pre-tokens are rare outside config 4.
-__device__ int bpe_warp_long(const DevTables& t, uint32_t* sym, int n) {
-    const unsigned full = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    while (n > 1) {
-        uint32_t best = kNone, best_new = 0;
-        uint32_t best_pos = 0;
-        for (int i = lane; i + 1 < n; i += 32) {
-            uint2 r = pair_lookup(t, sym[i], sym[i + 1]);
-            if (r.x < best) { best = r.x; best_new = r.y; best_pos = (uint32_t)i; }   // strict <: leftmost within the lane
-        }
-        // lowest rank, then leftmost position, across lanes
-        unsigned long long key = best == kNone ? ~0ull : ((unsigned long long)best << 32) | best_pos;
-        unsigned long long k2 = key;
-        for (int o = 16; o; o >>= 1) { unsigned long long v = __shfl_xor_sync(full, k2, o); k2 = v < k2 ? v : k2; }
-        if (k2 == ~0ull) break;
-        int idx = (int)(uint32_t)k2;
-        int owner = __ffs(__ballot_sync(full, key == k2)) - 1;
-        uint32_t new_id = __shfl_sync(full, best_new, owner);
-        __syncwarp();
-        // shift left by one beyond idx, in rounds of 32 so reads happen before writes
-        for (int base = idx + 1; base < n - 1; base += 32) {
-            int i = base + lane;
-            uint32_t v = (i < n - 1) ? sym[i + 1] : 0u;
-            __syncwarp();
-            if (i < n - 1) sym[i] = v;
-            __syncwarp();
-        }
-        if (lane == 0) sym[idx] = new_id;
-        __syncwarp();
-        --n;
-    }
-    return n;
-}
-
 // one warp per pre-token
 __global__ void __launch_bounds__(256) k_bpe(DevTables t, const uint8_t* __restrict__ text, uint64_t n_bytes,
                                              const uint32_t* __restrict__ starts, uint32_t n_pre,

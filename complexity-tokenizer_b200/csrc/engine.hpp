@@ -65,6 +65,8 @@ struct Engine {
     Workspace ws;
     std::mutex mu;                      // serialises device work issued through this tokenizer
     bool cache_persistent = false;
+    bool cache_valid = false;           // the pre-token cache holds entries of earlier calls
+    bool use_general = false;           // debug: run the multi-kernel pipeline instead of the fused kernel
     // pinned staging for error flags / counters
     uint32_t* h_flags = nullptr;
     uint8_t* last_decode_out = nullptr;   // decode_device(d_out = NULL) leaves its output here
@@ -109,6 +111,8 @@ struct Engine {
 
 int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
               const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st);
+int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
+                 uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                    uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off, size_t n, uint64_t total_ids,
