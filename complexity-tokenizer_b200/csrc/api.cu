@@ -31,13 +31,6 @@ int Engine::finish(const uint32_t* d_err, const uint64_t* d_off_out, size_t n, u
     return CTK_OK;
 }
 
-struct Result {
-    size_t n = 0;
-    uint32_t* ids = nullptr;      // pinned
-    uint64_t* off = nullptr;      // pinned
-    uint8_t* bytes = nullptr;     // pinned
-};
-
 static int upload(Engine& eng) {
     cudaError_t e;
 #define UP(slot, dst, src, bytes)                                                                     \
@@ -80,11 +73,15 @@ static int upload(Engine& eng) {
 #undef UP
     e = cudaHostAlloc((void**)&eng.h_flags, 64, cudaHostAllocDefault);
     if (e != cudaSuccess) return eng.cuda_fail(e, "cudaHostAlloc");
+    for (cudaStream_t* sp : {&eng.st_h2d, &eng.st_comp, &eng.st_d2h}) {
+        e = cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return eng.cuda_fail(e, "cudaStreamCreate");
+    }
     return CTK_OK;
 }
 
 // normaliser -> pre-tokenise -> BPE -> emit, all on the device (mod.rs:551-613 for every document)
-static int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n, uint64_t n_bytes, uint32_t* d_ids,
+int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n, uint64_t n_bytes, uint32_t* d_ids,
                          uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st) {
     if (n_bytes && (reinterpret_cast<uintptr_t>(d_text) & 15)) return eng.fail(CTK_ERR_ARG, "device text buffer must be 16-byte aligned");
     const uint8_t* t2; const uint64_t* o2; uint64_t b2;
@@ -158,6 +155,8 @@ void ctk_free(ctk_tokenizer* tok) {
     eng->ws.release();
     for (void* p : eng->d_table_mem) if (p) cudaFree(p);
     if (eng->h_flags) cudaFreeHost(eng->h_flags);
+    for (cudaStream_t sp : {eng->st_h2d, eng->st_comp, eng->st_d2h}) if (sp) cudaStreamDestroy(sp);
+    for (cudaEvent_t ev : eng->ev_pool) cudaEventDestroy(ev);
     delete eng;
 }
 
@@ -234,93 +233,6 @@ int ctk_decode_batch_device(const ctk_tokenizer* tok, const uint32_t* d_ids, con
     if (e != cudaSuccess) return eng->cuda_fail(e, "cudaSetDevice");
     return decode_device(*eng, d_ids, d_ids_off, n, total_ids, skip_special_tokens, clean_up_tokenization_spaces, d_text_out,
                          text_cap, d_text_off_out, n_bytes_host, (cudaStream_t)stream);
-}
-
-#define CKE(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = eng->cuda_fail(e_, #x); goto done; } } while (0)
-
-int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64_t* text_off, size_t n, ctk_result** res) {
-    if (!tok || !text_off || !res) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
-    *res = nullptr;
-    Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
-    if (text_off[0] != 0) { set_last_error("text_off[0] must be 0"); return CTK_ERR_ARG; }
-    uint64_t B = text_off[n];
-    if (B && !text) { set_last_error("NULL text"); return CTK_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(eng->mu);
-    int rc = CTK_OK;
-    Result* r = new Result();
-    r->n = n;
-    uint8_t* d_text; uint64_t *d_off, *d_ids_off; uint32_t* d_ids;
-    uint64_t total = 0;
-    cudaStream_t st = 0;
-    CKE(cudaSetDevice(eng->device));
-    CKE(eng->ws.get(20, B + 64, (void**)&d_text));
-    CKE(eng->ws.get(21, (n + 1) * 8, (void**)&d_off));
-    CKE(eng->ws.get(22, (n + 1) * 8, (void**)&d_ids_off));
-    CKE(eng->ws.get(23, (3 * B + n + 16) * 4, (void**)&d_ids));   // NFC can grow text up to 3x
-    if (B) CKE(cudaMemcpyAsync(d_text, text, B, cudaMemcpyHostToDevice, st));
-    CKE(cudaMemcpyAsync(d_off, text_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    CKE(cudaMemsetAsync(d_text + B, 0, 64, st));
-    rc = encode_device(*eng, d_text, d_off, n, B, d_ids, 3 * B + n + 16, d_ids_off, &total, st);
-    if (rc != CTK_OK) goto done;
-    CKE(cudaHostAlloc((void**)&r->off, (n + 1) * 8, cudaHostAllocDefault));
-    CKE(cudaHostAlloc((void**)&r->ids, (total + 1) * 4, cudaHostAllocDefault));
-    CKE(cudaMemcpyAsync(r->off, d_ids_off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (total) CKE(cudaMemcpyAsync(r->ids, d_ids, total * 4, cudaMemcpyDeviceToHost, st));
-    CKE(cudaStreamSynchronize(st));
-done:
-    if (rc != CTK_OK) { ctk_result_free(reinterpret_cast<ctk_result*>(r)); return rc; }
-    *res = reinterpret_cast<ctk_result*>(r);
-    return CTK_OK;
-}
-
-int ctk_decode_batch(const ctk_tokenizer* tok, const uint32_t* ids, const uint64_t* ids_off, size_t n, int skip_special_tokens,
-                     int clean_up_tokenization_spaces, ctk_result** res) {
-    if (!tok || !ids_off || !res) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
-    *res = nullptr;
-    Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
-    if (ids_off[0] != 0) { set_last_error("ids_off[0] must be 0"); return CTK_ERR_ARG; }
-    for (size_t i = 0; i < n; ++i) if (ids_off[i + 1] < ids_off[i]) { set_last_error("ids_off must be non-decreasing"); return CTK_ERR_ARG; }
-    uint64_t T = ids_off[n];
-    if (T && !ids) { set_last_error("NULL ids"); return CTK_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(eng->mu);
-    int rc = CTK_OK;
-    Result* r = new Result();
-    r->n = n;
-    uint32_t* d_ids; uint64_t *d_off, *d_out_off; uint8_t* d_out;
-    uint64_t total = 0;
-    cudaStream_t st = 0;
-    CKE(cudaSetDevice(eng->device));
-    CKE(eng->ws.get(24, (T + 1) * 4, (void**)&d_ids));
-    CKE(eng->ws.get(21, (n + 1) * 8, (void**)&d_off));
-    CKE(eng->ws.get(22, (n + 1) * 8, (void**)&d_out_off));
-    if (T) CKE(cudaMemcpyAsync(d_ids, ids, T * 4, cudaMemcpyHostToDevice, st));
-    CKE(cudaMemcpyAsync(d_off, ids_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    rc = decode_device(*eng, d_ids, d_off, n, T, skip_special_tokens, clean_up_tokenization_spaces, nullptr, 0, d_out_off, &total, st);
-    if (rc != CTK_OK) goto done;
-    d_out = eng->last_decode_out;
-    CKE(cudaHostAlloc((void**)&r->off, (n + 1) * 8, cudaHostAllocDefault));
-    CKE(cudaHostAlloc((void**)&r->bytes, total + 1, cudaHostAllocDefault));
-    CKE(cudaMemcpyAsync(r->off, d_out_off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (total) CKE(cudaMemcpyAsync(r->bytes, d_out, total, cudaMemcpyDeviceToHost, st));
-    CKE(cudaStreamSynchronize(st));
-done:
-    if (rc != CTK_OK) { ctk_result_free(reinterpret_cast<ctk_result*>(r)); return rc; }
-    *res = reinterpret_cast<ctk_result*>(r);
-    return CTK_OK;
-}
-
-const uint32_t* ctk_result_ids(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->ids; }
-const uint64_t* ctk_result_offsets(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->off; }
-const uint8_t* ctk_result_bytes(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->bytes; }
-size_t ctk_result_count(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->n; }
-
-void ctk_result_free(ctk_result* res) {
-    if (!res) return;
-    Result* r = reinterpret_cast<Result*>(res);
-    if (r->ids) cudaFreeHost(r->ids);
-    if (r->off) cudaFreeHost(r->off);
-    if (r->bytes) cudaFreeHost(r->bytes);
-    delete r;
 }
 
 // debug: select the multi-kernel general pipeline (1) or the fused kernel (0, default)

@@ -454,7 +454,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.err = ctrl; p.ticket = ctrl + 2; p.ovf_cursor = ctrl + 3; p.long_cursor = reinterpret_cast<unsigned long long*>(ctrl + 4);
     p.out = d_ids; p.out_cap = ids_cap; p.ids_off = d_ids_off;
     eng.mark(nullptr, st);
-    if (!eng.cache_persistent || !eng.cache_valid) {
+    if (!((eng.cache_persistent || eng.keep_cache_once) && eng.cache_valid)) {
         CK(cudaMemsetAsync(p.cache, 0xFF, (uint64_t)cache_slots * sizeof(CacheSlot), st));
         CK(cudaMemsetAsync(ctrl, 0, 256, st));
         eng.cache_valid = true;

@@ -69,7 +69,9 @@ struct Engine {
     bool use_general = false;           // debug: run the multi-kernel pipeline instead of the fused kernel
     // pinned staging for error flags / counters
     uint32_t* h_flags = nullptr;
-    uint8_t* last_decode_out = nullptr;   // decode_device(d_out = NULL) leaves its output here
+    uint8_t* last_decode_out = nullptr;
+    cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;   // host-buffer pipeline: copy in / compute / copy out
+    bool keep_cache_once = false;       // next encode call continues the current batch (chunked host-buffer path)   // decode_device(d_out = NULL) leaves its output here
 
     // optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
     bool profile = false;
@@ -111,6 +113,8 @@ struct Engine {
 
 int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
               const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st);
+int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n, uint64_t n_bytes, uint32_t* d_ids,
+                  uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                  uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,

@@ -1,0 +1,224 @@
+// Host-buffer entry points of the C ABI: ctk_encode_batch / ctk_decode_batch.
+//
+// These are what the reference's PyO3 methods would call (bindings/tokenizer.rs:207-210, 226-238).
+// encode_batch pipelines the batch in chunks of whole documents over three streams so that the PCIe
+// copy in, the kernels and the copy out overlap:
+//     st_h2d : text chunk c+1, c+2, ...      (pinned user memory is DMA'd directly)
+//     st_comp: NFC check + fused encode of chunk c
+//     st_d2h : ids of chunk c-1 into a pooled pinned result buffer
+// The pre-token cache is cleared at the first chunk only: the chunks are one batch.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "engine.hpp"
+
+namespace ctk {
+
+// process-wide pool of pinned host buffers (pinning a GiB costs far more than encoding it)
+struct PinnedPool {
+    struct Buf { void* p; size_t cap; };
+    std::mutex mu;
+    std::vector<Buf> free_;
+    cudaError_t get(size_t bytes, void** out, size_t* cap) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            int best = -1;
+            for (int i = 0; i < (int)free_.size(); ++i)
+                if (free_[i].cap >= bytes && (best < 0 || free_[i].cap < free_[best].cap)) best = i;
+            if (best >= 0) { *out = free_[best].p; *cap = free_[best].cap; free_.erase(free_.begin() + best); return cudaSuccess; }
+        }
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(out, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) { want = bytes + 64; e = cudaHostAlloc(out, want, cudaHostAllocDefault); }
+        *cap = want;
+        return e;
+    }
+    void put(void* p, size_t cap) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_.size() >= 8) {                         // drop the smallest
+            int s = 0;
+            for (int i = 1; i < (int)free_.size(); ++i) if (free_[i].cap < free_[s].cap) s = i;
+            if (free_[s].cap < cap) { cudaFreeHost(free_[s].p); free_[s] = {p, cap}; } else cudaFreeHost(p);
+            return;
+        }
+        free_.push_back({p, cap});
+    }
+};
+static PinnedPool g_pinned;
+
+struct Result {
+    size_t n = 0;
+    void *ids = nullptr, *off = nullptr, *bytes = nullptr;
+    size_t ids_cap = 0, off_cap = 0, bytes_cap = 0;
+};
+
+static void free_result(Result* r) {
+    if (!r) return;
+    g_pinned.put(r->ids, r->ids_cap);
+    g_pinned.put(r->off, r->off_cap);
+    g_pinned.put(r->bytes, r->bytes_cap);
+    delete r;
+}
+
+}  // namespace ctk
+
+using namespace ctk;
+
+#define CKE(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = eng->cuda_fail(e_, #x); goto done; } } while (0)
+
+extern "C" {
+
+int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64_t* text_off, size_t n, ctk_result** res) {
+    if (!tok || !text_off || !res) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
+    *res = nullptr;
+    Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
+    if (text_off[0] != 0) { set_last_error("text_off[0] must be 0"); return CTK_ERR_ARG; }
+    const uint64_t B = text_off[n];
+    if (B && !text) { set_last_error("NULL text"); return CTK_ERR_ARG; }
+    // chunks of whole documents, about 64 MiB each (16-byte aligned starts are not needed: each
+    // chunk is copied to a 256-byte aligned place of its own)
+    const uint64_t target = 64ull << 20;
+    struct Chunk { size_t d0, d1; uint64_t b0, b1, dev_text; size_t roff; };
+    std::vector<Chunk> chunks;
+    {
+        size_t d = 0;
+        uint64_t dev = 0;
+        size_t ro = 0;
+        while (d < n) {
+            size_t e = d;
+            uint64_t b0 = text_off[d];
+            while (e < n && (e == d || text_off[e + 1] - b0 <= target)) {
+                if (text_off[e + 1] < text_off[e]) { set_last_error("text_off must be non-decreasing"); return CTK_ERR_ARG; }
+                ++e;
+            }
+            uint64_t b1 = text_off[e];
+            if (b1 - b0 >= 0xFFFFFFF0ull) { set_last_error("a single document of 4 GiB or more is not supported"); return CTK_ERR_ARG; }
+            chunks.push_back({d, e, b0, b1, dev, ro});
+            dev += ((b1 - b0 + 64 + 255) / 256) * 256;
+            ro += (e - d) + 1;
+            d = e;
+        }
+    }
+    std::lock_guard<std::mutex> lk(eng->mu);
+    int rc = CTK_OK;
+    Result* r = new Result();
+    r->n = n;
+    uint8_t* d_text = nullptr; uint64_t *d_roff = nullptr, *d_ids_off = nullptr; uint32_t* d_ids = nullptr;
+    uint64_t* h_roff = nullptr; size_t h_roff_cap = 0;
+    uint64_t* h_ioff = nullptr; size_t h_ioff_cap = 0;
+    uint64_t total = 0, dev_text_bytes = 0, ids_cap = 0;
+    size_t n_roff = n + chunks.size() + 1;
+    std::vector<cudaEvent_t> evs;
+    std::vector<uint64_t> chunk_base;
+    CKE(cudaSetDevice(eng->device));
+    dev_text_bytes = chunks.empty() ? 256 : chunks.back().dev_text + ((chunks.back().b1 - chunks.back().b0 + 64 + 255) / 256) * 256;
+    ids_cap = B + B / 8 + n + 1024;
+    CKE(eng->ws.get(20, dev_text_bytes, (void**)&d_text));
+    CKE(eng->ws.get(21, n_roff * 8, (void**)&d_roff));
+    CKE(eng->ws.get(22, n_roff * 8, (void**)&d_ids_off));
+    CKE(eng->ws.get(23, ids_cap * 4, (void**)&d_ids));
+    CKE(g_pinned.get(n_roff * 8, (void**)&h_roff, &h_roff_cap));
+    CKE(g_pinned.get(n_roff * 8, (void**)&h_ioff, &h_ioff_cap));
+    CKE(g_pinned.get((n + 1) * 8, &r->off, &r->off_cap));
+    CKE(g_pinned.get((B / 3 + n + 1024) * 4, &r->ids, &r->ids_cap));
+    // document offsets relative to their chunk
+    for (const Chunk& c : chunks)
+        for (size_t d = c.d0; d <= c.d1; ++d) h_roff[c.roff + (d - c.d0)] = text_off[d] - c.b0;
+    CKE(cudaMemcpyAsync(d_roff, h_roff, n_roff * 8, cudaMemcpyHostToDevice, eng->st_h2d));
+    evs.resize(chunks.size());
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        const Chunk& ch = chunks[c];
+        if (!eng->ev_pool.empty()) { evs[c] = eng->ev_pool.back(); eng->ev_pool.pop_back(); }
+        else CKE(cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming));
+        if (ch.b1 > ch.b0) CKE(cudaMemcpyAsync(d_text + ch.dev_text, text + ch.b0, ch.b1 - ch.b0, cudaMemcpyHostToDevice, eng->st_h2d));
+        CKE(cudaMemsetAsync(d_text + ch.dev_text + (ch.b1 - ch.b0), 0, 64, eng->st_h2d));
+        CKE(cudaEventRecord(evs[c], eng->st_h2d));
+    }
+    chunk_base.resize(chunks.size() + 1, 0);
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        const Chunk& ch = chunks[c];
+        CKE(cudaStreamWaitEvent(eng->st_comp, evs[c], 0));
+        uint64_t cnt = 0;
+        eng->keep_cache_once = c > 0;
+        rc = encode_device(*eng, d_text + ch.dev_text, d_roff + ch.roff, ch.d1 - ch.d0, ch.b1 - ch.b0, d_ids + total, ids_cap - total,
+                           d_ids_off + ch.roff, &cnt, eng->st_comp);
+        eng->keep_cache_once = false;
+        if (rc != CTK_OK) goto done;
+        // copy out while the next chunk is being encoded
+        if ((total + cnt + 1) * 4 > r->ids_cap) {                     // grow the pinned result (rare)
+            CKE(cudaStreamSynchronize(eng->st_d2h));
+            void* nb; size_t ncap;
+            uint64_t est = (uint64_t)((double)(total + cnt) * (double)B / (double)std::max<uint64_t>(ch.b1, 1) * 1.1) + 4096;
+            CKE(g_pinned.get(std::max<uint64_t>(est, total + cnt + 1) * 4, &nb, &ncap));
+            memcpy(nb, r->ids, total * 4);
+            g_pinned.put(r->ids, r->ids_cap);
+            r->ids = nb; r->ids_cap = ncap;
+        }
+        if (cnt) CKE(cudaMemcpyAsync((uint32_t*)r->ids + total, d_ids + total, cnt * 4, cudaMemcpyDeviceToHost, eng->st_d2h));
+        CKE(cudaMemcpyAsync(h_ioff + ch.roff, d_ids_off + ch.roff, (ch.d1 - ch.d0 + 1) * 8, cudaMemcpyDeviceToHost, eng->st_d2h));
+        chunk_base[c] = total;
+        total += cnt;
+    }
+    CKE(cudaStreamSynchronize(eng->st_d2h));
+    {
+        uint64_t* off = (uint64_t*)r->off;
+        for (size_t c = 0; c < chunks.size(); ++c) {
+            const Chunk& ch = chunks[c];
+            for (size_t d = ch.d0; d < ch.d1; ++d) off[d] = chunk_base[c] + h_ioff[ch.roff + (d - ch.d0)];
+        }
+        off[n] = total;
+    }
+done:
+    for (cudaEvent_t ev : evs) if (ev) eng->ev_pool.push_back(ev);
+    g_pinned.put(h_roff, h_roff_cap);
+    g_pinned.put(h_ioff, h_ioff_cap);
+    if (rc != CTK_OK) { cudaStreamSynchronize(eng->st_h2d); cudaStreamSynchronize(eng->st_d2h); free_result(r); return rc; }
+    *res = reinterpret_cast<ctk_result*>(r);
+    return CTK_OK;
+}
+
+int ctk_decode_batch(const ctk_tokenizer* tok, const uint32_t* ids, const uint64_t* ids_off, size_t n, int skip_special_tokens,
+                     int clean_up_tokenization_spaces, ctk_result** res) {
+    if (!tok || !ids_off || !res) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
+    *res = nullptr;
+    Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
+    if (ids_off[0] != 0) { set_last_error("ids_off[0] must be 0"); return CTK_ERR_ARG; }
+    for (size_t i = 0; i < n; ++i) if (ids_off[i + 1] < ids_off[i]) { set_last_error("ids_off must be non-decreasing"); return CTK_ERR_ARG; }
+    const uint64_t T = ids_off[n];
+    if (T && !ids) { set_last_error("NULL ids"); return CTK_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(eng->mu);
+    int rc = CTK_OK;
+    Result* r = new Result();
+    r->n = n;
+    uint32_t* d_ids; uint64_t *d_off, *d_out_off; uint8_t* d_out;
+    uint64_t total = 0;
+    cudaStream_t st = eng->st_comp;
+    CKE(cudaSetDevice(eng->device));
+    CKE(eng->ws.get(24, (T + 1) * 4, (void**)&d_ids));
+    CKE(eng->ws.get(21, (n + 1) * 8, (void**)&d_off));
+    CKE(eng->ws.get(22, (n + 1) * 8, (void**)&d_out_off));
+    if (T) CKE(cudaMemcpyAsync(d_ids, ids, T * 4, cudaMemcpyHostToDevice, st));
+    CKE(cudaMemcpyAsync(d_off, ids_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    rc = decode_device(*eng, d_ids, d_off, n, T, skip_special_tokens, clean_up_tokenization_spaces, nullptr, 0, d_out_off, &total, st);
+    if (rc != CTK_OK) goto done;
+    d_out = eng->last_decode_out;
+    CKE(g_pinned.get((n + 1) * 8, &r->off, &r->off_cap));
+    CKE(g_pinned.get(total + 1, &r->bytes, &r->bytes_cap));
+    CKE(cudaMemcpyAsync(r->off, d_out_off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (total) CKE(cudaMemcpyAsync(r->bytes, d_out, total, cudaMemcpyDeviceToHost, st));
+    CKE(cudaStreamSynchronize(st));
+done:
+    if (rc != CTK_OK) { free_result(r); return rc; }
+    *res = reinterpret_cast<ctk_result*>(r);
+    return CTK_OK;
+}
+
+const uint32_t* ctk_result_ids(const ctk_result* res) { return (const uint32_t*)reinterpret_cast<const Result*>(res)->ids; }
+const uint64_t* ctk_result_offsets(const ctk_result* res) { return (const uint64_t*)reinterpret_cast<const Result*>(res)->off; }
+const uint8_t* ctk_result_bytes(const ctk_result* res) { return (const uint8_t*)reinterpret_cast<const Result*>(res)->bytes; }
+size_t ctk_result_count(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->n; }
+void ctk_result_free(ctk_result* res) { free_result(reinterpret_cast<Result*>(res)); }
+
+}  // extern "C"
