@@ -1,25 +1,33 @@
-// Fused single-pass encode kernel: text in, packed ids + per-document offsets out, one read of the
-// text and one write of the ids (algorithmic traffic B + 4T + 16(D+1)).
+// Fused encode: text in, packed ids + per-document offsets out.
 //
-// Work decomposition
-//   CTA  = 8 warps = one tile of 8 x 448 bytes; tiles are handed out by an atomic ticket so that a
-//          tile never waits on a tile that has not started (decoupled look-back, below).
-//   warp = one 512-byte chunk: 16 bytes of left context + 448 OWNED bytes + 48 bytes of right
-//          context.  Lane l holds bytes [16 l, 16 l + 16) of the chunk in registers (one coalesced
-//          16-byte load per lane) and the chunk is mirrored in shared memory for unaligned access.
-// Stages inside a warp (reference lines in brackets)
+//   k_first_doc      per 448-byte slice: first document that can start in it (documents are independent,
+//                    mod.rs:694-696, so every slice must know where they start)
+//   k_encode_slices  ALL of normalised-text -> ids: classes, pre-token boundaries, pre-token cache, BPE.
+//                    One warp per slice, warps fully independent (no barrier, no inter-warp order).
+//                    Writes the slice's ids to a fixed-stride scratch run and its count.
+//   (device scan of the per-slice counts)
+//   k_compact        moves every slice's run to its final place in the packed output
+//   k_doc_fixup      ids_off[d] (written slice-relative by k_encode_slices) += base of its slice
+//
+// A single-pass variant (decoupled look-back, ids staged in shared memory) was measured first
+// (profiles/r1_v1_fused_full_summary.txt, r1_v2_lookback_summary.txt): with variable work per tile the
+// look-back chain stalled workers ~50% of the time, and the kernel is issue-bound, not HBM-bound, so
+// the extra 8T bytes of scratch traffic are the cheaper price.
+//
+// Inside a warp (reference lines in brackets); lane l holds bytes [16 l, 16 l + 16) of a 512-byte chunk
+// = 16 bytes of left context + 448 OWNED bytes + 48 bytes of right context:
 //   1 classify: SWAR class masks per lane, trie for non-ASCII   [pretokenizers.rs:13 \p{L} \p{N} \s]
 //   2 boundaries: 32-bit window logic + warp shuffles           [pretokenizers.rs:13, :158-185]
-//   3 compaction: ballot-free prefix sum of per-lane popcounts -> list of pre-token starts
+//   3 compaction: prefix sum of per-lane popcounts -> list of pre-token starts
 //   4 per pre-token, 32 at a time:
-//       <= 16 bytes: look up the batch's pre-token cache (one 32-byte L2 sector per probe); BPE of a
-//                    pre-token is a pure function of its bytes, so each distinct pre-token of a batch is
-//                    merged once and every other occurrence copies the ids  [bpe.rs:88-153 is pure]
+//       <= 16 bytes: look up the batch's pre-token cache (one 32-byte L2 sector per probe, one 256-bit
+//                    load); BPE of a pre-token is a pure function of its bytes, so each distinct
+//                    pre-token of a batch is merged once and every other occurrence copies the ids
 //       miss or 17..32 bytes: warp-cooperative merge loop (bpe_warp32)        [bpe.rs:104-153]
 //       > 32 bytes: deferred to the end of the warp's work, merged in global scratch
-//   5 ids are staged in shared memory in pre-token order (mod.rs:562-612 `result.extend`)
-// Then per CTA: sum of the 8 warp totals -> decoupled look-back over tile_state -> coalesced copy of
-// the staged ids to their final place, and ids_off[d] for every document that starts in the tile.
+//   5 ids leave in pre-token order (mod.rs:562-612 `result.extend`)
+#include <cub/device/device_scan.cuh>
+
 #include "engine.hpp"
 #include "start_window.cuh"
 
@@ -29,22 +37,29 @@ constexpr int FW = 8;            // warps per CTA
 constexpr int SLICE = 448;       // bytes owned by a warp
 constexpr int CHUNK = 512;       // bytes a warp looks at
 constexpr int LCTX = 16;         // left context
-constexpr int STAGE = 480;       // ids a warp can stage: owned pre-tokens of <= 32 bytes cover < 480 bytes
+constexpr int STAGE = 480;       // ids of one slice from pre-tokens of <= 32 bytes (they cover < 480 bytes)
 constexpr int MAXLONG = 14;      // pre-tokens longer than 32 bytes that can start in 448 bytes
 constexpr uint32_t META_EMPTY = 0xFFFFFFFFu, META_BUSY = 0xFFFFFFFEu;
 constexpr int PROBES = 4;
 constexpr uint32_t END_UNKNOWN = 0xFFFFu;
 
+struct LongDesc { uint32_t at, pool, cnt; };            // `cnt` ids at long_pool[pool..] go before run position `at`
+
 struct FusedParams {
     DevTables t;
     const uint8_t* text; uint64_t n_bytes;
     const uint64_t* off; uint64_t n_docs;
-    const uint32_t* first_doc; uint64_t n_slices;
+    const uint32_t* first_doc; uint64_t n_slices; uint32_t n_tiles;
     CacheSlot* cache; uint32_t cache_mask;
+    uint32_t id_bits, n_inline;                          // ids packed inline in a cache slot: n_inline x id_bits <= 96
     uint32_t* ovf_pool; uint32_t ovf_cap; uint32_t* ovf_cursor;
     uint32_t* long_pool; unsigned long long long_cap; unsigned long long* long_cursor;
-    unsigned long long* tile_state; uint32_t* ticket;
-    uint32_t* out; uint64_t out_cap; uint64_t* ids_off; uint32_t* err;
+    LongDesc* desc; uint32_t desc_cap; uint32_t* desc_cursor;
+    uint32_t* runs;                                      // n_slices x STAGE
+    uint32_t* slice_cnt;                                 // ids of the slice (short + long)
+    uint32_t* slice_info;                                // staged count | n_long << 16
+    uint32_t* slice_desc;                                // first LongDesc of the slice (if n_long > 0)
+    uint64_t* ids_off; uint32_t* err;
 };
 
 struct __align__(16) WarpSmem {
@@ -52,10 +67,9 @@ struct __align__(16) WarpSmem {
     uint8_t chunk[CHUNK];
     uint8_t pad1[16];
     uint32_t ds[32];
-    uint32_t stage[STAGE];
     uint16_t list[SLICE + 8];
     uint16_t l_at[MAXLONG + 2], l_k[MAXLONG + 2], l_pos[MAXLONG + 2], l_len[MAXLONG + 2];
-    uint32_t l_pool[MAXLONG + 2], l_cnt[MAXLONG + 2];
+    uint32_t l_cnt[MAXLONG + 2];
 };
 
 // first_doc[s] = smallest d with off[d] >= s*SLICE - LCTX ; also validates the offsets
@@ -74,6 +88,16 @@ __global__ void k_first_doc(const uint64_t* __restrict__ off, uint64_t n_docs, u
     for (uint64_t s = s_lo; s <= s_hi; ++s) first_doc[s] = (uint32_t)d;
 }
 
+// ids_off[d] was written relative to the slice that owns position off[d]; add that slice's base
+__global__ void k_doc_fixup(const uint64_t* __restrict__ off, uint64_t n_docs, uint64_t n_slices,
+                            const uint32_t* __restrict__ slice_base, uint64_t* __restrict__ ids_off) {
+    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d > n_docs) return;
+    uint64_t s = off[d] / SLICE;
+    if (s >= n_slices) s = n_slices - 1;
+    ids_off[d] += slice_base[s];
+}
+
 __device__ __forceinline__ void load_slot(const CacheSlot* p, uint64_t& k0, uint64_t& k1, uint32_t& meta, uint32_t& t0,
                                           uint32_t& t1, uint32_t& t2) {
     uint64_t c, d;
@@ -81,11 +105,10 @@ __device__ __forceinline__ void load_slot(const CacheSlot* p, uint64_t& k0, uint
     meta = (uint32_t)c; t0 = (uint32_t)(c >> 32); t1 = (uint32_t)d; t2 = (uint32_t)(d >> 32);
 }
 
-__device__ __forceinline__ uint32_t key_hash(uint64_t k0, uint64_t k1, uint32_t len) {
-    uint64_t h = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull) ^ len) * 0xD6E8FEB86659FD93ull;
-    h ^= h >> 32;
-    h *= 0xD6E8FEB86659FD93ull;
-    return (uint32_t)(h >> 32);
+__device__ __forceinline__ uint32_t key_hash(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t len) {
+    uint32_t h = x0 * 0x9E3779B1u ^ x1 * 0x85EBCA77u ^ x2 * 0xC2B2AE3Du ^ x3 * 0x27D4EB2Fu ^ len * 0x165667B1u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
 }
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t& total) {
@@ -118,26 +141,26 @@ __device__ __forceinline__ int init_symbols32(const uint32_t* s_byte_init, const
     return __popc(have);
 }
 
-__global__ void __launch_bounds__(FW * 32, 5) k_encode_fused(const FusedParams p) {
+__global__ void __launch_bounds__(FW * 32, 6) k_encode_slices(const FusedParams p) {
     const unsigned full = 0xFFFFFFFFu;
     __shared__ WarpSmem sm[FW];
     __shared__ uint32_t s_byte_init[256];
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_wtot[FW];
-    __shared__ unsigned long long s_tile_base;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     s_byte_init[tid] = __ldg(p.t.byte_init + tid);
-    if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint64_t slice = (uint64_t)tile * FW + w;
-    const bool active = slice < p.n_slices;
     WarpSmem& S = sm[w];
-    const long long lo = (long long)slice * SLICE, cb = lo - LCTX;     // chunk base (may be -16 for slice 0)
-    const uint32_t d0 = active ? __ldg(p.first_doc + slice) : 0;
-    uint32_t n_owned = 0, stage_cnt = 0, n_long = 0, first_k = 0, ownm = 0, long_total = 0;
+    if (lane == 0) {
+        *reinterpret_cast<uint4*>(S.pad0) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(S.pad1) = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
 
-    if (active) {
+    for (uint64_t slice = (uint64_t)blockIdx.x * FW + w; slice < p.n_slices; slice += (uint64_t)gridDim.x * FW) {
+        const long long lo = (long long)slice * SLICE, cb = lo - LCTX;     // chunk base (may be -16 for slice 0)
+        const uint32_t d0 = __ldg(p.first_doc + slice);
+        uint32_t* run = p.runs + slice * STAGE;
+        uint32_t n_owned = 0, stage_cnt = 0, n_long = 0, first_k = 0, ownm = 0, long_total = 0;
+        bool docs_here = false;
+
         // ---- 1. load the chunk: one 16-byte vector per lane, zero beyond the text
         const long long q = cb + 16 * lane;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -153,21 +176,26 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_fused(const FusedParams p
                 v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             }
         }
+        __syncwarp();                                                  // previous slice's readers are done
         *reinterpret_cast<uint4*>(S.chunk + 16 * lane) = v;
-        if (lane == 0) { *reinterpret_cast<uint4*>(S.pad0) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(S.pad1) = make_uint4(0, 0, 0, 0); }
-        S.ds[lane] = 0;
-        __syncwarp();
         // ---- document starts inside the chunk (position n_bytes = off[n_docs] counts as one)
-        for (uint64_t d = (uint64_t)d0 + lane;; d += 32) {
-            uint64_t pos = d <= p.n_docs ? __ldg(p.off + d) : ~0ull;
-            bool in = (long long)pos < cb + CHUNK && pos != ~0ull;
-            if (in) { uint32_t rel = (uint32_t)((long long)pos - cb); atomicOr(&S.ds[rel >> 4], 1u << (rel & 15)); }
-            if (!__all_sync(full, in)) break;
+        uint32_t ds16 = 0;
+        docs_here = (long long)__ldg(p.off + d0) < cb + CHUNK;         // warp-uniform
+        if (docs_here) {
+            S.ds[lane] = 0;
+            __syncwarp();
+            for (uint64_t d = (uint64_t)d0 + lane;; d += 32) {
+                uint64_t pos = d <= p.n_docs ? __ldg(p.off + d) : ~0ull;
+                bool in = (long long)pos < cb + CHUNK && pos != ~0ull;
+                if (in) { uint32_t rel = (uint32_t)((long long)pos - cb); atomicOr(&S.ds[rel >> 4], 1u << (rel & 15)); }
+                if (!__all_sync(full, in)) break;
+            }
+            __syncwarp();
+            ds16 = S.ds[lane];
         }
         __syncwarp();
         // ---- 2. classes and boundaries
         Masks16 m = classify16(S.chunk, 16 * lane, v.x, v.y, v.z, v.w, p.t.trie_index, p.t.trie_blocks);
-        uint32_t ds16 = S.ds[lane];
         uint32_t pa = m.L | (m.N << 16), pb = m.W | (m.SP << 16), pc = m.AP | (m.CONT << 16);
         uint32_t ua = __shfl_up_sync(full, pa, 1), ub = __shfl_up_sync(full, pb, 1), uc = __shfl_up_sync(full, pc, 1),
                  ud = __shfl_up_sync(full, ds16, 1);
@@ -180,12 +208,11 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_fused(const FusedParams p
                                     window(uc & 0xFFFF, m.AP, nc & 0xFFFF), window(uc >> 16, m.CONT, nc >> 16),
                                     window(ud, ds16, nd), S.chunk + 16 * lane - 8);
         uint32_t own16 = (S32 >> 8) & 0xFFFFu;
-        // positions at or beyond the end of the text are not pre-token starts of anything we own
         {
             long long room = (long long)p.n_bytes - q;               // valid positions in this group
             uint32_t valid = room >= 16 ? 0xFFFFu : (room <= 0 ? 0u : ((1u << room) - 1u));
             ownm = (lane >= 1 && lane <= 28) ? (own16 & valid) : 0u;
-            // ---- 3. compaction: list of owned pre-token starts, then the sentinel (first start in the right context)
+            // ---- 3. compaction: list of owned pre-token starts, then the sentinel (first start after them)
             uint32_t c = __popc(ownm);
             first_k = warp_excl_scan(c, n_owned);
             uint32_t bits = ownm, o = first_k;
@@ -209,7 +236,7 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_fused(const FusedParams p
             uint32_t pos = have ? S.list[k] : 0, end = have ? S.list[k + 1] : 0;
             uint32_t len = end - pos;
             __syncwarp();
-            // kind: 0 nothing, 1 cache hit (<= 3 ids inline), 2 cache hit (ids in the overflow pool), 3 needs merging, 4 long
+            // kind: 0 nothing, 1 cache hit (ids inline), 2 cache hit (ids in the overflow pool), 3 needs merging, 4 long
             int kind = 0;
             uint32_t ntok = 0, t0 = 0, t1 = 0, t2 = 0, ins = kNone;
             uint64_t k0 = 0, k1 = 0;
@@ -220,13 +247,17 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_fused(const FusedParams p
                     const uint32_t* wp = reinterpret_cast<const uint32_t*>(S.chunk + (pos & ~3u));
                     uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
                     uint32_t sh = (pos & 3u) * 8;
-                    uint32_t x0 = __funnelshift_r(a0, a1, sh), x1 = __funnelshift_r(a1, a2, sh), x2 = __funnelshift_r(a2, a3, sh),
-                             x3 = __funnelshift_r(a3, a4, sh);
+                    uint32_t x0 = __funnelshift_r(a0, a1, sh), x1 = __funnelshift_r(a1, a2, sh),
+                             x2 = __funnelshift_r(a2, a3, sh), x3 = __funnelshift_r(a3, a4, sh);
+                    // zero the bytes beyond len
+                    int l0 = (int)len, l1 = l0 - 4, l2 = l0 - 8, l3 = l0 - 12;
+                    x0 = l0 >= 4 ? x0 : (x0 & ((1u << (8 * l0)) - 1u));
+                    x1 = l1 >= 4 ? x1 : (l1 <= 0 ? 0u : (x1 & ((1u << (8 * l1)) - 1u)));
+                    x2 = l2 >= 4 ? x2 : (l2 <= 0 ? 0u : (x2 & ((1u << (8 * l2)) - 1u)));
+                    x3 = l3 >= 4 ? x3 : (l3 <= 0 ? 0u : (x3 & ((1u << (8 * l3)) - 1u)));
                     k0 = x0 | ((uint64_t)x1 << 32);
                     k1 = x2 | ((uint64_t)x3 << 32);
-                    if (len < 8) { k0 &= (1ull << (8 * len)) - 1ull; k1 = 0; }
-                    else if (len < 16) k1 &= (1ull << (8 * (len - 8))) - 1ull;
-                    uint32_t h = key_hash(k0, k1, len);
+                    uint32_t h = key_hash(x0, x1, x2, x3, len);
                     kind = 3;
                     for (int pr = 0; pr < PROBES; ++pr) {
                         uint32_t idx = (h + pr) & p.cache_mask;
@@ -235,61 +266,73 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_fused(const FusedParams p
                         if (meta == META_EMPTY) { ins = idx; break; }
                         if (meta < META_BUSY && (meta & 0xFFu) == len && s0 == k0 && s1 == k1) {
                             ntok = (meta >> 8) & 0xFFu; t0 = u0; t1 = u1; t2 = u2;
-                            kind = ntok <= 3 ? 1 : 2;
+                            kind = ntok <= p.n_inline ? 1 : 2;
                             break;
                         }
                     }
                 }
             }
-            uint32_t hit_total;
-            uint32_t E = warp_excl_scan((kind == 1 || kind == 2) ? ntok : 0u, hit_total);
             // misses and 17..32-byte pre-tokens: merge cooperatively, one after the other, in lane order
-            uint32_t extra = 0;
             unsigned mm = __ballot_sync(full, kind == 3);
-            while (mm) {
-                const int src = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const uint32_t spos = __shfl_sync(full, pos, src), slen = __shfl_sync(full, len, src);
-                uint32_t sym;
-                int n = init_symbols32(s_byte_init, S.chunk + spos, (int)slen, sym);
-                int cnt = n ? bpe_warp32(p.t, sym, n) : 0;
-                const uint32_t o = stage_cnt + __shfl_sync(full, E, src) + extra;
-                if (lane < cnt) S.stage[o + lane] = sym;
-                const uint32_t sins = __shfl_sync(full, ins, src);
-                if (sins != kNone) {                                   // publish in the batch cache
-                    uint32_t a0 = __shfl_sync(full, sym, 0), a1 = __shfl_sync(full, sym, 1), a2 = __shfl_sync(full, sym, 2);
-                    bool ok = true;
-                    if (cnt > 3) {
-                        uint32_t rec = 0;
-                        if (lane == src) rec = atomicAdd(p.ovf_cursor, 1u);
-                        rec = __shfl_sync(full, rec, src);
-                        ok = rec < p.ovf_cap;
-                        if (ok && lane < cnt) p.ovf_pool[(uint64_t)rec * 16 + lane] = sym;
-                        a0 = rec;
-                    }
-                    if (ok && lane == src) {
-                        CacheSlot* sl = p.cache + sins;
-                        if (atomicCAS(&sl->meta, META_EMPTY, META_BUSY) == META_EMPTY) {
-                            sl->k0 = k0; sl->k1 = k1; sl->tok[0] = a0; sl->tok[1] = a1; sl->tok[2] = a2;
-                            __threadfence();
-                            *reinterpret_cast<volatile uint32_t*>(&sl->meta) = slen | ((uint32_t)cnt << 8);
+            if (mm) {
+                uint32_t hit_total;
+                uint32_t E = warp_excl_scan((kind == 1 || kind == 2) ? ntok : 0u, hit_total);
+                uint32_t extra = 0;
+                while (mm) {
+                    const int src = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const uint32_t spos = __shfl_sync(full, pos, src), slen = __shfl_sync(full, len, src);
+                    uint32_t sym;
+                    int n = init_symbols32(s_byte_init, S.chunk + spos, (int)slen, sym);
+                    int cnt = n ? bpe_warp32(p.t, sym, n) : 0;
+                    const uint32_t o = stage_cnt + __shfl_sync(full, E, src) + extra;
+                    if (lane < cnt) run[o + lane] = sym;
+                    const uint32_t sins = __shfl_sync(full, ins, src);
+                    if (sins != kNone) {                               // publish in the batch cache
+                        uint32_t w0 = 0, w1 = 0, w2 = 0;
+                        bool ok = true;
+                        if ((uint32_t)cnt <= p.n_inline) {             // pack ids, id_bits each, first id lowest
+                            unsigned long long lo64 = 0, hi64 = 0;
+                            for (int i = (int)p.n_inline - 1; i >= 0; --i) {
+                                uint32_t ti = __shfl_sync(full, sym, i);
+                                hi64 = (hi64 << p.id_bits) | (lo64 >> (64 - p.id_bits));
+                                lo64 = (lo64 << p.id_bits) | (i < cnt ? ti : 0u);
+                            }
+                            w0 = (uint32_t)lo64; w1 = (uint32_t)(lo64 >> 32); w2 = (uint32_t)hi64;
+                        } else {
+                            uint32_t rec = 0;
+                            if (lane == src) rec = atomicAdd(p.ovf_cursor, 1u);
+                            rec = __shfl_sync(full, rec, src);
+                            ok = rec < p.ovf_cap;
+                            if (ok && lane < cnt) p.ovf_pool[(uint64_t)rec * 16 + lane] = sym;
+                            w0 = rec;
+                        }
+                        if (ok && lane == src) {
+                            CacheSlot* sl = p.cache + sins;
+                            if (atomicCAS(&sl->meta, META_EMPTY, META_BUSY) == META_EMPTY) {
+                                sl->k0 = k0; sl->k1 = k1; sl->tok[0] = w0; sl->tok[1] = w1; sl->tok[2] = w2;
+                                __threadfence();
+                                *reinterpret_cast<volatile uint32_t*>(&sl->meta) = slen | ((uint32_t)cnt << 8);
+                            }
                         }
                     }
+                    if (lane == src) { ntok = (uint32_t)cnt; kind = 5; }
+                    extra += (uint32_t)cnt;
                 }
-                if (lane == src) { ntok = (uint32_t)cnt; kind = 5; }
-                extra += (uint32_t)cnt;
             }
             uint32_t round_total;
             uint32_t F = warp_excl_scan(kind == 4 ? 0u : ntok, round_total);
             const uint32_t o = stage_cnt + F;
             if (kind == 1) {
-                if (ntok > 0) S.stage[o] = t0;
-                if (ntok > 1) S.stage[o + 1] = t1;
-                if (ntok > 2) S.stage[o + 2] = t2;
+                const uint32_t mask = (1u << p.id_bits) - 1u, bits = p.id_bits;
+                for (uint32_t i = 0; i < ntok; ++i) {
+                    run[o + i] = t0 & mask;
+                    t0 = __funnelshift_r(t0, t1, bits); t1 = __funnelshift_r(t1, t2, bits); t2 >>= bits;
+                }
             } else if (kind == 2) {
-                for (uint32_t i = 0; i < ntok; ++i) S.stage[o + i] = p.ovf_pool[(uint64_t)t0 * 16 + i];
+                for (uint32_t i = 0; i < ntok; ++i) run[o + i] = p.ovf_pool[(uint64_t)t0 * 16 + i];
             }
-            // the list entry now becomes the pre-token's id offset inside the warp's stage (for ids_off)
+            // the list entry now becomes the pre-token's id offset inside the slice's run (for ids_off)
             if (have) S.list[k] = (uint16_t)o;
             unsigned lm = __ballot_sync(full, kind == 4);
             while (lm) {
@@ -307,7 +350,14 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_fused(const FusedParams p
         }
         if (lane == 0) S.list[n_owned] = (uint16_t)stage_cnt;
 
-        // ---- long pre-tokens: merged in global scratch (symbols compacted in place)
+        // ---- long pre-tokens: merged in global scratch (symbols compacted in place), described for k_compact
+        uint32_t desc0 = 0;
+        if (n_long) {
+            if (n_long > MAXLONG) { n_long = MAXLONG; if (lane == 0) atomicOr(p.err, ERRF_POOL); }
+            if (lane == 0) desc0 = atomicAdd(p.desc_cursor, n_long);
+            desc0 = __shfl_sync(full, desc0, 0);
+            if (desc0 + n_long > p.desc_cap) { if (lane == 0) atomicOr(p.err, ERRF_POOL); n_long = 0; }
+        }
         for (uint32_t j = 0; j < n_long; ++j) {
             const uint64_t gstart = (uint64_t)(cb + S.l_pos[j]);
             uint64_t len = S.l_len[j];
@@ -340,87 +390,80 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_fused(const FusedParams p
                 __syncwarp();
                 cnt = (uint32_t)bpe_warp_long(p.t, sym, (int)n);
             } else if (lane == 0) atomicOr(p.err, ERRF_POOL);
-            if (lane == 0) { S.l_pool[j] = (uint32_t)po; S.l_cnt[j] = cnt; }
+            if (lane == 0) { S.l_cnt[j] = cnt; p.desc[desc0 + j] = LongDesc{S.l_at[j], (uint32_t)po, cnt}; }
             long_total += cnt;
         }
         __syncwarp();
-    }
 
-    // ---- per CTA: tile total, decoupled look-back, final positions
-    if (lane == 0) s_wtot[w] = stage_cnt + long_total;
-    __syncthreads();
-    if (w == 0) {
-        uint32_t tv = lane < FW ? s_wtot[lane] : 0u, tile_total;
-        warp_excl_scan(tv, tile_total);
-        volatile unsigned long long* st = p.tile_state;
-        unsigned long long excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st[0] = (2ull << 62) | tile_total;
-        } else {
-            if (lane == 0) st[tile] = (1ull << 62) | tile_total;
-            long long look = (long long)tile - 1;
-            for (;;) {
-                long long idx = look - lane;
-                unsigned long long sv;
-                do { sv = idx >= 0 ? st[idx] : (2ull << 62); } while (__any_sync(full, (sv >> 62) == 0));
-                unsigned pm = __ballot_sync(full, (sv >> 62) == 2);
-                unsigned long long val = sv & ((1ull << 62) - 1);
-                if (pm) {
-                    int first = __ffs(pm) - 1;
-                    if (lane > first) val = 0;
+        // ---- ids_off (relative to this slice) for the documents that start in the owned bytes, or at
+        //      the very end of the text (owned by the last slice)
+        if (docs_here) {
+            const bool last_slice = slice + 1 == p.n_slices;
+            for (uint64_t d = (uint64_t)d0 + lane;; d += 32) {
+                uint64_t pos = d <= p.n_docs ? __ldg(p.off + d) : ~0ull;
+                bool in = (long long)pos < cb + CHUNK && pos != ~0ull;
+                bool own = in && (((long long)pos >= lo && (long long)pos < lo + SLICE) ||
+                                  (last_slice && pos == p.n_bytes && (long long)pos >= lo));
+                uint32_t rel = own ? (uint32_t)((long long)pos - cb) : 0u;
+                uint32_t fk = __shfl_sync(full, first_k, rel >> 4), sb = __shfl_sync(full, ownm, rel >> 4);
+                if (own) {
+                    uint32_t k = fk + __popc(sb & ((1u << (rel & 15)) - 1u));
+                    if (k > n_owned) k = n_owned;
+                    unsigned long long tokoff = S.list[k];
+                    for (uint32_t j = 0; j < n_long; ++j) if (S.l_k[j] < k) tokoff += S.l_cnt[j];
+                    p.ids_off[d] = tokoff;
                 }
-                for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(full, val, o);
-                excl += val;
-                if (pm) break;
-                look -= 32;
+                if (!__all_sync(full, in)) break;
             }
-            if (lane == 0) st[tile] = (2ull << 62) | (excl + tile_total);
         }
-        if (lane == 0) s_tile_base = excl;
+        if (lane == 0) {
+            p.slice_cnt[slice] = stage_cnt + long_total;
+            p.slice_info[slice] = stage_cnt | (n_long << 16);
+            if (n_long) p.slice_desc[slice] = desc0;
+        }
     }
-    __syncthreads();
-    if (!active) return;
-    unsigned long long base = s_tile_base;
-    for (int k = 0; k < w; ++k) base += s_wtot[k];
-    const uint32_t wtotal = stage_cnt + long_total;
-    if (base + wtotal > p.out_cap) { if (lane == 0) atomicOr(p.err, ERRF_CAPACITY); return; }
-    uint32_t* out = p.out + base;
-    if (n_long == 0) {
-        for (uint32_t i = lane; i < stage_cnt; i += 32) out[i] = S.stage[i];
-    } else {
-        // staged ids interleaved with the long pre-tokens' ids (rare)
-        uint32_t nl = n_long < MAXLONG ? n_long : MAXLONG;
-        for (uint32_t i = lane; i < stage_cnt; i += 32) {
-            uint32_t add = 0;
-            for (uint32_t j = 0; j < nl; ++j) if (S.l_at[j] <= i) add += S.l_cnt[j];
-            out[i + add] = S.stage[i];
+}
+
+// one warp per 32 consecutive slices: each slice's run -> its final place
+__global__ void __launch_bounds__(256) k_compact(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ slice_base,
+                                                 const uint32_t* __restrict__ slice_info, const uint32_t* __restrict__ slice_desc,
+                                                 const LongDesc* __restrict__ desc, const uint32_t* __restrict__ long_pool,
+                                                 uint64_t n_slices, uint32_t* __restrict__ out, uint64_t out_cap,
+                                                 uint32_t* __restrict__ err) {
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t s0 = warp * 32;
+    if (s0 >= n_slices) return;
+    const uint64_t my = s0 + lane;
+    uint32_t base = my < n_slices ? slice_base[my] : 0, info = my < n_slices ? slice_info[my] : 0;
+    uint32_t nxt = my < n_slices ? slice_base[my + 1] : 0;
+    int ns = (int)(n_slices - s0 < 32 ? n_slices - s0 : 32);
+    if (my < n_slices && (uint64_t)nxt > out_cap) atomicOr(err, ERRF_CAPACITY);
+    unsigned bad = __ballot_sync(full, my < n_slices && (uint64_t)nxt > out_cap);
+    if (bad) return;
+    for (int j = 0; j < ns; ++j) {
+        const uint32_t b = __shfl_sync(full, base, j), inf = __shfl_sync(full, info, j);
+        const uint32_t n_stage = inf & 0xFFFFu, n_long = inf >> 16;
+        const uint32_t* src = runs + (s0 + j) * STAGE;
+        uint32_t* dst = out + b;
+        if (n_long == 0) {
+            for (uint32_t i = lane; i < n_stage; i += 32) dst[i] = src[i];
+        } else {                                        // run ids interleaved with long pre-tokens' ids (rare)
+            const LongDesc* dd = desc + slice_desc[s0 + j];
+            for (uint32_t i = lane; i < n_stage; i += 32) {
+                uint32_t add = 0;
+                for (uint32_t q = 0; q < n_long; ++q) if (dd[q].at <= i) add += dd[q].cnt;
+                dst[i + add] = src[i];
+            }
+            uint32_t before = 0;
+            for (uint32_t q = 0; q < n_long; ++q) {
+                const uint32_t* ls = long_pool + dd[q].pool;
+                uint32_t* ld = dst + dd[q].at + before;
+                for (uint32_t i = lane; i < dd[q].cnt; i += 32) ld[i] = ls[i];
+                before += dd[q].cnt;
+            }
         }
-        uint32_t before = 0;
-        for (uint32_t j = 0; j < nl; ++j) {
-            const uint32_t* src = p.long_pool + S.l_pool[j];
-            uint32_t* dst = out + S.l_at[j] + before;
-            for (uint32_t i = lane; i < S.l_cnt[j]; i += 32) dst[i] = src[i];
-            before += S.l_cnt[j];
-        }
-        if (n_long > MAXLONG && lane == 0) atomicOr(p.err, ERRF_POOL);
-    }
-    // ---- ids_off for the documents that start in the owned bytes (or at the very end of the text)
-    const bool last_slice = slice + 1 == p.n_slices;
-    for (uint64_t d = (uint64_t)d0 + lane;; d += 32) {
-        uint64_t pos = d <= p.n_docs ? __ldg(p.off + d) : ~0ull;
-        bool in = (long long)pos < cb + CHUNK && pos != ~0ull;
-        bool own = in && (((long long)pos >= lo && (long long)pos < lo + SLICE) || (last_slice && pos == p.n_bytes && (long long)pos >= lo));
-        uint32_t rel = own ? (uint32_t)((long long)pos - cb) : 0u;
-        uint32_t fk = __shfl_sync(full, first_k, rel >> 4), sb = __shfl_sync(full, ownm, rel >> 4);
-        if (own) {
-            uint32_t k = fk + __popc(sb & ((1u << (rel & 15)) - 1u));
-            if (k > n_owned) k = n_owned;
-            unsigned long long tokoff = S.list[k];
-            uint32_t nl = n_long < MAXLONG ? n_long : MAXLONG;
-            for (uint32_t j = 0; j < nl; ++j) if (S.l_k[j] < k) tokoff += S.l_cnt[j];
-            p.ids_off[d] = base + tokoff;
-        }
-        if (!__all_sync(full, in)) break;
     }
 }
 
@@ -434,25 +477,43 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         if (n_ids_host) { CK(cudaStreamSynchronize(st)); *n_ids_host = 0; }
         return CTK_OK;
     }
+    if (eng.fused_grid == 0) {
+        int per_sm = 0, sms = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_slices, FW * 32, 0));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, eng.device));
+        if (per_sm < 1) return eng.fail(CTK_ERR_CUDA, "encode kernel does not fit on an SM");
+        eng.fused_grid = per_sm * sms;
+    }
     Workspace& ws = eng.ws;
     FusedParams p{};
     p.t = eng.tables;
     p.text = d_text; p.n_bytes = n_bytes; p.off = d_off; p.n_docs = n_docs;
     p.n_slices = (n_bytes + SLICE - 1) / SLICE;
-    uint32_t n_tiles = (uint32_t)((p.n_slices + FW - 1) / FW);
+    p.n_tiles = (uint32_t)((p.n_slices + FW - 1) / FW);
     const uint32_t cache_slots = 1u << 20, ovf_cap = 1u << 18;
-    uint32_t *first_doc, *ctrl;
+    uint32_t *first_doc, *ctrl, *slice_base;
     CK(ws.get(0, (p.n_slices + 1) * 4, (void**)&first_doc));
     CK(ws.get(18, (uint64_t)cache_slots * sizeof(CacheSlot), (void**)&p.cache));
     CK(ws.get(19, (uint64_t)ovf_cap * 64, (void**)&p.ovf_pool));
-    CK(ws.get(3, ((uint64_t)n_tiles + 1) * 8, (void**)&p.tile_state));
     CK(ws.get(4, 256, (void**)&ctrl));
+    CK(ws.get(1, (p.n_slices + 2) * 4, (void**)&p.slice_cnt));
+    CK(ws.get(2, (p.n_slices + 2) * 4, (void**)&slice_base));
+    CK(ws.get(3, (p.n_slices + 2) * 4, (void**)&p.slice_info));
+    CK(ws.get(6, (p.n_slices + 2) * 4, (void**)&p.slice_desc));
+    CK(ws.get(8, p.n_slices * (uint64_t)STAGE * 4, (void**)&p.runs));
     p.long_cap = n_bytes + 64;
     CK(ws.get(7, p.long_cap * 4, (void**)&p.long_pool));
+    p.desc_cap = (uint32_t)(n_bytes / 33 + 16);
+    CK(ws.get(9, (uint64_t)p.desc_cap * sizeof(LongDesc), (void**)&p.desc));
     p.first_doc = first_doc; p.cache_mask = cache_slots - 1; p.ovf_cap = ovf_cap;
-    // ctrl words: [0] err flags, [2] ticket, [3] ovf cursor, [4..5] long cursor
-    p.err = ctrl; p.ticket = ctrl + 2; p.ovf_cursor = ctrl + 3; p.long_cursor = reinterpret_cast<unsigned long long*>(ctrl + 4);
-    p.out = d_ids; p.out_cap = ids_cap; p.ids_off = d_ids_off;
+    uint32_t max_id = eng.model.id_present.empty() ? 1u : (uint32_t)eng.model.id_present.size() - 1;
+    p.id_bits = 1;
+    while ((1ull << p.id_bits) <= max_id) ++p.id_bits;
+    p.n_inline = 96 / p.id_bits;
+    if (p.n_inline > 16) p.n_inline = 16;
+    // ctrl words: [0] err flags, [2] desc cursor, [3] ovf cursor, [4..5] long cursor
+    p.err = ctrl; p.desc_cursor = ctrl + 2; p.ovf_cursor = ctrl + 3; p.long_cursor = reinterpret_cast<unsigned long long*>(ctrl + 4);
+    p.ids_off = d_ids_off;
     eng.mark(nullptr, st);
     if (!((eng.cache_persistent || eng.keep_cache_once) && eng.cache_valid)) {
         CK(cudaMemsetAsync(p.cache, 0xFF, (uint64_t)cache_slots * sizeof(CacheSlot), st));
@@ -462,12 +523,25 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         CK(cudaMemsetAsync(ctrl, 0, 12, st));                          // keep the overflow cursor
         CK(cudaMemsetAsync(ctrl + 4, 0, 8, st));
     }
-    CK(cudaMemsetAsync(p.tile_state, 0, ((uint64_t)n_tiles + 1) * 8, st));
-    eng.mark("memset(cache,state)", st);
-    k_first_doc<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_off, n_docs, n_bytes, p.n_slices, first_doc, p.err);
+    eng.mark("memset(cache)", st);
+    unsigned doc_grid = (unsigned)((n_docs + 1 + 255) / 256);
+    k_first_doc<<<doc_grid, 256, 0, st>>>(d_off, n_docs, n_bytes, p.n_slices, first_doc, p.err);
     eng.launched(1); eng.mark("k_first_doc", st);
-    k_encode_fused<<<n_tiles, FW * 32, 0, st>>>(p);
-    eng.launched(1); eng.mark("k_encode_fused", st);
+    unsigned grid = p.n_tiles < (uint32_t)eng.fused_grid ? p.n_tiles : (unsigned)eng.fused_grid;
+    k_encode_slices<<<grid, FW * 32, 0, st>>>(p);
+    eng.launched(1); eng.mark("k_encode_slices", st);
+    size_t cub_bytes = 0;
+    void* cub_tmp;
+    CK(cudaMemsetAsync(p.slice_cnt + p.n_slices, 0, 4, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, p.slice_cnt, slice_base, p.n_slices + 1, st));
+    CK(ws.get(5, cub_bytes + 16, &cub_tmp));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, p.slice_cnt, slice_base, p.n_slices + 1, st));
+    eng.launched(1); eng.mark("scan(slice counts)", st);
+    k_compact<<<(unsigned)((p.n_slices + 255) / 256), 256, 0, st>>>(p.runs, slice_base, p.slice_info, p.slice_desc, p.desc, p.long_pool,
+                                                                    p.n_slices, d_ids, ids_cap, p.err);
+    eng.launched(1); eng.mark("k_compact", st);
+    k_doc_fixup<<<doc_grid, 256, 0, st>>>(d_off, n_docs, p.n_slices, slice_base, d_ids_off);
+    eng.launched(1); eng.mark("k_doc_fixup", st);
     CK(cudaGetLastError());
     return eng.finish(p.err, d_ids_off, n_docs, n_ids_host, st);
 }

@@ -55,8 +55,11 @@ CTK_HD Masks16 classify16(const uint8_t* chunk, int pos, uint32_t w0, uint32_t w
     uint32_t non_ascii = movemask4(w0 & 0x80808080u) | (movemask4(w1 & 0x80808080u) << 4) |
                          (movemask4(w2 & 0x80808080u) << 8) | (movemask4(w3 & 0x80808080u) << 12);
     while (non_ascii) {                                                // rare path: multi-byte code points
-        int b = 0;
-        while (!((non_ascii >> b) & 1u)) ++b;
+#if defined(__CUDA_ARCH__)
+        int b = __ffs(non_ascii) - 1;
+#else
+        int b = __builtin_ctz(non_ascii);
+#endif
         non_ascii &= non_ascii - 1;
         int i = pos + b;
         uint32_t c = chunk[i];
@@ -97,8 +100,11 @@ CTK_HD uint32_t start_window(uint32_t L, uint32_t N, uint32_t W, uint32_t SP, ui
     uint32_t C1 = 0, C2 = 0;                                          // contraction starts of length 2 / 3
     uint32_t cand = AP & (DS | P1(L | N) | P1(W & ~G)) & 0x1FFFFFF8u; // apostrophe where the regex tries a new match
     while (cand) {
-        int j = 0;
-        while (!((cand >> j) & 1u)) ++j;
+#if defined(__CUDA_ARCH__)
+        int j = __ffs(cand) - 1;
+#else
+        int j = __builtin_ctz(cand);
+#endif
         cand &= cand - 1;
         if ((DS >> (j + 1)) & 1u) continue;
         uint32_t c1 = wbytes[j + 1];
