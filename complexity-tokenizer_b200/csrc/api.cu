@@ -296,3 +296,11 @@ int ctk_debug_load_only(const uint8_t* json, size_t len, uint64_t* n_pairs, uint
 }
 
 }  // extern "C"
+
+// debug: 16 counters the encode kernel keeps when CTK_ABLATE=9 (slow-path categories), see encode_fused.cu
+extern "C" int ctk_debug_counters(ctk_tokenizer* tok, uint32_t* out16) {
+    ctk::Engine* eng = reinterpret_cast<ctk::Engine*>(tok);
+    if (!eng->ws.p[4]) return CTK_ERR_ARG;
+    cudaSetDevice(eng->device);
+    return cudaMemcpy(out16, (const uint32_t*)eng->ws.p[4] + 16, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? CTK_OK : CTK_ERR_CUDA;
+}

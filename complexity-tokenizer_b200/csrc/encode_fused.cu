@@ -19,14 +19,15 @@
 //   1 classify: SWAR class masks per lane, trie for non-ASCII   [pretokenizers.rs:13 \p{L} \p{N} \s]
 //   2 boundaries: 32-bit window logic + warp shuffles           [pretokenizers.rs:13, :158-185]
 //   3 compaction: prefix sum of per-lane popcounts -> list of pre-token starts
-//   4 per pre-token, 32 at a time:
-//       <= 16 bytes: look up the batch's pre-token cache (one 32-byte L2 sector per probe, one 256-bit
-//                    load); BPE of a pre-token is a pure function of its bytes, so each distinct
-//                    pre-token of a batch is merged once and every other occurrence copies the ids
-//       miss or 17..32 bytes: warp-cooperative merge loop (bpe_warp32)        [bpe.rs:104-153]
-//       > 32 bytes: deferred to the end of the warp's work, merged in global scratch
+//   4 per pre-token, 32 at a time, straight-line: extract <= 16 key bytes, hash, ONE 256-bit load of the
+//     batch's pre-token cache slot (BPE of a pre-token is a pure function of its bytes, so each distinct
+//     pre-token of a batch is merged once and every other occurrence copies the ids), unpack the ids.
+//     Everything else (cache miss, 17..32 bytes, ids that do not fit inline, > 32 bytes) takes the
+//     warp-cooperative slow path: bpe_warp32 [bpe.rs:104-153] or, for long ones, global scratch.
 //   5 ids leave in pre-token order (mod.rs:562-612 `result.extend`)
 #include <cub/device/device_scan.cuh>
+
+#include <cstdlib>
 
 #include "engine.hpp"
 #include "start_window.cuh"
@@ -39,6 +40,7 @@ constexpr int CHUNK = 512;       // bytes a warp looks at
 constexpr int LCTX = 16;         // left context
 constexpr int STAGE = 480;       // ids of one slice from pre-tokens of <= 32 bytes (they cover < 480 bytes)
 constexpr int MAXLONG = 14;      // pre-tokens longer than 32 bytes that can start in 448 bytes
+constexpr int MAXINLINE = 6;     // ids the straight-line path unpacks
 constexpr uint32_t META_EMPTY = 0xFFFFFFFFu, META_BUSY = 0xFFFFFFFEu;
 constexpr int PROBES = 4;
 constexpr uint32_t END_UNKNOWN = 0xFFFFu;
@@ -60,6 +62,7 @@ struct FusedParams {
     uint32_t* slice_info;                                // staged count | n_long << 16
     uint32_t* slice_desc;                                // first LongDesc of the slice (if n_long > 0)
     uint64_t* ids_off; uint32_t* err;
+    int ablate;                                          // debug: 1 = stop after boundaries, 2 = no slow path, 3 = no probe
 };
 
 struct __align__(16) WarpSmem {
@@ -98,11 +101,11 @@ __global__ void k_doc_fixup(const uint64_t* __restrict__ off, uint64_t n_docs, u
     ids_off[d] += slice_base[s];
 }
 
-__device__ __forceinline__ void load_slot(const CacheSlot* p, uint64_t& k0, uint64_t& k1, uint32_t& meta, uint32_t& t0,
-                                          uint32_t& t1, uint32_t& t2) {
-    uint64_t c, d;
-    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k0), "=l"(k1), "=l"(c), "=l"(d) : "l"(p));
-    meta = (uint32_t)c; t0 = (uint32_t)(c >> 32); t1 = (uint32_t)d; t2 = (uint32_t)(d >> 32);
+// one L2 sector, one instruction: {key[4], meta, ids[3]}
+__device__ __forceinline__ void load_slot(const CacheSlot* p, uint32_t& k0, uint32_t& k1, uint32_t& k2, uint32_t& k3,
+                                          uint32_t& meta, uint32_t& t0, uint32_t& t1, uint32_t& t2) {
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(k0), "=r"(k1), "=r"(k2), "=r"(k3), "=r"(meta), "=r"(t0), "=r"(t1), "=r"(t2) : "l"(p));
 }
 
 __device__ __forceinline__ uint32_t key_hash(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t len) {
@@ -111,9 +114,8 @@ __device__ __forceinline__ uint32_t key_hash(uint32_t x0, uint32_t x1, uint32_t 
     return h;
 }
 
-__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t& total) {
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t& total, int lane) {
     const unsigned full = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(full, incl, o); if (lane >= o) incl += u; }
@@ -122,9 +124,8 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t& total) 
 }
 
 // initial ids of `len` bytes at text[...] into lanes (<= 32), unknown bytes dropped (bpe.rs:94-97); returns count
-__device__ __forceinline__ int init_symbols32(const uint32_t* s_byte_init, const uint8_t* bytes, int len, uint32_t& sym) {
+__device__ __forceinline__ int init_symbols32(const uint32_t* s_byte_init, const uint8_t* bytes, int len, uint32_t& sym, int lane) {
     const unsigned full = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
     sym = lane < len ? s_byte_init[bytes[lane]] : kNone;
     unsigned have = __ballot_sync(full, sym != kNone);
     unsigned want = len == 32 ? full : ((1u << len) - 1u);
@@ -141,46 +142,51 @@ __device__ __forceinline__ int init_symbols32(const uint32_t* s_byte_init, const
     return __popc(have);
 }
 
-__global__ void __launch_bounds__(FW * 32, 6) k_encode_slices(const FusedParams p) {
+__global__ void __launch_bounds__(FW * 32, 5) k_encode_slices(const FusedParams p) {
     const unsigned full = 0xFFFFFFFFu;
     __shared__ WarpSmem sm[FW];
     __shared__ uint32_t s_byte_init[256];
+    __shared__ uint4 s_kmask[17];                       // byte masks: keep the first n bytes of 16
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     s_byte_init[tid] = __ldg(p.t.byte_init + tid);
+    if (tid < 17) {
+        uint32_t m[4];
+        for (int j = 0; j < 4; ++j) { int b = tid - 4 * j; m[j] = b >= 4 ? 0xFFFFFFFFu : (b <= 0 ? 0u : ((1u << (8 * b)) - 1u)); }
+        s_kmask[tid] = make_uint4(m[0], m[1], m[2], m[3]);
+    }
     WarpSmem& S = sm[w];
     if (lane == 0) {
         *reinterpret_cast<uint4*>(S.pad0) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(S.pad1) = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
+    const CacheSlot* const cache = p.cache;
+    const uint32_t cmask = p.cache_mask, idb = p.id_bits, idmask = (1u << p.id_bits) - 1u, ninl = p.n_inline;
+    const uint8_t* const text = p.text;
+    const uint64_t n_bytes = p.n_bytes;
 
     for (uint64_t slice = (uint64_t)blockIdx.x * FW + w; slice < p.n_slices; slice += (uint64_t)gridDim.x * FW) {
         const long long lo = (long long)slice * SLICE, cb = lo - LCTX;     // chunk base (may be -16 for slice 0)
         const uint32_t d0 = __ldg(p.first_doc + slice);
-        uint32_t* run = p.runs + slice * STAGE;
+        uint32_t* const run = p.runs + slice * STAGE;
         uint32_t n_owned = 0, stage_cnt = 0, n_long = 0, first_k = 0, ownm = 0, long_total = 0;
-        bool docs_here = false;
 
         // ---- 1. load the chunk: one 16-byte vector per lane, zero beyond the text
         const long long q = cb + 16 * lane;
+        const long long room = (long long)n_bytes - q;                     // valid bytes from this lane's first byte on
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (q >= 0 && (uint64_t)q < p.n_bytes) {
-            v = __ldg(reinterpret_cast<const uint4*>(p.text + q));
-            if ((uint64_t)q + 16 > p.n_bytes) {
-                int keep = (int)(p.n_bytes - (uint64_t)q);             // 1..15 valid bytes
-                uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-                for (int k = 0; k < 4; ++k) {
-                    int b = keep - 4 * k;
-                    wv[k] = b >= 4 ? wv[k] : (b <= 0 ? 0u : (wv[k] & ((1u << (8 * b)) - 1u)));
-                }
-                v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        if (q >= 0 && room > 0) {
+            v = __ldg(reinterpret_cast<const uint4*>(text + q));
+            if (room < 16) {                                               // last bytes of the text: zero the rest
+                uint4 km = s_kmask[room];
+                v.x &= km.x; v.y &= km.y; v.z &= km.z; v.w &= km.w;
             }
         }
-        __syncwarp();                                                  // previous slice's readers are done
+        __syncwarp();                                                      // previous slice's readers are done
         *reinterpret_cast<uint4*>(S.chunk + 16 * lane) = v;
         // ---- document starts inside the chunk (position n_bytes = off[n_docs] counts as one)
         uint32_t ds16 = 0;
-        docs_here = (long long)__ldg(p.off + d0) < cb + CHUNK;         // warp-uniform
+        const bool docs_here = (long long)__ldg(p.off + d0) < cb + CHUNK;  // warp-uniform
         if (docs_here) {
             S.ds[lane] = 0;
             __syncwarp();
@@ -195,28 +201,33 @@ __global__ void __launch_bounds__(FW * 32, 6) k_encode_slices(const FusedParams 
         }
         __syncwarp();
         // ---- 2. classes and boundaries
-        Masks16 m = classify16(S.chunk, 16 * lane, v.x, v.y, v.z, v.w, p.t.trie_index, p.t.trie_blocks);
-        uint32_t pa = m.L | (m.N << 16), pb = m.W | (m.SP << 16), pc = m.AP | (m.CONT << 16);
-        uint32_t ua = __shfl_up_sync(full, pa, 1), ub = __shfl_up_sync(full, pb, 1), uc = __shfl_up_sync(full, pc, 1),
-                 ud = __shfl_up_sync(full, ds16, 1);
-        uint32_t na = __shfl_down_sync(full, pa, 1), nb = __shfl_down_sync(full, pb, 1), nc = __shfl_down_sync(full, pc, 1),
-                 nd = __shfl_down_sync(full, ds16, 1);
-        if (lane == 0) { ua = ub = uc = ud = 0; }
-        if (lane == 31) { na = nb = nc = nd = 0; }
-        uint32_t S32 = start_window(window(ua & 0xFFFF, m.L, na & 0xFFFF), window(ua >> 16, m.N, na >> 16),
-                                    window(ub & 0xFFFF, m.W, nb & 0xFFFF), window(ub >> 16, m.SP, nb >> 16),
-                                    window(uc & 0xFFFF, m.AP, nc & 0xFFFF), window(uc >> 16, m.CONT, nc >> 16),
-                                    window(ud, ds16, nd), S.chunk + 16 * lane - 8);
-        uint32_t own16 = (S32 >> 8) & 0xFFFFu;
         {
-            long long room = (long long)p.n_bytes - q;               // valid positions in this group
+            Masks16 m = classify16(S.chunk, 16 * lane, v.x, v.y, v.z, v.w, p.t.trie_index, p.t.trie_blocks);
+            uint32_t pa = m.L | (m.N << 16), pb = m.W | (m.SP << 16), pc = m.AP | (m.CONT << 16);
+            uint32_t ua = __shfl_up_sync(full, pa, 1), ub = __shfl_up_sync(full, pb, 1), uc = __shfl_up_sync(full, pc, 1),
+                     ud = __shfl_up_sync(full, ds16, 1);
+            uint32_t na = __shfl_down_sync(full, pa, 1), nb = __shfl_down_sync(full, pb, 1), nc = __shfl_down_sync(full, pc, 1),
+                     nd = __shfl_down_sync(full, ds16, 1);
+            if (lane == 0) { ua = ub = uc = ud = 0; }
+            if (lane == 31) { na = nb = nc = nd = 0; }
+            uint32_t S32 = start_window(window(ua & 0xFFFF, m.L, na & 0xFFFF), window(ua >> 16, m.N, na >> 16),
+                                        window(ub & 0xFFFF, m.W, nb & 0xFFFF), window(ub >> 16, m.SP, nb >> 16),
+                                        window(uc & 0xFFFF, m.AP, nc & 0xFFFF), window(uc >> 16, m.CONT, nc >> 16),
+                                        window(ud, ds16, nd), S.chunk + 16 * lane - 8);
+            uint32_t own16 = (S32 >> 8) & 0xFFFFu;
             uint32_t valid = room >= 16 ? 0xFFFFu : (room <= 0 ? 0u : ((1u << room) - 1u));
             ownm = (lane >= 1 && lane <= 28) ? (own16 & valid) : 0u;
             // ---- 3. compaction: list of owned pre-token starts, then the sentinel (first start after them)
             uint32_t c = __popc(ownm);
-            first_k = warp_excl_scan(c, n_owned);
-            uint32_t bits = ownm, o = first_k;
-            while (bits) { int b = __ffs(bits) - 1; bits &= bits - 1; S.list[o++] = (uint16_t)(16 * lane + b); }
+            first_k = warp_excl_scan(c, n_owned, lane);
+            uint32_t bits = ownm;
+            uint16_t* lp = S.list + first_k;
+            const uint32_t lb = 16 * lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (bits) { *lp++ = (uint16_t)(lb + __ffs(bits) - 1); bits &= bits - 1; }
+            }
+            while (bits) { *lp++ = (uint16_t)(lb + __ffs(bits) - 1); bits &= bits - 1; }
             // sentinel candidates: starts in the right context (lanes 29, 30) and the end of the text
             // (position n_bytes is a start thanks to its DS bit) wherever it falls
             uint32_t rc = 0;
@@ -225,126 +236,136 @@ __global__ void __launch_bounds__(FW * 32, 6) k_encode_slices(const FusedParams 
             unsigned bal = __ballot_sync(full, rc != 0);
             uint32_t sent = END_UNKNOWN;
             if (bal) { int sl = __ffs(bal) - 1; uint32_t r2 = __shfl_sync(full, rc, sl); sent = 16 * sl + (__ffs(r2) - 1); }
-            if (lane == 0) S.list[n_owned] = (uint16_t)sent;
+            if (lane == 0) { S.list[n_owned] = (uint16_t)sent; S.list[n_owned + 1] = (uint16_t)sent; }
         }
         __syncwarp();
 
+        if (p.ablate == 1) { if (lane == 0) { p.slice_cnt[slice] = n_owned; p.slice_info[slice] = 0; } continue; }
         // ---- 4. pre-tokens, 32 per round
         for (uint32_t base_k = 0; base_k < n_owned; base_k += 32) {
             const uint32_t k = base_k + lane;
             const bool have = k < n_owned;
-            uint32_t pos = have ? S.list[k] : 0, end = have ? S.list[k + 1] : 0;
-            uint32_t len = end - pos;
+            const uint32_t kk = have ? k : n_owned;                        // clamp: list[n_owned], list[n_owned+1] exist
+            const uint32_t pos = S.list[kk], end = S.list[kk + 1];
+            const uint32_t len = end - pos;                                // huge when the end is unknown
             __syncwarp();
-            // kind: 0 nothing, 1 cache hit (ids inline), 2 cache hit (ids in the overflow pool), 3 needs merging, 4 long
-            int kind = 0;
-            uint32_t ntok = 0, t0 = 0, t1 = 0, t2 = 0, ins = kNone;
-            uint64_t k0 = 0, k1 = 0;
-            if (have) {
-                if (end == END_UNKNOWN || len > 32) kind = 4;
-                else if (len > 16) kind = 3;
-                else {
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(S.chunk + (pos & ~3u));
-                    uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
-                    uint32_t sh = (pos & 3u) * 8;
-                    uint32_t x0 = __funnelshift_r(a0, a1, sh), x1 = __funnelshift_r(a1, a2, sh),
-                             x2 = __funnelshift_r(a2, a3, sh), x3 = __funnelshift_r(a3, a4, sh);
-                    // zero the bytes beyond len
-                    int l0 = (int)len, l1 = l0 - 4, l2 = l0 - 8, l3 = l0 - 12;
-                    x0 = l0 >= 4 ? x0 : (x0 & ((1u << (8 * l0)) - 1u));
-                    x1 = l1 >= 4 ? x1 : (l1 <= 0 ? 0u : (x1 & ((1u << (8 * l1)) - 1u)));
-                    x2 = l2 >= 4 ? x2 : (l2 <= 0 ? 0u : (x2 & ((1u << (8 * l2)) - 1u)));
-                    x3 = l3 >= 4 ? x3 : (l3 <= 0 ? 0u : (x3 & ((1u << (8 * l3)) - 1u)));
-                    k0 = x0 | ((uint64_t)x1 << 32);
-                    k1 = x2 | ((uint64_t)x3 << 32);
-                    uint32_t h = key_hash(x0, x1, x2, x3, len);
-                    kind = 3;
-                    for (int pr = 0; pr < PROBES; ++pr) {
-                        uint32_t idx = (h + pr) & p.cache_mask;
-                        uint64_t s0, s1; uint32_t meta, u0, u1, u2;
-                        load_slot(p.cache + idx, s0, s1, meta, u0, u1, u2);
-                        if (meta == META_EMPTY) { ins = idx; break; }
-                        if (meta < META_BUSY && (meta & 0xFFu) == len && s0 == k0 && s1 == k1) {
-                            ntok = (meta >> 8) & 0xFFu; t0 = u0; t1 = u1; t2 = u2;
-                            kind = ntok <= p.n_inline ? 1 : 2;
-                            break;
-                        }
+            // straight line: key bytes, hash, one slot load, compare
+            const uint32_t pc = pos < CHUNK ? pos : 0u;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(S.chunk + (pc & ~3u));
+            const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
+            const uint32_t sh = (pc & 3u) * 8;
+            const uint4 km = s_kmask[len < 16 ? len : 16];
+            const uint32_t x0 = __funnelshift_r(a0, a1, sh) & km.x, x1 = __funnelshift_r(a1, a2, sh) & km.y,
+                           x2 = __funnelshift_r(a2, a3, sh) & km.z, x3 = __funnelshift_r(a3, a4, sh) & km.w;
+            const uint32_t h = key_hash(x0, x1, x2, x3, len);
+            uint32_t s0, s1, s2, s3, meta, t0, t1, t2;
+            load_slot(cache + (h & cmask), s0, s1, s2, s3, meta, t0, t1, t2);
+            bool match = have && len <= 16 && (meta & 0xFFu) == len && (((s0 ^ x0) | (s1 ^ x1)) | ((s2 ^ x2) | (s3 ^ x3))) == 0;
+            // displaced keys (0.8% of occurrences): the lane itself walks on; the others idle for a few instructions
+            uint32_t ins_slot = kNone;
+            {
+                bool open = have && len <= 16 && !match;
+                if (open && meta == META_EMPTY) { ins_slot = h & cmask; open = false; }
+                for (int pr = 1; pr < PROBES && __any_sync(full, open); ++pr) {
+                    if (open) {
+                        uint32_t r0, r1, r2, r3, rm, v0, v1, v2;
+                        const uint32_t idx = (h + pr) & cmask;
+                        load_slot(cache + idx, r0, r1, r2, r3, rm, v0, v1, v2);
+                        if ((rm & 0xFFu) == len && (((r0 ^ x0) | (r1 ^ x1)) | ((r2 ^ x2) | (r3 ^ x3))) == 0) {
+                            match = true; open = false; meta = rm; t0 = v0; t1 = v1; t2 = v2;
+                        } else if (rm == META_EMPTY) { ins_slot = idx; open = false; }
                     }
                 }
             }
-            // misses and 17..32-byte pre-tokens: merge cooperatively, one after the other, in lane order
-            unsigned mm = __ballot_sync(full, kind == 3);
-            if (mm) {
+            uint32_t ntok = (meta >> 8) & 0xFFu;
+            const bool fast = match && ntok <= ninl;
+            if (!fast) ntok = 0;
+            // everything else: warp-cooperative, one pre-token after the other, in lane order
+            unsigned slow = __ballot_sync(full, have && !fast);
+            if (p.ablate == 2) slow = 0;
+            if (slow) {
                 uint32_t hit_total;
-                uint32_t E = warp_excl_scan((kind == 1 || kind == 2) ? ntok : 0u, hit_total);
-                uint32_t extra = 0;
-                while (mm) {
-                    const int src = __ffs(mm) - 1;
-                    mm &= mm - 1;
+                const uint32_t E = warp_excl_scan(ntok, hit_total, lane);  // ids of fast lanes before each lane
+                uint32_t extra = 0;                                        // ids of slow lanes handled so far
+                unsigned lm = 0;                                           // lanes whose pre-token is long
+                while (slow) {
+                    const int src = __ffs(slow) - 1;
+                    slow &= slow - 1;
                     const uint32_t spos = __shfl_sync(full, pos, src), slen = __shfl_sync(full, len, src);
-                    uint32_t sym;
-                    int n = init_symbols32(s_byte_init, S.chunk + spos, (int)slen, sym);
-                    int cnt = n ? bpe_warp32(p.t, sym, n) : 0;
+                    if (slen > 32) { lm |= 1u << src; if (p.ablate == 9 && lane == 0) atomicAdd(p.err + 16, 1u); continue; }          // also END_UNKNOWN
                     const uint32_t o = stage_cnt + __shfl_sync(full, E, src) + extra;
-                    if (lane < cnt) run[o + lane] = sym;
-                    const uint32_t sins = __shfl_sync(full, ins, src);
-                    if (sins != kNone) {                               // publish in the batch cache
-                        uint32_t w0 = 0, w1 = 0, w2 = 0;
-                        bool ok = true;
-                        if ((uint32_t)cnt <= p.n_inline) {             // pack ids, id_bits each, first id lowest
-                            unsigned long long lo64 = 0, hi64 = 0;
-                            for (int i = (int)p.n_inline - 1; i >= 0; --i) {
-                                uint32_t ti = __shfl_sync(full, sym, i);
-                                hi64 = (hi64 << p.id_bits) | (lo64 >> (64 - p.id_bits));
-                                lo64 = (lo64 << p.id_bits) | (i < cnt ? ti : 0u);
+                    int cnt = -1;
+                    const uint32_t ins = __shfl_sync(full, ins_slot, src);
+                    const uint32_t y0 = __shfl_sync(full, x0, src), y1 = __shfl_sync(full, x1, src), y2 = __shfl_sync(full, x2, src),
+                                   y3 = __shfl_sync(full, x3, src);
+                    if (__shfl_sync(full, (uint32_t)match, src)) {         // cached, but its ids live in the overflow pool
+                        cnt = (int)((__shfl_sync(full, meta, src) >> 8) & 0xFFu);
+                        const uint32_t rec = __shfl_sync(full, t0, src);
+                        if (lane < cnt) run[o + lane] = p.ovf_pool[(uint64_t)rec * 16 + lane];
+                        if (p.ablate == 9 && lane == 0) atomicAdd(p.err + 17, 1u);
+                    }
+                    if (cnt < 0) {                                         // merge now
+                        uint32_t sym;
+                        if (p.ablate == 9 && lane == 0) atomicAdd(p.err + 19 + (slen > 16 ? 1 : 0) + (slen <= 16 && ins == kNone ? 2 : 0), 1u);
+                        int n = init_symbols32(s_byte_init, S.chunk + spos, (int)slen, sym, lane);
+                        cnt = n ? bpe_warp32(p.t, sym, n) : 0;
+                        if (lane < cnt) run[o + lane] = sym;
+                        if (ins != kNone) {                                // publish in the batch cache
+                            uint32_t w0 = 0, w1 = 0, w2 = 0;
+                            bool ok = true;
+                            if ((uint32_t)cnt <= ninl) {                   // pack ids, id_bits each, first id lowest
+                                unsigned long long lo64 = 0, hi64 = 0;
+                                for (int i = (int)ninl - 1; i >= 0; --i) {
+                                    uint32_t ti = __shfl_sync(full, sym, i);
+                                    hi64 = (hi64 << idb) | (lo64 >> (64 - idb));
+                                    lo64 = (lo64 << idb) | (i < cnt ? ti : 0u);
+                                }
+                                w0 = (uint32_t)lo64; w1 = (uint32_t)(lo64 >> 32); w2 = (uint32_t)hi64;
+                            } else {
+                                uint32_t rec = 0;
+                                if (lane == 0) rec = atomicAdd(p.ovf_cursor, 1u);
+                                rec = __shfl_sync(full, rec, 0);
+                                ok = rec < p.ovf_cap;
+                                if (ok && lane < cnt) p.ovf_pool[(uint64_t)rec * 16 + lane] = sym;
+                                w0 = rec;
                             }
-                            w0 = (uint32_t)lo64; w1 = (uint32_t)(lo64 >> 32); w2 = (uint32_t)hi64;
-                        } else {
-                            uint32_t rec = 0;
-                            if (lane == src) rec = atomicAdd(p.ovf_cursor, 1u);
-                            rec = __shfl_sync(full, rec, src);
-                            ok = rec < p.ovf_cap;
-                            if (ok && lane < cnt) p.ovf_pool[(uint64_t)rec * 16 + lane] = sym;
-                            w0 = rec;
-                        }
-                        if (ok && lane == src) {
-                            CacheSlot* sl = p.cache + sins;
-                            if (atomicCAS(&sl->meta, META_EMPTY, META_BUSY) == META_EMPTY) {
-                                sl->k0 = k0; sl->k1 = k1; sl->tok[0] = w0; sl->tok[1] = w1; sl->tok[2] = w2;
-                                __threadfence();
-                                *reinterpret_cast<volatile uint32_t*>(&sl->meta) = slen | ((uint32_t)cnt << 8);
+                            if (ok && lane == 0) {
+                                CacheSlot* sl = p.cache + ins;
+                                if (atomicCAS(&sl->meta, META_EMPTY, META_BUSY) == META_EMPTY) {
+                                    sl->k0 = y0 | ((uint64_t)y1 << 32); sl->k1 = y2 | ((uint64_t)y3 << 32);
+                                    sl->tok[0] = w0; sl->tok[1] = w1; sl->tok[2] = w2;
+                                    __threadfence();
+                                    *reinterpret_cast<volatile uint32_t*>(&sl->meta) = slen | ((uint32_t)cnt << 8);
+                                }
                             }
                         }
                     }
-                    if (lane == src) { ntok = (uint32_t)cnt; kind = 5; }
+                    if (lane == src) ntok = (uint32_t)cnt;                 // so that the scan below covers slow lanes too
                     extra += (uint32_t)cnt;
                 }
+                while (lm) {                                               // long pre-tokens: remember them
+                    const int src = __ffs(lm) - 1;
+                    lm &= lm - 1;
+                    const uint32_t lpv = __shfl_sync(full, pos, src), le = __shfl_sync(full, end, src);
+                    if (lane == 0 && n_long < MAXLONG) {
+                        S.l_k[n_long] = (uint16_t)(base_k + src); S.l_pos[n_long] = (uint16_t)lpv;
+                        S.l_len[n_long] = (uint16_t)(le == END_UNKNOWN ? END_UNKNOWN : le - lpv);
+                    }
+                    ++n_long;
+                }
             }
+            // ids of all lower lanes (fast and slow): the slow lanes wrote theirs at exactly these offsets
             uint32_t round_total;
-            uint32_t F = warp_excl_scan(kind == 4 ? 0u : ntok, round_total);
-            const uint32_t o = stage_cnt + F;
-            if (kind == 1) {
-                const uint32_t mask = (1u << p.id_bits) - 1u, bits = p.id_bits;
-                for (uint32_t i = 0; i < ntok; ++i) {
-                    run[o + i] = t0 & mask;
-                    t0 = __funnelshift_r(t0, t1, bits); t1 = __funnelshift_r(t1, t2, bits); t2 >>= bits;
+            const uint32_t o = stage_cnt + warp_excl_scan(ntok, round_total, lane);
+            if (fast) {
+#pragma unroll
+                for (int i = 0; i < MAXINLINE; ++i) {
+                    if (i < (int)ntok) run[o + i] = t0 & idmask;
+                    t0 = __funnelshift_r(t0, t1, idb); t1 = __funnelshift_r(t1, t2, idb); t2 >>= idb;
                 }
-            } else if (kind == 2) {
-                for (uint32_t i = 0; i < ntok; ++i) run[o + i] = p.ovf_pool[(uint64_t)t0 * 16 + i];
             }
-            // the list entry now becomes the pre-token's id offset inside the slice's run (for ids_off)
-            if (have) S.list[k] = (uint16_t)o;
-            unsigned lm = __ballot_sync(full, kind == 4);
-            while (lm) {
-                const int src = __ffs(lm) - 1;
-                lm &= lm - 1;
-                uint32_t at = __shfl_sync(full, o, src), lp = __shfl_sync(full, pos, src), le = __shfl_sync(full, end, src);
-                if (lane == 0 && n_long < MAXLONG) {
-                    S.l_at[n_long] = (uint16_t)at; S.l_k[n_long] = (uint16_t)(base_k + src); S.l_pos[n_long] = (uint16_t)lp;
-                    S.l_len[n_long] = (uint16_t)(le == END_UNKNOWN ? END_UNKNOWN : le - lp);
-                }
-                ++n_long;
-            }
+            // the list entry now becomes the pre-token's id offset inside the slice's run (ids_off, long ones)
+            if (have && (docs_here || n_long)) S.list[k] = (uint16_t)o;
             stage_cnt += round_total;
             __syncwarp();
         }
@@ -357,14 +378,16 @@ __global__ void __launch_bounds__(FW * 32, 6) k_encode_slices(const FusedParams 
             if (lane == 0) desc0 = atomicAdd(p.desc_cursor, n_long);
             desc0 = __shfl_sync(full, desc0, 0);
             if (desc0 + n_long > p.desc_cap) { if (lane == 0) atomicOr(p.err, ERRF_POOL); n_long = 0; }
+            __syncwarp();
         }
         for (uint32_t j = 0; j < n_long; ++j) {
             const uint64_t gstart = (uint64_t)(cb + S.l_pos[j]);
+            const uint32_t at = S.list[S.l_k[j]];                          // run position its ids go before
             uint64_t len = S.l_len[j];
-            if (len == END_UNKNOWN) {                                  // runs past the chunk: find its end
-                uint64_t dl = 0, dh = p.n_docs;                        // last doc with off[d] <= gstart
+            if (len == END_UNKNOWN) {                                      // runs past the chunk: find its end
+                uint64_t dl = 0, dh = p.n_docs;                            // last doc with off[d] <= gstart
                 while (dl + 1 < dh) { uint64_t mid = (dl + dh) >> 1; if (__ldg(p.off + mid) <= gstart) dl = mid; else dh = mid; }
-                TextView tv{p.text, p.n_bytes, nullptr, p.t.trie_index, p.t.trie_blocks, __ldg(p.off + dl), __ldg(p.off + dl + 1)};
+                TextView tv{text, n_bytes, nullptr, p.t.trie_index, p.t.trie_blocks, __ldg(p.off + dl), __ldg(p.off + dl + 1)};
                 uint64_t e = 0;
                 for (uint64_t i = (uint64_t)(cb + CHUNK - 16) + lane;; i += 32) {
                     bool s = i >= tv.dhi || tv.is_start(i);
@@ -382,7 +405,7 @@ __global__ void __launch_bounds__(FW * 32, 6) k_encode_slices(const FusedParams 
                 uint32_t n = 0;
                 for (uint64_t b0 = 0; b0 < len; b0 += 32) {
                     uint64_t i = b0 + lane;
-                    uint32_t sv = i < len ? s_byte_init[__ldg(p.text + gstart + i)] : kNone;
+                    uint32_t sv = i < len ? s_byte_init[__ldg(text + gstart + i)] : kNone;
                     unsigned hv = __ballot_sync(full, sv != kNone);
                     if (sv != kNone) sym[n + __popc(hv & ((1u << lane) - 1u))] = sv;
                     n += __popc(hv);
@@ -390,7 +413,7 @@ __global__ void __launch_bounds__(FW * 32, 6) k_encode_slices(const FusedParams 
                 __syncwarp();
                 cnt = (uint32_t)bpe_warp_long(p.t, sym, (int)n);
             } else if (lane == 0) atomicOr(p.err, ERRF_POOL);
-            if (lane == 0) { S.l_cnt[j] = cnt; p.desc[desc0 + j] = LongDesc{S.l_at[j], (uint32_t)po, cnt}; }
+            if (lane == 0) { S.l_cnt[j] = cnt; p.desc[desc0 + j] = LongDesc{at, (uint32_t)po, cnt}; }
             long_total += cnt;
         }
         __syncwarp();
@@ -403,7 +426,7 @@ __global__ void __launch_bounds__(FW * 32, 6) k_encode_slices(const FusedParams 
                 uint64_t pos = d <= p.n_docs ? __ldg(p.off + d) : ~0ull;
                 bool in = (long long)pos < cb + CHUNK && pos != ~0ull;
                 bool own = in && (((long long)pos >= lo && (long long)pos < lo + SLICE) ||
-                                  (last_slice && pos == p.n_bytes && (long long)pos >= lo));
+                                  (last_slice && pos == n_bytes && (long long)pos >= lo));
                 uint32_t rel = own ? (uint32_t)((long long)pos - cb) : 0u;
                 uint32_t fk = __shfl_sync(full, first_k, rel >> 4), sb = __shfl_sync(full, ownm, rel >> 4);
                 if (own) {
@@ -418,6 +441,7 @@ __global__ void __launch_bounds__(FW * 32, 6) k_encode_slices(const FusedParams 
         }
         if (lane == 0) {
             p.slice_cnt[slice] = stage_cnt + long_total;
+            if (p.ablate == 9) atomicAdd(p.err + 24, n_owned);
             p.slice_info[slice] = stage_cnt | (n_long << 16);
             if (n_long) p.slice_desc[slice] = desc0;
         }
@@ -510,10 +534,11 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.id_bits = 1;
     while ((1ull << p.id_bits) <= max_id) ++p.id_bits;
     p.n_inline = 96 / p.id_bits;
-    if (p.n_inline > 16) p.n_inline = 16;
+    if (p.n_inline > MAXINLINE) p.n_inline = MAXINLINE;
     // ctrl words: [0] err flags, [2] desc cursor, [3] ovf cursor, [4..5] long cursor
     p.err = ctrl; p.desc_cursor = ctrl + 2; p.ovf_cursor = ctrl + 3; p.long_cursor = reinterpret_cast<unsigned long long*>(ctrl + 4);
     p.ids_off = d_ids_off;
+    { const char* a = getenv("CTK_ABLATE"); p.ablate = a ? atoi(a) : 0; }
     eng.mark(nullptr, st);
     if (!((eng.cache_persistent || eng.keep_cache_once) && eng.cache_valid)) {
         CK(cudaMemsetAsync(p.cache, 0xFF, (uint64_t)cache_slots * sizeof(CacheSlot), st));
