@@ -45,7 +45,9 @@ constexpr uint32_t META_EMPTY = 0xFFFFFFFFu, META_BUSY = 0xFFFFFFFEu;
 constexpr int PROBES = 4;
 constexpr uint32_t END_UNKNOWN = 0xFFFFu;
 
-struct LongDesc { uint32_t at, pool, cnt; };            // `cnt` ids at long_pool[pool..] go before run position `at`
+// A pre-token longer than 32 bytes: found by k_encode_slices, merged by k_encode_long.
+// Its `cnt` ids at long_pool[pool..] go before position `at` of the slice's run; `k` is its pre-token index.
+struct LongDesc { uint64_t gstart; uint32_t len, slice, k_at, pool, cnt, chunk_end; };
 
 struct FusedParams {
     DevTables t;
@@ -92,13 +94,23 @@ __global__ void k_first_doc(const uint64_t* __restrict__ off, uint64_t n_docs, u
 }
 
 // ids_off[d] was written relative to the slice that owns position off[d]; add that slice's base
+// (k_encode_slices left run position | pre-token index << 32; long pre-tokens before that index add their ids)
 __global__ void k_doc_fixup(const uint64_t* __restrict__ off, uint64_t n_docs, uint64_t n_slices,
-                            const uint32_t* __restrict__ slice_base, uint64_t* __restrict__ ids_off) {
+                            const uint32_t* __restrict__ slice_base, const uint32_t* __restrict__ slice_info,
+                            const uint32_t* __restrict__ slice_desc, const LongDesc* __restrict__ desc,
+                            uint64_t* __restrict__ ids_off) {
     uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (d > n_docs) return;
     uint64_t s = off[d] / SLICE;
     if (s >= n_slices) s = n_slices - 1;
-    ids_off[d] += slice_base[s];
+    const uint64_t v = ids_off[d];
+    const uint32_t rel = (uint32_t)v, k = (uint32_t)(v >> 32), n_long = slice_info[s] >> 16;
+    uint64_t extra = 0;
+    if (n_long) {
+        const LongDesc* dd = desc + slice_desc[s];
+        for (uint32_t q = 0; q < n_long; ++q) if ((dd[q].k_at >> 16) < k) extra += dd[q].cnt;
+    }
+    ids_off[d] = (uint64_t)slice_base[s] + rel + extra;
 }
 
 // one L2 sector, one instruction: {key[4], meta, ids[3]}
@@ -142,6 +154,10 @@ __device__ __forceinline__ int init_symbols32(const uint32_t* s_byte_init, const
     return __popc(have);
 }
 
+}  // namespace ctk
+#include "encode_long.cuh"
+namespace ctk {
+
 __global__ void __launch_bounds__(FW * 32, 5) k_encode_slices(const FusedParams p) {
     const unsigned full = 0xFFFFFFFFu;
     __shared__ WarpSmem sm[FW];
@@ -169,7 +185,7 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_slices(const FusedParams 
         const long long lo = (long long)slice * SLICE, cb = lo - LCTX;     // chunk base (may be -16 for slice 0)
         const uint32_t d0 = __ldg(p.first_doc + slice);
         uint32_t* const run = p.runs + slice * STAGE;
-        uint32_t n_owned = 0, stage_cnt = 0, n_long = 0, first_k = 0, ownm = 0, long_total = 0;
+        uint32_t n_owned = 0, stage_cnt = 0, n_long = 0, first_k = 0, ownm = 0;
 
         // ---- 1. load the chunk: one 16-byte vector per lane, zero beyond the text
         const long long q = cb + 16 * lane;
@@ -371,7 +387,7 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_slices(const FusedParams 
         }
         if (lane == 0) S.list[n_owned] = (uint16_t)stage_cnt;
 
-        // ---- long pre-tokens: merged in global scratch (symbols compacted in place), described for k_compact
+        // ---- long pre-tokens (> 32 bytes): described here, merged by k_encode_long
         uint32_t desc0 = 0;
         if (n_long) {
             if (n_long > MAXLONG) { n_long = MAXLONG; if (lane == 0) atomicOr(p.err, ERRF_POOL); }
@@ -379,42 +395,15 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_slices(const FusedParams 
             desc0 = __shfl_sync(full, desc0, 0);
             if (desc0 + n_long > p.desc_cap) { if (lane == 0) atomicOr(p.err, ERRF_POOL); n_long = 0; }
             __syncwarp();
-        }
-        for (uint32_t j = 0; j < n_long; ++j) {
-            const uint64_t gstart = (uint64_t)(cb + S.l_pos[j]);
-            const uint32_t at = S.list[S.l_k[j]];                          // run position its ids go before
-            uint64_t len = S.l_len[j];
-            if (len == END_UNKNOWN) {                                      // runs past the chunk: find its end
-                uint64_t dl = 0, dh = p.n_docs;                            // last doc with off[d] <= gstart
-                while (dl + 1 < dh) { uint64_t mid = (dl + dh) >> 1; if (__ldg(p.off + mid) <= gstart) dl = mid; else dh = mid; }
-                TextView tv{text, n_bytes, nullptr, p.t.trie_index, p.t.trie_blocks, __ldg(p.off + dl), __ldg(p.off + dl + 1)};
-                uint64_t e = 0;
-                for (uint64_t i = (uint64_t)(cb + CHUNK - 16) + lane;; i += 32) {
-                    bool s = i >= tv.dhi || tv.is_start(i);
-                    unsigned b = __ballot_sync(full, s);
-                    if (b) { e = i - lane + (__ffs(b) - 1); break; }
-                }
-                len = e - gstart;
+            if (lane < (int)n_long) {
+                LongDesc dd;
+                dd.gstart = (uint64_t)(cb + S.l_pos[lane]);
+                dd.len = S.l_len[lane] == END_UNKNOWN ? 0xFFFFFFFFu : (uint32_t)S.l_len[lane];
+                dd.slice = (uint32_t)slice;
+                dd.k_at = ((uint32_t)S.l_k[lane] << 16) | (uint32_t)S.list[S.l_k[lane]];
+                dd.pool = 0; dd.cnt = 0; dd.chunk_end = (uint32_t)(CHUNK - 16) - (uint32_t)S.l_pos[lane];
+                p.desc[desc0 + lane] = dd;
             }
-            unsigned long long po = 0;
-            if (lane == 0) po = atomicAdd(p.long_cursor, (unsigned long long)len);
-            po = __shfl_sync(full, po, 0);
-            uint32_t cnt = 0;
-            if (po + len <= p.long_cap) {
-                uint32_t* sym = p.long_pool + po;
-                uint32_t n = 0;
-                for (uint64_t b0 = 0; b0 < len; b0 += 32) {
-                    uint64_t i = b0 + lane;
-                    uint32_t sv = i < len ? s_byte_init[__ldg(text + gstart + i)] : kNone;
-                    unsigned hv = __ballot_sync(full, sv != kNone);
-                    if (sv != kNone) sym[n + __popc(hv & ((1u << lane) - 1u))] = sv;
-                    n += __popc(hv);
-                }
-                __syncwarp();
-                cnt = (uint32_t)bpe_warp_long(p.t, sym, (int)n);
-            } else if (lane == 0) atomicOr(p.err, ERRF_POOL);
-            if (lane == 0) { S.l_cnt[j] = cnt; p.desc[desc0 + j] = LongDesc{at, (uint32_t)po, cnt}; }
-            long_total += cnt;
         }
         __syncwarp();
 
@@ -432,15 +421,13 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_slices(const FusedParams 
                 if (own) {
                     uint32_t k = fk + __popc(sb & ((1u << (rel & 15)) - 1u));
                     if (k > n_owned) k = n_owned;
-                    unsigned long long tokoff = S.list[k];
-                    for (uint32_t j = 0; j < n_long; ++j) if (S.l_k[j] < k) tokoff += S.l_cnt[j];
-                    p.ids_off[d] = tokoff;
+                    p.ids_off[d] = (unsigned long long)S.list[k] | ((unsigned long long)k << 32);   // + long ids: k_doc_fixup
                 }
                 if (!__all_sync(full, in)) break;
             }
         }
         if (lane == 0) {
-            p.slice_cnt[slice] = stage_cnt + long_total;
+            p.slice_cnt[slice] = stage_cnt;                                // k_encode_long adds its ids
             if (p.ablate == 9) atomicAdd(p.err + 24, n_owned);
             p.slice_info[slice] = stage_cnt | (n_long << 16);
             if (n_long) p.slice_desc[slice] = desc0;
@@ -477,13 +464,13 @@ __global__ void __launch_bounds__(256) k_compact(const uint32_t* __restrict__ ru
             const LongDesc* dd = desc + slice_desc[s0 + j];
             for (uint32_t i = lane; i < n_stage; i += 32) {
                 uint32_t add = 0;
-                for (uint32_t q = 0; q < n_long; ++q) if (dd[q].at <= i) add += dd[q].cnt;
+                for (uint32_t q = 0; q < n_long; ++q) if ((dd[q].k_at & 0xFFFFu) <= i) add += dd[q].cnt;
                 dst[i + add] = src[i];
             }
             uint32_t before = 0;
             for (uint32_t q = 0; q < n_long; ++q) {
                 const uint32_t* ls = long_pool + dd[q].pool;
-                uint32_t* ld = dst + dd[q].at + before;
+                uint32_t* ld = dst + (dd[q].k_at & 0xFFFFu) + before;
                 for (uint32_t i = lane; i < dd[q].cnt; i += 32) ld[i] = ls[i];
                 before += dd[q].cnt;
             }
@@ -507,6 +494,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, eng.device));
         if (per_sm < 1) return eng.fail(CTK_ERR_CUDA, "encode kernel does not fit on an SM");
         eng.fused_grid = per_sm * sms;
+        eng.long_grid = sms * 4;
     }
     Workspace& ws = eng.ws;
     FusedParams p{};
@@ -555,6 +543,8 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     unsigned grid = p.n_tiles < (uint32_t)eng.fused_grid ? p.n_tiles : (unsigned)eng.fused_grid;
     k_encode_slices<<<grid, FW * 32, 0, st>>>(p);
     eng.launched(1); eng.mark("k_encode_slices", st);
+    k_encode_long<<<eng.long_grid, 256, 0, st>>>(p);
+    eng.launched(1); eng.mark("k_encode_long", st);
     size_t cub_bytes = 0;
     void* cub_tmp;
     CK(cudaMemsetAsync(p.slice_cnt + p.n_slices, 0, 4, st));
@@ -565,7 +555,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     k_compact<<<(unsigned)((p.n_slices + 255) / 256), 256, 0, st>>>(p.runs, slice_base, p.slice_info, p.slice_desc, p.desc, p.long_pool,
                                                                     p.n_slices, d_ids, ids_cap, p.err);
     eng.launched(1); eng.mark("k_compact", st);
-    k_doc_fixup<<<doc_grid, 256, 0, st>>>(d_off, n_docs, p.n_slices, slice_base, d_ids_off);
+    k_doc_fixup<<<doc_grid, 256, 0, st>>>(d_off, n_docs, p.n_slices, slice_base, p.slice_info, p.slice_desc, p.desc, d_ids_off);
     eng.launched(1); eng.mark("k_doc_fixup", st);
     CK(cudaGetLastError());
     return eng.finish(p.err, d_ids_off, n_docs, n_ids_host, st);

@@ -67,6 +67,7 @@ struct Engine {
     bool cache_persistent = false;
     bool cache_valid = false;           // the pre-token cache holds entries of earlier calls
     bool use_general = false;           // debug: run the multi-kernel pipeline instead of the fused kernel
+    int long_grid = 0;
     int fused_grid = 0;                 // co-resident CTAs of k_encode_fused (SMs x occupancy), computed once
     // pinned staging for error flags / counters
     uint32_t* h_flags = nullptr;

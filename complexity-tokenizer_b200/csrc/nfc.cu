@@ -127,10 +127,11 @@ __device__ __forceinline__ uint32_t dec_cp(const uint8_t* s, uint64_t n, uint64_
     return r;
 }
 
-// one thread per 16 bytes: any suspect code point -> mark its document
+// one thread per 16 bytes: any suspect code point -> set its bit in `susp` and mark its document
 __global__ void __launch_bounds__(256) k_nfc_flag(NfcTables t, const uint8_t* __restrict__ text, uint64_t n,
                                                   const uint64_t* __restrict__ off, uint64_t n_docs,
-                                                  uint8_t* __restrict__ doc_flag, uint32_t* __restrict__ any) {
+                                                  uint8_t* __restrict__ doc_flag, uint32_t* __restrict__ susp,
+                                                  uint32_t* __restrict__ any) {
     uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
     if (base >= n) return;
     uint4 v = *reinterpret_cast<const uint4*>(text + base);          // text buffers are 16-byte aligned and padded
@@ -149,34 +150,77 @@ __global__ void __launch_bounds__(256) k_nfc_flag(NfcTables t, const uint8_t* __
             uint64_t lo = 0, hi2 = n_docs;                            // last doc with off[d] <= i
             while (lo + 1 < hi2) { uint64_t mid = (lo + hi2) >> 1; if (off[mid] <= i) lo = mid; else hi2 = mid; }
             doc_flag[lo] = 1;
+            atomicOr(&susp[i >> 5], 1u << (i & 31));
             *any = 1;
         }
     }
 }
 
-// one warp per document: flagged -> lane 0 normalises (count or write); else length / coalesced copy
+// One warp per document.  Clean documents are copied.  In a flagged document only the SEGMENTS around
+// suspect code points change: a segment is the code point before a run of suspect code points (a
+// starter with NFC_QC=Yes, so nothing before it can interact) plus the run; lane 0 normalises it with
+// the streaming UAX #15 pass, the whole warp copies the unchanged stretches in between.
 __global__ void __launch_bounds__(256) k_nfc_doc(NfcTables t, const uint8_t* __restrict__ text, const uint64_t* __restrict__ off,
                                                  uint64_t n_docs, const uint8_t* __restrict__ doc_flag,
-                                                 const uint64_t* __restrict__ new_off, uint8_t* out, uint64_t* __restrict__ new_len,
-                                                 uint32_t* __restrict__ err) {
+                                                 const uint32_t* __restrict__ susp, const uint64_t* __restrict__ new_off, uint8_t* out,
+                                                 uint64_t* __restrict__ new_len, uint32_t* __restrict__ err) {
+    const unsigned full = 0xFFFFFFFFu;
     uint64_t d = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     if (d >= n_docs) return;
-    int lane = threadIdx.x & 31;
-    const uint8_t* s = text + off[d];
-    uint64_t n = off[d + 1] - off[d];
+    const int lane = threadIdx.x & 31;
+    const uint64_t lo = off[d], hi = off[d + 1];
+    uint8_t* o = out ? out + new_off[d] : nullptr;
     if (!doc_flag[d]) {
-        if (!out) { if (lane == 0) new_len[d] = n; return; }
-        uint8_t* o = out + new_off[d];
-        for (uint64_t i = lane; i < n; i += 32) o[i] = s[i];
+        if (!out) { if (lane == 0) new_len[d] = hi - lo; return; }
+        for (uint64_t i = lo + lane; i < hi; i += 32) o[i - lo] = text[i];
         return;
     }
-    if (lane) return;
-    NfcSink sink{out ? out + new_off[d] : nullptr, 0};
-    NfcStream st(t, sink);
-    for (uint64_t i = 0; i < n;) st.push(dec_cp(s, n, i));
-    st.flush();
-    if (st.overflow) atomicOr(err, ERRF_NFC_LONG);
-    if (!out) new_len[d] = sink.n;
+    uint64_t cur_in = lo, cur_out = 0;
+    bool overflow = false;
+    for (uint64_t w0 = lo >> 5; w0 * 32 < hi; w0 += 32) {              // 32 bitmap words per step
+        const uint64_t wi = w0 + lane, pb = wi * 32;
+        uint32_t word = pb < hi ? susp[wi] : 0u;
+        if (pb < lo) word &= (lo - pb >= 32) ? 0u : (~0u << (lo - pb));
+        if (pb + 32 > hi) word &= (hi <= pb) ? 0u : ((hi - pb >= 32) ? ~0u : ((1u << (hi - pb)) - 1u));
+        unsigned nz = __ballot_sync(full, word != 0);
+        while (nz) {
+            const int l = __ffs(nz) - 1;
+            nz &= nz - 1;
+            uint32_t wv = __shfl_sync(full, word, l);
+            const uint64_t base = (w0 + l) * 32;
+            while (wv) {
+                const int b = __ffs(wv) - 1;
+                wv &= wv - 1;
+                const uint64_t p = base + b;                             // lead byte of a suspect code point
+                if (p < cur_in) continue;                                // inside the segment just handled
+                uint64_t s0 = p;                                         // segment start: the code point before, if any
+                if (p > cur_in) { s0 = p - 1; while (s0 > cur_in && (text[s0] & 0xC0) == 0x80) --s0; }
+                if (o) for (uint64_t i = cur_in + lane; i < s0; i += 32) o[cur_out + (i - cur_in)] = text[i];
+                cur_out += s0 - cur_in;
+                uint64_t seg_end = 0, seg_out = 0;
+                if (lane == 0) {
+                    NfcSink sink{o ? o + cur_out : nullptr, 0};
+                    NfcStream st(t, sink);
+                    uint64_t i = s0;
+                    st.push(dec_cp(text, hi, i));                        // the base (or the first suspect one at a document start)
+                    while (i < hi && ((susp[i >> 5] >> (i & 31)) & 1u)) st.push(dec_cp(text, hi, i));
+                    st.flush();
+                    overflow = overflow || st.overflow;
+                    seg_end = i; seg_out = sink.n;
+                }
+                seg_end = __shfl_sync(full, seg_end, 0);
+                seg_out = __shfl_sync(full, seg_out, 0);
+                cur_in = seg_end;
+                cur_out += seg_out;
+            }
+        }
+    }
+    if (o) for (uint64_t i = cur_in + lane; i < hi; i += 32) o[cur_out + (i - cur_in)] = text[i];
+    cur_out += hi - cur_in;
+    if (lane == 0) {
+        if (overflow) atomicOr(err, ERRF_NFC_LONG);
+        if (!out) new_len[d] = cur_out;
+    }
 }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
@@ -191,11 +235,15 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
     uint8_t* flag; uint32_t* any;
     CK(ws.get(26, n_docs + 16, (void**)&flag));
     CK(ws.get(27, 64, (void**)&any));
+    uint32_t* susp;
+    CK(ws.get(31, (n_bytes / 32 + 2) * 4, (void**)&susp));
+    eng.mark(nullptr, st);
     CK(cudaMemsetAsync(flag, 0, n_docs + 16, st));
     CK(cudaMemsetAsync(any, 0, 64, st));
+    CK(cudaMemsetAsync(susp, 0, (n_bytes / 32 + 2) * 4, st));
     NfcTables t = eng.nfc;
-    k_nfc_flag<<<(unsigned)(((n_bytes + 15) / 16 + 255) / 256), 256, 0, st>>>(t, d_text, n_bytes, d_off, n_docs, flag, any);
-    eng.launched(1);
+    k_nfc_flag<<<(unsigned)(((n_bytes + 15) / 16 + 255) / 256), 256, 0, st>>>(t, d_text, n_bytes, d_off, n_docs, flag, susp, any);
+    eng.launched(1); eng.mark("k_nfc_flag", st);
     CK(cudaMemcpyAsync(eng.h_flags + 8, any, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (!eng.h_flags[8]) return CTK_OK;
@@ -203,8 +251,9 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
     CK(ws.get(28, (n_docs + 2) * 8, (void**)&new_len));
     CK(ws.get(29, (n_docs + 2) * 8, (void**)&new_off));
     unsigned grid = (unsigned)((n_docs * 32 + 255) / 256);
-    k_nfc_doc<<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, nullptr, nullptr, new_len, any + 1);
-    eng.launched(1);
+    eng.mark(nullptr, st);
+    k_nfc_doc<<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, susp, nullptr, nullptr, new_len, any + 1);
+    eng.launched(1); eng.mark("k_nfc_doc(count)", st);
     CK(cudaMemsetAsync(new_len + n_docs, 0, 8, st));
     size_t cub_bytes = 0; void* cub_tmp;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, new_len, new_off, n_docs + 1, st));
@@ -217,8 +266,9 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
     uint8_t* out;
     CK(ws.get(30, total + 64, (void**)&out));
     CK(cudaMemsetAsync(out + total, 0, 64, st));
-    k_nfc_doc<<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, new_off, out, nullptr, any + 1);
-    eng.launched(1);
+    eng.mark(nullptr, st);
+    k_nfc_doc<<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, susp, new_off, out, nullptr, any + 1);
+    eng.launched(1); eng.mark("k_nfc_doc(write)", st);
     CK(cudaMemcpyAsync(eng.h_flags + 8, any + 1, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (eng.h_flags[8] & ERRF_NFC_LONG)
