@@ -180,6 +180,7 @@ def main():
     import torch.distributed as dist
     import complexity_tokenizer as ct
     import synth
+    from complexity_tokenizer.sharding import exchange_shard_metadata
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -210,9 +211,8 @@ def main():
 
     def step():
         n = tok.encode_device(d_text.data_ptr(), d_off.data_ptr(), D, B, d_ids.data_ptr(), ids_cap, d_ids_off.data_ptr(), stream=stream)
-        if world > 1:                       # the only cross-shard exchange: per-shard id counts (metadata)
-            count.fill_(n)
-            dist.all_reduce(count)
+        if world > 1:                       # the only cross-shard exchange: per-shard (first_doc, n_docs, n_ids) metadata
+            exchange_shard_metadata(rank * D, D, n)
         return n
 
     for _ in range(max(3, args.warmup)):

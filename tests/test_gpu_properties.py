@@ -1,0 +1,136 @@
+"""More GPU parity: randomised fuzzing against the oracle, slice/chunk boundary stress, long pre-tokens,
+the two device pipelines against each other, and size-independent properties at larger sizes
+(round trip, batch-splitting invariance, idempotence).  Bit-exact everywhere.  Run with -m gpu."""
+import unicodedata
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(path):
+    import c_oracle
+    return c_oracle.COracle.from_file(path)
+
+
+def _tok(path):
+    import complexity_tokenizer as ct
+    return ct.Tokenizer.from_file(path)
+
+
+ALPHABET = ["a", "b", "e", "s", "t", "r", "v", "l", "m", "d", "'", " ", " ", " ", "\n", "\t", "1", "9", ".", ",", "!", "-", "é", "ü",
+            "ñ", "中", "文", "あ", "　", " ", "\U0001F600", "\U0001F44D", "́", "̧", "x", "'s", "'ll", "  ", "Ⅷ", "²", "_", "٣",
+            "ß", "'re", "'ve", "'d", "'m", "'t", "Å", "豈", "각", "ᄀ", "ᅡ", "ᆨ", "the", " the", " of", "ing", "tion", "\r\n", "\x00", "=-"]
+
+
+def _random_docs(rng, n_docs, max_len):
+    docs = []
+    for _ in range(n_docs):
+        k = int(rng.integers(0, max_len))
+        docs.append(''.join(ALPHABET[int(i)] for i in rng.integers(0, len(ALPHABET), size=k)))
+    return docs
+
+
+@pytest.mark.parametrize('cfg', ['config1', 'config3'])
+def test_fuzz_many_small_documents(built_lib, tok_paths, cfg):
+    """8 000 random documents of 0-60 pieces in one batch: document, slice and chunk boundaries everywhere."""
+    rng = np.random.default_rng(17)
+    docs = _random_docs(rng, 8000, 60)
+    tok, orc = _tok(tok_paths[cfg]), _oracle(tok_paths[cfg])
+    got, want = tok.encode_batch(docs), orc.encode_batch(docs)
+    bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert not bad, (bad[:5], docs[bad[0]] if bad else None)
+    back = tok.decode_batch_with_options(got, False, False)
+    assert back == [unicodedata.normalize('NFC', d) for d in docs]
+    assert tok.decode_batch(got) == orc.decode_batch(got)
+
+
+def test_slice_boundary_stress(built_lib, tok_paths):
+    """Documents whose lengths straddle the 448-byte slice / 512-byte chunk geometry, and pre-tokens of
+    1..700 bytes placed across slice boundaries (short, 17..32, > 32, > 256, unknown-end paths)."""
+    tok, orc = _tok(tok_paths['config2']), _oracle(tok_paths['config2'])
+    docs = []
+    for n in list(range(430, 470)) + list(range(880, 912)) + [447, 448, 449, 463, 464, 465, 479, 480, 481, 495, 496, 497, 511, 512, 513]:
+        docs.append(('ab ' * n)[:n])
+        docs.append('x' * n)
+        docs.append(' ' * n)
+    for plen in [1, 15, 16, 17, 31, 32, 33, 34, 63, 64, 65, 127, 128, 129, 255, 256, 257, 300, 511, 700]:
+        for lead in [0, 1, 430, 440, 447, 448, 460, 478, 479, 480, 481]:
+            docs.append('.' * lead + ' ' + 'q' * plen + ' tail words here')
+            docs.append('é' * (lead // 2) + ' ' + '中' * (plen // 3 + 1) + '!')
+    got, want = tok.encode_batch(docs), orc.encode_batch(docs)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g == w, (i, len(docs[i]), docs[i][:40])
+
+
+def test_long_pretokens_match_oracle(built_lib, tok_paths):
+    """config-4 shape at sizes the O(n^2) oracle finishes quickly: letter runs, space runs, punctuation runs."""
+    import synth
+    tok, orc = _tok(tok_paths['config2']), _oracle(tok_paths['config2'])
+    docs = [d.decode() for d in synth.gen_long_docs(doc_bytes=3000, n_docs=12)]
+    assert tok.encode_batch(docs) == orc.encode_batch(docs)
+
+
+def test_fused_and_general_pipelines_agree(built_lib, tok_paths):
+    """The multi-kernel general pipeline and the fused kernels are two implementations of one function."""
+    import complexity_tokenizer as ct
+    import synth
+    for cfg, kind in (('config2', 'ascii'), ('config3', 'mixed')):
+        tok = _tok(tok_paths[cfg])
+        text, offs = synth.gen_corpus(kind, 321, 6 << 20, doc_median=2000)
+        a_ids, a_off = tok.encode_packed(text, offs)
+        ct._lib().ctk_debug_use_general(tok._h, 1)
+        b_ids, b_off = tok.encode_packed(text, offs)
+        ct._lib().ctk_debug_use_general(tok._h, 0)
+        assert np.array_equal(a_off, b_off) and np.array_equal(a_ids, b_ids)
+
+
+def test_properties_at_larger_size(built_lib, tok_paths):
+    """256 MiB of the bench corpus (the oracle would need minutes): properties that need no oracle.
+    (1) decode(encode(x)) == x byte-exact through decode_batch_with_options(False, False);
+    (2) idempotence: a second encode gives identical ids;
+    (3) batch-splitting invariance: encoding the two halves separately gives the same ids (documents are independent);
+    (4) a 1 % sample of documents equals the oracle."""
+    import synth
+    tok, orc = _tok(tok_paths['config2']), _oracle(tok_paths['config2'])
+    text, offs = synth.gen_corpus('ascii', 5000, 256 << 20, doc_median=4096, doc_min=256, doc_max=65536)
+    ids, ioff = tok.encode_packed(text, offs)
+    assert int(ioff[-1]) == ids.size and ids.size > 0
+    b, boff = tok.decode_packed(ids, ioff, False, False)
+    assert np.array_equal(boff, offs) and np.array_equal(b, text)
+    ids2, ioff2 = tok.encode_packed(text, offs)
+    assert np.array_equal(ids, ids2) and np.array_equal(ioff, ioff2)
+    h = (len(offs) - 1) // 2
+    cut = int(offs[h])
+    ia, oa = tok.encode_packed(text[:cut], offs[:h + 1])
+    ib, ob = tok.encode_packed(text[cut:], offs[h:] - offs[h])
+    assert np.array_equal(np.concatenate([ia, ib]), ids)
+    assert np.array_equal(np.concatenate([oa[:-1], ob + oa[-1]]), ioff)
+    n = len(offs) - 1
+    for d in range(0, n, 100):
+        w, _ = orc.encode_packed(text[int(offs[d]):int(offs[d + 1])], np.array([0, offs[d + 1] - offs[d]], dtype=np.uint64), threads=1)
+        assert np.array_equal(ids[int(ioff[d]):int(ioff[d + 1])], w), d
+
+
+def test_unsupported_and_errors(built_lib, tok_paths, small_tok_json):
+    import json
+    import complexity_tokenizer as ct
+    with pytest.raises(IOError):
+        ct.Tokenizer.from_file('/nonexistent/tokenizer.json')
+    with pytest.raises(IOError):
+        ct.Tokenizer.from_str('{"model": ')
+    tj = json.loads(small_tok_json)
+    tj['pre_tokenizer'] = {'type': 'Whitespace'}
+    with pytest.raises(ct.UnsupportedTokenizerError):
+        ct.Tokenizer.from_str(json.dumps(tj))
+    tj = json.loads(small_tok_json)
+    tj['added_tokens'].append({'id': 5, 'content': 'hello', 'special': False})
+    with pytest.raises(ct.UnsupportedTokenizerError):
+        ct.Tokenizer.from_str(json.dumps(tj))
+    tok = ct.Tokenizer.from_str(small_tok_json)
+    with pytest.raises(TypeError):
+        tok.encode_batch('not a list')
+    with pytest.raises(UnicodeEncodeError):
+        tok.encode('\ud800')
+    assert tok.encode('') == [] and tok.decode([]) == ''
