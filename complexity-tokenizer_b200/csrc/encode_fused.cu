@@ -122,7 +122,7 @@ __device__ __forceinline__ void load_slot(const CacheSlot* p, uint32_t& k0, uint
 
 __device__ __forceinline__ uint32_t key_hash(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t len) {
     uint32_t h = x0 * 0x9E3779B1u ^ x1 * 0x85EBCA77u ^ x2 * 0xC2B2AE3Du ^ x3 * 0x27D4EB2Fu ^ len * 0x165667B1u;
-    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
     return h;
 }
 
@@ -158,7 +158,7 @@ __device__ __forceinline__ int init_symbols32(const uint32_t* s_byte_init, const
 #include "encode_long.cuh"
 namespace ctk {
 
-__global__ void __launch_bounds__(FW * 32, 5) k_encode_slices(const FusedParams p) {
+__global__ void __launch_bounds__(FW * 32, 4) k_encode_slices(const FusedParams p) {
     const unsigned full = 0xFFFFFFFFu;
     __shared__ WarpSmem sm[FW];
     __shared__ uint32_t s_byte_init[256];
@@ -226,10 +226,13 @@ __global__ void __launch_bounds__(FW * 32, 5) k_encode_slices(const FusedParams 
                      nd = __shfl_down_sync(full, ds16, 1);
             if (lane == 0) { ua = ub = uc = ud = 0; }
             if (lane == 31) { na = nb = nc = nd = 0; }
-            uint32_t S32 = start_window(window(ua & 0xFFFF, m.L, na & 0xFFFF), window(ua >> 16, m.N, na >> 16),
-                                        window(ub & 0xFFFF, m.W, nb & 0xFFFF), window(ub >> 16, m.SP, nb >> 16),
-                                        window(uc & 0xFFFF, m.AP, nc & 0xFFFF), window(uc >> 16, m.CONT, nc >> 16),
-                                        window(ud, ds16, nd), S.chunk + 16 * lane - 8);
+            // windows = [previous lane's byte 1 | own bytes 0,1 | next lane's byte 0] of each 16-bit mask: two PRMT each
+            #define WLO(u, o, nx) __byte_perm(__byte_perm(u, o, 0x0541), nx, 0x4210)
+            #define WHI(u, o, nx) __byte_perm(__byte_perm(u, o, 0x0763), nx, 0x6210)
+            uint32_t S32 = start_window(WLO(ua, pa, na), WHI(ua, pa, na), WLO(ub, pb, nb), WHI(ub, pb, nb),
+                                        WLO(uc, pc, nc), WHI(uc, pc, nc), WLO(ud, ds16, nd), S.chunk + 16 * lane - 8);
+            #undef WLO
+            #undef WHI
             uint32_t own16 = (S32 >> 8) & 0xFFFFu;
             uint32_t valid = room >= 16 ? 0xFFFFu : (room <= 0 ? 0u : ((1u << room) - 1u));
             ownm = (lane >= 1 && lane <= 28) ? (own16 & valid) : 0u;

@@ -37,8 +37,11 @@ CTK_HD Masks16 classify16(const uint8_t* chunk, int pos, uint32_t w0, uint32_t w
                           const uint8_t* trie_index, const uint8_t* trie_blocks) {
     Masks16 m;
     uint32_t l, n, w, sp, ap;
-    m.L = m.N = m.W = m.SP = m.AP = m.CONT = 0;
+    m.CONT = 0;
     uint32_t words[4] = {w0, w1, w2, w3};
+    // bit 7 of byte k times 0x00204081 lands on bit 28 + k (no carries: all partial products are distinct bits);
+    // four words are funnelled into the top 16 bits of an accumulator, 3 instructions per word and mask
+    uint32_t aL = 0, aN = 0, aW = 0, aS = 0, aA = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -46,12 +49,13 @@ CTK_HD Masks16 classify16(const uint8_t* chunk, int pos, uint32_t w0, uint32_t w
         uint32_t x = words[k] & 0x7F7F7F7Fu;                           // non-ASCII bytes are fixed up below
         classify_word_ascii(x, l, n, w, sp, ap);
         uint32_t ascii = ~words[k] & 0x80808080u;
-        m.L |= movemask4(l & ascii) << (4 * k);
-        m.N |= movemask4(n & ascii) << (4 * k);
-        m.W |= movemask4(w & ascii) << (4 * k);
-        m.SP |= movemask4(sp & ascii) << (4 * k);
-        m.AP |= movemask4(ap & ascii) << (4 * k);
+        aL = (aL >> 4) | (((l & ascii) * 0x00204081u) & 0xF0000000u);
+        aN = (aN >> 4) | (((n & ascii) * 0x00204081u) & 0xF0000000u);
+        aW = (aW >> 4) | (((w & ascii) * 0x00204081u) & 0xF0000000u);
+        aS = (aS >> 4) | (((sp & ascii) * 0x00204081u) & 0xF0000000u);
+        aA = (aA >> 4) | (((ap & ascii) * 0x00204081u) & 0xF0000000u);
     }
+    m.L = aL >> 16; m.N = aN >> 16; m.W = aW >> 16; m.SP = aS >> 16; m.AP = aA >> 16;
     uint32_t non_ascii = movemask4(w0 & 0x80808080u) | (movemask4(w1 & 0x80808080u) << 4) |
                          (movemask4(w2 & 0x80808080u) << 8) | (movemask4(w3 & 0x80808080u) << 12);
     while (non_ascii) {                                                // rare path: multi-byte code points
