@@ -87,6 +87,8 @@ int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, siz
     const uint8_t* t2; const uint64_t* o2; uint64_t b2;
     int rc = nfc_stage(eng, d_text, d_off, n, n_bytes, &t2, &o2, &b2, st);
     if (rc != CTK_OK) return rc;
+    rc = prefix_space_stage(eng, t2, o2, n, b2, &t2, &o2, &b2, st);
+    if (rc != CTK_OK) return rc;
     if (eng.use_general) return encode_general(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st);
     return encode_fused(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st);
 }
@@ -101,11 +103,6 @@ static int create(const uint8_t* json, size_t len, int device, ctk_tokenizer** o
     if (rc != CTK_OK) { set_last_error(err); delete eng; return rc; }
     if (eng->model.any_added_may_match) {
         set_last_error("an added token can occur inside a single pre-token; in-word added-token matching is not supported yet");
-        delete eng;
-        return CTK_ERR_UNSUPPORTED;
-    }
-    if (eng->model.add_prefix_space) {
-        set_last_error("ByteLevel add_prefix_space=true is not supported yet");
         delete eng;
         return CTK_ERR_UNSUPPORTED;
     }
@@ -157,6 +154,7 @@ void ctk_free(ctk_tokenizer* tok) {
     if (eng->h_flags) cudaFreeHost(eng->h_flags);
     for (cudaStream_t sp : {eng->st_h2d, eng->st_comp, eng->st_d2h}) if (sp) cudaStreamDestroy(sp);
     for (cudaEvent_t ev : eng->ev_pool) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : eng->sync_ev_pool) cudaEventDestroy(ev);
     delete eng;
 }
 

@@ -69,19 +69,53 @@ __device__ __forceinline__ int utf8_seq(const uint8_t* p, uint64_t i, uint64_t n
     return need + 1;
 }
 
-__global__ void k_dec_valid(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off, uint64_t n_docs,
-                            uint32_t* __restrict__ any_invalid) {
-    // one thread per 64-byte chunk of a document would be the fast version; documents are checked
-    // independently because a sequence may not straddle two documents.
+// Is the concatenation valid UTF-8?  16 bytes per thread; a sequence that starts in the group may read up
+// to 3 bytes of the next one.  Document edges are checked separately (k_dec_valid_docs).
+__global__ void __launch_bounds__(256) k_dec_valid_bytes(const uint8_t* __restrict__ raw, uint64_t n,
+                                                         uint32_t* __restrict__ any_invalid) {
+    uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
+    if (base >= n) return;
+    if (base + 16 <= n) {
+        uint4 v = *reinterpret_cast<const uint4*>(raw + base);            // raw is 16-byte aligned
+        if (((v.x | v.y | v.z | v.w) & 0x80808080u) == 0) return;          // all ASCII
+    }
+    uint64_t end = base + 16 < n ? base + 16 : n;
+    for (uint64_t i = base; i < end; ++i) {
+        uint8_t c = raw[i];
+        if (c < 0x80) continue;
+        if ((c & 0xC0) == 0x80) {
+            // continuation: some lead within the previous 3 bytes must cover it
+            bool ok = false;
+            for (int k = 1; k <= 3 && (uint64_t)k <= i; ++k) {
+                uint8_t p = raw[i - k];
+                if ((p & 0xC0) == 0x80) continue;
+                int need = p >= 0xF0 ? 3 : (p >= 0xE0 ? 2 : (p >= 0xC0 ? 1 : 0));
+                ok = need >= k;
+                break;
+            }
+            if (!ok) { atomicOr(any_invalid, 1u); return; }
+        } else {
+            int bad, L = utf8_seq(raw, i, n, &bad);
+            if (!L) { atomicOr(any_invalid, 1u); return; }
+        }
+    }
+}
+// a document may not begin with a continuation byte nor end inside a sequence
+__global__ void k_dec_valid_docs(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off, uint64_t n_docs,
+                                 uint32_t* __restrict__ any_invalid) {
     uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (d >= n_docs) return;
-    const uint8_t* p = raw + raw_off[d];
-    uint64_t n = raw_off[d + 1] - raw_off[d];
-    for (uint64_t i = 0; i < n;) {
-        int bad, L = utf8_seq(p, i, n, &bad);
-        if (!L) { atomicOr(any_invalid, 1u); return; }
-        i += L;
+    uint64_t lo = raw_off[d], hi = raw_off[d + 1];
+    if (lo == hi) return;
+    bool bad = (raw[lo] & 0xC0) == 0x80;
+    for (uint64_t k = 1; k <= 3 && hi - k >= lo && hi >= k; ++k) {
+        uint8_t p = raw[hi - k];
+        if ((p & 0xC0) == 0x80) continue;
+        int need = p >= 0xF0 ? 3 : (p >= 0xE0 ? 2 : (p >= 0xC0 ? 1 : 0));
+        if ((uint64_t)need >= k) bad = true;                                // its tail would lie in the next document
+        break;
     }
+    if (bad) atomicOr(any_invalid, 1u);
 }
 
 // White_Space (Rust char::is_whitespace) at p[i] in valid UTF-8: byte length or 0
@@ -183,38 +217,47 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
     CK(ws.get(10, (T + 2) * 4, (void**)&len));
     CK(ws.get(11, (T + 2) * 8, (void**)&boff));
     CK(ws.get(12, (n_docs + 2) * 8, (void**)&raw_off));
+    eng.mark(nullptr, st);
     k_dec_len<<<(unsigned)((T + 1 + 255) / 256), 256, 0, st>>>(eng.dec, d_ids, T, skip_special, len);
-    eng.launched(1);
+    eng.launched(1); eng.mark("k_dec_len", st);
     cub::TransformInputIterator<uint64_t, ToU64, const uint32_t*> it(len, ToU64());
     size_t cub_bytes = 0;
     void* cub_tmp;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, boff, T + 1, st));
     CK(ws.get(5, cub_bytes + 16, &cub_tmp));
     CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, it, boff, T + 1, st));
-    eng.launched(1);
+    eng.launched(1); eng.mark("scan(id lengths)", st);
     uint64_t raw_total = 0;
     CK(cudaMemcpyAsync(&raw_total, boff + T, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     uint8_t* raw;
     CK(ws.get(13, raw_total + 16, (void**)&raw));
+    eng.mark(nullptr, st);
     if (T) { k_dec_gather<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(eng.dec, d_ids, T, skip_special, boff, raw); eng.launched(1); }
+    
     k_dec_doc_off<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_ids_off, n_docs, boff, raw_off);
-    eng.launched(1);
-    bool need_post = cleanup != 0;
-    if (!need_post && n_docs) {
-        k_dec_valid<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(raw, raw_off, n_docs, err + 1);
-        eng.launched(1);
+    eng.launched(1); eng.mark("k_dec_gather+doc_off", st);
+    // Is the gathered byte string already valid UTF-8?  Then String::from_utf8_lossy is the identity.
+    bool invalid = false;
+    if (n_docs && raw_total) {
+        k_dec_valid_bytes<<<(unsigned)(((raw_total + 15) / 16 + 255) / 256), 256, 0, st>>>(raw, raw_total, err + 1);
+        k_dec_valid_docs<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(raw, raw_off, n_docs, err + 1);
+        eng.launched(2); eng.mark("k_dec_valid", st);
         uint32_t inv = 0;
         CK(cudaMemcpyAsync(&inv, err + 1, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        need_post = inv != 0;
+        invalid = inv != 0;
     }
+    const bool need_post = invalid;                        // sequential per-document path only for invalid UTF-8
     if (!d_out) {                                          // host-buffer entry point: output lives in the workspace
         out_cap = need_post ? 3 * raw_total + 16 : raw_total + 16;
         CK(ws.get(25, out_cap, (void**)&d_out));
         eng.last_decode_out = d_out;
     }
-    if (!need_post) {
+    if (!need_post && cleanup) {
+        int rc = clean_parallel(eng, raw, raw_off, n_docs, raw_total, d_out, out_cap, d_out_off, err, st);
+        if (rc != CTK_OK) return rc;
+    } else if (!need_post) {
         if (raw_total > out_cap) return eng.fail(CTK_ERR_ARG, "decode output capacity too small");
         if (raw_total) CK(cudaMemcpyAsync(d_out, raw, raw_total, cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(d_out_off, raw_off, (n_docs + 1) * 8, cudaMemcpyDeviceToDevice, st));
@@ -227,8 +270,9 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
         CK(ws.get(16, (n_docs + 2) * 8, (void**)&out_len));
         CK(ws.get(17, n_docs + 16, (void**)&which));
         if (n_docs) {
+            eng.mark(nullptr, st);
             k_dec_post<<<(unsigned)((n_docs + 127) / 128), 128, 0, st>>>(raw, raw_off, n_docs, cleanup, bufA, bufB, out_len, which);
-            eng.launched(1);
+            eng.launched(1); eng.mark("k_dec_post", st);
         }
         CK(cudaMemsetAsync(out_len + n_docs, 0, 8, st));
         CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, out_len, d_out_off, n_docs + 1, st));

@@ -1,0 +1,203 @@
+// clean_up_tokenization_spaces (reference: src/huggingface/mod.rs:749-769), data-parallel and exact.
+//
+// The reference applies 15 ordered str::replace calls and then split_whitespace().join(" ").
+// Every replace only DELETES U+0020 characters:
+//   rules 1-6   " ." " ," " !" " ?" " :" " ;"      delete the space right before  . , ! ? : ;
+//   rules 7-14  "\" " " \"" "' " " '" "( " " )" "[ " " ]"   delete the space right after " ' ( [  / right before " ' ) ]
+//   rule 15     " - " -> "-"                        deletes the space on both sides of a hyphen, if both exist then
+// so the outcome is decided per maximal RUN of U+0020 (length m, left neighbour X, right neighbour Y):
+//   after rules 1-14:  rem = max(0, m - [X in "'(\[] - [Y in .,!?:;"')\]])     (one rule per side at most, and a
+//   single str::replace pass never revisits a position), then rule 15, left to right and non-overlapping: a hyphen
+//   with rem >= 1 on both sides takes one space from each; only a shared run with rem == 1 couples two hyphens.
+// Finally every maximal White_Space REGION collapses to one ' ' if anything of it is left (another whitespace
+// character, or a run with rem >= 1), to nothing if it is all gone or touches a document edge (trim).
+// tests: the oracle applies the 15 replaces literally; tests/test_gpu_parity.py and test_gpu_properties.py compare.
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "engine.hpp"
+
+namespace ctk {
+
+constexpr uint8_t F_WS = 1, F_SP = 2, F_DS = 4;
+
+__device__ __forceinline__ int ws_len_at(const uint8_t* p, uint64_t i, uint64_t n) {   // White_Space char starting at i
+    uint8_t c = p[i];
+    if (c == 0x20 || (c >= 9 && c <= 13)) return 1;
+    if (c == 0xC2 && i + 1 < n && (p[i + 1] == 0x85 || p[i + 1] == 0xA0)) return 2;
+    if (i + 2 < n) {
+        uint8_t d = p[i + 1], e = p[i + 2];
+        if (c == 0xE1 && d == 0x9A && e == 0x80) return 3;
+        if (c == 0xE2 && d == 0x80 && ((e >= 0x80 && e <= 0x8A) || e == 0xA8 || e == 0xA9 || e == 0xAF)) return 3;
+        if (c == 0xE2 && d == 0x81 && e == 0x9F) return 3;
+        if (c == 0xE3 && d == 0x80 && e == 0x80) return 3;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_clean_flags(const uint8_t* __restrict__ R, uint64_t n, uint8_t* __restrict__ f,
+                                                     uint8_t* __restrict__ emit) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t c = R[i];
+    bool ws = false;
+    if (c < 0x80) ws = c == 0x20 || (c >= 9 && c <= 13);
+    else {
+        for (int back = 0; back <= 2 && (uint64_t)back <= i; ++back) {          // the lead is at most 2 bytes back
+            int L = ws_len_at(R, i - back, n);
+            if (L > back) { ws = true; break; }
+            if ((R[i - back] & 0xC0) != 0x80) break;                            // reached a lead that is not whitespace
+        }
+    }
+    f[i] = (ws ? F_WS : 0) | (c == 0x20 ? F_SP : 0);
+    emit[i] = ws ? 0 : 1;
+}
+
+__global__ void k_clean_docstarts(const uint64_t* __restrict__ raw_off, uint64_t n_docs, uint64_t n, uint8_t* __restrict__ f) {
+    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d > n_docs) return;
+    uint64_t p = raw_off[d];
+    if (p < n) f[p] |= F_DS;                        // several empty documents may share a start: same value written
+}
+
+// one thread per byte; acts where a run of U+0020 starts
+__global__ void __launch_bounds__(256) k_clean_runs(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                    uint8_t* __restrict__ rr) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t fi = f[i];
+    if (!(fi & F_SP)) return;
+    if (!(fi & F_DS) && i > 0 && (f[i - 1] & F_SP)) return;                    // not the first space of its run
+    uint64_t b = i + 1;
+    while (b < n && (f[b] & (F_SP | F_DS)) == F_SP) ++b;
+    uint64_t m = b - i;
+    int dec = 0;
+    if (!(fi & F_DS) && i > 0) { uint8_t X = R[i - 1]; dec += (X == '"' || X == '\'' || X == '(' || X == '['); }
+    if (b < n && !(f[b] & F_DS)) {
+        uint8_t Y = R[b];
+        dec += (Y == '.' || Y == ',' || Y == '!' || Y == '?' || Y == ':' || Y == ';' || Y == '"' || Y == '\'' || Y == ')' || Y == ']');
+    }
+    uint64_t rem = m > (uint64_t)dec ? m - dec : 0;
+    uint8_t v = (uint8_t)(rem > 3 ? 3 : rem);
+    rr[i] = v;
+    rr[b - 1] = v;
+}
+
+// rule 15 along hyphen chains; one thread per byte, acts at chain heads
+__global__ void __launch_bounds__(256) k_clean_hyphens(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                       const uint8_t* __restrict__ rr, uint8_t* __restrict__ fire) {
+    uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (h >= n || R[h] != '-') return;
+    auto candidate = [&](uint64_t q) -> bool {      // '-' with a space on both sides inside one document
+        return q > 0 && q + 1 < n && R[q] == '-' && !(f[q] & F_DS) && (f[q - 1] & F_SP) && !(f[q + 1] & F_DS) && (f[q + 1] & F_SP);
+    };
+    if (!candidate(h)) return;
+    // dependent on the previous hyphen?  only through a shared left run with rem == 1 (then the run has <= 3 spaces)
+    if (rr[h - 1] == 1) {
+        uint64_t a = h - 1;
+        while (a > 0 && !(f[a] & F_DS) && (f[a - 1] & F_SP)) --a;
+        if (a > 0 && !(f[a] & F_DS) && candidate(a - 1)) return;               // the head of the chain handles us
+    }
+    uint64_t cur = h;
+    int left = rr[cur - 1];
+    for (;;) {
+        int right = rr[cur + 1];
+        int fr = left >= 1 && right >= 1;
+        fire[cur] = (uint8_t)fr;
+        if (right != 1) break;                                                  // a run with rem == 1 has <= 3 spaces: walk it
+        uint64_t e = cur + 1;
+        while (e < n && (f[e] & (F_SP | F_DS)) == F_SP) ++e;
+        if (!(e < n && candidate(e))) break;
+        left = 1 - fr;
+        cur = e;
+    }
+}
+
+// one thread per byte; acts where a whitespace region starts
+__global__ void __launch_bounds__(256) k_clean_regions(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                       const uint8_t* __restrict__ rr, const uint8_t* __restrict__ fire,
+                                                       uint8_t* __restrict__ emit) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t fi = f[i];
+    if (!(fi & F_WS)) return;
+    if (!(fi & F_DS) && i > 0 && (f[i - 1] & F_WS)) return;                    // not the first byte of its region
+    bool alive = false;
+    int cur = -1;                                                               // rem of the run we are inside, -1 outside
+    uint64_t e = i;
+    for (;; ++e) {
+        bool in = e < n && (f[e] & F_WS) && !(e > i && (f[e] & F_DS));
+        bool sp = in && (f[e] & F_SP);
+        if (cur >= 0 && !sp) {                                                  // the run ended at e
+            if (e < n && !(f[e] & F_DS) && R[e] == '-') cur -= fire[e];
+            alive = alive || cur >= 1;
+            cur = -1;
+        }
+        if (!in) break;
+        if (sp) {
+            if (cur < 0) {                                                      // a run starts at e
+                cur = rr[e];
+                if (!(f[e] & F_DS) && e > 0 && R[e - 1] == '-') cur -= fire[e - 1];
+            }
+        } else alive = true;                                                    // another whitespace character: never deleted
+    }
+    bool interior = !(fi & F_DS) && i > 0 && e < n && !(f[e] & F_DS);
+    if (alive && interior) emit[i] = 1;
+}
+
+struct U8ToU32 { __host__ __device__ uint32_t operator()(uint8_t v) const { return v; } };
+
+__global__ void __launch_bounds__(256) k_clean_scatter(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                       const uint8_t* __restrict__ emit, const uint32_t* __restrict__ pos,
+                                                       uint8_t* __restrict__ out, uint64_t out_cap, uint32_t* __restrict__ err) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n || !emit[i]) return;
+    uint32_t p = pos[i];
+    if (p >= out_cap) { atomicOr(err, ERRF_CAPACITY); return; }
+    out[p] = (f[i] & F_WS) ? (uint8_t)' ' : R[i];
+}
+
+__global__ void k_clean_doc_off(const uint64_t* __restrict__ raw_off, uint64_t n_docs, const uint32_t* __restrict__ pos,
+                                uint64_t* __restrict__ out_off) {
+    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d <= n_docs) out_off[d] = pos[raw_off[d]];
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
+
+// raw: valid UTF-8 (so from_utf8_lossy is the identity), n bytes, raw_off[n_docs+1].
+int clean_parallel(Engine& eng, const uint8_t* raw, const uint64_t* raw_off, size_t n_docs, uint64_t n, uint8_t* d_out,
+                   uint64_t out_cap, uint64_t* d_out_off, uint32_t* err, cudaStream_t st) {
+    if (n >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_ARG, "one decode call handles less than 4 GiB of text");
+    Workspace& ws = eng.ws;
+    uint8_t *f, *rr, *fire, *emit;
+    uint32_t* pos;
+    CK(ws.get(14, n + 64, (void**)&f));
+    CK(ws.get(15, n + 64, (void**)&rr));
+    CK(ws.get(16, n + 64, (void**)&fire));
+    CK(ws.get(17, n + 64, (void**)&emit));
+    CK(ws.get(26, (n + 2) * 4, (void**)&pos));
+    unsigned gb = (unsigned)((n + 255) / 256), gd = (unsigned)((n_docs + 1 + 255) / 256);
+    eng.mark(nullptr, st);
+    CK(cudaMemsetAsync(fire, 0, n + 64, st));
+    CK(cudaMemsetAsync(emit + n, 0, 64, st));
+    if (n) {
+        k_clean_flags<<<gb, 256, 0, st>>>(raw, n, f, emit);
+        k_clean_docstarts<<<gd, 256, 0, st>>>(raw_off, n_docs, n, f);
+        k_clean_runs<<<gb, 256, 0, st>>>(raw, n, f, rr);
+        k_clean_hyphens<<<gb, 256, 0, st>>>(raw, n, f, rr, fire);
+        k_clean_regions<<<gb, 256, 0, st>>>(raw, n, f, rr, fire, emit);
+        eng.launched(5);
+    }
+    cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> it(emit, U8ToU32());
+    size_t cub_bytes = 0; void* cub_tmp;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, pos, n + 1, st));
+    CK(ws.get(5, cub_bytes + 16, &cub_tmp));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, it, pos, n + 1, st));
+    if (n) k_clean_scatter<<<gb, 256, 0, st>>>(raw, n, f, emit, pos, d_out, out_cap, err);
+    k_clean_doc_off<<<gd, 256, 0, st>>>(raw_off, n_docs, pos, d_out_off);
+    eng.launched(3); eng.mark("clean_up (parallel)", st);
+    return CTK_OK;
+}
+
+}  // namespace ctk

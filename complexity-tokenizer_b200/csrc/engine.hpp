@@ -79,7 +79,8 @@ struct Engine {
     bool profile = false;
     struct Mark { const char* name; cudaEvent_t ev; };
     std::vector<Mark> marks;
-    std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> ev_pool;                             // timing events (profile marks)
+    std::vector<cudaEvent_t> sync_ev_pool;                        // cudaEventDisableTiming events (host pipeline)
     std::map<std::string, std::pair<double, uint64_t>> prof;      // name -> (total ms, launches)
     void mark(const char* name, cudaStream_t st) {                // call once before the first kernel (name = nullptr) and after each kernel
         if (!profile) return;
@@ -115,12 +116,16 @@ struct Engine {
 
 int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
               const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st);
+int prefix_space_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
+                       const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st);
 int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n, uint64_t n_bytes, uint32_t* d_ids,
                   uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                  uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                    uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
+int clean_parallel(Engine& eng, const uint8_t* raw, const uint64_t* raw_off, size_t n_docs, uint64_t n, uint8_t* d_out,
+                   uint64_t out_cap, uint64_t* d_out_off, uint32_t* err, cudaStream_t st);
 int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off, size_t n, uint64_t total_ids,
                   int skip_special, int cleanup, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off,
                   uint64_t* n_bytes_host, cudaStream_t st);

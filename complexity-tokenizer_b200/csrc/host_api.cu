@@ -130,7 +130,7 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
     evs.resize(chunks.size());
     for (size_t c = 0; c < chunks.size(); ++c) {
         const Chunk& ch = chunks[c];
-        if (!eng->ev_pool.empty()) { evs[c] = eng->ev_pool.back(); eng->ev_pool.pop_back(); }
+        if (!eng->sync_ev_pool.empty()) { evs[c] = eng->sync_ev_pool.back(); eng->sync_ev_pool.pop_back(); }
         else CKE(cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming));
         if (ch.b1 > ch.b0) CKE(cudaMemcpyAsync(d_text + ch.dev_text, text + ch.b0, ch.b1 - ch.b0, cudaMemcpyHostToDevice, eng->st_h2d));
         CKE(cudaMemsetAsync(d_text + ch.dev_text + (ch.b1 - ch.b0), 0, 64, eng->st_h2d));
@@ -171,7 +171,7 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
         off[n] = total;
     }
 done:
-    for (cudaEvent_t ev : evs) if (ev) eng->ev_pool.push_back(ev);
+    for (cudaEvent_t ev : evs) if (ev) eng->sync_ev_pool.push_back(ev);
     g_pinned.put(h_roff, h_roff_cap);
     g_pinned.put(h_ioff, h_ioff_cap);
     if (rc != CTK_OK) { cudaStreamSynchronize(eng->st_h2d); cudaStreamSynchronize(eng->st_d2h); free_result(r); return rc; }

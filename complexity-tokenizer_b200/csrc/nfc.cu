@@ -278,3 +278,59 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
 }
 
 }  // namespace ctk
+
+// ---------------------------------------------------------------------------------------------
+// ByteLevel add_prefix_space (reference: byte_level_pretokenize, src/pretokenizers.rs:163-167):
+// a document that is not empty and does not start with U+0020 gets one prepended (after normalisation).
+namespace ctk {
+
+__global__ void k_prefix_len(const uint8_t* __restrict__ text, const uint64_t* __restrict__ off, uint64_t n_docs,
+                             uint64_t* __restrict__ new_len) {
+    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d > n_docs) return;
+    if (d == n_docs) { new_len[d] = 0; return; }
+    uint64_t lo = off[d], hi = off[d + 1];
+    new_len[d] = (hi - lo) + ((hi > lo && text[lo] != ' ') ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(256) k_prefix_copy(const uint8_t* __restrict__ text, const uint64_t* __restrict__ off,
+                                                     uint64_t n_docs, const uint64_t* __restrict__ new_off, uint8_t* __restrict__ out) {
+    uint64_t d = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_docs) return;
+    const int lane = threadIdx.x & 31;
+    const uint64_t lo = off[d], hi = off[d + 1];
+    uint8_t* o = out + new_off[d];
+    const uint64_t shift = (new_off[d + 1] - new_off[d]) - (hi - lo);          // 0 or 1
+    if (shift && lane == 0) o[0] = ' ';
+    for (uint64_t i = lo + lane; i < hi; i += 32) o[shift + (i - lo)] = text[i];
+}
+
+#define CKP(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
+
+int prefix_space_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
+                       const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st) {
+    *o_text = d_text; *o_off = d_off; *o_bytes = n_bytes;
+    if (!eng.model.add_prefix_space || n_docs == 0 || n_bytes == 0) return CTK_OK;
+    Workspace& ws = eng.ws;
+    uint64_t *new_len, *new_off;
+    uint8_t* out;
+    CKP(ws.get(12, (n_docs + 2) * 8, (void**)&new_len));
+    CKP(ws.get(13, (n_docs + 2) * 8, (void**)&new_off));
+    CKP(ws.get(14, n_bytes + n_docs + 128, (void**)&out));
+    eng.mark(nullptr, st);
+    k_prefix_len<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_text, d_off, n_docs, new_len);
+    size_t cub_bytes = 0; void* cub_tmp;
+    CKP(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, new_len, new_off, n_docs + 1, st));
+    CKP(ws.get(5, cub_bytes + 16, &cub_tmp));
+    CKP(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, new_len, new_off, n_docs + 1, st));
+    k_prefix_copy<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, st>>>(d_text, d_off, n_docs, new_off, out);
+    eng.launched(3); eng.mark("prefix_space", st);
+    uint64_t total = 0;
+    CKP(cudaMemcpyAsync(&total, new_off + n_docs, 8, cudaMemcpyDeviceToHost, st));
+    CKP(cudaStreamSynchronize(st));
+    CKP(cudaMemsetAsync(out + total, 0, 64, st));
+    *o_text = out; *o_off = new_off; *o_bytes = total;
+    return CTK_OK;
+}
+
+}  // namespace ctk

@@ -134,3 +134,56 @@ def test_unsupported_and_errors(built_lib, tok_paths, small_tok_json):
     with pytest.raises(UnicodeEncodeError):
         tok.encode('\ud800')
     assert tok.encode('') == [] and tok.decode([]) == ''
+
+
+def test_add_prefix_space(built_lib, small_tok_json):
+    """ByteLevel{add_prefix_space: true} (pretokenizers.rs:163-167): a leading space is added to non-empty
+    documents that do not start with one -- after NFC, before the pattern."""
+    import json
+    import c_oracle
+    import complexity_tokenizer as ct
+    tj = json.loads(small_tok_json)
+    tj['pre_tokenizer'] = {'type': 'ByteLevel', 'add_prefix_space': True, 'trim_offsets': True}
+    js = json.dumps(tj, ensure_ascii=False)
+    tok, orc = ct.Tokenizer.from_str(js), c_oracle.COracle.from_str(js)
+    rng = np.random.default_rng(23)
+    docs = ['', ' ', 'a', ' a', "'s", " 's", '\n x', 'hello world', 'é', '中文', '12 34', '  two'] + _random_docs(rng, 3000, 40)
+    got, want = tok.encode_batch(docs), orc.encode_batch(docs)
+    assert want == orc.twin.encode_batch(docs)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g == w, (i, docs[i])
+
+
+def _byte_tokenizer_json():
+    """vocab = the 256 byte symbols, id == byte value: decode(ids) reproduces arbitrary byte strings"""
+    import json
+    import py_oracle
+    vocab = {c: b for b, c in py_oracle.BYTE_ENCODER.items()}
+    return json.dumps({'model': {'type': 'BPE', 'vocab': vocab, 'merges': []}}, ensure_ascii=False)
+
+
+def test_cleanup_fuzz_against_sequential_replaces(built_lib):
+    """clean_up_tokenization_spaces (mod.rs:749-769): the data-parallel formulation on the GPU against the oracle,
+    which applies the 15 str::replace calls literally.  Space/punctuation/hyphen-heavy random strings."""
+    import c_oracle
+    import complexity_tokenizer as ct
+    js = _byte_tokenizer_json()
+    tok, orc = ct.Tokenizer.from_str(js), c_oracle.COracle.from_str(js)
+    rng = np.random.default_rng(41)
+    pieces = [' ', ' ', ' ', ' ', '-', '-', '.', ',', '"', "'", '(', ')', '[', ']', '!', '?', ':', ';', 'a', 'b', 'xyz', '\n', '\t',
+              ' ', '　', 'é', ' - ', ' -', '- ', '  ', '   ', ' .', '" ', " '", '( ', ' )', '--', ' - - ', '\r\n']
+    batch = []
+    for _ in range(30000):
+        k = int(rng.integers(0, 24))
+        s = ''.join(pieces[int(i)] for i in rng.integers(0, len(pieces), size=k))
+        batch.append(list(s.encode('utf-8')))
+    batch += [list(b' - - - '), list(b'say " hi " now'), list(b'  .  ,'), list(b'( a ) [ b ]'), list(b'a -  - b'), list(b'(-  -)'),
+              list(b' -  -  - '), list(b'x - - - - - - y'), list(b'- - -'), list(b' '), [], list(b'-'), list(b' - ')]
+    got = tok.decode_batch(batch)
+    want = orc.decode_batch(batch)
+    bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert not bad, (len(bad), bytes(batch[bad[0]]), got[bad[0]], want[bad[0]])
+    # invalid UTF-8 mixed in: from_utf8_lossy + clean-up through the per-document path
+    weird = [list(b'a \xe2\x82 . b'), list(b'\xff - \xc3'), list(b'ok . fine'), list(b'\xf0\x9f\x98 ,')]
+    for opts in ((False, True), (False, False)):
+        assert tok.decode_batch_with_options(weird, *opts) == orc.decode_batch(weird, *opts)

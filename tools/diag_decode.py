@@ -16,4 +16,4 @@ for clean in (False, True):
     torch.cuda.synchronize(); t=time.perf_counter()
     for _ in range(3): n=tok.decode_device(d_ids.data_ptr(),d_ioff.data_ptr(),D,T,d_out.data_ptr(),B+1024,d_ooff.data_ptr(),False,clean)
     torch.cuda.synchronize(); dt=(time.perf_counter()-t)/3
-    print('decode clean=%s: %d ids -> %d bytes, %.2f ms = %.1f GB/s out'%(clean,T,n,dt*1e3,n/dt/1e9))
+    print("decode clean=%s: %d ids -> %d bytes, %.2f ms = %.1f GB/s out"%(clean,T,n,dt*1e3,n/dt/1e9), {k:round(v[0]/v[1],3) for k,v in tok.profile_report().items()})
