@@ -70,6 +70,19 @@ static int upload(Engine& eng) {
     UP(12, eng.nfc.qkey, CTK_CCC_KEY, sizeof(CTK_CCC_KEY));
     UP(13, eng.nfc.qval, CTK_CCC_VAL, sizeof(CTK_CCC_VAL));
     eng.nfc.trie_index = eng.tables.trie_index; eng.nfc.trie_blocks = eng.tables.trie_blocks;
+    {   // added tokens that can occur inside one pre-token (loader.cpp: analyse_added)
+        std::vector<uint8_t> blob; std::vector<uint4> meta;
+        for (const AddedTok& a : m.added) {
+            if (!a.may_match) continue;
+            meta.push_back(make_uint4((uint32_t)blob.size(), (uint32_t)a.bytes.size(), a.id,
+                                      (a.single_word ? 1u : 0u) | (a.lstrip ? 2u : 0u) | (a.rstrip ? 4u : 0u)));
+            blob.insert(blob.end(), a.bytes.begin(), a.bytes.end());
+        }
+        eng.tables.n_added = (uint32_t)meta.size();
+        UP(14, eng.tables.added_blob, blob.data(), blob.size());
+        UP(15, eng.tables.added_meta, meta.data(), meta.size() * sizeof(uint4));
+        UP(16, eng.tables.mapped_alnum, CTK_MAPPED_ALNUM, sizeof(CTK_MAPPED_ALNUM));
+    }
 #undef UP
     e = cudaHostAlloc((void**)&eng.h_flags, 64, cudaHostAllocDefault);
     if (e != cudaSuccess) return eng.cuda_fail(e, "cudaHostAlloc");
@@ -101,11 +114,6 @@ static int create(const uint8_t* json, size_t len, int device, ctk_tokenizer** o
     std::string err;
     int rc = load_model(json, len, eng->model, err);
     if (rc != CTK_OK) { set_last_error(err); delete eng; return rc; }
-    if (eng->model.any_added_may_match) {
-        set_last_error("an added token can occur inside a single pre-token; in-word added-token matching is not supported yet");
-        delete eng;
-        return CTK_ERR_UNSUPPORTED;
-    }
     if (eng->model.pairs.size() >= (1u << 26)) { set_last_error("too many merges"); delete eng; return CTK_ERR_UNSUPPORTED; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

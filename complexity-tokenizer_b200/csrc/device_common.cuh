@@ -36,6 +36,11 @@ struct DevTables {
     const uint32_t* byte_init;  // [256] byte -> initial id (kNone: mapped char not in vocab, symbol is dropped)
     const uint8_t* trie_index;  // [0x1100] cp >> 8 -> block
     const uint8_t* trie_blocks; // 128 B per block: 4 bits per cp (bits 0-1 class, bit 2 NFC-suspect)
+    // added tokens that can occur inside one pre-token (mod.rs:566-675 searches words, not raw text)
+    const uint8_t* added_blob;  // their contents translated back to raw bytes
+    const uint4* added_meta;    // {offset, length, id, flags: 1 single_word, 2 lstrip, 4 rstrip}
+    uint32_t n_added;
+    const uint8_t* mapped_alnum;// [256] char::is_alphanumeric of the byte-mapped character of each byte
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -30,6 +30,7 @@
 #include <cstdlib>
 
 #include "engine.hpp"
+#include "added_tokens.cuh"
 #include "start_window.cuh"
 
 namespace ctk {
@@ -326,9 +327,29 @@ __global__ void __launch_bounds__(FW * 32, 4) k_encode_slices(const FusedParams 
                     if (cnt < 0) {                                         // merge now
                         uint32_t sym;
                         if (p.ablate == 9 && lane == 0) atomicAdd(p.err + 19 + (slen > 16 ? 1 : 0) + (slen <= 16 && ins == kNone ? 2 : 0), 1u);
-                        int n = init_symbols32(s_byte_init, S.chunk + spos, (int)slen, sym, lane);
-                        cnt = n ? bpe_warp32(p.t, sym, n) : 0;
-                        if (lane < cnt) run[o + lane] = sym;
+                        if (p.t.n_added == 0) {
+                            int n = init_symbols32(s_byte_init, S.chunk + spos, (int)slen, sym, lane);
+                            cnt = n ? bpe_warp32(p.t, sym, n) : 0;
+                            if (lane < cnt) run[o + lane] = sym;
+                        } else {                                           // mod.rs:566-610: added tokens inside the word
+                            int r = 0;
+                            cnt = 0;
+                            while (r < (int)slen) {
+                                uint32_t aid;
+                                const int pl = added_next_piece(p.t, S.chunk + spos + r, (int)slen - r, lane, &aid);
+                                if (aid != kNone) { if (lane == 0) run[o + cnt] = aid; cnt += 1; }
+                                else {
+                                    uint32_t ps;
+                                    int n = init_symbols32(s_byte_init, S.chunk + spos + r, pl, ps, lane);
+                                    int c = n ? bpe_warp32(p.t, ps, n) : 0;
+                                    if (lane < c) run[o + cnt + lane] = ps;
+                                    cnt += c;
+                                }
+                                r += pl;
+                            }
+                            __syncwarp();
+                            sym = lane < cnt ? __ldcg(run + o + lane) : kNone;  // back into lanes for the cache entry
+                        }
                         if (ins != kNone) {                                // publish in the batch cache
                             uint32_t w0 = 0, w1 = 0, w2 = 0;
                             bool ok = true;

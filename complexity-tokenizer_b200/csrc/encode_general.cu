@@ -144,6 +144,7 @@ __global__ void k_doc_offsets(const uint64_t* __restrict__ text_off, uint64_t n_
 int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                    uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st) {
     if (n_bytes >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_ARG, "one device call handles less than 4 GiB of text");
+    if (eng.tables.n_added) return eng.fail(CTK_ERR_UNSUPPORTED, "the debug general pipeline does not match added tokens inside words");
     if (n_bytes == 0) {
         CK(cudaMemsetAsync(d_ids_off, 0, (n_docs + 1) * 8, st));
         if (n_ids_host) { CK(cudaStreamSynchronize(st)); *n_ids_host = 0; }

@@ -102,6 +102,29 @@ __device__ __forceinline__ uint32_t long_in_regs(const FusedParams& p, const uin
     return (uint32_t)m;
 }
 
+// ids of src[0..len) (no added tokens inside) -> out; returns their number
+__device__ __forceinline__ uint32_t long_piece(const FusedParams& p, const uint8_t* src, uint64_t len, uint32_t* out, int lane) {
+    const unsigned full = 0xFFFFFFFFu;
+    bool ok = false;
+    uint32_t cnt = 0;
+    if (len <= 64) cnt = long_in_regs<2>(p, src, (int)len, out, lane, ok);
+    else if (len <= 128) cnt = long_in_regs<4>(p, src, (int)len, out, lane, ok);
+    else if (len <= 256) cnt = long_in_regs<8>(p, src, (int)len, out, lane, ok);
+    if (!ok) {                                                 // very long, or a byte that is dropped
+        uint32_t n = 0;
+        for (uint64_t b0 = 0; b0 < len; b0 += 32) {
+            uint64_t q = b0 + lane;
+            uint32_t sv = q < len ? __ldg(p.t.byte_init + __ldg(src + q)) : kNone;
+            unsigned hv = __ballot_sync(full, sv != kNone);
+            if (sv != kNone) out[n + __popc(hv & ((1u << lane) - 1u))] = sv;
+            n += __popc(hv);
+        }
+        __syncwarp();
+        cnt = (uint32_t)bpe_warp_long(p.t, out, (int)n);
+    }
+    return cnt;
+}
+
 __global__ void __launch_bounds__(256) k_encode_long(const FusedParams p) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -130,21 +153,18 @@ __global__ void __launch_bounds__(256) k_encode_long(const FusedParams p) {
         if (po + len <= p.long_cap) {
             uint32_t* out = p.long_pool + po;
             const uint8_t* src = p.text + dd.gstart;
-            bool ok = false;
-            if (len <= 64) cnt = long_in_regs<2>(p, src, (int)len, out, lane, ok);
-            else if (len <= 128) cnt = long_in_regs<4>(p, src, (int)len, out, lane, ok);
-            else if (len <= 256) cnt = long_in_regs<8>(p, src, (int)len, out, lane, ok);
-            if (!ok) {                                             // very long, or a byte that is dropped
-                uint32_t n = 0;
-                for (uint64_t b0 = 0; b0 < len; b0 += 32) {
-                    uint64_t q = b0 + lane;
-                    uint32_t sv = q < len ? __ldg(p.t.byte_init + __ldg(src + q)) : kNone;
-                    unsigned hv = __ballot_sync(full, sv != kNone);
-                    if (sv != kNone) out[n + __popc(hv & ((1u << lane) - 1u))] = sv;
-                    n += __popc(hv);
+            if (p.t.n_added == 0) cnt = long_piece(p, src, len, out, lane);
+            else {                                                 // mod.rs:566-610: added tokens inside the word
+                uint64_t r = 0;
+                while (r < len) {
+                    uint32_t aid;
+                    const uint64_t left = len - r;
+                    const int pl = added_next_piece(p.t, src + r, left > 0x7FFFFFFFull ? 0x7FFFFFFF : (int)left, lane, &aid);
+                    if (aid != kNone) { if (lane == 0) out[cnt] = aid; cnt += 1; }
+                    else cnt += long_piece(p, src + r, (uint64_t)pl, out + cnt, lane);
+                    r += (uint64_t)pl;
+                    __syncwarp();
                 }
-                __syncwarp();
-                cnt = (uint32_t)bpe_warp_long(p.t, out, (int)n);
             }
         } else if (lane == 0) atomicOr(p.err, ERRF_POOL);
         if (lane == 0) {

@@ -61,7 +61,7 @@ struct Engine {
     DevTables tables{};
     DecodeTables dec{};
     NfcTables nfc{};
-    void* d_table_mem[16] = {};
+    void* d_table_mem[24] = {};
     Workspace ws;
     std::mutex mu;                      // serialises device work issued through this tokenizer
     bool cache_persistent = false;

@@ -124,10 +124,6 @@ def test_unsupported_and_errors(built_lib, tok_paths, small_tok_json):
     tj['pre_tokenizer'] = {'type': 'Whitespace'}
     with pytest.raises(ct.UnsupportedTokenizerError):
         ct.Tokenizer.from_str(json.dumps(tj))
-    tj = json.loads(small_tok_json)
-    tj['added_tokens'].append({'id': 5, 'content': 'hello', 'special': False})
-    with pytest.raises(ct.UnsupportedTokenizerError):
-        ct.Tokenizer.from_str(json.dumps(tj))
     tok = ct.Tokenizer.from_str(small_tok_json)
     with pytest.raises(TypeError):
         tok.encode_batch('not a list')
@@ -187,3 +183,34 @@ def test_cleanup_fuzz_against_sequential_replaces(built_lib):
     weird = [list(b'a \xe2\x82 . b'), list(b'\xff - \xc3'), list(b'ok . fine'), list(b'\xf0\x9f\x98 ,')]
     for opts in ((False, True), (False, False)):
         assert tok.decode_batch_with_options(weird, *opts) == orc.decode_batch(weird, *opts)
+
+
+def test_added_tokens_inside_words(built_lib, small_tok_json):
+    """mod.rs:566-675: added tokens are searched inside each byte-mapped pre-token (longest at position 0,
+    first occurrence only, single_word / lstrip / rstrip flags).  Tokens such as <s> can never match; all-letter,
+    all-digit or all-punctuation ones can."""
+    import json
+    import c_oracle
+    import complexity_tokenizer as ct
+    tj = json.loads(small_tok_json)
+    nid = max(tj['model']['vocab'].values()) + 1
+    extra = [('hello', {}), ('he', {}), ('hell', {}), ('Ġworld', {}), ('ing', {'single_word': True}), ('tion', {'rstrip': True}),
+             ('pre', {'lstrip': True}), ('...', {}), ('42', {}), ('zz', {'single_word': True, 'special': True}), ('Ġthe', {'rstrip': True}),
+             ('é', {}), ('<mask>', {'special': True})]
+    for k, (content, flags) in enumerate(extra):
+        t = {'id': nid + k, 'content': content, 'special': False, 'single_word': False, 'lstrip': False, 'rstrip': False, 'normalized': False}
+        t.update(flags)
+        tj['added_tokens'].append(t)
+    js = json.dumps(tj, ensure_ascii=False)
+    tok, orc = ct.Tokenizer.from_str(js), c_oracle.COracle.from_str(js)
+    rng = np.random.default_rng(5)
+    words = ['hello', 'hell', 'he', 'help', 'shell', 'hellohello', ' world', 'world', ' worldly', 'ing', 'sing', 'inging', 'ing!', 'tion',
+             'nation', 'nations', 'pre', 'prefix', 'unpre', '...', '....', '.....', '42', '1423', '4242', 'zz', 'zzz', 'azz', ' the', ' then',
+             'the', 'é', 'été', 'cafés', '<mask>', 'x', ' ', '\n', ',', "'s", 'hello' * 9, 'ab' * 30 + 'hello' + 'cd' * 40, '4' * 40 + '42' * 30]
+    docs = [''.join(words[int(i)] if rng.random() < 0.7 else ' ' + words[int(i)] for i in rng.integers(0, len(words), size=int(rng.integers(0, 12))))
+            for _ in range(4000)] + words
+    got, want = tok.encode_batch(docs), orc.encode_batch(docs)
+    assert orc.encode_batch(docs[:300]) == orc.twin.encode_batch(docs[:300])
+    bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert not bad, (len(bad), docs[bad[0]], got[bad[0]], want[bad[0]])
+    assert any(nid <= t < nid + len(extra) for ids in want for t in ids)          # the added tokens really fire
