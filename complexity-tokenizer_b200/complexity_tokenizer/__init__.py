@@ -66,6 +66,8 @@ def _lib():
         'ctk_debug_starts_host': (I, [P, U64, P, S, P]),
         'ctk_debug_starts_window_host': (I, [P, U64, P, S, P]),
         'ctk_debug_load_only': (I, [P, S, ctypes.POINTER(U64), ctypes.POINTER(U64), ctypes.POINTER(I), ctypes.POINTER(I)]),
+        'ctk_debug_merge_props': (I, [P, S, ctypes.POINTER(I), ctypes.POINTER(ctypes.c_uint32)]),
+        'ctk_debug_xlong_rounds': (I, [P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

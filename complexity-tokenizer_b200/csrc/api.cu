@@ -15,10 +15,27 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
 std::atomic<uint64_t> g_kernel_launches{0};
 
+struct PubArgs { const uint32_t* src[4]; int words[4]; int dst[4]; int n; };
+__global__ void k_publish(PubArgs a, uint32_t* __restrict__ host) {
+    for (int k = 0; k < a.n; ++k)
+        for (int w = threadIdx.x; w < a.words[k]; w += blockDim.x) host[a.dst[k] + w] = a.src[k][w];
+    __threadfence_system();
+}
+
+cudaError_t Engine::publish(std::initializer_list<Pub> items, cudaStream_t st) {
+    PubArgs a{};
+    for (const Pub& it : items) {
+        if (a.n >= 4) return cudaErrorInvalidValue;
+        a.src[a.n] = static_cast<const uint32_t*>(it.src); a.words[a.n] = it.words; a.dst[a.n] = it.dst_word; ++a.n;
+    }
+    k_publish<<<1, 32, 0, st>>>(a, h_flags_dev);
+    launched(1);
+    return cudaGetLastError();
+}
+
 int Engine::finish(const uint32_t* d_err, const uint64_t* d_off_out, size_t n, uint64_t* total_host, cudaStream_t st) {
     if (!total_host) return CTK_OK;                       // asynchronous use: flags are checked by the next synchronous call
-    cudaError_t e = cudaMemcpyAsync(h_flags, d_err, 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_flags + 2, d_off_out + n, 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = publish({{d_err, 2, 0}, {d_off_out + n, 2, 2}}, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "finish");
     collect_marks();
@@ -84,8 +101,11 @@ static int upload(Engine& eng) {
         UP(16, eng.tables.mapped_alnum, CTK_MAPPED_ALNUM, sizeof(CTK_MAPPED_ALNUM));
     }
 #undef UP
-    e = cudaHostAlloc((void**)&eng.h_flags, 64, cudaHostAllocDefault);
+    e = cudaHostAlloc((void**)&eng.h_flags, 256, cudaHostAllocMapped);
     if (e != cudaSuccess) return eng.cuda_fail(e, "cudaHostAlloc");
+    memset(eng.h_flags, 0, 256);
+    e = cudaHostGetDevicePointer((void**)&eng.h_flags_dev, eng.h_flags, 0);
+    if (e != cudaSuccess) return eng.cuda_fail(e, "cudaHostGetDevicePointer");
     for (cudaStream_t* sp : {&eng.st_h2d, &eng.st_comp, &eng.st_d2h}) {
         e = cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking);
         if (e != cudaSuccess) return eng.cuda_fail(e, "cudaStreamCreate");
@@ -301,7 +321,22 @@ int ctk_debug_load_only(const uint8_t* json, size_t len, uint64_t* n_pairs, uint
     return CTK_OK;
 }
 
+// model-only load: is the merge table monotone (round-parallel path for very long pre-tokens allowed), and the
+// longest merged token in initial symbols
+int ctk_debug_merge_props(const uint8_t* json, size_t len, int* monotone, uint32_t* max_span) {
+    HostModel m;
+    std::string err;
+    int rc = load_model(json, len, m, err);
+    if (rc != CTK_OK) { set_last_error(err); return rc; }
+    if (monotone) *monotone = m.merges_monotone;
+    if (max_span) *max_span = m.max_token_span;
+    return CTK_OK;
+}
+
 }  // extern "C"
+
+// rounds of the last very-long-pre-token pass (diagnostics)
+extern "C" int ctk_debug_xlong_rounds(ctk_tokenizer* tok) { return reinterpret_cast<ctk::Engine*>(tok)->xl_last_rounds; }
 
 // debug: 16 counters the encode kernel keeps when CTK_ABLATE=9 (slow-path categories), see encode_fused.cu
 extern "C" int ctk_debug_counters(ctk_tokenizer* tok, uint32_t* out16) {

@@ -11,6 +11,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <cstring>
+
 #include "engine.hpp"
 
 namespace ctk {
@@ -228,8 +230,9 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
     CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, it, boff, T + 1, st));
     eng.launched(1); eng.mark("scan(id lengths)", st);
     uint64_t raw_total = 0;
-    CK(cudaMemcpyAsync(&raw_total, boff + T, 8, cudaMemcpyDeviceToHost, st));
+    CK(eng.publish({{boff + T, 2, 12}}, st));
     CK(cudaStreamSynchronize(st));
+    memcpy(&raw_total, eng.h_flags + 12, 8);
     uint8_t* raw;
     CK(ws.get(13, raw_total + 16, (void**)&raw));
     eng.mark(nullptr, st);
@@ -244,8 +247,9 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
         k_dec_valid_docs<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(raw, raw_off, n_docs, err + 1);
         eng.launched(2); eng.mark("k_dec_valid", st);
         uint32_t inv = 0;
-        CK(cudaMemcpyAsync(&inv, err + 1, 4, cudaMemcpyDeviceToHost, st));
+        CK(eng.publish({{err + 1, 1, 14}}, st));
         CK(cudaStreamSynchronize(st));
+        inv = eng.h_flags[14];
         invalid = inv != 0;
     }
     const bool need_post = invalid;                        // sequential per-document path only for invalid UTF-8

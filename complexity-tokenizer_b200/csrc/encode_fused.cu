@@ -28,6 +28,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "engine.hpp"
 #include "added_tokens.cuh"
@@ -49,6 +50,9 @@ constexpr uint32_t END_UNKNOWN = 0xFFFFu;
 // A pre-token longer than 32 bytes: found by k_encode_slices, merged by k_encode_long.
 // Its `cnt` ids at long_pool[pool..] go before position `at` of the slice's run; `k` is its pre-token index.
 struct LongDesc { uint64_t gstart; uint32_t len, slice, k_at, pool, cnt, chunk_end; };
+// A VERY long pre-token (encode_xlong.cuh): its LongDesc and where its symbols start in the round array X
+struct XlEntry { uint32_t desc, pad; unsigned long long xoff; };
+constexpr int XL_IDX_SHIFT = 40;                 // one atomic hands out (list index << 40 | X offset)
 
 struct FusedParams {
     DevTables t;
@@ -64,6 +68,11 @@ struct FusedParams {
     uint32_t* slice_cnt;                                 // ids of the slice (short + long)
     uint32_t* slice_info;                                // staged count | n_long << 16
     uint32_t* slice_desc;                                // first LongDesc of the slice (if n_long > 0)
+    uint16_t* slice_first;                               // chunk-relative position of the slice's first owned start, 0xFFFF if none
+    int xl_enabled;                                      // monotone table, no in-word added tokens, synchronous call
+    unsigned long long* xl_cursor;                       // list index << XL_IDX_SHIFT | symbols handed out
+    XlEntry* xl_list;
+    uint64_t* ids_off_rel;                               // slice-relative document offsets (k_doc_fixup makes them absolute)
     uint64_t* ids_off; uint32_t* err;
     int ablate;                                          // debug: 1 = stop after boundaries, 2 = no slow path, 3 = no probe
 };
@@ -99,12 +108,12 @@ __global__ void k_first_doc(const uint64_t* __restrict__ off, uint64_t n_docs, u
 __global__ void k_doc_fixup(const uint64_t* __restrict__ off, uint64_t n_docs, uint64_t n_slices,
                             const uint32_t* __restrict__ slice_base, const uint32_t* __restrict__ slice_info,
                             const uint32_t* __restrict__ slice_desc, const LongDesc* __restrict__ desc,
-                            uint64_t* __restrict__ ids_off) {
+                            const uint64_t* __restrict__ ids_off_rel, uint64_t* __restrict__ ids_off) {
     uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (d > n_docs) return;
     uint64_t s = off[d] / SLICE;
     if (s >= n_slices) s = n_slices - 1;
-    const uint64_t v = ids_off[d];
+    const uint64_t v = ids_off_rel[d];
     const uint32_t rel = (uint32_t)v, k = (uint32_t)(v >> 32), n_long = slice_info[s] >> 16;
     uint64_t extra = 0;
     if (n_long) {
@@ -157,6 +166,7 @@ __device__ __forceinline__ int init_symbols32(const uint32_t* s_byte_init, const
 
 }  // namespace ctk
 #include "encode_long.cuh"
+#include "encode_xlong.cuh"
 namespace ctk {
 
 __global__ void __launch_bounds__(FW * 32, 4) k_encode_slices(const FusedParams p) {
@@ -259,6 +269,7 @@ __global__ void __launch_bounds__(FW * 32, 4) k_encode_slices(const FusedParams 
             if (lane == 0) { S.list[n_owned] = (uint16_t)sent; S.list[n_owned + 1] = (uint16_t)sent; }
         }
         __syncwarp();
+        if (lane == 0) p.slice_first[slice] = n_owned ? S.list[0] : (uint16_t)0xFFFFu;
 
         if (p.ablate == 1) { if (lane == 0) { p.slice_cnt[slice] = n_owned; p.slice_info[slice] = 0; } continue; }
         // ---- 4. pre-tokens, 32 per round
@@ -445,7 +456,7 @@ __global__ void __launch_bounds__(FW * 32, 4) k_encode_slices(const FusedParams 
                 if (own) {
                     uint32_t k = fk + __popc(sb & ((1u << (rel & 15)) - 1u));
                     if (k > n_owned) k = n_owned;
-                    p.ids_off[d] = (unsigned long long)S.list[k] | ((unsigned long long)k << 32);   // + long ids: k_doc_fixup
+                    p.ids_off_rel[d] = (unsigned long long)S.list[k] | ((unsigned long long)k << 32);   // + long ids: k_doc_fixup
                 }
                 if (!__all_sync(full, in)) break;
             }
@@ -495,7 +506,8 @@ __global__ void __launch_bounds__(256) k_compact(const uint32_t* __restrict__ ru
             for (uint32_t q = 0; q < n_long; ++q) {
                 const uint32_t* ls = long_pool + dd[q].pool;
                 uint32_t* ld = dst + (dd[q].k_at & 0xFFFFu) + before;
-                for (uint32_t i = lane; i < dd[q].cnt; i += 32) ld[i] = ls[i];
+                if (dd[q].pool != kNone)                       // kNone: a very long one, placed by k_xl_place
+                    for (uint32_t i = lane; i < dd[q].cnt; i += 32) ld[i] = ls[i];
                 before += dd[q].cnt;
             }
         }
@@ -503,6 +515,79 @@ __global__ void __launch_bounds__(256) k_compact(const uint32_t* __restrict__ ru
 }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
+
+// Round-parallel merging of the very long pre-tokens k_encode_long set aside (encode_xlong.cuh).
+// `cursor` = list entries << XL_IDX_SHIFT | symbols (incl. one separator per entry), read back by the caller.
+struct XlState { const uint32_t* xs; uint32_t n, n_list; const uint32_t* sep_pos; uint32_t* region_dst; };
+
+static int xlong_rounds(Engine& eng, const FusedParams& p, uint64_t cursor, uint32_t* ctrl, XlState& out, cudaStream_t st) {
+    const uint64_t n_list64 = cursor >> XL_IDX_SHIFT, total = cursor & ((1ull << XL_IDX_SHIFT) - 1);
+    if (n_list64 > p.desc_cap || total >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_CUDA, "internal scratch pool exhausted (very long pre-tokens)");
+    const uint32_t n_list = (uint32_t)n_list64;
+    Workspace& ws = eng.ws;
+    eng.mark(nullptr, st);
+    uint32_t *xa, *xb, *rank, *newid, *flags, *pos, *sep_pos;
+    unsigned long long* sv;
+    void* tmp;
+    CK(ws.get(32, (total + 2) * 4, (void**)&xa));
+    CK(ws.get(33, (total + 2) * 4, (void**)&xb));
+    CK(ws.get(34, total * 4, (void**)&rank));
+    CK(ws.get(35, total * 4, (void**)&newid));
+    CK(ws.get(36, total * 8, (void**)&sv));
+    CK(ws.get(37, total * 4, (void**)&flags));
+    CK(ws.get(38, total * 4, (void**)&pos));
+    CK(ws.get(39, (uint64_t)n_list * 4 + 16, (void**)&sep_pos));
+    size_t t1 = 0, t2 = 0;
+    cub::TransformInputIterator<uint32_t, XlKeep, const uint32_t*> keep_it(flags, XlKeep());
+    CK(cub::DeviceScan::InclusiveScan(nullptr, t1, sv, sv, XlSegOp(), (int)total, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, t2, keep_it, pos, (int)total, st));
+    const size_t tmp_bytes = (t1 > t2 ? t1 : t2) + 16;
+    CK(ws.get(40, tmp_bytes, &tmp));
+    uint32_t* holes = ctrl + 8;
+    uint32_t* n_out = ctrl + 9;
+    {
+        unsigned gy = n_list < 65535u ? n_list : 65535u;
+        uint64_t per = total / n_list / 2048 + 1;
+        unsigned gx = (unsigned)(per < 128 ? per : 128);
+        k_xl_init<<<dim3(gx, gy), 256, 0, st>>>(p, p.xl_list, n_list, xa, holes);
+        eng.launched(1);
+    }
+    CK(eng.publish({{holes, 1, 7}}, st));
+    CK(cudaStreamSynchronize(st));
+    bool drop_holes = eng.h_flags[7] != 0;                   // a byte without a vocab entry: one merge-free round removes them
+    const uint32_t W = eng.model.max_token_span < 1 ? 1u : eng.model.max_token_span;
+    const size_t smem = 2 * (size_t)(XL_TILE + 2 * W) * 4;
+    uint32_t n = (uint32_t)total;
+    int rounds = 0;
+    for (;;) {
+        const unsigned g256 = (n + 255) / 256;
+        k_xl_rank<<<(n + XL_TILE - 1) / XL_TILE, XL_THREADS, smem, st>>>(p.t, xa, n, W, drop_holes ? 1 : 0, rank, newid, sv);
+        size_t tb = tmp_bytes;
+        CK(cub::DeviceScan::InclusiveScan(tmp, tb, sv, sv, XlSegOp(), (int)n, st));
+        k_xl_flags<<<g256, 256, 0, st>>>(xa, rank, sv, n, flags);
+        tb = tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(tmp, tb, keep_it, pos, (int)n, st));
+        k_xl_scatter<<<g256, 256, 0, st>>>(xa, newid, flags, pos, n, xb, n_out);
+        eng.launched(5);
+        CK(eng.publish({{n_out, 1, 6}}, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t n_new = eng.h_flags[6];
+        uint32_t* t = xa; xa = xb; xb = t;
+        ++rounds;
+        if (!drop_holes && n_new == n) break;                  // nothing was selected: every region is final
+        drop_holes = false;
+        n = n_new;
+    }
+    eng.mark("xlong rounds", st);
+    k_xl_seps<<<(n + 255) / 256, 256, 0, st>>>(xa, n, sep_pos);
+    k_xl_count<<<(n_list + 255) / 256, 256, 0, st>>>(p, p.xl_list, n_list, sep_pos);
+    eng.launched(2);
+    eng.mark("k_xl_count", st);
+    eng.xl_last_rounds = rounds;
+    CK(cudaGetLastError());
+    out = XlState{xa, n, n_list, sep_pos, xb};                 // xb is free now: region destinations
+    return CTK_OK;
+}
 
 int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                  uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st) {
@@ -541,13 +626,19 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     CK(ws.get(7, p.long_cap * 4, (void**)&p.long_pool));
     p.desc_cap = (uint32_t)(n_bytes / 33 + 16);
     CK(ws.get(9, (uint64_t)p.desc_cap * sizeof(LongDesc), (void**)&p.desc));
+    CK(ws.get(41, (uint64_t)p.desc_cap * sizeof(XlEntry), (void**)&p.xl_list));
+    CK(ws.get(42, (p.n_slices + 2) * 2, (void**)&p.slice_first));
+    CK(ws.get(43, (n_docs + 1) * 8, (void**)&p.ids_off_rel));
+    p.xl_enabled = n_ids_host != nullptr && eng.model.merges_monotone && eng.model.max_token_span <= XL_MAX_WINDOW &&
+                   eng.tables.n_added == 0 && !getenv("CTK_NO_XLONG");
     p.first_doc = first_doc; p.cache_mask = cache_slots - 1; p.ovf_cap = ovf_cap;
     uint32_t max_id = eng.model.id_present.empty() ? 1u : (uint32_t)eng.model.id_present.size() - 1;
     p.id_bits = 1;
     while ((1ull << p.id_bits) <= max_id) ++p.id_bits;
     p.n_inline = 96 / p.id_bits;
     if (p.n_inline > MAXINLINE) p.n_inline = MAXINLINE;
-    // ctrl words: [0] err flags, [2] desc cursor, [3] ovf cursor, [4..5] long cursor
+    // ctrl words: [0] err flags, [2] desc cursor, [3] ovf cursor, [4..5] long cursor, [6..7] xlong cursor, [8] holes, [9] round size
+    p.xl_cursor = reinterpret_cast<unsigned long long*>(ctrl + 6);
     p.err = ctrl; p.desc_cursor = ctrl + 2; p.ovf_cursor = ctrl + 3; p.long_cursor = reinterpret_cast<unsigned long long*>(ctrl + 4);
     p.ids_off = d_ids_off;
     { const char* a = getenv("CTK_ABLATE"); p.ablate = a ? atoi(a) : 0; }
@@ -558,7 +649,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         eng.cache_valid = true;
     } else {
         CK(cudaMemsetAsync(ctrl, 0, 12, st));                          // keep the overflow cursor
-        CK(cudaMemsetAsync(ctrl + 4, 0, 8, st));
+        CK(cudaMemsetAsync(ctrl + 4, 0, 24, st));
     }
     eng.mark("memset(cache)", st);
     unsigned doc_grid = (unsigned)((n_docs + 1 + 255) / 256);
@@ -574,15 +665,31 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     CK(cudaMemsetAsync(p.slice_cnt + p.n_slices, 0, 4, st));
     CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, p.slice_cnt, slice_base, p.n_slices + 1, st));
     CK(ws.get(5, cub_bytes + 16, &cub_tmp));
-    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, p.slice_cnt, slice_base, p.n_slices + 1, st));
-    eng.launched(1); eng.mark("scan(slice counts)", st);
-    k_compact<<<(unsigned)((p.n_slices + 255) / 256), 256, 0, st>>>(p.runs, slice_base, p.slice_info, p.slice_desc, p.desc, p.long_pool,
-                                                                    p.n_slices, d_ids, ids_cap, p.err);
-    eng.launched(1); eng.mark("k_compact", st);
-    k_doc_fixup<<<doc_grid, 256, 0, st>>>(d_off, n_docs, p.n_slices, slice_base, p.slice_info, p.slice_desc, p.desc, d_ids_off);
-    eng.launched(1); eng.mark("k_doc_fixup", st);
-    CK(cudaGetLastError());
-    return eng.finish(p.err, d_ids_off, n_docs, n_ids_host, st);
+    XlState xl{};
+    for (int pass = 0;; ++pass) {
+        CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, p.slice_cnt, slice_base, p.n_slices + 1, st));
+        eng.launched(1); eng.mark("scan(slice counts)", st);
+        k_compact<<<(unsigned)((p.n_slices + 255) / 256), 256, 0, st>>>(p.runs, slice_base, p.slice_info, p.slice_desc, p.desc, p.long_pool,
+                                                                        p.n_slices, d_ids, ids_cap, p.err);
+        eng.launched(1); eng.mark("k_compact", st);
+        if (pass == 1) {
+            k_xl_dst<<<(xl.n_list + 255) / 256, 256, 0, st>>>(p, p.xl_list, xl.n_list, slice_base, xl.region_dst);
+            k_xl_place<<<(xl.n + 255) / 256, 256, 0, st>>>(xl.xs, xl.n, xl.n_list, xl.sep_pos, xl.region_dst, d_ids, ids_cap);
+            eng.launched(2); eng.mark("k_xl_place", st);
+        }
+        k_doc_fixup<<<doc_grid, 256, 0, st>>>(d_off, n_docs, p.n_slices, slice_base, p.slice_info, p.slice_desc, p.desc, p.ids_off_rel, d_ids_off);
+        eng.launched(1); eng.mark("k_doc_fixup", st);
+        CK(cudaGetLastError());
+        if (p.xl_enabled && pass == 0) CK(eng.publish({{ctrl + 6, 2, 4}}, st));
+        int rc = eng.finish(p.err, d_ids_off, n_docs, n_ids_host, st);
+        if (rc != CTK_OK || !p.xl_enabled || pass == 1) return rc;
+        // very long pre-tokens were set aside (rare): merge them in rounds, then place every id again
+        uint64_t cursor;
+        memcpy(&cursor, eng.h_flags + 4, 8);
+        if ((cursor >> XL_IDX_SHIFT) == 0) return rc;
+        rc = xlong_rounds(eng, p, cursor, ctrl, xl, st);
+        if (rc != CTK_OK) return rc;
+    }
 }
 
 }  // namespace ctk

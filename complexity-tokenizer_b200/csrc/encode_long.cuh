@@ -11,6 +11,8 @@
 
 namespace ctk {
 
+constexpr uint32_t XL_MIN = 256;                 // pre-tokens longer than this take the round-parallel path (encode_xlong.cuh)
+
 template <int K>
 __device__ __forceinline__ int bpe_warp_regs(const DevTables& t, uint32_t (&s)[K], int n, int lane) {
     const unsigned full = 0xFFFFFFFFu;
@@ -134,23 +136,35 @@ __global__ void __launch_bounds__(256) k_encode_long(const FusedParams p) {
     for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_desc; i += n_warps) {
         LongDesc dd = p.desc[i];
         uint64_t len = dd.len;
-        if (dd.len == 0xFFFFFFFFu) {                               // runs past its chunk: find the end
-            uint64_t dl = 0, dh = p.n_docs;                        // last doc with off[d] <= gstart
-            while (dl + 1 < dh) { uint64_t mid = (dl + dh) >> 1; if (__ldg(p.off + mid) <= dd.gstart) dl = mid; else dh = mid; }
-            TextView tv{p.text, p.n_bytes, nullptr, p.t.trie_index, p.t.trie_blocks, __ldg(p.off + dl), __ldg(p.off + dl + 1)};
-            uint64_t e = 0;
-            for (uint64_t q = dd.gstart + dd.chunk_end + lane;; q += 32) {
-                bool st = q >= tv.dhi || tv.is_start(q);
-                unsigned b = __ballot_sync(full, st);
-                if (b) { e = q - lane + (__ffs(b) - 1); break; }
+        if (dd.len == 0xFFFFFFFFu) {                               // runs past its chunk: it ends at the next start, which is
+            uint64_t e = p.n_bytes;                                // the first owned start of a later slice (or the text's end)
+            for (uint64_t s0 = (uint64_t)dd.slice + 1; s0 < p.n_slices; s0 += 32) {
+                const uint64_t s = s0 + lane;
+                const uint32_t f = s < p.n_slices ? p.slice_first[s] : 0xFFFFu;
+                const unsigned b = __ballot_sync(full, f != 0xFFFFu);
+                if (b) {
+                    const int src = __ffs(b) - 1;
+                    e = (s0 + src) * SLICE - LCTX + __shfl_sync(full, f, src);
+                    break;
+                }
             }
             len = e - dd.gstart;
+            if (lane == 0) p.desc[i].len = (uint32_t)len;
         }
         unsigned long long po = 0;
-        if (lane == 0) po = atomicAdd(p.long_cursor, (unsigned long long)len);
-        po = __shfl_sync(full, po, 0);
+        if (!(p.xl_enabled && len > XL_MIN)) {
+            if (lane == 0) po = atomicAdd(p.long_cursor, (unsigned long long)len);
+            po = __shfl_sync(full, po, 0);
+        }
         uint32_t cnt = 0;
-        if (po + len <= p.long_cap) {
+        if (p.xl_enabled && len > XL_MIN) {                        // merged in rounds by encode_xlong.cuh, after this kernel
+            po = kNone;                                            // no room in the long pool: k_xl_place writes the output directly
+            if (lane == 0) {
+                const unsigned long long t = atomicAdd(p.xl_cursor, (1ull << XL_IDX_SHIFT) | (unsigned long long)(len + 1));
+                const unsigned long long idx = t >> XL_IDX_SHIFT;
+                if (idx < p.desc_cap) p.xl_list[idx] = XlEntry{i, 0u, t & ((1ull << XL_IDX_SHIFT) - 1)};
+            }
+        } else if (po + len <= p.long_cap) {
             uint32_t* out = p.long_pool + po;
             const uint8_t* src = p.text + dd.gstart;
             if (p.t.n_added == 0) cnt = long_piece(p, src, len, out, lane);

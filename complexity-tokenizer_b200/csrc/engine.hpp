@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <initializer_list>
 #include <map>
 #include <mutex>
 #include <string>
@@ -23,7 +24,7 @@ extern std::atomic<uint64_t> g_kernel_launches;
 // Grow-only device scratch, one buffer per slot.  Growing frees the old buffer (cudaFree
 // synchronises the device, so nothing in flight can still be using it).
 struct Workspace {
-    static constexpr int kSlots = 32;
+    static constexpr int kSlots = 48;
     void* p[kSlots] = {};
     size_t cap[kSlots] = {};
     cudaError_t get(int slot, size_t bytes, void** out) {
@@ -68,9 +69,16 @@ struct Engine {
     bool cache_valid = false;           // the pre-token cache holds entries of earlier calls
     bool use_general = false;           // debug: run the multi-kernel pipeline instead of the fused kernel
     int long_grid = 0;
+    int xl_last_rounds = 0;             // rounds the last very-long-pre-token pass took (diagnostics)
     int fused_grid = 0;                 // co-resident CTAs of k_encode_fused (SMs x occupancy), computed once
     // pinned staging for error flags / counters
-    uint32_t* h_flags = nullptr;
+    uint32_t* h_flags = nullptr;        // 64 words of MAPPED pinned memory; h_flags_dev is the same memory as the device sees it
+    uint32_t* h_flags_dev = nullptr;
+    // Small device->host readbacks (flags, totals) are stored by a one-thread kernel straight into mapped host
+    // memory.  A 4-byte cudaMemcpyAsync would queue on the D2H copy engine behind the host pipeline's 64 MiB result
+    // copies and hold the next chunk's kernels back for a millisecond (measured: 31 -> 4x GB/s end to end).
+    struct Pub { const void* src; int words; int dst_word; };
+    cudaError_t publish(std::initializer_list<Pub> items, cudaStream_t st);
     uint8_t* last_decode_out = nullptr;
     cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;   // host-buffer pipeline: copy in / compute / copy out
     bool keep_cache_once = false;       // next encode call continues the current batch (chunked host-buffer path)   // decode_device(d_out = NULL) leaves its output here

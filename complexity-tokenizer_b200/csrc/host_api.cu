@@ -1,14 +1,17 @@
 // Host-buffer entry points of the C ABI: ctk_encode_batch / ctk_decode_batch.
 //
 // These are what the reference's PyO3 methods would call (bindings/tokenizer.rs:207-210, 226-238).
-// encode_batch pipelines the batch in chunks of whole documents over three streams so that the PCIe
+// encode_batch pipelines the batch in chunks of whole documents (4 .. 64 MiB) over three streams so that the PCIe
 // copy in, the kernels and the copy out overlap:
 //     st_h2d : text chunk c+1, c+2, ...      (pinned user memory is DMA'd directly)
 //     st_comp: NFC check + fused encode of chunk c
 //     st_d2h : ids of chunk c-1 into a pooled pinned result buffer
 // The pre-token cache is cleared at the first chunk only: the chunks are one batch.
 #include <algorithm>
+#include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "engine.hpp"
@@ -54,6 +57,20 @@ struct Result {
     size_t ids_cap = 0, off_cap = 0, bytes_cap = 0;
 };
 
+// DMA between the device and an UNALIGNED pinned host address runs ~10 % slower (tools/diag_pcie.py: 42.4 vs
+// 46.6 GB/s per direction with both directions busy): copy the few bytes up to the next 4 KiB boundary of the
+// host address separately, then the aligned rest.
+static cudaError_t copy_host_aligned(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    const uintptr_t host = kind == cudaMemcpyHostToDevice ? (uintptr_t)src : (uintptr_t)dst;
+    const size_t head = (size_t)((0 - host) & 4095u);
+    if (head && bytes > head + (64u << 10)) {
+        cudaError_t e = cudaMemcpyAsync(dst, src, head, kind, st);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync((char*)dst + head, (const char*)src + head, bytes - head, kind, st);
+    }
+    return cudaMemcpyAsync(dst, src, bytes, kind, st);
+}
+
 static void free_result(Result* r) {
     if (!r) return;
     g_pinned.put(r->ids, r->ids_cap);
@@ -77,9 +94,12 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
     if (text_off[0] != 0) { set_last_error("text_off[0] must be 0"); return CTK_ERR_ARG; }
     const uint64_t B = text_off[n];
     if (B && !text) { set_last_error("NULL text"); return CTK_ERR_ARG; }
-    // chunks of whole documents, about 64 MiB each (16-byte aligned starts are not needed: each
-    // chunk is copied to a 256-byte aligned place of its own)
-    const uint64_t target = 64ull << 20;
+    // Chunks of whole documents.  Steady state 64 MiB (fewer DMA operations measured faster than 16 or 32 MiB: tools/diag_e2e.py); the first chunks are small so that the copy out starts early
+    // and the last ones shrink so that the drain (kernels + copy out of the last chunk) is short.  Each chunk is
+    // copied to a 256-byte aligned place of its own on the device.
+    uint64_t steady = 64ull << 20;
+    if (const char* e = getenv("CTK_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 2048) steady = (uint64_t)v << 20; }
+    const uint64_t small = std::min<uint64_t>(steady, 4ull << 20);
     struct Chunk { size_t d0, d1; uint64_t b0, b1, dev_text; size_t roff; };
     std::vector<Chunk> chunks;
     {
@@ -89,6 +109,8 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
         while (d < n) {
             size_t e = d;
             uint64_t b0 = text_off[d];
+            uint64_t target = std::min<uint64_t>(steady, small << std::min<size_t>(chunks.size(), 16));
+            if (B - b0 < 2 * target) target = std::max<uint64_t>(small, (B - b0) / 2);
             while (e < n && (e == d || text_off[e + 1] - b0 <= target)) {
                 if (text_off[e + 1] < text_off[e]) { set_last_error("text_off must be non-decreasing"); return CTK_ERR_ARG; }
                 ++e;
@@ -112,6 +134,13 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
     size_t n_roff = n + chunks.size() + 1;
     std::vector<cudaEvent_t> evs;
     std::vector<uint64_t> chunk_base;
+    // CTK_TRACE=1: per-chunk timeline (H2D done, kernels done, D2H done; ms since the call started) on stderr
+    const bool trace = getenv("CTK_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tr_h, tr_c, tr_d;
+    std::vector<double> tr_host;
+    cudaEvent_t tr0 = nullptr;
+    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double host0 = now_ms();
     CKE(cudaSetDevice(eng->device));
     dev_text_bytes = chunks.empty() ? 256 : chunks.back().dev_text + ((chunks.back().b1 - chunks.back().b0 + 64 + 255) / 256) * 256;
     ids_cap = B + B / 8 + n + 1024;
@@ -128,13 +157,20 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
         for (size_t d = c.d0; d <= c.d1; ++d) h_roff[c.roff + (d - c.d0)] = text_off[d] - c.b0;
     CKE(cudaMemcpyAsync(d_roff, h_roff, n_roff * 8, cudaMemcpyHostToDevice, eng->st_h2d));
     evs.resize(chunks.size());
+    if (trace) {
+        tr_h.resize(chunks.size()); tr_c.resize(chunks.size()); tr_d.resize(chunks.size()); tr_host.resize(chunks.size());
+        cudaEventCreate(&tr0);
+        for (size_t c = 0; c < chunks.size(); ++c) { cudaEventCreate(&tr_h[c]); cudaEventCreate(&tr_c[c]); cudaEventCreate(&tr_d[c]); }
+        cudaEventRecord(tr0, eng->st_h2d);
+    }
     for (size_t c = 0; c < chunks.size(); ++c) {
         const Chunk& ch = chunks[c];
         if (!eng->sync_ev_pool.empty()) { evs[c] = eng->sync_ev_pool.back(); eng->sync_ev_pool.pop_back(); }
         else CKE(cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming));
-        if (ch.b1 > ch.b0) CKE(cudaMemcpyAsync(d_text + ch.dev_text, text + ch.b0, ch.b1 - ch.b0, cudaMemcpyHostToDevice, eng->st_h2d));
+        if (ch.b1 > ch.b0) CKE(copy_host_aligned(d_text + ch.dev_text, text + ch.b0, ch.b1 - ch.b0, cudaMemcpyHostToDevice, eng->st_h2d));
         CKE(cudaMemsetAsync(d_text + ch.dev_text + (ch.b1 - ch.b0), 0, 64, eng->st_h2d));
         CKE(cudaEventRecord(evs[c], eng->st_h2d));
+        if (trace) cudaEventRecord(tr_h[c], eng->st_h2d);
     }
     chunk_base.resize(chunks.size() + 1, 0);
     for (size_t c = 0; c < chunks.size(); ++c) {
@@ -146,6 +182,7 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
                            d_ids_off + ch.roff, &cnt, eng->st_comp);
         eng->keep_cache_once = false;
         if (rc != CTK_OK) goto done;
+        if (trace) { cudaEventRecord(tr_c[c], eng->st_comp); tr_host[c] = now_ms() - host0; }
         // copy out while the next chunk is being encoded
         if ((total + cnt + 1) * 4 > r->ids_cap) {                     // grow the pinned result (rare)
             CKE(cudaStreamSynchronize(eng->st_d2h));
@@ -156,12 +193,23 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
             g_pinned.put(r->ids, r->ids_cap);
             r->ids = nb; r->ids_cap = ncap;
         }
-        if (cnt) CKE(cudaMemcpyAsync((uint32_t*)r->ids + total, d_ids + total, cnt * 4, cudaMemcpyDeviceToHost, eng->st_d2h));
+        if (cnt && !getenv("CTK_DIAG_NO_D2H")) CKE(copy_host_aligned((uint32_t*)r->ids + total, d_ids + total, cnt * 4, cudaMemcpyDeviceToHost, eng->st_d2h));
         CKE(cudaMemcpyAsync(h_ioff + ch.roff, d_ids_off + ch.roff, (ch.d1 - ch.d0 + 1) * 8, cudaMemcpyDeviceToHost, eng->st_d2h));
+        if (trace) cudaEventRecord(tr_d[c], eng->st_d2h);
         chunk_base[c] = total;
         total += cnt;
     }
     CKE(cudaStreamSynchronize(eng->st_d2h));
+    if (trace) {
+        fprintf(stderr, "[ctk trace] %zu chunks, %.1f MiB in; host: pipeline issued+drained at %.3f ms\n", chunks.size(), B / 1048576.0, now_ms() - host0);
+        for (size_t c = 0; c < chunks.size(); ++c) {
+            float h = 0, k = 0, d = 0;
+            cudaEventElapsedTime(&h, tr0, tr_h[c]); cudaEventElapsedTime(&k, tr0, tr_c[c]); cudaEventElapsedTime(&d, tr0, tr_d[c]);
+            fprintf(stderr, "[ctk trace] chunk %2zu  h2d done %8.3f  kernels done %8.3f  d2h done %8.3f  (host saw kernels done at %8.3f)\n", c, h, k, d, tr_host[c]);
+            cudaEventDestroy(tr_h[c]); cudaEventDestroy(tr_c[c]); cudaEventDestroy(tr_d[c]);
+        }
+        cudaEventDestroy(tr0);
+    }
     {
         uint64_t* off = (uint64_t*)r->off;
         for (size_t c = 0; c < chunks.size(); ++c) {

@@ -221,6 +221,27 @@ int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err) 
         m.pairs.push_back({(uint32_t)(kv.first >> 32), (uint32_t)kv.first, kv.second, ops_new_id[kv.second]});
     }
     std::sort(m.pairs.begin(), m.pairs.end(), [](const PairEntry& x, const PairEntry& y) { return x.rank < y.rank; });
+    {   // monotone?  (a trainer's table is: a token exists before any pair uses it; duplicates / the rank quirk can break it)
+        std::unordered_map<uint32_t, uint32_t> made_at;        // id -> highest rank of a merge producing it
+        for (const PairEntry& p : m.pairs) { auto it = made_at.find(p.new_id); if (it == made_at.end() || it->second < p.rank) made_at[p.new_id] = p.rank; }
+        m.merges_monotone = true;
+        for (const PairEntry& p : m.pairs) {
+            auto ia = made_at.find(p.a), ib = made_at.find(p.b);
+            if ((ia != made_at.end() && ia->second >= p.rank) || (ib != made_at.end() && ib->second >= p.rank)) { m.merges_monotone = false; break; }
+        }
+        m.max_token_span = 1;
+        if (m.merges_monotone) {                               // spans in rank order: components are final before they are used
+            std::unordered_map<uint32_t, uint32_t> span;
+            for (const PairEntry& p : m.pairs) {
+                auto ia = span.find(p.a), ib = span.find(p.b);
+                uint64_t s = (uint64_t)(ia == span.end() ? 1u : ia->second) + (ib == span.end() ? 1u : ib->second);
+                if (s > 0x7FFFFFFFull) s = 0x7FFFFFFFull;
+                uint32_t& dst = span[p.new_id];
+                if (dst < s) dst = (uint32_t)s;
+                if (m.max_token_span < s) m.max_token_span = (uint32_t)s;
+            }
+        }
+    }
 
     // ---- added tokens (mod.rs:274-305)
     const JValue* aj = root.get("added_tokens");

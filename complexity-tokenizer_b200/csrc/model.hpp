@@ -36,6 +36,10 @@ struct HostModel {
     std::vector<uint8_t> dec_special;                      // 1 if the token string is in special_tokens
     size_t dec_max_bytes = 0;
     bool any_added_may_match = false;
+    // Round-parallel merging of very long pre-tokens (encode_xlong.cuh) is exact only for MONOTONE tables:
+    // every pair that contains a merged token ranks after every merge producing that token.
+    bool merges_monotone = false;
+    uint32_t max_token_span = 1;                           // longest merged token, in initial symbols
 };
 
 // Returns a CTK_* code; on failure `err` holds the message.

@@ -8,6 +8,8 @@
 // (UAX #15) and every other document is copied, into a fresh packed buffer with new offsets.
 #include <cub/device/device_scan.cuh>
 
+#include <cstring>
+
 #include "engine.hpp"
 
 namespace ctk {
@@ -244,7 +246,7 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
     NfcTables t = eng.nfc;
     k_nfc_flag<<<(unsigned)(((n_bytes + 15) / 16 + 255) / 256), 256, 0, st>>>(t, d_text, n_bytes, d_off, n_docs, flag, susp, any);
     eng.launched(1); eng.mark("k_nfc_flag", st);
-    CK(cudaMemcpyAsync(eng.h_flags + 8, any, 4, cudaMemcpyDeviceToHost, st));
+    CK(eng.publish({{any, 1, 8}}, st));
     CK(cudaStreamSynchronize(st));
     if (!eng.h_flags[8]) return CTK_OK;
     uint64_t *new_len, *new_off;
@@ -261,15 +263,16 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
     CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, new_len, new_off, n_docs + 1, st));
     eng.launched(1);
     uint64_t total = 0;
-    CK(cudaMemcpyAsync(&total, new_off + n_docs, 8, cudaMemcpyDeviceToHost, st));
+    CK(eng.publish({{new_off + n_docs, 2, 10}}, st));
     CK(cudaStreamSynchronize(st));
+    memcpy(&total, eng.h_flags + 10, 8);
     uint8_t* out;
     CK(ws.get(30, total + 64, (void**)&out));
     CK(cudaMemsetAsync(out + total, 0, 64, st));
     eng.mark(nullptr, st);
     k_nfc_doc<<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, susp, new_off, out, nullptr, any + 1);
     eng.launched(1); eng.mark("k_nfc_doc(write)", st);
-    CK(cudaMemcpyAsync(eng.h_flags + 8, any + 1, 4, cudaMemcpyDeviceToHost, st));
+    CK(eng.publish({{any + 1, 1, 8}}, st));
     CK(cudaStreamSynchronize(st));
     if (eng.h_flags[8] & ERRF_NFC_LONG)
         return eng.fail(CTK_ERR_UNSUPPORTED, "a combining sequence longer than 48 code points needs NFC; not supported");

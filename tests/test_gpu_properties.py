@@ -214,3 +214,90 @@ def test_added_tokens_inside_words(built_lib, small_tok_json):
     bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
     assert not bad, (len(bad), docs[bad[0]], got[bad[0]], want[bad[0]])
     assert any(nid <= t < nid + len(extra) for ids in want for t in ids)          # the added tokens really fire
+
+
+# ---- very long pre-tokens: the round-parallel path (csrc/encode_xlong.cuh) ---------------------------------
+
+def _xlong_docs():
+    import synth
+    docs = [d.decode() for d in synth.gen_long_docs(doc_bytes=9000, n_docs=8)]
+    docs += ['a' * 5000, 'ab' * 3000, ' ' * 4097 + 'word', 'x' + ' ' * 3000, '=' * 257, '-' * 256, 'q' * 258 + ' ' + 'z' * 300,
+             'The start of a normal sentence, then ' + 'lorem' * 400 + ' and an ordinary tail. ' * 30,
+             '\n'.join('w' * n for n in (255, 256, 257, 258, 300, 447, 448, 449, 600, 1000))]
+    return docs
+
+
+def test_xlong_rounds_match_oracle(built_lib, tok_paths):
+    """Pre-tokens of 257 .. 9000 bytes (letter runs, runs of one symbol, spaces, punctuation) merged in parallel
+    rounds must equal the reference's one-merge-at-a-time order (bpe.rs:104-153) as restated by the oracle."""
+    import complexity_tokenizer as ct
+    for cfg in ('config2', 'config1'):
+        tok, orc = _tok(tok_paths[cfg]), _oracle(tok_paths[cfg])
+        docs = _xlong_docs()
+        got, want = tok.encode_batch(docs), orc.encode_batch(docs)
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert g == w, (cfg, i, len(docs[i]), docs[i][:30])
+        assert ct._lib().ctk_debug_xlong_rounds(tok._h) > 0          # the rounds did run
+
+
+def test_xlong_rounds_equal_sequential_device_path(built_lib, tok_paths):
+    """Same inputs through the sequential warp path (CTK_NO_XLONG) and the rounds: identical ids."""
+    import os
+    tok = _tok(tok_paths['config2'])
+    docs = _xlong_docs()
+    a = tok.encode_batch(docs)
+    os.environ['CTK_NO_XLONG'] = '1'
+    try:
+        b = tok.encode_batch(docs)
+    finally:
+        del os.environ['CTK_NO_XLONG']
+    assert a == b
+
+
+def test_xlong_with_dropped_bytes_and_non_monotone_table(built_lib, small_tok_json):
+    """(1) a byte whose mapped char is not in the vocab is dropped before merging (bpe.rs:94-97), also inside a very long
+    pre-token; (2) a non-monotone merge table keeps the sequential path and still matches the oracle."""
+    import json
+    import c_oracle
+    import complexity_tokenizer as ct
+    tj = json.loads(small_tok_json)
+    v = tj['model']['vocab']
+    del v['q']
+    tj['model']['merges'] = [m for m in tj['model']['merges'] if 'q' not in (m if isinstance(m, str) else ''.join(m))]
+    for k in [k for k in v if 'q' in k]:
+        del v[k]
+    docs = ['qa' * 700 + 'q', 'the' * 300 + 'q' * 10 + 'and' * 200, 'q' * 600, ' ' * 500 + 'q']
+    data = json.dumps(tj, ensure_ascii=False)
+    tok, orc = ct.Tokenizer.from_str(data), c_oracle.COracle.from_str(data)
+    assert tok.encode_batch(docs) == orc.encode_batch(docs)
+    assert ct._lib().ctk_debug_xlong_rounds(tok._h) > 0
+    tj2 = json.loads(small_tok_json)
+    ms = tj2['model']['merges']
+    tj2['model']['merges'] = ms[300:] + ms[:300]                  # pairs now outrank the merges that make their parts
+    data2 = json.dumps(tj2, ensure_ascii=False)
+    tok2, orc2 = ct.Tokenizer.from_str(data2), c_oracle.COracle.from_str(data2)
+    docs2 = [d[:1500] for d in _xlong_docs()]
+    assert tok2.encode_batch(docs2) == orc2.encode_batch(docs2)
+    assert ct._lib().ctk_debug_xlong_rounds(tok2._h) == 0
+
+
+def test_config4_full_size_properties(built_lib, tok_paths):
+    """BASELINE config 4 at full size (64 documents of 1 MiB; single pre-tokens of up to 2^20 symbols; the O(n^2)
+    reference order would need hours on the CPU): size-independent properties.
+    (1) decode(encode(x)) == x byte-exact; (2) idempotence; (3) a document encodes the same alone as in the batch;
+    (4) a 1 MiB run of spaces is ceil-log-many tokens of the longest space tokens: every id decodes to spaces only."""
+    import synth
+    tok = _tok(tok_paths['config2'])
+    docs = synth.gen_long_docs()
+    text, offs = synth.pack(docs)
+    ids, ioff = tok.encode_packed(text, offs)
+    b, boff = tok.decode_packed(ids, ioff, False, False)
+    assert np.array_equal(boff, offs) and np.array_equal(b, text)
+    ids2, ioff2 = tok.encode_packed(text, offs)
+    assert np.array_equal(ids, ids2) and np.array_equal(ioff, ioff2)
+    for d in (0, 1, 2, 3, 63):
+        one, _ = tok.encode_packed(text[int(offs[d]):int(offs[d + 1])], np.array([0, int(offs[d + 1] - offs[d])], dtype=np.uint64))
+        assert np.array_equal(one, ids[int(ioff[d]):int(ioff[d + 1])]), d
+    sp = ids[int(ioff[2]):int(ioff[3])]
+    assert sp.size <= (1 << 20) // 2
+    assert set(tok.decode([int(x) for x in np.unique(sp)]).replace(' ', '')) == set()

@@ -143,3 +143,48 @@ def test_start_predicate_on_corpora(built_lib):
         text, offs = synth.gen_corpus(kind, seed, 96 << 10, doc_median=700)
         docs = synth.split_docs(text, offs)
         assert _starts_product(built_lib, docs) == _starts_oracle(docs)
+
+
+def _merge_props(lib, tj):
+    data = json.dumps(tj, ensure_ascii=False).encode()
+    buf = ctypes.create_string_buffer(data, len(data))
+    mono, span = ctypes.c_int(), ctypes.c_uint32()
+    rc = lib.ctk_debug_merge_props(ctypes.addressof(buf), len(data), ctypes.byref(mono), ctypes.byref(span))
+    assert rc == 0
+    return mono.value, span.value
+
+
+def test_merge_table_monotonicity(built_lib, tok_paths):
+    """The round-parallel path for very long pre-tokens (encode_xlong.cuh) is only allowed for monotone tables:
+    every pair that contains a merged token ranks after every merge producing that token."""
+    lib = built_lib
+    vocab = {'a': 0, 'b': 1, 'c': 2, 'ab': 3, 'abc': 4, 'bc': 5}
+    mono = {'model': {'type': 'BPE', 'vocab': vocab, 'merges': ['a b', 'ab c']}}
+    assert _merge_props(lib, mono) == (1, 3)
+    # 'ab c' is listed before the merge that makes 'ab': a pair would outrank its own component
+    assert _merge_props(lib, {'model': {'type': 'BPE', 'vocab': vocab, 'merges': ['ab c', 'a b']}})[0] == 0
+    # two producers of 'abc', and a pair using 'abc' ranked between them
+    v2 = dict(vocab, abca=6)
+    assert _merge_props(lib, {'model': {'type': 'BPE', 'vocab': v2, 'merges': ['a b', 'ab c', 'abc a', 'b c', 'a bc']}})[0] == 0
+    assert _merge_props(lib, {'model': {'type': 'BPE', 'vocab': v2, 'merges': ['a b', 'ab c', 'b c', 'a bc', 'abc a']}}) == (1, 4)
+    # the trained fixtures are monotone, with the longest token well inside the kernel's window limit
+    for cfg in ('config1', 'config2', 'config3'):
+        with open(tok_paths[cfg], encoding='utf-8') as f:
+            m, span = _merge_props(lib, json.load(f))
+        assert m == 1 and 2 <= span <= 1024, (cfg, m, span)
+
+
+def test_round_parallel_rule_matches_sequential_order():
+    """tools/verify_window_merge.py: the rule encode_xlong.cuh applies equals one-merge-at-a-time for monotone tables."""
+    import importlib.util
+    import os
+    import random
+    spec = importlib.util.spec_from_file_location('vwm', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools', 'verify_window_merge.py'))
+    vwm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vwm)
+    rng = random.Random(11)
+    bad = 0
+    for _ in range(150):
+        b, _r = vwm.trial(rng, rng.choice([1, 2, 3, 4]), rng.choice([2, 3, 4, 5, 6]), rng.choice([3, 6, 12, 30, 60]), 100, True)
+        bad += b
+    assert bad == 0

@@ -16,6 +16,7 @@ def run(name, tokpath, text, offs, reps=3, check=None):
     for _ in range(reps): T=tok.encode_device(d_text.data_ptr(),d_off.data_ptr(),D,B,d_ids.data_ptr(),cap,d_ioff.data_ptr())
     torch.cuda.synchronize(); dt=(time.perf_counter()-t)/reps
     r=tok.profile_report()
+    print('   xlong rounds of the last call:', ct._lib().ctk_debug_xlong_rounds(tok._h))
     print('%s: %.1f MiB, %d docs, %d ids: %.2f ms/call = %.1f GB/s | %s'%(name,B/2**20,D,T,dt*1e3,B/dt/1e9,{k:round(v[0]/v[1],3) for k,v in r.items()}))
     if check:
         import c_oracle
@@ -30,6 +31,7 @@ if which=='3':
     run('config3 mixed/100K', synth.tokenizer_config3(), text, offs, check=2000)
 elif which=='4':
     size=int(sys.argv[2]) if len(sys.argv)>2 else 4096
-    docs=synth.gen_long_docs(doc_bytes=size, n_docs=16)
+    nd=int(sys.argv[3]) if len(sys.argv)>3 else 16
+    docs=synth.gen_long_docs(doc_bytes=size, n_docs=nd)
     text,offs=synth.pack(docs)
-    run('config4 long pre-tokens (%d B docs)'%size, synth.tokenizer_config2(), text, offs, reps=1, check=16)
+    run('config4 long pre-tokens (%d docs of %d B)'%(nd,size), synth.tokenizer_config2(), text, offs, reps=2, check=16 if size<=16384 else None)
