@@ -30,7 +30,7 @@ def _lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.path.join(_HERE, 'libctk.so')
+    path = os.environ.get('CTK_LIB_VARIANT') or os.path.join(_HERE, 'libctk.so')   # variant: kernel A/B experiments (tools/variants.py)
     if not os.path.exists(path):
         raise ImportError('libctk.so is not built (run `python complexity-tokenizer_b200/build.py`); '
                           'this package has no CPU fallback')

@@ -100,6 +100,8 @@ static int upload(Engine& eng) {
         UP(15, eng.tables.added_meta, meta.data(), meta.size() * sizeof(uint4));
         UP(16, eng.tables.mapped_alnum, CTK_MAPPED_ALNUM, sizeof(CTK_MAPPED_ALNUM));
     }
+    eng.tables.round_parallel = m.round_parallel ? 1u : 0u;
+    UP(17, eng.tables.reach, m.reach.data(), m.reach.size() * 4);
 #undef UP
     e = cudaHostAlloc((void**)&eng.h_flags, 256, cudaHostAllocMapped);
     if (e != cudaSuccess) return eng.cuda_fail(e, "cudaHostAlloc");
@@ -328,7 +330,7 @@ int ctk_debug_merge_props(const uint8_t* json, size_t len, int* monotone, uint32
     std::string err;
     int rc = load_model(json, len, m, err);
     if (rc != CTK_OK) { set_last_error(err); return rc; }
-    if (monotone) *monotone = m.merges_monotone;
+    if (monotone) *monotone = m.merges_monotone | (m.round_parallel ? 2 : 0);
     if (max_span) *max_span = m.max_token_span;
     return CTK_OK;
 }

@@ -41,6 +41,8 @@ struct DevTables {
     const uint4* added_meta;    // {offset, length, id, flags: 1 single_word, 2 lstrip, 4 rstrip}
     uint32_t n_added;
     const uint8_t* mapped_alnum;// [256] char::is_alphanumeric of the byte-mapped character of each byte
+    const uint32_t* reach;      // [n ids] token reach left | right << 16 (model.hpp); only if round_parallel
+    uint32_t round_parallel;    // the round-parallel merge rule is exact for this table (loader.cpp: token_reach)
 };
 
 // ------------------------------------------------------------------------------------------------

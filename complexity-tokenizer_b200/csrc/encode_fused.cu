@@ -70,6 +70,7 @@ struct FusedParams {
     uint32_t* slice_desc;                                // first LongDesc of the slice (if n_long > 0)
     uint16_t* slice_first;                               // chunk-relative position of the slice's first owned start, 0xFFFF if none
     int xl_enabled;                                      // monotone table, no in-word added tokens, synchronous call
+    int no_rounds;                                       // debug (CTK_NO_ROUNDS): sequential merging in k_encode_long
     unsigned long long* xl_cursor;                       // list index << XL_IDX_SHIFT | symbols handed out
     XlEntry* xl_list;
     uint64_t* ids_off_rel;                               // slice-relative document offsets (k_doc_fixup makes them absolute)
@@ -87,7 +88,7 @@ struct __align__(16) WarpSmem {
     uint32_t l_cnt[MAXLONG + 2];
 };
 
-// first_doc[s] = smallest d with off[d] >= s*SLICE - LCTX ; also validates the offsets
+// first_doc[s] = smallest d with off[d] >= s*SLICE - LCTX (bits 0..30); also validates the offsets
 __global__ void k_first_doc(const uint64_t* __restrict__ off, uint64_t n_docs, uint64_t n_bytes, uint64_t n_slices,
                             uint32_t* __restrict__ first_doc, uint32_t* __restrict__ err) {
     uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -100,7 +101,9 @@ __global__ void k_first_doc(const uint64_t* __restrict__ off, uint64_t n_docs, u
     uint64_t s_lo = d ? (off[d - 1] + LCTX) / SLICE + 1 : 0;
     uint64_t s_hi = (p + LCTX) / SLICE;
     if (s_hi >= n_slices) s_hi = n_slices - 1;
-    for (uint64_t s = s_lo; s <= s_hi; ++s) first_doc[s] = (uint32_t)d;
+    // bit 31: a document start (or the end of the text) lies inside the slice's 512-byte chunk
+    for (uint64_t s = s_lo; s <= s_hi; ++s)
+        first_doc[s] = (uint32_t)d | ((long long)p < (long long)(s * SLICE) - LCTX + CHUNK ? 0x80000000u : 0u);
 }
 
 // ids_off[d] was written relative to the slice that owns position off[d]; add that slice's base
@@ -169,7 +172,13 @@ __device__ __forceinline__ int init_symbols32(const uint32_t* s_byte_init, const
 #include "encode_xlong.cuh"
 namespace ctk {
 
-__global__ void __launch_bounds__(FW * 32, 4) k_encode_slices(const FusedParams p) {
+#ifndef CTK_LB
+#define CTK_LB 4
+#endif
+#ifndef CTK_PREFETCH
+#define CTK_PREFETCH 0   // measured: loading the next slice one iteration ahead costs more (registers) than it hides
+#endif
+__global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedParams p) {
     const unsigned full = 0xFFFFFFFFu;
     __shared__ WarpSmem sm[FW];
     __shared__ uint32_t s_byte_init[256];
@@ -192,28 +201,46 @@ __global__ void __launch_bounds__(FW * 32, 4) k_encode_slices(const FusedParams 
     const uint8_t* const text = p.text;
     const uint64_t n_bytes = p.n_bytes;
 
-    for (uint64_t slice = (uint64_t)blockIdx.x * FW + w; slice < p.n_slices; slice += (uint64_t)gridDim.x * FW) {
+    // one 16-byte vector per lane, zero beyond the text (the tail is masked when it is used)
+    auto load_vec = [&](uint64_t sl) -> uint4 {
+        const long long qq = (long long)sl * SLICE - LCTX + 16 * lane;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (qq >= 0 && qq < (long long)n_bytes) r = __ldg(reinterpret_cast<const uint4*>(text + qq));
+        return r;
+    };
+    const uint64_t stride = (uint64_t)gridDim.x * FW;
+    uint64_t slice = (uint64_t)blockIdx.x * FW + w;
+#if CTK_PREFETCH
+    uint4 vn = make_uint4(0, 0, 0, 0);
+    uint32_t fdn = 0;
+    if (slice < p.n_slices) { vn = load_vec(slice); fdn = __ldg(p.first_doc + slice); }
+#endif
+    for (; slice < p.n_slices; slice += stride) {
         const long long lo = (long long)slice * SLICE, cb = lo - LCTX;     // chunk base (may be -16 for slice 0)
-        const uint32_t d0 = __ldg(p.first_doc + slice);
         uint32_t* const run = p.runs + slice * STAGE;
         uint32_t n_owned = 0, stage_cnt = 0, n_long = 0, first_k = 0, ownm = 0;
 
-        // ---- 1. load the chunk: one 16-byte vector per lane, zero beyond the text
+        // ---- 1. the chunk (loaded one slice ahead: its latency hides behind the previous slice's work)
         const long long q = cb + 16 * lane;
         const long long room = (long long)n_bytes - q;                     // valid bytes from this lane's first byte on
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (q >= 0 && room > 0) {
-            v = __ldg(reinterpret_cast<const uint4*>(text + q));
-            if (room < 16) {                                               // last bytes of the text: zero the rest
-                uint4 km = s_kmask[room];
-                v.x &= km.x; v.y &= km.y; v.z &= km.z; v.w &= km.w;
-            }
+#if CTK_PREFETCH
+        uint4 v = vn;
+        const uint32_t fd = fdn;
+        if (slice + stride < p.n_slices) { vn = load_vec(slice + stride); fdn = __ldg(p.first_doc + slice + stride); }
+#else
+        uint4 v = load_vec(slice);
+        const uint32_t fd = __ldg(p.first_doc + slice);
+#endif
+        const uint32_t d0 = fd & 0x7FFFFFFFu;
+        if (room > 0 && room < 16) {                                       // last bytes of the text: zero the rest
+            uint4 km = s_kmask[room];
+            v.x &= km.x; v.y &= km.y; v.z &= km.z; v.w &= km.w;
         }
         __syncwarp();                                                      // previous slice's readers are done
         *reinterpret_cast<uint4*>(S.chunk + 16 * lane) = v;
         // ---- document starts inside the chunk (position n_bytes = off[n_docs] counts as one)
         uint32_t ds16 = 0;
-        const bool docs_here = (long long)__ldg(p.off + d0) < cb + CHUNK;  // warp-uniform
+        const bool docs_here = (fd >> 31) != 0;                            // warp-uniform
         if (docs_here) {
             S.ds[lane] = 0;
             __syncwarp();
@@ -470,46 +497,47 @@ __global__ void __launch_bounds__(FW * 32, 4) k_encode_slices(const FusedParams 
     }
 }
 
-// one warp per 32 consecutive slices: each slice's run -> its final place
+// one warp per slice: the slice's run -> its final place (four loads in flight per lane)
 __global__ void __launch_bounds__(256) k_compact(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ slice_base,
                                                  const uint32_t* __restrict__ slice_info, const uint32_t* __restrict__ slice_desc,
                                                  const LongDesc* __restrict__ desc, const uint32_t* __restrict__ long_pool,
                                                  uint64_t n_slices, uint32_t* __restrict__ out, uint64_t out_cap,
                                                  uint32_t* __restrict__ err) {
-    const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-    const uint64_t s0 = warp * 32;
-    if (s0 >= n_slices) return;
-    const uint64_t my = s0 + lane;
-    uint32_t base = my < n_slices ? slice_base[my] : 0, info = my < n_slices ? slice_info[my] : 0;
-    uint32_t nxt = my < n_slices ? slice_base[my + 1] : 0;
-    int ns = (int)(n_slices - s0 < 32 ? n_slices - s0 : 32);
-    if (my < n_slices && (uint64_t)nxt > out_cap) atomicOr(err, ERRF_CAPACITY);
-    unsigned bad = __ballot_sync(full, my < n_slices && (uint64_t)nxt > out_cap);
-    if (bad) return;
-    for (int j = 0; j < ns; ++j) {
-        const uint32_t b = __shfl_sync(full, base, j), inf = __shfl_sync(full, info, j);
-        const uint32_t n_stage = inf & 0xFFFFu, n_long = inf >> 16;
-        const uint32_t* src = runs + (s0 + j) * STAGE;
-        uint32_t* dst = out + b;
-        if (n_long == 0) {
-            for (uint32_t i = lane; i < n_stage; i += 32) dst[i] = src[i];
-        } else {                                        // run ids interleaved with long pre-tokens' ids (rare)
-            const LongDesc* dd = desc + slice_desc[s0 + j];
-            for (uint32_t i = lane; i < n_stage; i += 32) {
-                uint32_t add = 0;
-                for (uint32_t q = 0; q < n_long; ++q) if ((dd[q].k_at & 0xFFFFu) <= i) add += dd[q].cnt;
-                dst[i + add] = src[i];
-            }
-            uint32_t before = 0;
-            for (uint32_t q = 0; q < n_long; ++q) {
-                const uint32_t* ls = long_pool + dd[q].pool;
-                uint32_t* ld = dst + (dd[q].k_at & 0xFFFFu) + before;
-                if (dd[q].pool != kNone)                       // kNone: a very long one, placed by k_xl_place
-                    for (uint32_t i = lane; i < dd[q].cnt; i += 32) ld[i] = ls[i];
-                before += dd[q].cnt;
-            }
+    const uint64_t s = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_slices) return;
+    const uint32_t b = __ldg(slice_base + s), nxt = __ldg(slice_base + s + 1), inf = __ldg(slice_info + s);
+    if ((uint64_t)nxt > out_cap) { if (lane == 0) atomicOr(err, ERRF_CAPACITY); return; }
+    const uint32_t n_stage = inf & 0xFFFFu, n_long = inf >> 16;
+    const uint32_t* src = runs + s * STAGE;
+    uint32_t* dst = out + b;
+    if (n_long == 0) {
+        for (uint32_t i0 = 0; i0 < n_stage; i0 += 128) {
+            const uint32_t i = i0 + lane;
+            uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            if (i < n_stage) v0 = __ldcs(src + i);
+            if (i + 32 < n_stage) v1 = __ldcs(src + i + 32);
+            if (i + 64 < n_stage) v2 = __ldcs(src + i + 64);
+            if (i + 96 < n_stage) v3 = __ldcs(src + i + 96);
+            if (i < n_stage) dst[i] = v0;
+            if (i + 32 < n_stage) dst[i + 32] = v1;
+            if (i + 64 < n_stage) dst[i + 64] = v2;
+            if (i + 96 < n_stage) dst[i + 96] = v3;
+        }
+    } else {                                            // run ids interleaved with long pre-tokens' ids (rare)
+        const LongDesc* dd = desc + slice_desc[s];
+        for (uint32_t i = lane; i < n_stage; i += 32) {
+            uint32_t add = 0;
+            for (uint32_t q = 0; q < n_long; ++q) if ((dd[q].k_at & 0xFFFFu) <= i) add += dd[q].cnt;
+            dst[i + add] = src[i];
+        }
+        uint32_t before = 0;
+        for (uint32_t q = 0; q < n_long; ++q) {
+            const uint32_t* ls = long_pool + dd[q].pool;
+            uint32_t* ld = dst + (dd[q].k_at & 0xFFFFu) + before;
+            if (dd[q].pool != kNone)                       // kNone: a very long one, placed by k_xl_place
+                for (uint32_t i = lane; i < dd[q].cnt; i += 32) ld[i] = ls[i];
+            before += dd[q].cnt;
         }
     }
 }
@@ -631,6 +659,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     CK(ws.get(43, (n_docs + 1) * 8, (void**)&p.ids_off_rel));
     p.xl_enabled = n_ids_host != nullptr && eng.model.merges_monotone && eng.model.max_token_span <= XL_MAX_WINDOW &&
                    eng.tables.n_added == 0 && !getenv("CTK_NO_XLONG");
+    p.no_rounds = getenv("CTK_NO_ROUNDS") != nullptr;
     p.first_doc = first_doc; p.cache_mask = cache_slots - 1; p.ovf_cap = ovf_cap;
     uint32_t max_id = eng.model.id_present.empty() ? 1u : (uint32_t)eng.model.id_present.size() - 1;
     p.id_bits = 1;
@@ -669,7 +698,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     for (int pass = 0;; ++pass) {
         CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, p.slice_cnt, slice_base, p.n_slices + 1, st));
         eng.launched(1); eng.mark("scan(slice counts)", st);
-        k_compact<<<(unsigned)((p.n_slices + 255) / 256), 256, 0, st>>>(p.runs, slice_base, p.slice_info, p.slice_desc, p.desc, p.long_pool,
+        k_compact<<<(unsigned)((p.n_slices + 7) / 8), 256, 0, st>>>(p.runs, slice_base, p.slice_info, p.slice_desc, p.desc, p.long_pool,
                                                                         p.n_slices, d_ids, ids_cap, p.err);
         eng.launched(1); eng.mark("k_compact", st);
         if (pass == 1) {

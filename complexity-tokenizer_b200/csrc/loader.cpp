@@ -156,6 +156,39 @@ void analyse_added(AddedTok& a, const std::unordered_map<uint32_t, uint8_t>& cp_
     a.may_match = true;
 }
 
+// Round-parallel merging (encode_long.cuh / encode_xlong.cuh) looks, for a pair (x, y), only as far as a token
+// around x or y can reach.  Needs: a monotone table, products that are the concatenation of their parts (the
+// rank quirk of bpe.rs:52-79 inactive), and one token per id.
+void token_reach(HostModel& m) {
+    m.round_parallel = false;
+    m.reach.clear();
+    if (!m.merges_monotone || m.pairs.empty()) return;
+    if (m.vocab.size() != (size_t)std::count(m.id_present.begin(), m.id_present.end(), (uint8_t)1)) return;   // two tokens, one id
+    for (const PairEntry& p : m.pairs) {
+        if (p.a >= m.id_to_token.size() || p.b >= m.id_to_token.size() || p.new_id >= m.id_to_token.size()) return;
+        if (m.id_to_token[p.a] + m.id_to_token[p.b] != m.id_to_token[p.new_id]) return;
+    }
+    std::vector<uint32_t> wl(m.id_to_token.size(), 0), wr(m.id_to_token.size(), 0);
+    std::vector<size_t> cut;                                    // byte offsets of the code points of one token
+    for (size_t id = 0; id < m.id_to_token.size(); ++id) {
+        if (!m.id_present[id]) continue;
+        const std::string& t = m.id_to_token[id];
+        cut.clear();
+        for (size_t i = 0; i < t.size();) { cut.push_back(i); next_cp(t, i); }
+        const size_t L = cut.size();
+        if (L > 0xFFFF) return;
+        for (size_t c = 1; c < L; ++c) {
+            auto ip = m.vocab.find(t.substr(0, cut[c]));
+            if (ip != m.vocab.end()) wr[ip->second] = std::max<uint32_t>(wr[ip->second], (uint32_t)(L - c));
+            auto is = m.vocab.find(t.substr(cut[c]));
+            if (is != m.vocab.end()) wl[is->second] = std::max<uint32_t>(wl[is->second], (uint32_t)c);
+        }
+    }
+    m.reach.resize(wl.size());
+    for (size_t i = 0; i < wl.size(); ++i) m.reach[i] = wl[i] | (wr[i] << 16);
+    m.round_parallel = true;
+}
+
 }  // namespace
 
 int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err) {
@@ -341,6 +374,7 @@ int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err) 
         if (special_map.count(tok)) m.dec_special[id] = 1;
     }
     m.dec_off[nid] = (uint32_t)m.dec_blob.size();
+    token_reach(m);
     return CTK_OK;
 }
 

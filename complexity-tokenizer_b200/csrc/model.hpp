@@ -40,6 +40,11 @@ struct HostModel {
     // every pair that contains a merged token ranks after every merge producing that token.
     bool merges_monotone = false;
     uint32_t max_token_span = 1;                           // longest merged token, in initial symbols
+    // Per-token reach (in initial symbols): how far a token that ENDS with this one extends to its left, and how far
+    // a token that STARTS with it extends to its right.  Packed left | right << 16, index = id.  Only filled when
+    // `round_parallel` holds: monotone table, every merge product is the concatenation of its parts, ids unique.
+    std::vector<uint32_t> reach;
+    bool round_parallel = false;
 };
 
 // Returns a CTK_* code; on failure `err` holds the message.

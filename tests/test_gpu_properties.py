@@ -301,3 +301,20 @@ def test_config4_full_size_properties(built_lib, tok_paths):
     sp = ids[int(ioff[2]):int(ioff[3])]
     assert sp.size <= (1 << 20) // 2
     assert set(tok.decode([int(x) for x in np.unique(sp)]).replace(' ', '')) == set()
+
+
+def test_warp_rounds_equal_sequential_merging_on_cjk(built_lib, tok_paths):
+    """Pre-tokens of 33..256 bytes (CJK runs in config 3) are merged in parallel rounds inside one warp
+    (encode_long.cuh: bpe_warp_rounds, per-symbol reach windows).  Same ids as the one-merge-per-iteration device
+    path (CTK_NO_ROUNDS), which test_corpus_bit_exact pins on the oracle for a prefix of the same corpus."""
+    import os
+    import synth
+    tok = _tok(tok_paths['config3'])
+    text, offs = synth.gen_corpus('mixed', 3003, 24 << 20, doc_median=4096)
+    a_ids, a_off = tok.encode_packed(text, offs)
+    os.environ['CTK_NO_ROUNDS'] = '1'
+    try:
+        b_ids, b_off = tok.encode_packed(text, offs)
+    finally:
+        del os.environ['CTK_NO_ROUNDS']
+    assert np.array_equal(a_off, b_off) and np.array_equal(a_ids, b_ids)

@@ -60,6 +60,58 @@ def par(toks, ranks, new, W):
                 out.append(toks[i]); i += 1
         toks = out
 
+def reaches(vocab_tokens):
+    """WL[t] = how far (in initial symbols) a token that ENDS with t can extend to the left of t,
+    WR[t] = how far a token that STARTS with t can extend to the right of t (csrc/loader.cpp: token_reach)."""
+    toks = set(vocab_tokens)
+    WL = {t: 0 for t in toks}; WR = {t: 0 for t in toks}
+    for t in toks:
+        for c in range(1, len(t)):
+            p_, s_ = t[:c], t[c:]
+            if p_ in toks: WR[p_] = max(WR[p_], len(t) - len(p_))
+            if s_ in toks: WL[s_] = max(WL[s_], len(t) - len(s_))
+    return WL, WR
+
+def par_reach(toks, ranks, new, WL, WR):
+    """Same rounds, but every pair only looks as far as tokens around its own two symbols can reach:
+    left of x = sym[j] up to WL[x] initial symbols, right of y = sym[j+1] up to WR[y]."""
+    toks = list(toks)
+    rounds = 0
+    while True:
+        n = len(toks)
+        pos = [0] * (n + 1)
+        for i, t in enumerate(toks): pos[i + 1] = pos[i] + len(t)
+        rk = [ranks.get((toks[i], toks[i + 1]), INF) for i in range(n - 1)]
+        blocked = [False] * (n - 1)
+        for j, r in enumerate(rk):
+            if r == INF: continue
+            x, y = toks[j], toks[j + 1]
+            k = j - 1
+            while k >= 0 and pos[j] - pos[k] <= WL[x]:
+                if rk[k] < r: blocked[j] = True; break
+                k -= 1
+            k = j + 1
+            while not blocked[j] and k <= n - 2 and pos[k + 2] - pos[j + 2] <= WR[y]:
+                if rk[k] < r: blocked[j] = True; break
+                k += 1
+        sel = set(); s0 = 0; bad = False
+        for i, r in enumerate(rk):
+            if i == 0 or rk[i - 1] != r:
+                s0 = i; bad = False
+            bad = bad or blocked[i]
+            if r != INF and not bad and (i - s0) % 2 == 0:
+                sel.add(i)
+        if not sel:
+            return toks, rounds
+        rounds += 1
+        out, i = [], 0
+        while i < n:
+            if i in sel:
+                out.append(new[(toks[i], toks[i + 1])]); i += 2
+            else:
+                out.append(toks[i]); i += 1
+        toks = out
+
 def make_table(rng, nsym, lmax, nmerge, monotone):
     base = [chr(97 + k) for k in range(nsym)]
     vocab = set(base)
@@ -96,10 +148,13 @@ def make_table(rng, nsym, lmax, nmerge, monotone):
     ranks = {p: r for r, p in enumerate(pairs)}
     newt = {p: p[0] + p[1] for p in pairs}
     W = max(len(t) for t in vocab)
+    make_table.last_vocab = set(base) | set(newt.values()) | {x for p in pairs for x in p}
     return base, ranks, newt, W
 
-def trial(rng, nsym, lmax, nmerge, textlen, monotone, W_override=None):
+def trial(rng, nsym, lmax, nmerge, textlen, monotone, W_override=None, reach=False):
     base, ranks, newt, W = make_table(rng, nsym, lmax, nmerge, monotone)
+    if reach:
+        WL, WR = reaches(make_table.last_vocab)
     bad = 0; rmax = 0
     for _ in range(20):
         if rng.random() < 0.3:                              # runs of one symbol: the parity rule
@@ -109,7 +164,7 @@ def trial(rng, nsym, lmax, nmerge, textlen, monotone, W_override=None):
         else:
             text = [rng.choice(base) for _ in range(rng.randint(1, textlen))]
         a = seq(text, ranks, newt)
-        b, rounds = par(text, ranks, newt, W_override or W)
+        b, rounds = par_reach(text, ranks, newt, WL, WR) if reach else par(text, ranks, newt, W_override or W)
         rmax = max(rmax, rounds)
         if a != b:
             bad += 1
@@ -117,11 +172,12 @@ def trial(rng, nsym, lmax, nmerge, textlen, monotone, W_override=None):
 
 if __name__ == '__main__':
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
-    for label, mono, wo in (('monotone table, window = longest token', True, None),
-                            ('NON-monotone table (expected > 0)', False, None),
-                            ('monotone table, window = 1 (expected > 0)', True, 1)):
+    for label, mono, wo, reach in (('monotone table, window = longest token', True, None, False),
+                                   ('monotone table, per-symbol reach windows', True, None, True),
+                                   ('NON-monotone table (expected > 0)', False, None, False),
+                                   ('monotone table, window = 1 (expected > 0)', True, 1, False)):
         rng = random.Random(7); tot = bad = 0; rmax = 0
         for it in range(N):
             nsym = rng.choice([1, 2, 2, 3, 4]); lmax = rng.choice([2, 3, 4, 5, 6]); nm = rng.choice([3, 6, 12, 30, 60])
-            b, r = trial(rng, nsym, lmax, nm, 120, mono, wo); bad += b; tot += 20; rmax = max(rmax, r)
+            b, r = trial(rng, nsym, lmax, nm, 120, mono, wo, reach); bad += b; tot += 20; rmax = max(rmax, r)
         print('%-46s mismatches %d / %d   (most rounds %d)' % (label, bad, tot, rmax))
