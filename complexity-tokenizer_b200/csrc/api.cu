@@ -1,5 +1,6 @@
 // C ABI (include/ctk.h): engine life cycle, table upload, host-buffer entry points.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <new>
@@ -40,6 +41,7 @@ int Engine::finish(const uint32_t* d_err, const uint64_t* d_off_out, size_t n, u
     if (e != cudaSuccess) return cuda_fail(e, "finish");
     collect_marks();
     uint32_t f = h_flags[0];
+    if (f & ERRF_NFC_SUSPECT) return CTK_RETRY_NFC;         // nothing else about this attempt counts
     if (f & ERRF_OFFSETS) return fail(CTK_ERR_ARG, "offsets must start at 0, be non-decreasing and end at the buffer length");
     if (f & ERRF_UTF8) return fail(CTK_ERR_INVALID_DATA, "input text is not valid UTF-8");
     if (f & ERRF_CAPACITY) return fail(CTK_ERR_ARG, "output capacity too small");
@@ -120,8 +122,19 @@ int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, siz
                          uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st) {
     if (n_bytes && (reinterpret_cast<uintptr_t>(d_text) & 15)) return eng.fail(CTK_ERR_ARG, "device text buffer must be 16-byte aligned");
     const uint8_t* t2; const uint64_t* o2; uint64_t b2;
-    int rc = nfc_stage(eng, d_text, d_off, n, n_bytes, &t2, &o2, &b2, st);
+    int rc;
+    if (eng.model.nfc && eng.nfc_optimistic && n_ids_host && !eng.use_general && !getenv("CTK_NO_NFC_OPTIMISM")) {
+        rc = prefix_space_stage(eng, d_text, d_off, n, n_bytes, &t2, &o2, &b2, st);
+        if (rc != CTK_OK) return rc;
+        const bool keep = eng.keep_cache_once;
+        rc = encode_fused(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st, true);
+        if (rc != CTK_RETRY_NFC) return rc;
+        eng.nfc_optimistic = false;                          // this text needs the normaliser: scan first from now on
+        eng.keep_cache_once = keep;
+    }
+    rc = nfc_stage(eng, d_text, d_off, n, n_bytes, &t2, &o2, &b2, st);
     if (rc != CTK_OK) return rc;
+    if (n_bytes) eng.nfc_optimistic = !eng.last_nfc_needed;  // a clean call switches the optimistic path back on
     rc = prefix_space_stage(eng, t2, o2, n, b2, &t2, &o2, &b2, st);
     if (rc != CTK_OK) return rc;
     if (eng.use_general) return encode_general(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st);

@@ -70,6 +70,7 @@ struct FusedParams {
     uint32_t* slice_desc;                                // first LongDesc of the slice (if n_long > 0)
     uint16_t* slice_first;                               // chunk-relative position of the slice's first owned start, 0xFFFF if none
     int xl_enabled;                                      // monotone table, no in-word added tokens, synchronous call
+    int check_nfc;                                       // optimistic call: report NFC-suspect code points (engine.hpp)
     int no_rounds;                                       // debug (CTK_NO_ROUNDS): sequential merging in k_encode_long
     unsigned long long* xl_cursor;                       // list index << XL_IDX_SHIFT | symbols handed out
     XlEntry* xl_list;
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
         // ---- 2. classes and boundaries
         {
             Masks16 m = classify16(S.chunk, 16 * lane, v.x, v.y, v.z, v.w, p.t.trie_index, p.t.trie_blocks);
+            if (m.SUSP && p.check_nfc) atomicOr(p.err, ERRF_NFC_SUSPECT);
             uint32_t pa = m.L | (m.N << 16), pb = m.W | (m.SP << 16), pc = m.AP | (m.CONT << 16);
             uint32_t ua = __shfl_up_sync(full, pa, 1), ub = __shfl_up_sync(full, pb, 1), uc = __shfl_up_sync(full, pc, 1),
                      ud = __shfl_up_sync(full, ds16, 1);
@@ -618,7 +620,7 @@ static int xlong_rounds(Engine& eng, const FusedParams& p, uint64_t cursor, uint
 }
 
 int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
-                 uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st) {
+                 uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st, bool check_nfc) {
     if (n_bytes >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_ARG, "one device call handles less than 4 GiB of text");
     if (n_bytes == 0) {
         CK(cudaMemsetAsync(d_ids_off, 0, (n_docs + 1) * 8, st));
@@ -660,6 +662,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.xl_enabled = n_ids_host != nullptr && eng.model.merges_monotone && eng.model.max_token_span <= XL_MAX_WINDOW &&
                    eng.tables.n_added == 0 && !getenv("CTK_NO_XLONG");
     p.no_rounds = getenv("CTK_NO_ROUNDS") != nullptr;
+    p.check_nfc = check_nfc ? 1 : 0;
     p.first_doc = first_doc; p.cache_mask = cache_slots - 1; p.ovf_cap = ovf_cap;
     uint32_t max_id = eng.model.id_present.empty() ? 1u : (uint32_t)eng.model.id_present.size() - 1;
     p.id_bits = 1;

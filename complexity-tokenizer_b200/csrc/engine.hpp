@@ -16,7 +16,8 @@
 namespace ctk {
 
 // device-side error flags (OR-ed into a word the host reads back)
-enum : uint32_t { ERRF_OFFSETS = 1, ERRF_CAPACITY = 2, ERRF_UTF8 = 4, ERRF_POOL = 8, ERRF_NFC_LONG = 16 };
+enum : uint32_t { ERRF_OFFSETS = 1, ERRF_CAPACITY = 2, ERRF_UTF8 = 4, ERRF_POOL = 8, ERRF_NFC_LONG = 16, ERRF_NFC_SUSPECT = 32 };
+constexpr int CTK_RETRY_NFC = 100;     // internal: the optimistic encode met a code point that needs NFC; run the normaliser and encode again
 
 void set_last_error(const std::string& s);
 extern std::atomic<uint64_t> g_kernel_launches;
@@ -81,6 +82,11 @@ struct Engine {
     cudaError_t publish(std::initializer_list<Pub> items, cudaStream_t st);
     uint8_t* last_decode_out = nullptr;
     cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;   // host-buffer pipeline: copy in / compute / copy out
+    // Almost all text is already NFC.  With `nfc_optimistic` the encode kernels run on the raw text and only REPORT an
+    // NFC-suspect code point (same trie bit the normaliser's own scan uses); the call then runs again through the
+    // normaliser, and later calls scan first, until a call comes back clean.  Saves one pass over the text.
+    bool nfc_optimistic = true;
+    bool last_nfc_needed = false;
     bool keep_cache_once = false;       // next encode call continues the current batch (chunked host-buffer path)   // decode_device(d_out = NULL) leaves its output here
 
     // optional per-kernel timing (CUDA events on the launching stream), for bench.py's roofline line
@@ -129,7 +135,7 @@ int prefix_space_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off
 int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n, uint64_t n_bytes, uint32_t* d_ids,
                   uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
-                 uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
+                 uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st, bool check_nfc = false);
 int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                    uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int clean_parallel(Engine& eng, const uint8_t* raw, const uint64_t* raw_off, size_t n_docs, uint64_t n, uint8_t* d_out,

@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256) k_nfc_doc(NfcTables t, const uint8_t* __r
 int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
               const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st) {
     *o_text = d_text; *o_off = d_off; *o_bytes = n_bytes;
+    eng.last_nfc_needed = false;
     if (!eng.model.nfc || n_bytes == 0 || n_docs == 0) return CTK_OK;
     Workspace& ws = eng.ws;
     uint8_t* flag; uint32_t* any;
@@ -249,6 +250,7 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
     CK(eng.publish({{any, 1, 8}}, st));
     CK(cudaStreamSynchronize(st));
     if (!eng.h_flags[8]) return CTK_OK;
+    eng.last_nfc_needed = true;
     uint64_t *new_len, *new_off;
     CK(ws.get(28, (n_docs + 2) * 8, (void**)&new_len));
     CK(ws.get(29, (n_docs + 2) * 8, (void**)&new_off));

@@ -14,6 +14,7 @@ struct Masks16 {            // one bit per byte of a 16-byte group
     uint32_t L, N, W;       // class of the code point containing the byte (Other = none of them)
     uint32_t SP, AP;        // byte == 0x20, byte == '\''
     uint32_t CONT;          // UTF-8 continuation byte
+    uint32_t SUSP;          // != 0: the group touches an NFC-suspect code point (NFC_QC != Yes or ccc != 0; trie bit 2)
 };
 
 CTK_HD uint32_t movemask4(uint32_t hi) {             // bit 7 of each byte -> 4 bits
@@ -38,6 +39,7 @@ CTK_HD Masks16 classify16(const uint8_t* chunk, int pos, uint32_t w0, uint32_t w
     Masks16 m;
     uint32_t l, n, w, sp, ap;
     m.CONT = 0;
+    m.SUSP = 0;
     uint32_t words[4] = {w0, w1, w2, w3};
     // bit 7 of byte k times 0x00204081 lands on bit 28 + k (no carries: all partial products are distinct bits);
     // four words are funnelled into the top 16 bits of an accumulator, 3 instructions per word and mask
@@ -77,7 +79,9 @@ CTK_HD Masks16 classify16(const uint8_t* chunk, int pos, uint32_t w0, uint32_t w
         if (c < 0xE0u) cp = ((c & 0x1Fu) << 6) | (chunk[lead + 1] & 63u);
         else if (c < 0xF0u) cp = ((c & 0x0Fu) << 12) | ((chunk[lead + 1] & 63u) << 6) | (chunk[lead + 2] & 63u);
         else cp = ((c & 7u) << 18) | ((chunk[lead + 1] & 63u) << 12) | ((chunk[lead + 2] & 63u) << 6) | (chunk[lead + 3] & 63u);
-        uint32_t cls = trie_nibble(trie_index, trie_blocks, cp) & 3u;
+        const uint32_t nib = trie_nibble(trie_index, trie_blocks, cp);
+        m.SUSP |= nib & 4u;
+        uint32_t cls = nib & 3u;
         if (cls == CLS_L) m.L |= 1u << b;
         else if (cls == CLS_N) m.N |= 1u << b;
         else if (cls == CLS_W) m.W |= 1u << b;

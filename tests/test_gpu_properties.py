@@ -318,3 +318,16 @@ def test_warp_rounds_equal_sequential_merging_on_cjk(built_lib, tok_paths):
     finally:
         del os.environ['CTK_NO_ROUNDS']
     assert np.array_equal(a_off, b_off) and np.array_equal(a_ids, b_ids)
+
+
+def test_optimistic_nfc_switches_back_and_forth(built_lib, tok_paths):
+    """The encode kernels run on the raw text and only report NFC-suspect code points; such a call is repeated through
+    the normaliser and later calls scan first until one comes back clean (engine.hpp: nfc_optimistic).  Whatever the
+    order of clean and dirty batches, the ids are the oracle's (normalizers.rs:45-47 then the rest of the pipeline)."""
+    tok, orc = _tok(tok_paths['config1']), _oracle(tok_paths['config1'])
+    clean = ['plain ascii text, nothing to normalise', 'déjà vu: precomposed é stays', '中文 and emoji \U0001F600']
+    dirty = ['café with a combining acute', 'Å ring, Å angstrom sign, 각 jamo', 'x' * 500 + 'é' + 'y' * 500]
+    for batch in (clean, dirty, dirty, clean, clean, dirty + clean, clean):
+        assert tok.encode_batch(batch) == orc.encode_batch(batch)
+        for t in batch[:2]:
+            assert tok.encode(t) == orc.twin.encode(t)
