@@ -35,22 +35,47 @@ __device__ __forceinline__ int ws_len_at(const uint8_t* p, uint64_t i, uint64_t 
     return 0;
 }
 
+// 16 bytes per thread (buffers are 16-byte aligned and padded); whitespace by SWAR for ASCII words, per byte otherwise
 __global__ void __launch_bounds__(256) k_clean_flags(const uint8_t* __restrict__ R, uint64_t n, uint8_t* __restrict__ f,
                                                      uint8_t* __restrict__ emit) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint8_t c = R[i];
-    bool ws = false;
-    if (c < 0x80) ws = c == 0x20 || (c >= 9 && c <= 13);
-    else {
-        for (int back = 0; back <= 2 && (uint64_t)back <= i; ++back) {          // the lead is at most 2 bytes back
-            int L = ws_len_at(R, i - back, n);
-            if (L > back) { ws = true; break; }
-            if ((R[i - back] & 0xC0) != 0x80) break;                            // reached a lead that is not whitespace
+    const uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
+    if (base >= n) return;
+    const uint4 v = *reinterpret_cast<const uint4*>(R + base);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t fo[4], eo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t x = w[q];
+        if (!(x & 0x80808080u) && base + 4 * q + 4 <= n) {
+            const uint32_t H = 0x80808080u;
+            const uint32_t sp = ~((x ^ 0x20202020u) + 0x7F7F7F7Fu) & H;                 // byte == ' '
+            const uint32_t ct = (x + 0x77777777u) & ~(x + 0x72727272u) & H;             // 9 <= byte <= 13
+            const uint32_t ws = sp | ct;
+            fo[q] = (ws >> 7) * F_WS | (sp >> 7) * F_SP;
+            eo[q] = (~ws & H) >> 7;
+        } else {
+            uint32_t fw = 0, ew = 0;
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t i = base + 4 * q + k;
+                if (i >= n) break;
+                const uint8_t c = (uint8_t)(x >> (8 * k));
+                bool ws = false;
+                if (c < 0x80) ws = c == 0x20 || (c >= 9 && c <= 13);
+                else {
+                    for (int back = 0; back <= 2 && (uint64_t)back <= i; ++back) {      // the lead is at most 2 bytes back
+                        int L = ws_len_at(R, i - back, n);
+                        if (L > back) { ws = true; break; }
+                        if ((R[i - back] & 0xC0) != 0x80) break;                        // reached a lead that is not whitespace
+                    }
+                }
+                fw |= (uint32_t)((ws ? F_WS : 0) | (c == 0x20 ? F_SP : 0)) << (8 * k);
+                ew |= (uint32_t)(ws ? 0 : 1) << (8 * k);
+            }
+            fo[q] = fw; eo[q] = ew;
         }
     }
-    f[i] = (ws ? F_WS : 0) | (c == 0x20 ? F_SP : 0);
-    emit[i] = ws ? 0 : 1;
+    *reinterpret_cast<uint4*>(f + base) = make_uint4(fo[0], fo[1], fo[2], fo[3]);
+    *reinterpret_cast<uint4*>(emit + base) = make_uint4(eo[0], eo[1], eo[2], eo[3]);
 }
 
 __global__ void k_clean_docstarts(const uint64_t* __restrict__ raw_off, uint64_t n_docs, uint64_t n, uint8_t* __restrict__ f) {
@@ -60,14 +85,33 @@ __global__ void k_clean_docstarts(const uint64_t* __restrict__ raw_off, uint64_t
     if (p < n) f[p] |= F_DS;                        // several empty documents may share a start: same value written
 }
 
-// one thread per byte; acts where a run of U+0020 starts
-__global__ void __launch_bounds__(256) k_clean_runs(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
-                                                    uint8_t* __restrict__ rr) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// 16 positions per thread: bit k of the result = position base + k carries `bit` and starts a run of it
+// (first of the document, or the byte before does not carry it)
+__device__ __forceinline__ uint32_t run_starts16(const uint8_t* __restrict__ f, uint64_t base, uint64_t n, uint8_t bit) {
+    const uint4 fv = *reinterpret_cast<const uint4*>(f + base);
+    const uint32_t w[4] = {fv.x, fv.y, fv.z, fv.w};
+    const uint32_t B = 0x01010101u * bit, D = 0x01010101u * F_DS;
+    const int ds_shift = bit == F_WS ? 2 : 1;                                   // moves the F_DS bit onto `bit`
+    if (!((w[0] | w[1] | w[2] | w[3]) & B)) return 0;
+    uint32_t prev = base ? (uint32_t)f[base - 1] : 0u;                          // flags of the byte before the group
+    uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t x = w[q];
+        const uint32_t before = (x << 8) | prev;                                // flags of each byte's predecessor
+        prev = x >> 24;
+        const uint32_t t = x & B & (~before | ((x & D) >> ds_shift));           // has the bit, and (no predecessor bit or doc start)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if ((t >> (8 * k)) & bit) m |= 1u << (4 * q + k);
+    }
+    if (n - base < 16) m &= (1u << (n - base)) - 1u;
+    return m;
+}
+
+// acts where a run of U+0020 starts
+__device__ __forceinline__ void clean_run_at(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                             uint8_t* __restrict__ rr, uint64_t i) {
     uint8_t fi = f[i];
-    if (!(fi & F_SP)) return;
-    if (!(fi & F_DS) && i > 0 && (f[i - 1] & F_SP)) return;                    // not the first space of its run
     uint64_t b = i + 1;
     while (b < n && (f[b] & (F_SP | F_DS)) == F_SP) ++b;
     uint64_t m = b - i;
@@ -83,11 +127,17 @@ __global__ void __launch_bounds__(256) k_clean_runs(const uint8_t* __restrict__ 
     rr[b - 1] = v;
 }
 
+__global__ void __launch_bounds__(256) k_clean_runs(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                    uint8_t* __restrict__ rr) {
+    const uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
+    if (base >= n) return;
+    uint32_t m = run_starts16(f, base, n, F_SP);
+    while (m) { const int k = __ffs(m) - 1; m &= m - 1; clean_run_at(R, n, f, rr, base + k); }
+}
+
 // rule 15 along hyphen chains; one thread per byte, acts at chain heads
-__global__ void __launch_bounds__(256) k_clean_hyphens(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
-                                                       const uint8_t* __restrict__ rr, uint8_t* __restrict__ fire) {
-    uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (h >= n || R[h] != '-') return;
+__device__ __forceinline__ void clean_hyphen_at(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                const uint8_t* __restrict__ rr, uint8_t* __restrict__ fire, uint64_t h) {
     auto candidate = [&](uint64_t q) -> bool {      // '-' with a space on both sides inside one document
         return q > 0 && q + 1 < n && R[q] == '-' && !(f[q] & F_DS) && (f[q - 1] & F_SP) && !(f[q + 1] & F_DS) && (f[q + 1] & F_SP);
     };
@@ -113,15 +163,29 @@ __global__ void __launch_bounds__(256) k_clean_hyphens(const uint8_t* __restrict
     }
 }
 
-// one thread per byte; acts where a whitespace region starts
-__global__ void __launch_bounds__(256) k_clean_regions(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
-                                                       const uint8_t* __restrict__ rr, const uint8_t* __restrict__ fire,
-                                                       uint8_t* __restrict__ emit) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void __launch_bounds__(256) k_clean_hyphens(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                       const uint8_t* __restrict__ rr, uint8_t* __restrict__ fire) {
+    const uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
+    if (base >= n) return;
+    const uint4 v = *reinterpret_cast<const uint4*>(R + base);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t any = 0, z[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                                              // bytes equal to '-' (exact zero-byte test)
+        const uint32_t x = w[q] ^ 0x2D2D2D2Du;
+        z[q] = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+        any |= z[q];
+    }
+    if (!any) return;
+    for (int k = 0; k < 16; ++k)
+        if ((z[k >> 2] >> (8 * (k & 3))) & 0x80u) { if (base + k < n) clean_hyphen_at(R, n, f, rr, fire, base + k); }
+}
+
+// acts where a whitespace region starts
+__device__ __forceinline__ void clean_region_at(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                const uint8_t* __restrict__ rr, const uint8_t* __restrict__ fire,
+                                                uint8_t* __restrict__ emit, uint64_t i) {
     uint8_t fi = f[i];
-    if (!(fi & F_WS)) return;
-    if (!(fi & F_DS) && i > 0 && (f[i - 1] & F_WS)) return;                    // not the first byte of its region
     bool alive = false;
     int cur = -1;                                                               // rem of the run we are inside, -1 outside
     uint64_t e = i;
@@ -145,16 +209,36 @@ __global__ void __launch_bounds__(256) k_clean_regions(const uint8_t* __restrict
     if (alive && interior) emit[i] = 1;
 }
 
+__global__ void __launch_bounds__(256) k_clean_regions(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                       const uint8_t* __restrict__ rr, const uint8_t* __restrict__ fire,
+                                                       uint8_t* __restrict__ emit) {
+    const uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
+    if (base >= n) return;
+    uint32_t m = run_starts16(f, base, n, F_WS);
+    while (m) { const int k = __ffs(m) - 1; m &= m - 1; clean_region_at(R, n, f, rr, fire, emit, base + k); }
+}
+
 struct U8ToU32 { __host__ __device__ uint32_t operator()(uint8_t v) const { return v; } };
 
+// 16 bytes per thread: one position load, then the survivors are consecutive
 __global__ void __launch_bounds__(256) k_clean_scatter(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
                                                        const uint8_t* __restrict__ emit, const uint32_t* __restrict__ pos,
                                                        uint8_t* __restrict__ out, uint64_t out_cap, uint32_t* __restrict__ err) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n || !emit[i]) return;
-    uint32_t p = pos[i];
-    if (p >= out_cap) { atomicOr(err, ERRF_CAPACITY); return; }
-    out[p] = (f[i] & F_WS) ? (uint8_t)' ' : R[i];
+    const uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
+    if (base >= n) return;
+    const uint4 ev = *reinterpret_cast<const uint4*>(emit + base);
+    if (!(ev.x | ev.y | ev.z | ev.w)) return;
+    const uint4 rv = *reinterpret_cast<const uint4*>(R + base), fv = *reinterpret_cast<const uint4*>(f + base);
+    const uint32_t e[4] = {ev.x, ev.y, ev.z, ev.w}, r[4] = {rv.x, rv.y, rv.z, rv.w}, ff[4] = {fv.x, fv.y, fv.z, fv.w};
+    uint64_t p = pos[base];
+    const int lim = n - base < 16 ? (int)(n - base) : 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (k < lim && ((e[k >> 2] >> (8 * (k & 3))) & 0xFFu)) {
+            if (p >= out_cap) { atomicOr(err, ERRF_CAPACITY); return; }
+            out[p++] = ((ff[k >> 2] >> (8 * (k & 3))) & F_WS) ? (uint8_t)' ' : (uint8_t)(r[k >> 2] >> (8 * (k & 3)));
+        }
+    }
 }
 
 __global__ void k_clean_doc_off(const uint64_t* __restrict__ raw_off, uint64_t n_docs, const uint32_t* __restrict__ pos,
@@ -177,16 +261,21 @@ int clean_parallel(Engine& eng, const uint8_t* raw, const uint64_t* raw_off, siz
     CK(ws.get(16, n + 64, (void**)&fire));
     CK(ws.get(17, n + 64, (void**)&emit));
     CK(ws.get(26, (n + 2) * 4, (void**)&pos));
-    unsigned gb = (unsigned)((n + 255) / 256), gd = (unsigned)((n_docs + 1 + 255) / 256);
+    unsigned gb = (unsigned)((n + 255) / 256), gd = (unsigned)((n_docs + 1 + 255) / 256), g16 = (unsigned)(((n + 15) / 16 + 255) / 256);
     eng.mark(nullptr, st);
     CK(cudaMemsetAsync(fire, 0, n + 64, st));
     CK(cudaMemsetAsync(emit + n, 0, 64, st));
     if (n) {
-        k_clean_flags<<<gb, 256, 0, st>>>(raw, n, f, emit);
+        eng.mark("clean: memsets", st);
+        k_clean_flags<<<g16, 256, 0, st>>>(raw, n, f, emit);
         k_clean_docstarts<<<gd, 256, 0, st>>>(raw_off, n_docs, n, f);
-        k_clean_runs<<<gb, 256, 0, st>>>(raw, n, f, rr);
-        k_clean_hyphens<<<gb, 256, 0, st>>>(raw, n, f, rr, fire);
-        k_clean_regions<<<gb, 256, 0, st>>>(raw, n, f, rr, fire, emit);
+        eng.mark("clean: k_clean_flags", st);
+        k_clean_runs<<<g16, 256, 0, st>>>(raw, n, f, rr);
+        eng.mark("clean: k_clean_runs", st);
+        k_clean_hyphens<<<g16, 256, 0, st>>>(raw, n, f, rr, fire);
+        eng.mark("clean: k_clean_hyphens", st);
+        k_clean_regions<<<g16, 256, 0, st>>>(raw, n, f, rr, fire, emit);
+        eng.mark("clean: k_clean_regions", st);
         eng.launched(5);
     }
     cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> it(emit, U8ToU32());
@@ -194,9 +283,10 @@ int clean_parallel(Engine& eng, const uint8_t* raw, const uint64_t* raw_off, siz
     CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, pos, n + 1, st));
     CK(ws.get(5, cub_bytes + 16, &cub_tmp));
     CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, it, pos, n + 1, st));
-    if (n) k_clean_scatter<<<gb, 256, 0, st>>>(raw, n, f, emit, pos, d_out, out_cap, err);
+    eng.mark("clean: scan", st);
+    if (n) k_clean_scatter<<<g16, 256, 0, st>>>(raw, n, f, emit, pos, d_out, out_cap, err);
     k_clean_doc_off<<<gd, 256, 0, st>>>(raw_off, n_docs, pos, d_out_off);
-    eng.launched(3); eng.mark("clean_up (parallel)", st);
+    eng.launched(3); eng.mark("clean: k_clean_scatter", st);
     return CTK_OK;
 }
 
