@@ -16,6 +16,7 @@ Keys of the JSON line (see the task contract):
                pinned host ids out, H2D and D2H inside the timed region
   roofline     dominant kernel: algorithmic bytes (B + 4T + 16(D+1)) / its CUDA-event time
   cpu_baseline the oracle's C core ("port" of the reference algorithm) on all host cores, bounded sample
+  decode_batch extra: device-resident decode of the ids of the last step (round trip must be byte-exact)
 The pre-token cache is cleared inside every step (ctk default), so no step reuses work of another.
 """
 import argparse
@@ -283,6 +284,35 @@ def main():
            'h2d_bytes_per_step': int(B + 8 * (D + 1)), 'd2h_bytes_per_step': int(4 * T + 8 * (D + 1)),
            'api': 'ctk_encode_batch (C ABI, pinned host buffers in and out)'}
 
+    # ---- decode_batch on the ids just produced (device-resident; BASELINE config 5's round-trip shape):
+    #      raw decode must give the input back byte for byte; the default decode (clean-up on) is timed next to it
+    d_back = torch.empty(B + 1024, dtype=torch.uint8, device=dev)
+    d_back_off = torch.empty(D + 1, dtype=torch.int64, device=dev)
+
+    def dec(clean):
+        return tok.decode_device(d_ids.data_ptr(), d_ids_off.data_ptr(), D, T, d_back.data_ptr(), B + 1024, d_back_off.data_ptr(), False, clean,
+                                 stream=stream)
+
+    dec_ms = {}
+    for clean in (False, True):
+        dec(clean)
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(args.steps):
+            nb_out = dec(clean)
+        d1.record()
+        barrier()
+        dec_ms[clean] = d0.elapsed_time(d1) / args.steps
+        if not clean:
+            roundtrip = bool(nb_out == B and torch.equal(d_back[:B], d_text[:B]) and torch.equal(d_back_off, d_off))
+    dt_ = torch.tensor([dec_ms[False], dec_ms[True], 0.0 if roundtrip else 1.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+    decode = {'value': B_all / (float(dt_[0]) * 1e-3) / 1e6, 'unit': 'MB/s (decoded bytes, device-resident, clean_up_tokenization_spaces=False)',
+              'ms_per_step': float(dt_[0]), 'roundtrip_exact': float(dt_[2]) == 0.0,
+              'default_clean_up_ms_per_step': float(dt_[1]), 'default_clean_up_value': B_all / (float(dt_[1]) * 1e-3) / 1e6}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -303,6 +333,16 @@ def main():
                     'algorithmic_bytes_per_launch': int(alg_bytes),
                     'input_bandwidth_frac_whole_step': (B / (ms_per_step * 1e-3) / 1e9) / peak,
                     'all_kernels_ms_per_step': {k: v[0] / args.steps for k, v in sorted(prof.items())}}
+    if roofline:                      # DRAM bytes of the dominant kernel from the committed ncu --set full capture of this workload
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+                tr = json.load(f)
+            ent = tr.get(roofline['kernel'])
+            if ent and int(ent['input_bytes']) == int(B):
+                roofline['traffic'] = int(ent['dram_bytes_per_launch'])
+                roofline['traffic_source'] = ent.get('source')
+        except Exception:
+            pass
     cpu = None
     if not args.no_cpu:
         cpu, _ = cpu_baseline(tok_path, h_np, offs)
@@ -313,7 +353,8 @@ def main():
         'config': {'workload': WORKLOAD, 'bytes_per_gpu': int(B), 'docs_per_gpu': int(D), 'tokens_per_gpu': int(T),
                    'lexicon_words': 50000, 'vocab': 50257, 'l2': 'inputs (1 GiB) larger than L2 (126 MB); no flush needed',
                    'pretoken_cache': 'cleared inside every step', 'parallelism': 'documents sharded over %d GPU(s), no collective on the data path' % world},
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
+        'decode_batch': decode}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
