@@ -72,6 +72,9 @@ struct FusedParams {
     int xl_enabled;                                      // monotone table, no in-word added tokens, synchronous call
     int check_nfc;                                       // optimistic call: report NFC-suspect code points (engine.hpp)
     int no_rounds;                                       // debug (CTK_NO_ROUNDS): sequential merging in k_encode_long
+    int mid_enabled;                                     // 33..128-byte pre-tokens go to k_encode_mid (one lane each)
+    uint32_t* work_list;                                 // 3 lists of LongDesc indices, desc_cap entries each (k_long_prep)
+    uint32_t* work_count;                                // their lengths
     unsigned long long* xl_cursor;                       // list index << XL_IDX_SHIFT | symbols handed out
     XlEntry* xl_list;
     uint64_t* ids_off_rel;                               // slice-relative document offsets (k_doc_fixup makes them absolute)
@@ -634,6 +637,12 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         if (per_sm < 1) return eng.fail(CTK_ERR_CUDA, "encode kernel does not fit on an SM");
         eng.fused_grid = per_sm * sms;
         eng.long_grid = sms * 4;
+        CK(cudaFuncSetAttribute(k_encode_mid<MID_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * MID_B * 32 + 256) * 4));
+        int a = 0, b = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_encode_mid<MID_A>, 32, (2 * MID_A * 32 + 256) * 4));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_encode_mid<MID_B>, 32, (2 * MID_B * 32 + 256) * 4));
+        eng.mid_grid_a = sms * (a > 0 ? a : 1);
+        eng.mid_grid_b = sms * (b > 0 ? b : 1);
     }
     Workspace& ws = eng.ws;
     FusedParams p{};
@@ -657,11 +666,13 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.desc_cap = (uint32_t)(n_bytes / 33 + 16);
     CK(ws.get(9, (uint64_t)p.desc_cap * sizeof(LongDesc), (void**)&p.desc));
     CK(ws.get(41, (uint64_t)p.desc_cap * sizeof(XlEntry), (void**)&p.xl_list));
+    CK(ws.get(44, 3ull * p.desc_cap * 4, (void**)&p.work_list));
     CK(ws.get(42, (p.n_slices + 2) * 2, (void**)&p.slice_first));
     CK(ws.get(43, (n_docs + 1) * 8, (void**)&p.ids_off_rel));
     p.xl_enabled = n_ids_host != nullptr && eng.model.merges_monotone && eng.model.max_token_span <= XL_MAX_WINDOW &&
                    eng.tables.n_added == 0 && !getenv("CTK_NO_XLONG");
     p.no_rounds = getenv("CTK_NO_ROUNDS") != nullptr;
+    p.mid_enabled = eng.tables.n_added == 0 && (eng.model.pairs.empty() || eng.model.pairs.back().rank < (1u << 24)) && !getenv("CTK_NO_MID");   // rank << 8 | slot keys
     p.check_nfc = check_nfc ? 1 : 0;
     p.first_doc = first_doc; p.cache_mask = cache_slots - 1; p.ovf_cap = ovf_cap;
     uint32_t max_id = eng.model.id_present.empty() ? 1u : (uint32_t)eng.model.id_present.size() - 1;
@@ -669,7 +680,9 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     while ((1ull << p.id_bits) <= max_id) ++p.id_bits;
     p.n_inline = 96 / p.id_bits;
     if (p.n_inline > MAXINLINE) p.n_inline = MAXINLINE;
-    // ctrl words: [0] err flags, [2] desc cursor, [3] ovf cursor, [4..5] long cursor, [6..7] xlong cursor, [8] holes, [9] round size
+    // ctrl words: [0] err flags, [2] desc cursor, [3] ovf cursor, [4..5] long cursor, [6..7] xlong cursor, [8] holes, [9] round size,
+    //             [10..12] work-list lengths
+    p.work_count = ctrl + 10;
     p.xl_cursor = reinterpret_cast<unsigned long long*>(ctrl + 6);
     p.err = ctrl; p.desc_cursor = ctrl + 2; p.ovf_cursor = ctrl + 3; p.long_cursor = reinterpret_cast<unsigned long long*>(ctrl + 4);
     p.ids_off = d_ids_off;
@@ -681,7 +694,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         eng.cache_valid = true;
     } else {
         CK(cudaMemsetAsync(ctrl, 0, 12, st));                          // keep the overflow cursor
-        CK(cudaMemsetAsync(ctrl + 4, 0, 24, st));
+        CK(cudaMemsetAsync(ctrl + 4, 0, 36, st));
     }
     eng.mark("memset(cache)", st);
     unsigned doc_grid = (unsigned)((n_docs + 1 + 255) / 256);
@@ -690,8 +703,14 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     unsigned grid = p.n_tiles < (uint32_t)eng.fused_grid ? p.n_tiles : (unsigned)eng.fused_grid;
     k_encode_slices<<<grid, FW * 32, 0, st>>>(p);
     eng.launched(1); eng.mark("k_encode_slices", st);
+    k_long_prep<<<eng.long_grid, 256, 0, st>>>(p);
+    if (p.mid_enabled) {
+        k_encode_mid<MID_A><<<eng.mid_grid_a, 32, (2 * MID_A * 32 + 256) * 4, st>>>(p, 0);
+        k_encode_mid<MID_B><<<eng.mid_grid_b, 32, (2 * MID_B * 32 + 256) * 4, st>>>(p, 1);
+        eng.launched(2);
+    }
     k_encode_long<<<eng.long_grid, 256, 0, st>>>(p);
-    eng.launched(1); eng.mark("k_encode_long", st);
+    eng.launched(2); eng.mark("k_long_prep+mid+long", st);
     size_t cub_bytes = 0;
     void* cub_tmp;
     CK(cudaMemsetAsync(p.slice_cnt + p.n_slices, 0, 4, st));

@@ -248,47 +248,173 @@ __device__ __forceinline__ uint32_t long_piece(const FusedParams& p, const uint8
     return cnt;
 }
 
-__global__ void __launch_bounds__(256) k_encode_long(const FusedParams p) {
+// ------------------------------------------------------------------------------------------------
+// k_long_prep: one thread per long pre-token.  Resolves the length of those that run past their chunk (the next
+// owned start of a later slice, or the end of the text), reserves room in the long pool (one atomic per warp) and
+// sorts the pre-token into a work list: MID_A (<= 64 bytes), MID_B (<= 128 bytes), REST.
+constexpr int MID_A = 64, MID_B = 128;
+__global__ void __launch_bounds__(256) k_long_prep(const FusedParams p) {
     const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    uint32_t n_desc = *p.desc_cursor;
+    if (n_desc > p.desc_cap) n_desc = p.desc_cap;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n_desc; i0 += gridDim.x * blockDim.x) {
+    const uint32_t i = i0 + lane;
+    const bool have = i < n_desc;
+    uint64_t len = 0;
+    if (have) {
+        const LongDesc dd = p.desc[i];
+        len = dd.len;
+        if (dd.len == 0xFFFFFFFFu) {
+            uint64_t e = p.n_bytes;
+            for (uint64_t s = (uint64_t)dd.slice + 1; s < p.n_slices; ++s) {
+                const uint32_t f = p.slice_first[s];
+                if (f != 0xFFFFu) { e = s * SLICE - LCTX + f; break; }
+            }
+            len = e - dd.gstart;
+            p.desc[i].len = (uint32_t)len;
+        }
+    }
+    const bool xl = have && p.xl_enabled && len > XL_MIN;          // placed by k_xl_place, no pool space
+    // pool space: exclusive scan of the lengths inside the warp, one atomic for all
+    unsigned long long need = have && !xl ? len : 0, incl = need;
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long u = __shfl_up_sync(full, incl, o); if (lane >= o) incl += u; }
+    unsigned long long base = 0;
+    if (lane == 31 && incl) base = atomicAdd(p.long_cursor, incl);
+    base = __shfl_sync(full, base, 31);
+    const unsigned long long po = base + incl - need;
+    bool ok = have && (xl || po + len <= p.long_cap);
+    if (have && !ok) atomicOr(p.err, ERRF_POOL);
+    if (have) { p.desc[i].pool = xl ? kNone : (uint32_t)po; p.desc[i].cnt = 0; }
+    const int which = !ok ? 3 : (!xl && p.mid_enabled && len <= MID_A) ? 0 : (!xl && p.mid_enabled && len <= MID_B) ? 1 : 2;
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+        const unsigned m = __ballot_sync(full, which == w);
+        if (!m) continue;
+        uint32_t b0 = 0;
+        if (lane == __ffs(m) - 1) b0 = atomicAdd(p.work_count + w, (uint32_t)__popc(m));
+        b0 = __shfl_sync(full, b0, __ffs(m) - 1);
+        if (which == w) p.work_list[(uint64_t)w * p.desc_cap + b0 + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_encode_mid<N>: pre-tokens of 33 .. N bytes, ONE LANE EACH (32 per warp at a time).  The reference's loop
+// (bpe.rs:104-153) verbatim and exact for every table: scan the pair ranks for the lowest, leftmost on ties,
+// merge that one pair, refresh the two pairs next to it.  Symbols and pair ranks live in shared memory as
+// [slot][lane] (conflict-free); a merged-away slot is marked DEAD and skipped, so nothing is ever shifted.
+// One lane per pre-token needs ~20x fewer warp instructions than one warp per pre-token for CJK-like runs.
+constexpr uint32_t MID_DEAD = 0xFFFFFFFEu;
+template <int N>
+__global__ void __launch_bounds__(32) k_encode_mid(const FusedParams p, int list_no) {
+    extern __shared__ uint32_t smem_mid[];
+    uint32_t* const sym = smem_mid;                                // [N][32]
+    uint32_t* const rnk = smem_mid + N * 32;                       // [N][32]; (rank << 8 | slot) of the pair that STARTS at the slot, kNone if none
+    uint32_t* const s_init = smem_mid + 2 * N * 32;                // [256]
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x;
+    for (int k = lane; k < 256; k += 32) s_init[k] = __ldg(p.t.byte_init + k);
+    __syncwarp();
+    const uint32_t count = min(p.work_count[list_no], p.desc_cap);
+    const uint32_t* list = p.work_list + (uint64_t)list_no * p.desc_cap;
+    for (uint32_t base = blockIdx.x * 32u; base < count; base += gridDim.x * 32u) {
+        const bool have = base + lane < count;
+        uint32_t di = 0;
+        LongDesc dd{};
+        if (have) { di = list[base + lane]; dd = p.desc[di]; }
+        const uint8_t* src = p.text + dd.gstart;
+        // initial ids; bytes without a vocab entry are dropped (bpe.rs:94-97)
+        int n = 0;
+        const int len = have ? (int)dd.len : 0;
+        for (int b = 0; b < len; b += 4) {                          // four byte loads in flight
+            uint32_t c[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = b + q < len ? __ldg(src + b + q) : 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t sv = s_init[c[q]];
+                if (b + q < len && sv != kNone) { sym[n * 32 + lane] = sv; ++n; }
+            }
+        }
+        for (int i = 0; i < n; i += 2) {                            // two independent lookups in flight
+            uint2 r1 = make_uint2(kNone, 0u), r2 = r1;
+            if (i + 2 < n) pair_lookup2(p.t, sym[i * 32 + lane], sym[(i + 1) * 32 + lane], sym[(i + 1) * 32 + lane], sym[(i + 2) * 32 + lane], r1, r2);
+            else if (i + 1 < n) r1 = pair_lookup(p.t, sym[i * 32 + lane], sym[(i + 1) * 32 + lane]);
+            rnk[i * 32 + lane] = r1.x == kNone ? kNone : (r1.x << 8) | (uint32_t)i;
+            if (i + 1 < n) rnk[(i + 1) * 32 + lane] = r2.x == kNone ? kNone : (r2.x << 8) | (uint32_t)(i + 1);
+        }
+        const int nmax = __reduce_max_sync(full, n);
+        for (int i = n; i < nmax; ++i) rnk[i * 32 + lane] = kNone;  // so that every lane can scan the same slots
+        bool busy = n > 1;
+        while (__any_sync(full, busy)) {
+            // lowest rank, leftmost on ties = the minimum of (rank << 8 | slot); four independent chains
+            uint32_t m[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m[q] = kNone;
+            int i = 0;
+            for (; i + 16 <= nmax; i += 16) {                       // sixteen loads in flight, eight independent minima
+                uint32_t v[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = rnk[(i + q) * 32 + lane];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) m[q & 7] = min(m[q & 7], v[q]);
+            }
+            for (; i < nmax; ++i) m[0] = min(m[0], rnk[i * 32 + lane]);
+            const uint32_t best = min(min(min(m[0], m[1]), min(m[2], m[3])), min(min(m[4], m[5]), min(m[6], m[7])));
+            const int bi = (int)(best & 0xFFu);
+            if (best == kNone) busy = false;
+            if (busy) {
+                int j = bi + 1;
+                while (sym[j * 32 + lane] == MID_DEAD) ++j;         // right symbol of the pair
+                const uint32_t a = sym[bi * 32 + lane], b = sym[j * 32 + lane];
+                const uint32_t nid = pair_lookup(p.t, a, b).y;
+                sym[bi * 32 + lane] = nid;
+                sym[j * 32 + lane] = MID_DEAD;
+                rnk[j * 32 + lane] = kNone;
+                int k = j + 1;
+                while (k < n && sym[k * 32 + lane] == MID_DEAD) ++k;
+                int h = bi - 1;
+                while (h >= 0 && sym[h * 32 + lane] == MID_DEAD) --h;
+                uint2 rr = make_uint2(kNone, 0u), rl = rr;                // the two pairs next to the new symbol, together
+                if (k < n && h >= 0) pair_lookup2(p.t, nid, sym[k * 32 + lane], sym[h * 32 + lane], nid, rr, rl);
+                else if (k < n) rr = pair_lookup(p.t, nid, sym[k * 32 + lane]);
+                else if (h >= 0) rl = pair_lookup(p.t, sym[h * 32 + lane], nid);
+                rnk[bi * 32 + lane] = rr.x == kNone ? kNone : (rr.x << 8) | (uint32_t)bi;
+                if (h >= 0) rnk[h * 32 + lane] = rl.x == kNone ? kNone : (rl.x << 8) | (uint32_t)h;
+            }
+        }
+        if (have) {
+            uint32_t* out = p.long_pool + dd.pool;
+            uint32_t cnt = 0;
+            for (int i = 0; i < n; ++i) { const uint32_t v = sym[i * 32 + lane]; if (v != MID_DEAD) out[cnt++] = v; }
+            p.desc[di].cnt = cnt;
+            atomicAdd(p.slice_cnt + dd.slice, cnt);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_encode_long(const FusedParams p) {
     const int lane = threadIdx.x & 31;
     __shared__ RoundBuf s_rb[8];
     RoundBuf* const rb = (p.t.round_parallel && !p.no_rounds) ? &s_rb[threadIdx.x >> 5] : nullptr;
-    uint32_t n_desc = *p.desc_cursor;
-    if (n_desc > p.desc_cap) n_desc = p.desc_cap;
+    const uint32_t count = min(p.work_count[2], p.desc_cap);
+    const uint32_t* list = p.work_list + 2ull * p.desc_cap;
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_desc; i += n_warps) {
-        LongDesc dd = p.desc[i];
-        uint64_t len = dd.len;
-        if (dd.len == 0xFFFFFFFFu) {                               // runs past its chunk: it ends at the next start, which is
-            uint64_t e = p.n_bytes;                                // the first owned start of a later slice (or the text's end)
-            for (uint64_t s0 = (uint64_t)dd.slice + 1; s0 < p.n_slices; s0 += 32) {
-                const uint64_t s = s0 + lane;
-                const uint32_t f = s < p.n_slices ? p.slice_first[s] : 0xFFFFu;
-                const unsigned b = __ballot_sync(full, f != 0xFFFFu);
-                if (b) {
-                    const int src = __ffs(b) - 1;
-                    e = (s0 + src) * SLICE - LCTX + __shfl_sync(full, f, src);
-                    break;
-                }
-            }
-            len = e - dd.gstart;
-            if (lane == 0) p.desc[i].len = (uint32_t)len;
-        }
-        unsigned long long po = 0;
-        if (!(p.xl_enabled && len > XL_MIN)) {
-            if (lane == 0) po = atomicAdd(p.long_cursor, (unsigned long long)len);
-            po = __shfl_sync(full, po, 0);
-        }
+    for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += n_warps) {
+        const uint32_t i = list[w];
+        const LongDesc dd = p.desc[i];
+        const uint64_t len = dd.len;
         uint32_t cnt = 0;
-        if (p.xl_enabled && len > XL_MIN) {                        // merged in rounds by encode_xlong.cuh, after this kernel
-            po = kNone;                                            // no room in the long pool: k_xl_place writes the output directly
+        if (dd.pool == kNone) {                                    // merged in rounds by encode_xlong.cuh, after this kernel
             if (lane == 0) {
                 const unsigned long long t = atomicAdd(p.xl_cursor, (1ull << XL_IDX_SHIFT) | (unsigned long long)(len + 1));
                 const unsigned long long idx = t >> XL_IDX_SHIFT;
                 if (idx < p.desc_cap) p.xl_list[idx] = XlEntry{i, 0u, t & ((1ull << XL_IDX_SHIFT) - 1)};
             }
-        } else if (po + len <= p.long_cap) {
-            uint32_t* out = p.long_pool + po;
+        } else {
+            uint32_t* out = p.long_pool + dd.pool;
             const uint8_t* src = p.text + dd.gstart;
             if (p.t.n_added == 0) cnt = long_piece(p, src, len, out, lane, rb);
             else {                                                 // mod.rs:566-610: added tokens inside the word
@@ -303,9 +429,8 @@ __global__ void __launch_bounds__(256) k_encode_long(const FusedParams p) {
                     __syncwarp();
                 }
             }
-        } else if (lane == 0) atomicOr(p.err, ERRF_POOL);
+        }
         if (lane == 0) {
-            p.desc[i].pool = (uint32_t)po;
             p.desc[i].cnt = cnt;
             atomicAdd(p.slice_cnt + dd.slice, cnt);
         }
