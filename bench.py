@@ -280,9 +280,12 @@ def main():
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_ms = float(et.item())
     assert n_e2e == T
+    hb, db = ctypes.c_uint64(), ctypes.c_uint64()
+    lib.ctk_last_transfer_bytes(tok._h, ctypes.byref(hb), ctypes.byref(db))
     e2e = {'value': B_all / (e2e_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': e2e_ms,
-           'h2d_bytes_per_step': int(B + 8 * (D + 1)), 'd2h_bytes_per_step': int(4 * T + 8 * (D + 1)),
-           'api': 'ctk_encode_batch (C ABI, pinned host buffers in and out)'}
+           'h2d_bytes_per_step': int(hb.value), 'd2h_bytes_per_step': int(db.value),
+           'api': 'ctk_encode_batch (C ABI, pinned host buffers in, uint32 ids in pinned host memory out)',
+           'result_bytes_in_host_memory': int(4 * T + 8 * (D + 1))}
 
     # ---- decode_batch on the ids just produced (device-resident; BASELINE config 5's round-trip shape):
     #      raw decode must give the input back byte for byte; the default decode (clean-up on) is timed next to it

@@ -68,6 +68,7 @@ def _lib():
         'ctk_debug_load_only': (I, [P, S, ctypes.POINTER(U64), ctypes.POINTER(U64), ctypes.POINTER(I), ctypes.POINTER(I)]),
         'ctk_debug_merge_props': (I, [P, S, ctypes.POINTER(I), ctypes.POINTER(ctypes.c_uint32)]),
         'ctk_debug_xlong_rounds': (I, [P]),
+        'ctk_last_transfer_bytes': (None, [P, ctypes.POINTER(U64), ctypes.POINTER(U64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

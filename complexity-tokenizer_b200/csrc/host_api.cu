@@ -12,6 +12,12 @@
 #include <cstdio>
 #include <cstring>
 #include <ctime>
+#include <atomic>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#include <condition_variable>
+#include <thread>
 #include <vector>
 
 #include "engine.hpp"
@@ -56,6 +62,132 @@ struct Result {
     void *ids = nullptr, *off = nullptr, *bytes = nullptr;
     size_t ids_cap = 0, off_cap = 0, bytes_cap = 0;
 };
+
+// ---- narrow ids on the wire ------------------------------------------------------------------------------
+// The result copy is as large as the input copy (4 bytes per ~4.4-byte token) and both share the PCIe link.
+// Ids are therefore packed on the device to 2 bytes (every id < 65 536) or 3 bytes (< 2^24) before the copy out
+// and widened to the uint32 the ABI promises by a few host threads while later chunks are still in flight.
+// Measured on the B200 box (1 GiB, tools/diag_e2e_threads.sh): 25.3 ms plain, 24.1 ms with 8 threads and streaming
+// stores, 26.9 ms with 4: host memory bandwidth, not the link, is what the narrower copy runs into.  Hence OPT-IN
+// (CTK_WIDEN_THREADS=n); the default copies plain uint32.
+__global__ void __launch_bounds__(256) k_pack_ids16(const uint32_t* __restrict__ ids, uint64_t n, uint32_t* __restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; 2 * i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = ids[2 * i], b = 2 * i + 1 < n ? ids[2 * i + 1] : 0u;
+        out[i] = (a & 0xFFFFu) | (b << 16);
+    }
+}
+__global__ void __launch_bounds__(256) k_pack_ids24(const uint32_t* __restrict__ ids, uint64_t n, uint32_t* __restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; 4 * i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = 4 * i + k < n ? ids[4 * i + k] & 0xFFFFFFu : 0u;
+        out[3 * i] = v[0] | (v[1] << 24);
+        out[3 * i + 1] = (v[1] >> 8) | (v[2] << 16);
+        out[3 * i + 2] = (v[2] >> 16) | (v[3] << 8);
+    }
+}
+
+static void widen_range(const uint8_t* src, uint32_t* dst, uint64_t lo, uint64_t hi, int width) {
+    if (width == 2) {
+        const uint16_t* s = reinterpret_cast<const uint16_t*>(src);
+        uint64_t i = lo;
+#if defined(__SSE2__)
+        // streaming stores: the result is not read again by this thread, and a plain store would first read the line
+        while (i < hi && (reinterpret_cast<uintptr_t>(dst + i) & 15)) { dst[i] = s[i]; ++i; }
+        const __m128i z = _mm_setzero_si128();
+        for (; i + 8 <= hi; i += 8) {
+            const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_unpacklo_epi16(v, z));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 4), _mm_unpackhi_epi16(v, z));
+        }
+        _mm_sfence();
+#endif
+        for (; i < hi; ++i) dst[i] = s[i];
+    } else {
+        for (uint64_t i = lo; i < hi; ++i) { const uint8_t* q = src + 3 * i; dst[i] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16); }
+    }
+}
+
+// A few persistent host threads.  One job = one ctk_encode_batch call; the caller publishes chunks as their copies are
+// issued, every worker waits for a chunk's copy (cudaEventSynchronize) and widens its share of it.
+struct WidenJob {
+    struct Chunk { cudaEvent_t ev; const uint8_t* src; uint32_t* dst; uint64_t n; };
+    std::vector<Chunk> chunks;                      // reserved up front: never reallocates while workers read it
+    std::atomic<size_t> published{0};
+    std::atomic<size_t> finished{0};                // chunk completions, counted once per worker
+    std::atomic<bool> closed{false};
+    int width = 4;
+};
+struct WidenPool {
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::vector<std::thread> threads;
+    WidenJob* job = nullptr;
+    uint64_t job_seq = 0;
+    std::mutex use_mu;                              // one encode call at a time uses the pool; others copy plain uint32
+    int active = 0;
+    bool stop = false;
+    int n_threads = 0;
+    void start(int n) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!threads.empty() || n <= 0) return;
+        n_threads = n;
+        for (int t = 0; t < n; ++t) threads.emplace_back([this, t] { run(t); });
+    }
+    void run(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            WidenJob* j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || (job && job_seq != seen); });
+                if (stop) return;
+                j = job; seen = job_seq; ++active;
+            }
+            size_t c = 0;
+            for (;;) {
+                while (c >= j->published.load(std::memory_order_acquire)) {
+                    if (j->closed.load(std::memory_order_acquire) && c >= j->published.load(std::memory_order_acquire)) goto done;
+                    std::this_thread::yield();
+                }
+                const WidenJob::Chunk& ch = j->chunks[c];
+                cudaEventSynchronize(ch.ev);
+                const uint64_t per = (ch.n + n_threads - 1) / n_threads;
+                const uint64_t lo = std::min<uint64_t>(ch.n, per * t), hi = std::min<uint64_t>(ch.n, lo + per);
+                widen_range(ch.src, ch.dst, lo, hi, j->width);
+                j->finished.fetch_add(1, std::memory_order_release);
+                ++c;
+            }
+        done:
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                --active;
+            }
+            cv_done.notify_all();
+        }
+    }
+    void begin(WidenJob* j) {
+        { std::lock_guard<std::mutex> lk(mu); job = j; ++job_seq; }
+        cv.notify_all();
+    }
+    // all chunks published so far are widened by every worker
+    void drain(WidenJob* j) {
+        const size_t want = j->published.load() * (size_t)n_threads;
+        while (j->finished.load(std::memory_order_acquire) < want) std::this_thread::yield();
+    }
+    void end(WidenJob* j) {
+        j->closed.store(true, std::memory_order_release);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return active == 0 && j->finished.load() >= j->published.load() * (size_t)n_threads; });
+        job = nullptr;
+    }
+    ~WidenPool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& th : threads) if (th.joinable()) th.join();
+    }
+};
+static WidenPool g_widen;
 
 // DMA between the device and an UNALIGNED pinned host address runs ~10 % slower (tools/diag_pcie.py: 42.4 vs
 // 46.6 GB/s per direction with both directions busy): copy the few bytes up to the next 4 KiB boundary of the
@@ -132,8 +264,16 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
     uint64_t* h_ioff = nullptr; size_t h_ioff_cap = 0;
     uint64_t total = 0, dev_text_bytes = 0, ids_cap = 0;
     size_t n_roff = n + chunks.size() + 1;
-    std::vector<cudaEvent_t> evs;
+    std::vector<cudaEvent_t> evs, evs_pk, evs_dh;
     std::vector<uint64_t> chunk_base;
+    // narrow ids on the wire (see k_pack_ids16): staging buffers, the job the widening threads work on
+    WidenJob job;
+    std::unique_lock<std::mutex> widen_lock;
+    bool packed = false;
+    int width = 4;
+    uint8_t *h_pack = nullptr, *d_pack = nullptr;
+    size_t h_pack_cap = 0;
+    uint64_t pk_off = 0, h2d_bytes = 0, d2h_bytes = 0;
     // CTK_TRACE=1: per-chunk timeline (H2D done, kernels done, D2H done; ms since the call started) on stderr
     const bool trace = getenv("CTK_TRACE") != nullptr;
     std::vector<cudaEvent_t> tr_h, tr_c, tr_d;
@@ -152,6 +292,27 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
     CKE(g_pinned.get(n_roff * 8, (void**)&h_ioff, &h_ioff_cap));
     CKE(g_pinned.get((n + 1) * 8, &r->off, &r->off_cap));
     CKE(g_pinned.get((B / 3 + n + 1024) * 4, &r->ids, &r->ids_cap));
+    {
+        uint64_t max_emit = eng->model.id_present.empty() ? 0 : eng->model.id_present.size() - 1;
+        for (const AddedTok& a : eng->model.added) if (a.may_match) max_emit = std::max<uint64_t>(max_emit, a.id);
+        int T = 0;                                                   // opt-in: measured +5 % end to end for 8 busy host threads
+        if (const char* e = getenv("CTK_WIDEN_THREADS")) T = atoi(e);
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0) T = std::min(T, std::max(1, hw - 2));
+        if (T > 0 && B >= (16ull << 20) && max_emit < (1ull << 24)) {
+            widen_lock = std::unique_lock<std::mutex>(g_widen.use_mu, std::try_to_lock);
+            if (widen_lock.owns_lock()) { g_widen.start(T); packed = g_widen.n_threads > 0; }
+        }
+        if (packed) {
+            width = max_emit < 65536 ? 2 : 3;
+            CKE(eng->ws.get(45, (uint64_t)width * ids_cap + 256 * (chunks.size() + 2), (void**)&d_pack));
+            CKE(g_pinned.get((uint64_t)width * (r->ids_cap / 4) + 256 * (chunks.size() + 2), (void**)&h_pack, &h_pack_cap));
+            job.chunks.reserve(chunks.size());
+            job.width = width;
+            evs_pk.assign(chunks.size(), nullptr); evs_dh.assign(chunks.size(), nullptr);
+            g_widen.begin(&job);
+        }
+    }
     // document offsets relative to their chunk
     for (const Chunk& c : chunks)
         for (size_t d = c.d0; d <= c.d1; ++d) h_roff[c.roff + (d - c.d0)] = text_off[d] - c.b0;
@@ -185,6 +346,7 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
         if (trace) { cudaEventRecord(tr_c[c], eng->st_comp); tr_host[c] = now_ms() - host0; }
         // copy out while the next chunk is being encoded
         if ((total + cnt + 1) * 4 > r->ids_cap) {                     // grow the pinned result (rare)
+            if (packed) g_widen.drain(&job);                           // everything copied so far is widened into r->ids
             CKE(cudaStreamSynchronize(eng->st_d2h));
             void* nb; size_t ncap;
             uint64_t est = (uint64_t)((double)(total + cnt) * (double)B / (double)std::max<uint64_t>(ch.b1, 1) * 1.1) + 4096;
@@ -192,15 +354,48 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
             memcpy(nb, r->ids, total * 4);
             g_pinned.put(r->ids, r->ids_cap);
             r->ids = nb; r->ids_cap = ncap;
+            if (packed) {                                              // the staging area follows; what it held is consumed
+                g_pinned.put(h_pack, h_pack_cap);
+                h_pack = nullptr;
+                CKE(g_pinned.get((uint64_t)width * (r->ids_cap / 4) + 256 * (chunks.size() + 2), (void**)&h_pack, &h_pack_cap));
+                pk_off = 0;
+            }
         }
-        if (cnt && !getenv("CTK_DIAG_NO_D2H")) CKE(copy_host_aligned((uint32_t*)r->ids + total, d_ids + total, cnt * 4, cudaMemcpyDeviceToHost, eng->st_d2h));
+        if (cnt && packed) {
+            const uint64_t pbytes = ((cnt * (uint64_t)width + 3) / 4) * 4;
+            for (std::vector<cudaEvent_t>* v : {&evs_pk, &evs_dh}) {
+                if (!eng->sync_ev_pool.empty()) { (*v)[c] = eng->sync_ev_pool.back(); eng->sync_ev_pool.pop_back(); }
+                else CKE(cudaEventCreateWithFlags(&(*v)[c], cudaEventDisableTiming));
+            }
+            const uint64_t units = (cnt + (width == 2 ? 1 : 3)) / (width == 2 ? 2 : 4);
+            const unsigned grid = (unsigned)std::min<uint64_t>((units + 255) / 256, 148 * 16);
+            if (width == 2) k_pack_ids16<<<grid, 256, 0, eng->st_comp>>>(d_ids + total, cnt, reinterpret_cast<uint32_t*>(d_pack + pk_off));
+            else k_pack_ids24<<<grid, 256, 0, eng->st_comp>>>(d_ids + total, cnt, reinterpret_cast<uint32_t*>(d_pack + pk_off));
+            eng->launched(1);
+            CKE(cudaEventRecord(evs_pk[c], eng->st_comp));
+            CKE(cudaStreamWaitEvent(eng->st_d2h, evs_pk[c], 0));
+            CKE(copy_host_aligned(h_pack + pk_off, d_pack + pk_off, pbytes, cudaMemcpyDeviceToHost, eng->st_d2h));
+            CKE(cudaEventRecord(evs_dh[c], eng->st_d2h));
+            job.chunks.push_back({evs_dh[c], h_pack + pk_off, (uint32_t*)r->ids + total, cnt});
+            job.published.fetch_add(1, std::memory_order_release);
+            pk_off += ((pbytes + 255) / 256) * 256;
+            d2h_bytes += pbytes;
+        } else if (cnt && !getenv("CTK_DIAG_NO_D2H")) {
+            CKE(copy_host_aligned((uint32_t*)r->ids + total, d_ids + total, cnt * 4, cudaMemcpyDeviceToHost, eng->st_d2h));
+            d2h_bytes += cnt * 4;
+        }
+        d2h_bytes += (ch.d1 - ch.d0 + 1) * 8;
         CKE(cudaMemcpyAsync(h_ioff + ch.roff, d_ids_off + ch.roff, (ch.d1 - ch.d0 + 1) * 8, cudaMemcpyDeviceToHost, eng->st_d2h));
         if (trace) cudaEventRecord(tr_d[c], eng->st_d2h);
         chunk_base[c] = total;
         total += cnt;
     }
+    if (packed) { g_widen.end(&job); packed = false; }
     CKE(cudaStreamSynchronize(eng->st_d2h));
+    h2d_bytes = B + n_roff * 8;
+    eng->last_h2d_bytes = h2d_bytes; eng->last_d2h_bytes = d2h_bytes;
     if (trace) {
+        fprintf(stderr, "[ctk trace] ids cross the link as %d bytes each\n", width);
         fprintf(stderr, "[ctk trace] %zu chunks, %.1f MiB in; host: pipeline issued+drained at %.3f ms\n", chunks.size(), B / 1048576.0, now_ms() - host0);
         for (size_t c = 0; c < chunks.size(); ++c) {
             float h = 0, k = 0, d = 0;
@@ -219,7 +414,11 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
         off[n] = total;
     }
 done:
+    if (packed) g_widen.end(&job);                                     // error path: the workers must let go of `job`
     for (cudaEvent_t ev : evs) if (ev) eng->sync_ev_pool.push_back(ev);
+    for (cudaEvent_t ev : evs_pk) if (ev) eng->sync_ev_pool.push_back(ev);
+    for (cudaEvent_t ev : evs_dh) if (ev) eng->sync_ev_pool.push_back(ev);
+    g_pinned.put(h_pack, h_pack_cap);
     g_pinned.put(h_roff, h_roff_cap);
     g_pinned.put(h_ioff, h_ioff_cap);
     if (rc != CTK_OK) { cudaStreamSynchronize(eng->st_h2d); cudaStreamSynchronize(eng->st_d2h); free_result(r); return rc; }
@@ -266,6 +465,11 @@ done:
 const uint32_t* ctk_result_ids(const ctk_result* res) { return (const uint32_t*)reinterpret_cast<const Result*>(res)->ids; }
 const uint64_t* ctk_result_offsets(const ctk_result* res) { return (const uint64_t*)reinterpret_cast<const Result*>(res)->off; }
 const uint8_t* ctk_result_bytes(const ctk_result* res) { return (const uint8_t*)reinterpret_cast<const Result*>(res)->bytes; }
+void ctk_last_transfer_bytes(const ctk_tokenizer* tok, uint64_t* h2d, uint64_t* d2h) {
+    const Engine* eng = reinterpret_cast<const Engine*>(tok);
+    if (h2d) *h2d = eng->last_h2d_bytes;
+    if (d2h) *d2h = eng->last_d2h_bytes;
+}
 size_t ctk_result_count(const ctk_result* res) { return reinterpret_cast<const Result*>(res)->n; }
 void ctk_result_free(ctk_result* res) { free_result(reinterpret_cast<Result*>(res)); }
 

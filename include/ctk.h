@@ -105,6 +105,9 @@ uint64_t ctk_kernel_launches(void);
  * one line per kernel: name <TAB> total milliseconds <TAB> launches; returns the full length. */
 void ctk_profile_enable(ctk_tokenizer* tok, int on);
 size_t ctk_profile_report(ctk_tokenizer* tok, char* buf, size_t cap);
+/* Bytes the last ctk_encode_batch call moved host->device and device->host.  (Opt-in, CTK_WIDEN_THREADS=n: ids cross
+ * the link packed to 2 or 3 bytes when every id fits and n host threads widen them to uint32.) */
+void ctk_last_transfer_bytes(const ctk_tokenizer* tok, uint64_t* h2d, uint64_t* d2h);
 /* Reset the per-batch pre-token cache policy: 0 = clear at the start of every encode call
  * (default; every call does all of its own work), 1 = keep entries across calls. */
 void ctk_set_cache_persistent(ctk_tokenizer* tok, int persistent);

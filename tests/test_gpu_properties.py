@@ -97,6 +97,13 @@ def test_properties_at_larger_size(built_lib, tok_paths):
     text, offs = synth.gen_corpus('ascii', 5000, 256 << 20, doc_median=4096, doc_min=256, doc_max=65536)
     ids, ioff = tok.encode_packed(text, offs)
     assert int(ioff[-1]) == ids.size and ids.size > 0
+    import os
+    os.environ['CTK_WIDEN_THREADS'] = '4'                         # opt-in narrow copy (2 bytes per id here): same result
+    try:
+        ids_n, ioff_n = tok.encode_packed(text, offs)
+    finally:
+        del os.environ['CTK_WIDEN_THREADS']
+    assert np.array_equal(ids, ids_n) and np.array_equal(ioff, ioff_n)
     b, boff = tok.decode_packed(ids, ioff, False, False)
     assert np.array_equal(boff, offs) and np.array_equal(b, text)
     ids2, ioff2 = tok.encode_packed(text, offs)
@@ -311,12 +318,17 @@ def test_warp_rounds_equal_sequential_merging_on_cjk(built_lib, tok_paths):
     import synth
     tok = _tok(tok_paths['config3'])
     text, offs = synth.gen_corpus('mixed', 3003, 24 << 20, doc_median=4096)
-    a_ids, a_off = tok.encode_packed(text, offs)
+    os.environ['CTK_WIDEN_THREADS'] = '3'                         # opt-in: ids cross PCIe packed to 3 bytes (100K vocab) ...
+    try:
+        a_ids, a_off = tok.encode_packed(text, offs)
+    finally:
+        del os.environ['CTK_WIDEN_THREADS']
     os.environ['CTK_NO_ROUNDS'] = '1'
+    os.environ['CTK_NO_MID'] = '1'                                # ... and here as plain uint32, merged sequentially
     try:
         b_ids, b_off = tok.encode_packed(text, offs)
     finally:
-        del os.environ['CTK_NO_ROUNDS']
+        del os.environ['CTK_NO_ROUNDS'], os.environ['CTK_NO_MID']
     assert np.array_equal(a_off, b_off) and np.array_equal(a_ids, b_ids)
 
 
