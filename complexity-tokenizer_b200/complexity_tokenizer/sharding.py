@@ -44,9 +44,10 @@ def exchange_shard_metadata(first_doc, n_docs, n_ids, group=None):
     world = dist.get_world_size(group)
     dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
     mine = torch.tensor([int(first_doc), int(n_docs), int(n_ids)], dtype=torch.int64, device=dev)
-    out = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(out, mine, group=group)
-    rows = [tuple(int(v) for v in t.tolist()) for t in out]
+    out = torch.empty(world * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)             # one collective, one read-back
+    flat = out.tolist()
+    rows = [tuple(flat[3 * r:3 * r + 3]) for r in range(world)]
     base, meta = 0, []
     for fd, nd, ni in rows:
         meta.append(dict(first_doc=fd, n_docs=nd, n_ids=ni, ids_base=base))

@@ -60,31 +60,54 @@ CTK_HD Masks16 classify16(const uint8_t* chunk, int pos, uint32_t w0, uint32_t w
     m.L = aL >> 16; m.N = aN >> 16; m.W = aW >> 16; m.SP = aS >> 16; m.AP = aA >> 16;
     uint32_t non_ascii = movemask4(w0 & 0x80808080u) | (movemask4(w1 & 0x80808080u) << 4) |
                          (movemask4(w2 & 0x80808080u) << 8) | (movemask4(w3 & 0x80808080u) << 12);
-    while (non_ascii) {                                                // rare path: multi-byte code points
+    if (non_ascii) {                                                   // rare path: multi-byte code points, ONE lookup per character
+        // continuation bytes 10xxxxxx: bit 7 set, bit 6 clear
+        uint32_t cont = 0;
 #if defined(__CUDA_ARCH__)
-        int b = __ffs(non_ascii) - 1;
-#else
-        int b = __builtin_ctz(non_ascii);
+#pragma unroll
 #endif
-        non_ascii &= non_ascii - 1;
-        int i = pos + b;
-        uint32_t c = chunk[i];
-        int lead = i;
-        if ((c & 0xC0u) == 0x80u) {
-            m.CONT |= 1u << b;
-            for (int k = 0; k < 3 && (chunk[lead] & 0xC0u) == 0x80u; ++k) --lead;
-            c = chunk[lead];
+        for (int k = 0; k < 4; ++k) cont |= movemask4(words[k] & 0x80808080u & ~(words[k] << 1)) << (4 * k);
+        m.CONT = cont;
+        uint32_t leads = non_ascii & ~cont;
+        // continuation bytes at the start of the group belong to a character that began in the previous group
+        const uint32_t run0 = cont & ~(cont + 1u);
+        if (run0) {
+            int lead = pos - 1;
+            for (int k = 0; k < 2 && (chunk[lead] & 0xC0u) == 0x80u; ++k) --lead;
+            const uint32_t c = chunk[lead];
+            uint32_t cp;
+            if (c < 0xE0u) cp = ((c & 0x1Fu) << 6) | (chunk[lead + 1] & 63u);
+            else if (c < 0xF0u) cp = ((c & 0x0Fu) << 12) | ((chunk[lead + 1] & 63u) << 6) | (chunk[lead + 2] & 63u);
+            else cp = ((c & 7u) << 18) | ((chunk[lead + 1] & 63u) << 12) | ((chunk[lead + 2] & 63u) << 6) | (chunk[lead + 3] & 63u);
+            const uint32_t nib = trie_nibble(trie_index, trie_blocks, cp);
+            m.SUSP |= nib & 4u;
+            const uint32_t cls = nib & 3u;
+            if (cls == CLS_L) m.L |= run0;
+            else if (cls == CLS_N) m.N |= run0;
+            else if (cls == CLS_W) m.W |= run0;
         }
-        uint32_t cp;
-        if (c < 0xE0u) cp = ((c & 0x1Fu) << 6) | (chunk[lead + 1] & 63u);
-        else if (c < 0xF0u) cp = ((c & 0x0Fu) << 12) | ((chunk[lead + 1] & 63u) << 6) | (chunk[lead + 2] & 63u);
-        else cp = ((c & 7u) << 18) | ((chunk[lead + 1] & 63u) << 12) | ((chunk[lead + 2] & 63u) << 6) | (chunk[lead + 3] & 63u);
-        const uint32_t nib = trie_nibble(trie_index, trie_blocks, cp);
-        m.SUSP |= nib & 4u;
-        uint32_t cls = nib & 3u;
-        if (cls == CLS_L) m.L |= 1u << b;
-        else if (cls == CLS_N) m.N |= 1u << b;
-        else if (cls == CLS_W) m.W |= 1u << b;
+        while (leads) {
+#if defined(__CUDA_ARCH__)
+            const int bb = __ffs(leads) - 1;
+#else
+            const int bb = __builtin_ctz(leads);
+#endif
+            leads &= leads - 1;
+            const int i = pos + bb;
+            const uint32_t c = chunk[i];
+            uint32_t cp, len;
+            if (c < 0xE0u) { cp = ((c & 0x1Fu) << 6) | (chunk[i + 1] & 63u); len = 2; }
+            else if (c < 0xF0u) { cp = ((c & 0x0Fu) << 12) | ((chunk[i + 1] & 63u) << 6) | (chunk[i + 2] & 63u); len = 3; }
+            else { cp = ((c & 7u) << 18) | ((chunk[i + 1] & 63u) << 12) | ((chunk[i + 2] & 63u) << 6) | (chunk[i + 3] & 63u); len = 4; }
+            const uint32_t nib = trie_nibble(trie_index, trie_blocks, cp);
+            m.SUSP |= nib & 4u;
+            const uint32_t cls = nib & 3u;
+            // the lead and the continuation bytes that follow it inside this group (never more than len - 1)
+            const uint32_t span = (((1u << len) - 1u) << bb) & 0xFFFFu & (cont | (1u << bb));
+            if (cls == CLS_L) m.L |= span;
+            else if (cls == CLS_N) m.N |= span;
+            else if (cls == CLS_W) m.W |= span;
+        }
     }
     return m;
 }
