@@ -664,10 +664,10 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         if (per_sm < 1) return eng.fail(CTK_ERR_CUDA, "encode kernel does not fit on an SM");
         eng.fused_grid = per_sm * sms;
         eng.long_grid = sms * 4;
-        CK(cudaFuncSetAttribute(k_encode_mid<MID_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * MID_B * 32 + 256) * 4));
+        CK(cudaFuncSetAttribute(k_encode_mid<MID_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * MID_B * 32 + MID_B * 4 + 256) * 4));
         int a = 0, b = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_encode_mid<MID_A>, 32, (2 * MID_A * 32 + 256) * 4));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_encode_mid<MID_B>, 32, (2 * MID_B * 32 + 256) * 4));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_encode_mid<MID_A>, 32, (2 * MID_A * 32 + MID_A * 4 + 256) * 4));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_encode_mid<MID_B>, 32, (2 * MID_B * 32 + MID_B * 4 + 256) * 4));
         eng.mid_grid_a = sms * (a > 0 ? a : 1);
         eng.mid_grid_b = sms * (b > 0 ? b : 1);
     }
@@ -732,8 +732,8 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     eng.launched(1); eng.mark("k_encode_slices", st);
     k_long_prep<<<eng.long_grid, 256, 0, st>>>(p);
     if (p.mid_enabled) {
-        k_encode_mid<MID_A><<<eng.mid_grid_a, 32, (2 * MID_A * 32 + 256) * 4, st>>>(p, 0);
-        k_encode_mid<MID_B><<<eng.mid_grid_b, 32, (2 * MID_B * 32 + 256) * 4, st>>>(p, 1);
+        k_encode_mid<MID_A><<<eng.mid_grid_a, 32, (2 * MID_A * 32 + MID_A * 4 + 256) * 4, st>>>(p, 0);
+        k_encode_mid<MID_B><<<eng.mid_grid_b, 32, (2 * MID_B * 32 + MID_B * 4 + 256) * 4, st>>>(p, 1);
         eng.launched(2);
     }
     k_encode_long<<<eng.long_grid, 256, 0, st>>>(p);

@@ -305,13 +305,16 @@ __global__ void __launch_bounds__(256) k_long_prep(const FusedParams p) {
 // merge that one pair, refresh the two pairs next to it.  Symbols and pair ranks live in shared memory as
 // [slot][lane] (conflict-free); a merged-away slot is marked DEAD and skipped, so nothing is ever shifted.
 // One lane per pre-token needs ~20x fewer warp instructions than one warp per pre-token for CJK-like runs.
+// (Tried and measured slower: the neighbours of a slot from a per-lane live bitmask in registers instead of
+// walking DEAD slots -- 9.0 -> 14.6 ms on config 3.)
 constexpr uint32_t MID_DEAD = 0xFFFFFFFEu;
 template <int N>
 __global__ void __launch_bounds__(32) k_encode_mid(const FusedParams p, int list_no) {
     extern __shared__ uint32_t smem_mid[];
     uint32_t* const sym = smem_mid;                                // [N][32]
     uint32_t* const rnk = smem_mid + N * 32;                       // [N][32]; (rank << 8 | slot) of the pair that STARTS at the slot, kNone if none
-    uint32_t* const s_init = smem_mid + 2 * N * 32;                // [256]
+    uint32_t* const bm = smem_mid + 2 * N * 32;                    // [N/8][32]: minimum key of each block of 8 slots
+    uint32_t* const s_init = bm + (N / 8) * 32;                    // [256]
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x;
     for (int k = lane; k < 256; k += 32) s_init[k] = __ldg(p.t.byte_init + k);
@@ -344,24 +347,27 @@ __global__ void __launch_bounds__(32) k_encode_mid(const FusedParams p, int list
             rnk[i * 32 + lane] = r1.x == kNone ? kNone : (r1.x << 8) | (uint32_t)i;
             if (i + 1 < n) rnk[(i + 1) * 32 + lane] = r2.x == kNone ? kNone : (r2.x << 8) | (uint32_t)(i + 1);
         }
-        const int nmax = __reduce_max_sync(full, n);
-        for (int i = n; i < nmax; ++i) rnk[i * 32 + lane] = kNone;  // so that every lane can scan the same slots
+        const int nb = (__reduce_max_sync(full, n) + 7) >> 3;        // blocks of 8 slots every lane looks at
+        for (int i = n; i < nb * 8; ++i) rnk[i * 32 + lane] = kNone;
+        auto block_min = [&](int blk) {
+            uint32_t v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = rnk[(blk * 8 + q) * 32 + lane];
+            bm[blk * 32 + lane] = min(min(min(v[0], v[1]), min(v[2], v[3])), min(min(v[4], v[5]), min(v[6], v[7])));
+        };
+        for (int blk = 0; blk < nb; ++blk) block_min(blk);
         bool busy = n > 1;
         while (__any_sync(full, busy)) {
-            // lowest rank, leftmost on ties = the minimum of (rank << 8 | slot); four independent chains
-            uint32_t m[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) m[q] = kNone;
+            // lowest rank, leftmost on ties = the minimum of (rank << 8 | slot): two levels, so that a merge costs a scan
+            // of the block minima plus the refresh of the (at most three) blocks it touched, not a scan of every slot
+            uint32_t m0 = kNone, m1 = kNone, m2 = kNone, m3 = kNone;
             int i = 0;
-            for (; i + 16 <= nmax; i += 16) {                       // sixteen loads in flight, eight independent minima
-                uint32_t v[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = rnk[(i + q) * 32 + lane];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) m[q & 7] = min(m[q & 7], v[q]);
+            for (; i + 4 <= nb; i += 4) {
+                m0 = min(m0, bm[i * 32 + lane]); m1 = min(m1, bm[(i + 1) * 32 + lane]);
+                m2 = min(m2, bm[(i + 2) * 32 + lane]); m3 = min(m3, bm[(i + 3) * 32 + lane]);
             }
-            for (; i < nmax; ++i) m[0] = min(m[0], rnk[i * 32 + lane]);
-            const uint32_t best = min(min(min(m[0], m[1]), min(m[2], m[3])), min(min(m[4], m[5]), min(m[6], m[7])));
+            for (; i < nb; ++i) m0 = min(m0, bm[i * 32 + lane]);
+            const uint32_t best = min(min(m0, m1), min(m2, m3));
             const int bi = (int)(best & 0xFFu);
             if (best == kNone) busy = false;
             if (busy) {
@@ -382,6 +388,9 @@ __global__ void __launch_bounds__(32) k_encode_mid(const FusedParams p, int list
                 else if (h >= 0) rl = pair_lookup(p.t, sym[h * 32 + lane], nid);
                 rnk[bi * 32 + lane] = rr.x == kNone ? kNone : (rr.x << 8) | (uint32_t)bi;
                 if (h >= 0) rnk[h * 32 + lane] = rl.x == kNone ? kNone : (rl.x << 8) | (uint32_t)h;
+                block_min(bi >> 3);
+                if ((j >> 3) != (bi >> 3)) block_min(j >> 3);
+                if (h >= 0 && (h >> 3) != (bi >> 3)) block_min(h >> 3);
             }
         }
         if (have) {
