@@ -80,6 +80,22 @@ static int upload(Engine& eng) {
     UP(4, eng.dec.blob, m.dec_blob.data(), m.dec_blob.size());
     UP(5, eng.dec.off, m.dec_off.data(), m.dec_off.size() * 4);
     UP(6, eng.dec.special, m.dec_special.data(), m.dec_special.size());
+    {
+        const size_t nid = m.dec_special.size();
+        std::vector<uint8_t> l8(nid + 1, 0), l8s(nid + 1, 0);
+        std::vector<uint4> rec(nid + 1, make_uint4(0, 0, 0, 0));
+        for (size_t id = 0; id < nid; ++id) {
+            const uint32_t b = m.dec_off[id], L = m.dec_off[id + 1] - b;
+            l8[id] = (uint8_t)(L < 255 ? L : 255);
+            l8s[id] = m.dec_special[id] ? 0 : l8[id];
+            uint32_t w[3] = {0, 0, 0};
+            for (uint32_t k = 0; k < L && k < 12; ++k) w[k >> 2] |= (uint32_t)m.dec_blob[b + k] << (8 * (k & 3));
+            rec[id] = make_uint4(w[0], w[1], w[2], L);
+        }
+        UP(18, eng.dec.len8, l8.data(), l8.size());
+        UP(19, eng.dec.len8_skip, l8s.data(), l8s.size());
+        UP(20, eng.dec.rec, rec.data(), rec.size() * sizeof(uint4));
+    }
     eng.nfc.nd = CTK_N_DECOMP; eng.nfc.nc = CTK_N_COMP; eng.nfc.nq = CTK_N_CCC;
     UP(7, eng.nfc.dkey, CTK_DECOMP_KEY, sizeof(CTK_DECOMP_KEY));
     UP(8, eng.nfc.da, CTK_DECOMP_A, sizeof(CTK_DECOMP_A));

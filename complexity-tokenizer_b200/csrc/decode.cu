@@ -1,6 +1,6 @@
 // decode_batch on the GPU.
 //
-//   k_dec_len / scan / k_dec_gather   ids -> token byte strings -> concatenation per document
+//   k_dec_tile_sums / scan / k_dec_write   ids -> token byte strings -> concatenation per document
 //                                      (mod.rs:717-735 filter + lookup, decoders.rs:94-116 with the
 //                                      char->byte map folded into the per-token blob at load)
 //   k_dec_valid                       is every document's byte string valid UTF-8?  (fast path: the
@@ -17,35 +17,121 @@
 
 namespace ctk {
 
-struct ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return v; } };
+struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return v; } };
 
-__global__ void k_dec_len(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
-                          uint32_t* __restrict__ len) {
-    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (j > n) return;
-    uint32_t L = 0;
-    if (j < n) {
-        uint32_t id = ids[j];
-        if (id < t.n_ids && !(skip_special && t.special[id])) L = t.off[id + 1] - t.off[id];
+// ---- ids -> bytes in two passes over the ids, no per-token offsets in global memory -------------------------------
+// A tile = DT consecutive tokens = one CTA.  Pass 1 sums the tile's token lengths; a scan of the (few) tile sums gives
+// every tile its place in the output.  Pass 2 re-derives the lengths, scans them inside the CTA, lays the tile's bytes
+// out in shared memory and writes them with aligned 16-byte stores; the documents that start inside the tile get their
+// byte offsets on the way.  (The first version wrote a uint64 offset per token -- 2 bytes of scratch traffic per
+// output byte -- and one thread copied each token's bytes to global memory.)
+constexpr int DT = 2048, DTH = 256, DPT = DT / DTH;
+constexpr int DSTAGE = 24 * 1024;                        // bytes of a tile staged in shared memory (a tile averages ~9 KB)
+
+__device__ __forceinline__ uint32_t dec_tok_len(const DecodeTables& t, uint32_t id, int skip_special) {
+    if (id >= t.n_ids) return 0;                                       // unknown ids are dropped (mod.rs:717-735)
+    const uint32_t L = __ldg((skip_special ? t.len8_skip : t.len8) + id);
+    return L < 255 ? L : __ldg(t.off + id + 1) - __ldg(t.off + id);    // (a special token is never that long)
+}
+
+__global__ void __launch_bounds__(DTH) k_dec_tile_sums(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
+                                                       uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t s_part[DTH / 32];
+    const uint64_t t0 = (uint64_t)blockIdx.x * DT;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const uint64_t j = t0 + (uint64_t)q * DTH + threadIdx.x;
+        if (j < n) sum += dec_tok_len(t, __ldg(ids + j), skip_special);
     }
-    len[j] = L;
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < DTH / 32; ++w) tot += s_part[w];
+        tile_sum[blockIdx.x] = tot;
+    }
 }
 
-__global__ void k_dec_gather(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
-                             const uint64_t* __restrict__ boff, uint8_t* __restrict__ raw) {
-    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint32_t id = ids[j];
-    if (id >= t.n_ids || (skip_special && t.special[id])) return;
-    uint32_t s = t.off[id], e = t.off[id + 1];
-    uint8_t* dst = raw + boff[j];
-    for (uint32_t k = s; k < e; ++k) dst[k - s] = t.blob[k];
-}
-
-__global__ void k_dec_doc_off(const uint64_t* __restrict__ ids_off, uint64_t n_docs, const uint64_t* __restrict__ boff,
-                              uint64_t* __restrict__ raw_off) {
-    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (d <= n_docs) raw_off[d] = boff[ids_off[d]];
+__global__ void __launch_bounds__(DTH) k_dec_write(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
+                                                   const uint64_t* __restrict__ tile_base, const uint64_t* __restrict__ ids_off,
+                                                   uint64_t n_docs, uint8_t* __restrict__ out, uint64_t out_cap,
+                                                   uint64_t* __restrict__ raw_off, uint32_t* __restrict__ err) {
+    __shared__ uint32_t s_off[DT + 1];                    // byte offset of every token inside the tile
+    __shared__ uint32_t s_warp[DTH / 32];
+    __shared__ __align__(16) uint8_t s_stage[DSTAGE + 16];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t t0 = (uint64_t)blockIdx.x * DT, base = tile_base[blockIdx.x];
+    const uint32_t total = (uint32_t)(tile_base[blockIdx.x + 1] - base);
+    if (base + total > out_cap) { if (tid == 0) atomicOr(err, ERRF_CAPACITY); return; }
+    // lengths of this thread's DPT consecutive tokens, exclusive scan over the CTA
+    uint32_t id[DPT], len[DPT], mine = 0;
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const uint64_t j = t0 + (uint64_t)tid * DPT + q;
+        id[q] = j < n ? __ldg(ids + j) : 0xFFFFFFFFu;
+        len[q] = j < n ? dec_tok_len(t, id[q], skip_special) : 0u;
+        mine += len[q];
+    }
+    uint32_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t off = incl - mine;
+    for (int w = 0; w < wid; ++w) off += s_warp[w];
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) { s_off[tid * DPT + q] = off; off += len[q]; }
+    if (tid == DTH - 1) s_off[DT] = off;
+    // bytes: staged in shared memory at the same alignment (mod 16) as their place in the output.  Tokens are taken in
+    // stripes (thread t: tokens t, t + 256, ...): neighbouring threads write neighbouring bytes, and a token of up to 12
+    // bytes comes out of ONE 16-byte record.
+    const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15u);
+    const bool staged = total + shift <= (uint32_t)DSTAGE;
+    uint8_t* const dst0 = staged ? s_stage + shift : out + base;
+    __syncthreads();                                                   // s_off complete
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const int j = q * DTH + tid;
+        const uint32_t o = s_off[j], L = s_off[j + 1] - o;
+        if (L == 0) continue;
+        const uint32_t tid_id = __ldg(ids + t0 + j);
+        uint8_t* d = dst0 + o;
+        if (L <= 12) {
+            const uint4 r = __ldg(t.rec + tid_id);
+            uint32_t w = r.x;
+#pragma unroll
+            for (uint32_t k = 0; k < 12; ++k) {
+                if (k == 4) w = r.y;
+                if (k == 8) w = r.z;
+                if (k < L) d[k] = (uint8_t)(w >> (8 * (k & 3)));
+            }
+        } else {
+            const uint8_t* src = t.blob + __ldg(t.off + tid_id);
+            for (uint32_t k = 0; k < L; ++k) d[k] = __ldg(src + k);
+        }
+    }
+    __syncthreads();
+    if (staged && total) {
+        uint8_t* const g = out + base;
+        const uint32_t head = min(total, (16u - shift) & 15u);            // bytes before the first aligned 16-byte group
+        if ((uint32_t)tid < head) g[tid] = s_stage[shift + tid];
+        const uint32_t body = (total - head) >> 4;
+        for (uint32_t v = tid; v < body; v += DTH)
+            *reinterpret_cast<uint4*>(g + head + 16 * v) = *reinterpret_cast<const uint4*>(s_stage + shift + head + 16 * v);
+        const uint32_t done = head + 16 * body;
+        if ((uint32_t)tid < total - done) g[done + tid] = s_stage[shift + done + tid];
+    }
+    // byte offsets of the documents whose first token lies in this tile (and, in the last tile, of those at the very end)
+    const uint64_t t1 = t0 + DT < n ? t0 + DT : n;
+    const bool last = t0 + DT >= n;
+    uint64_t lo = 0, hi = n_docs + 1;                                     // first d with ids_off[d] >= t0
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (ids_off[mid] >= t0) hi = mid; else lo = mid + 1; }
+    for (uint64_t d = lo + tid; d <= n_docs; d += DTH) {
+        const uint64_t j = ids_off[d];
+        if (j < t1 || (last && j == n)) raw_off[d] = base + s_off[j - t0];
+        else break;
+    }
 }
 
 // length of a well-formed UTF-8 sequence at p[i] (maximal-subpart rules), 0 if ill-formed;
@@ -212,34 +298,41 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
                   int skip_special, int cleanup, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off,
                   uint64_t* n_bytes_host, cudaStream_t st) {
     Workspace& ws = eng.ws;
-    uint32_t *len, *err;
-    uint64_t *boff, *raw_off;
+    uint32_t *tile_sum, *err;
+    uint64_t *tile_base, *raw_off;
+    const uint64_t n_tiles = (T + DT - 1) / DT;
     CK(ws.get(4, 256, (void**)&err));
     CK(cudaMemsetAsync(err, 0, 256, st));
-    CK(ws.get(10, (T + 2) * 4, (void**)&len));
-    CK(ws.get(11, (T + 2) * 8, (void**)&boff));
+    CK(ws.get(10, (n_tiles + 2) * 4, (void**)&tile_sum));
+    CK(ws.get(11, (n_tiles + 2) * 8, (void**)&tile_base));
     CK(ws.get(12, (n_docs + 2) * 8, (void**)&raw_off));
     eng.mark(nullptr, st);
-    k_dec_len<<<(unsigned)((T + 1 + 255) / 256), 256, 0, st>>>(eng.dec, d_ids, T, skip_special, len);
-    eng.launched(1); eng.mark("k_dec_len", st);
-    cub::TransformInputIterator<uint64_t, ToU64, const uint32_t*> it(len, ToU64());
+    if (n_tiles) { k_dec_tile_sums<<<(unsigned)n_tiles, DTH, 0, st>>>(eng.dec, d_ids, T, skip_special, tile_sum); eng.launched(1); }
+    CK(cudaMemsetAsync(tile_sum + n_tiles, 0, 4, st));
+    eng.mark("k_dec_tile_sums", st);
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(tile_sum, U32ToU64());
     size_t cub_bytes = 0;
     void* cub_tmp;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, boff, T + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, tile_base, n_tiles + 1, st));
     CK(ws.get(5, cub_bytes + 16, &cub_tmp));
-    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, it, boff, T + 1, st));
-    eng.launched(1); eng.mark("scan(id lengths)", st);
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, it, tile_base, n_tiles + 1, st));
+    eng.launched(1); eng.mark("scan(tile sums)", st);
     uint64_t raw_total = 0;
-    CK(eng.publish({{boff + T, 2, 12}}, st));
+    CK(eng.publish({{tile_base + n_tiles, 2, 12}}, st));
     CK(cudaStreamSynchronize(st));
     memcpy(&raw_total, eng.h_flags + 12, 8);
+    // Without clean-up the gathered bytes are the result (if they are valid UTF-8): write them where they belong.
+    const bool direct = !cleanup && d_out && raw_total <= out_cap && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;
     uint8_t* raw;
-    CK(ws.get(13, raw_total + 16, (void**)&raw));
+    if (direct) raw = d_out;
+    else CK(ws.get(13, raw_total + 16, (void**)&raw));
     eng.mark(nullptr, st);
-    if (T) { k_dec_gather<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(eng.dec, d_ids, T, skip_special, boff, raw); eng.launched(1); }
-    
-    k_dec_doc_off<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_ids_off, n_docs, boff, raw_off);
-    eng.launched(1); eng.mark("k_dec_gather+doc_off", st);
+    if (n_tiles) {
+        k_dec_write<<<(unsigned)n_tiles, DTH, 0, st>>>(eng.dec, d_ids, T, skip_special, tile_base, d_ids_off, n_docs, raw,
+                                                       direct ? out_cap : raw_total + 16, raw_off, err);
+        eng.launched(1);
+    } else CK(cudaMemsetAsync(raw_off, 0, (n_docs + 1) * 8, st));
+    eng.mark("k_dec_write", st);
     // Is the gathered byte string already valid UTF-8?  Then String::from_utf8_lossy is the identity.
     bool invalid = false;
     if (n_docs && raw_total) {
@@ -253,6 +346,12 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
         invalid = inv != 0;
     }
     const bool need_post = invalid;                        // sequential per-document path only for invalid UTF-8
+    if (need_post && direct) {                             // rare: the post-processing reads `raw` and writes d_out
+        uint8_t* scratch;
+        CK(ws.get(13, raw_total + 16, (void**)&scratch));
+        CK(cudaMemcpyAsync(scratch, raw, raw_total, cudaMemcpyDeviceToDevice, st));
+        raw = scratch;
+    }
     if (!d_out) {                                          // host-buffer entry point: output lives in the workspace
         out_cap = need_post ? 3 * raw_total + 16 : raw_total + 16;
         CK(ws.get(25, out_cap, (void**)&d_out));
@@ -263,7 +362,7 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
         if (rc != CTK_OK) return rc;
     } else if (!need_post) {
         if (raw_total > out_cap) return eng.fail(CTK_ERR_ARG, "decode output capacity too small");
-        if (raw_total) CK(cudaMemcpyAsync(d_out, raw, raw_total, cudaMemcpyDeviceToDevice, st));
+        if (raw_total && raw != d_out) CK(cudaMemcpyAsync(d_out, raw, raw_total, cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(d_out_off, raw_off, (n_docs + 1) * 8, cudaMemcpyDeviceToDevice, st));
     } else {
         uint8_t *bufA, *bufB, *which;

@@ -47,6 +47,11 @@ struct DecodeTables {
     const uint8_t* blob = nullptr;
     const uint32_t* off = nullptr;      // n_ids + 1
     const uint8_t* special = nullptr;   // n_ids
+    // compact copies for the gather: length per id (255 = look at off[]), the same with special tokens zeroed,
+    // and one 16-byte record per id {first 12 bytes, length} so that a token costs ONE table access per pass
+    const uint8_t* len8 = nullptr;
+    const uint8_t* len8_skip = nullptr;
+    const uint4* rec = nullptr;
     uint32_t n_ids = 0;
 };
 
