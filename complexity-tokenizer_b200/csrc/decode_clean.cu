@@ -218,33 +218,91 @@ __global__ void __launch_bounds__(256) k_clean_regions(const uint8_t* __restrict
     while (m) { const int k = __ffs(m) - 1; m &= m - 1; clean_region_at(R, n, f, rr, fire, emit, base + k); }
 }
 
-struct U8ToU32 { __host__ __device__ uint32_t operator()(uint8_t v) const { return v; } };
+// ---- survivors -> output, without a position per byte in global memory -----------------------------------------
+// A tile = 4096 bytes = one CTA, 16 bytes per thread.  Pass 1 counts the tile's survivors; a scan of the tile counts
+// places the tiles; pass 2 scans inside the CTA, lays the surviving bytes out in shared memory and writes them with
+// aligned 16-byte stores, and gives the documents that start inside the tile their output offsets.
+constexpr int CT = 4096, CTH = 256;
 
-// 16 bytes per thread: one position load, then the survivors are consecutive
-__global__ void __launch_bounds__(256) k_clean_scatter(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
-                                                       const uint8_t* __restrict__ emit, const uint32_t* __restrict__ pos,
-                                                       uint8_t* __restrict__ out, uint64_t out_cap, uint32_t* __restrict__ err) {
-    const uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
-    if (base >= n) return;
-    const uint4 ev = *reinterpret_cast<const uint4*>(emit + base);
-    if (!(ev.x | ev.y | ev.z | ev.w)) return;
-    const uint4 rv = *reinterpret_cast<const uint4*>(R + base), fv = *reinterpret_cast<const uint4*>(f + base);
-    const uint32_t e[4] = {ev.x, ev.y, ev.z, ev.w}, r[4] = {rv.x, rv.y, rv.z, rv.w}, ff[4] = {fv.x, fv.y, fv.z, fv.w};
-    uint64_t p = pos[base];
-    const int lim = n - base < 16 ? (int)(n - base) : 16;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        if (k < lim && ((e[k >> 2] >> (8 * (k & 3))) & 0xFFu)) {
-            if (p >= out_cap) { atomicOr(err, ERRF_CAPACITY); return; }
-            out[p++] = ((ff[k >> 2] >> (8 * (k & 3))) & F_WS) ? (uint8_t)' ' : (uint8_t)(r[k >> 2] >> (8 * (k & 3)));
-        }
+__global__ void __launch_bounds__(CTH) k_clean_tile_sums(const uint8_t* __restrict__ emit, uint64_t n, uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t s_part[CTH / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * CT + threadIdx.x * 16;
+    uint32_t c = 0;
+    if (base < n) {                                                  // emit[] is zero beyond n (64 bytes of padding)
+        const uint4 e = *reinterpret_cast<const uint4*>(emit + base);
+        c = __popc(e.x) + __popc(e.y) + __popc(e.z) + __popc(e.w);  // flags are 0 or 1
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < CTH / 32; ++w) tot += s_part[w];
+        tile_sum[blockIdx.x] = tot;
     }
 }
 
-__global__ void k_clean_doc_off(const uint64_t* __restrict__ raw_off, uint64_t n_docs, const uint32_t* __restrict__ pos,
-                                uint64_t* __restrict__ out_off) {
-    uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (d <= n_docs) out_off[d] = pos[raw_off[d]];
+__global__ void __launch_bounds__(CTH) k_clean_write(const uint8_t* __restrict__ R, uint64_t n, const uint8_t* __restrict__ f,
+                                                     const uint8_t* __restrict__ emit, const uint32_t* __restrict__ tile_base,
+                                                     const uint64_t* __restrict__ raw_off, uint64_t n_docs,
+                                                     uint8_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ out_off,
+                                                     uint32_t* __restrict__ err) {
+    __shared__ uint32_t s_thr[CTH + 1];                               // survivors before each thread's 16 bytes
+    __shared__ uint32_t s_warp[CTH / 32];
+    __shared__ __align__(16) uint8_t s_emit[CT];
+    __shared__ __align__(16) uint8_t s_stage[CT + 16];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t t0 = (uint64_t)blockIdx.x * CT, gb = t0 + tid * 16;
+    const uint32_t base = tile_base[blockIdx.x], total = tile_base[blockIdx.x + 1] - base;
+    if ((uint64_t)base + total > out_cap) { if (tid == 0) atomicOr(err, ERRF_CAPACITY); return; }
+    uint4 ev = make_uint4(0, 0, 0, 0), rv = ev, fv = ev;
+    if (gb < n) {
+        ev = *reinterpret_cast<const uint4*>(emit + gb);
+        if (ev.x | ev.y | ev.z | ev.w) { rv = *reinterpret_cast<const uint4*>(R + gb); fv = *reinterpret_cast<const uint4*>(f + gb); }
+    }
+    *reinterpret_cast<uint4*>(s_emit + tid * 16) = ev;
+    const uint32_t mine = __popc(ev.x) + __popc(ev.y) + __popc(ev.z) + __popc(ev.w);
+    uint32_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t off = incl - mine;
+    for (int w = 0; w < wid; ++w) off += s_warp[w];
+    s_thr[tid] = off;
+    if (tid == CTH - 1) s_thr[CTH] = off + mine;
+    const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15u);
+    const uint32_t e[4] = {ev.x, ev.y, ev.z, ev.w}, r[4] = {rv.x, rv.y, rv.z, rv.w}, ff[4] = {fv.x, fv.y, fv.z, fv.w};
+    if (mine) {
+        uint8_t* d = s_stage + shift + off;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if ((e[k >> 2] >> (8 * (k & 3))) & 0xFFu)
+                *d++ = ((ff[k >> 2] >> (8 * (k & 3))) & F_WS) ? (uint8_t)' ' : (uint8_t)(r[k >> 2] >> (8 * (k & 3)));
+    }
+    __syncthreads();
+    if (total) {
+        uint8_t* const g = out + base;
+        const uint32_t head = min(total, (16u - shift) & 15u);
+        if ((uint32_t)tid < head) g[tid] = s_stage[shift + tid];
+        const uint32_t body = (total - head) >> 4;
+        for (uint32_t v = tid; v < body; v += CTH)
+            *reinterpret_cast<uint4*>(g + head + 16 * v) = *reinterpret_cast<const uint4*>(s_stage + shift + head + 16 * v);
+        const uint32_t done = head + 16 * body;
+        if ((uint32_t)tid < total - done) g[done + tid] = s_stage[shift + done + tid];
+    }
+    // output offsets of the documents that start in this tile (in the last tile also of those at the very end)
+    const uint64_t t1 = t0 + CT < n ? t0 + CT : n;
+    const bool last = t0 + CT >= n;
+    uint64_t lo = 0, hi = n_docs + 1;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (raw_off[mid] >= t0) hi = mid; else lo = mid + 1; }
+    for (uint64_t d = lo + tid; d <= n_docs; d += CTH) {
+        const uint64_t pz = raw_off[d];
+        if (!(pz < t1 || (last && pz == n))) break;
+        const uint32_t q = (uint32_t)(pz - t0);                       // 0 .. CT
+        uint32_t before = q < (uint32_t)CT ? s_thr[q >> 4] : s_thr[CTH];
+        for (uint32_t k = q & ~15u; k < q && k < (uint32_t)CT; ++k) before += s_emit[k];
+        out_off[d] = (uint64_t)base + before;
+    }
 }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
@@ -255,12 +313,10 @@ int clean_parallel(Engine& eng, const uint8_t* raw, const uint64_t* raw_off, siz
     if (n >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_ARG, "one decode call handles less than 4 GiB of text");
     Workspace& ws = eng.ws;
     uint8_t *f, *rr, *fire, *emit;
-    uint32_t* pos;
     CK(ws.get(14, n + 64, (void**)&f));
     CK(ws.get(15, n + 64, (void**)&rr));
     CK(ws.get(16, n + 64, (void**)&fire));
     CK(ws.get(17, n + 64, (void**)&emit));
-    CK(ws.get(26, (n + 2) * 4, (void**)&pos));
     unsigned gb = (unsigned)((n + 255) / 256), gd = (unsigned)((n_docs + 1 + 255) / 256), g16 = (unsigned)(((n + 15) / 16 + 255) / 256);
     eng.mark(nullptr, st);
     CK(cudaMemsetAsync(fire, 0, n + 64, st));
@@ -278,15 +334,20 @@ int clean_parallel(Engine& eng, const uint8_t* raw, const uint64_t* raw_off, siz
         eng.mark("clean: k_clean_regions", st);
         eng.launched(5);
     }
-    cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> it(emit, U8ToU32());
+    const uint64_t n_tiles = (n + CT - 1) / CT;
+    uint32_t *tile_sum, *tile_base;
+    CK(ws.get(26, (n_tiles + 2) * 4, (void**)&tile_sum));
+    CK(ws.get(46, (n_tiles + 2) * 4, (void**)&tile_base));
+    if (n_tiles) k_clean_tile_sums<<<(unsigned)n_tiles, CTH, 0, st>>>(emit, n, tile_sum);
+    CK(cudaMemsetAsync(tile_sum + n_tiles, 0, 4, st));
     size_t cub_bytes = 0; void* cub_tmp;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, pos, n + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, tile_sum, tile_base, n_tiles + 1, st));
     CK(ws.get(5, cub_bytes + 16, &cub_tmp));
-    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, it, pos, n + 1, st));
-    eng.mark("clean: scan", st);
-    if (n) k_clean_scatter<<<g16, 256, 0, st>>>(raw, n, f, emit, pos, d_out, out_cap, err);
-    k_clean_doc_off<<<gd, 256, 0, st>>>(raw_off, n_docs, pos, d_out_off);
-    eng.launched(3); eng.mark("clean: k_clean_scatter", st);
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, tile_sum, tile_base, n_tiles + 1, st));
+    eng.mark("clean: tile sums + scan", st);
+    if (n_tiles) k_clean_write<<<(unsigned)n_tiles, CTH, 0, st>>>(raw, n, f, emit, tile_base, raw_off, n_docs, d_out, out_cap, d_out_off, err);
+    else CK(cudaMemsetAsync(d_out_off, 0, (n_docs + 1) * 8, st));
+    eng.launched(3); eng.mark("clean: k_clean_write", st);
     return CTK_OK;
 }
 
