@@ -91,7 +91,32 @@ __global__ void __launch_bounds__(XL_THREADS) k_xl_rank(const DevTables t, const
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < XL_ITEMS; ++q) left_r[q] = A[iW + q * XL_THREADS + tid - 1];     // W >= 1
-    // left-aligned window minima by doubling: with width w done, A[j] = min of pairs j .. j + w - 1
+    if (t.round_parallel) {
+        // per-token reach (encode_long.cuh): pair (x, y) looks left as far as a token ending with x can extend and right
+        // as far as a token starting with y can extend, counted in SYMBOLS here (a symbol is at least one initial
+        // symbol long, so this window contains the exact one).  Three times fewer rounds than the uniform window W.
+#pragma unroll
+        for (int q = 0; q < XL_ITEMS; ++q) {
+            const int own = q * XL_THREADS + tid;
+            const long long i = t0 + own;
+            if (i >= (long long)n) continue;
+            const uint32_t r = my_r[q];
+            bool blocked = false;
+            if (r != kNone) {
+                const uint32_t wl = min(__ldg(t.reach + xs[i]) & 0xFFFFu, W), wr = min(__ldg(t.reach + xs[i + 1]) >> 16, W);
+                const int j = own + iW;
+                for (uint32_t d = 1; d <= max(wl, wr); ++d) {
+                    const uint32_t a = d <= wl ? A[j - (int)d] : kNone, b = d <= wr ? A[j + (int)d] : kNone;
+                    if (min(a, b) < r) { blocked = true; break; }
+                }
+            }
+            const bool head = r == kNone || left_r[q] != r;
+            rank[i] = r; newid[i] = my_v[q];
+            scanv[i] = ((unsigned long long)(head ? (uint32_t)i + 1u : 0u) << 32) | (blocked ? 1u : 0u);
+        }
+        return;
+    }
+    // uniform window W: left-aligned window minima by doubling: with width w done, A[j] = min of pairs j .. j + w - 1
     uint32_t w = 1;
     while (w * 2 <= 2 * W + 1) {
         for (int j = tid; j < span; j += XL_THREADS) {

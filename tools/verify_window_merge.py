@@ -72,7 +72,7 @@ def reaches(vocab_tokens):
             if s_ in toks: WL[s_] = max(WL[s_], len(t) - len(s_))
     return WL, WR
 
-def par_reach(toks, ranks, new, WL, WR):
+def par_reach(toks, ranks, new, WL, WR, in_symbols=False):
     """Same rounds, but every pair only looks as far as tokens around its own two symbols can reach:
     left of x = sym[j] up to WL[x] initial symbols, right of y = sym[j+1] up to WR[y]."""
     toks = list(toks)
@@ -80,7 +80,7 @@ def par_reach(toks, ranks, new, WL, WR):
     while True:
         n = len(toks)
         pos = [0] * (n + 1)
-        for i, t in enumerate(toks): pos[i + 1] = pos[i] + len(t)
+        for i, t in enumerate(toks): pos[i + 1] = pos[i] + (1 if in_symbols else len(t))   # in_symbols: the grid-wide kernels' conservative unit
         rk = [ranks.get((toks[i], toks[i + 1]), INF) for i in range(n - 1)]
         blocked = [False] * (n - 1)
         for j, r in enumerate(rk):
@@ -151,7 +151,7 @@ def make_table(rng, nsym, lmax, nmerge, monotone):
     make_table.last_vocab = set(base) | set(newt.values()) | {x for p in pairs for x in p}
     return base, ranks, newt, W
 
-def trial(rng, nsym, lmax, nmerge, textlen, monotone, W_override=None, reach=False):
+def trial(rng, nsym, lmax, nmerge, textlen, monotone, W_override=None, reach=False, in_symbols=False):
     base, ranks, newt, W = make_table(rng, nsym, lmax, nmerge, monotone)
     if reach:
         WL, WR = reaches(make_table.last_vocab)
@@ -164,7 +164,7 @@ def trial(rng, nsym, lmax, nmerge, textlen, monotone, W_override=None, reach=Fal
         else:
             text = [rng.choice(base) for _ in range(rng.randint(1, textlen))]
         a = seq(text, ranks, newt)
-        b, rounds = par_reach(text, ranks, newt, WL, WR) if reach else par(text, ranks, newt, W_override or W)
+        b, rounds = par_reach(text, ranks, newt, WL, WR, in_symbols) if reach else par(text, ranks, newt, W_override or W)
         rmax = max(rmax, rounds)
         if a != b:
             bad += 1
@@ -174,10 +174,11 @@ if __name__ == '__main__':
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
     for label, mono, wo, reach in (('monotone table, window = longest token', True, None, False),
                                    ('monotone table, per-symbol reach windows', True, None, True),
+                                   ('monotone table, reach counted in symbols', True, None, 'sym'),
                                    ('NON-monotone table (expected > 0)', False, None, False),
                                    ('monotone table, window = 1 (expected > 0)', True, 1, False)):
         rng = random.Random(7); tot = bad = 0; rmax = 0
         for it in range(N):
             nsym = rng.choice([1, 2, 2, 3, 4]); lmax = rng.choice([2, 3, 4, 5, 6]); nm = rng.choice([3, 6, 12, 30, 60])
-            b, r = trial(rng, nsym, lmax, nm, 120, mono, wo, reach); bad += b; tot += 20; rmax = max(rmax, r)
+            b, r = trial(rng, nsym, lmax, nm, 120, mono, wo, bool(reach), reach == 'sym'); bad += b; tot += 20; rmax = max(rmax, r)
         print('%-46s mismatches %d / %d   (most rounds %d)' % (label, bad, tot, rmax))
