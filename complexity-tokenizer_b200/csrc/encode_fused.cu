@@ -576,6 +576,8 @@ __global__ void __launch_bounds__(256) k_compact(const uint32_t* __restrict__ ru
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
 
+static constexpr size_t mid_smem(int n) { return (size_t)(2 * n * 32 + n * 4 + 256) * 4; }   // k_encode_mid<n>: symbols, keys, block minima, byte LUT
+
 // Round-parallel merging of the very long pre-tokens k_encode_long set aside (encode_xlong.cuh).
 // `cursor` = list entries << XL_IDX_SHIFT | symbols (incl. one separator per entry), read back by the caller.
 struct XlState { const uint32_t* xs; uint32_t n, n_list; const uint32_t* sep_pos; uint32_t* region_dst; };
@@ -664,12 +666,11 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         if (per_sm < 1) return eng.fail(CTK_ERR_CUDA, "encode kernel does not fit on an SM");
         eng.fused_grid = per_sm * sms;
         eng.long_grid = sms * 4;
-        CK(cudaFuncSetAttribute(k_encode_mid<MID_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * MID_B * 32 + MID_B * 4 + 256) * 4));
-        int a = 0, b = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_encode_mid<MID_A>, 32, (2 * MID_A * 32 + MID_A * 4 + 256) * 4));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_encode_mid<MID_B>, 32, (2 * MID_B * 32 + MID_B * 4 + 256) * 4));
-        eng.mid_grid_a = sms * (a > 0 ? a : 1);
-        eng.mid_grid_b = sms * (b > 0 ? b : 1);
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode_mid<MID_N0>, 32, mid_smem(MID_N0))); eng.mid_grid[0] = sms * (occ > 0 ? occ : 1);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode_mid<MID_N1>, 32, mid_smem(MID_N1))); eng.mid_grid[1] = sms * (occ > 0 ? occ : 1);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode_mid<MID_N2>, 32, mid_smem(MID_N2))); eng.mid_grid[2] = sms * (occ > 0 ? occ : 1);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode_mid<MID_N3>, 32, mid_smem(MID_N3))); eng.mid_grid[3] = sms * (occ > 0 ? occ : 1);
     }
     Workspace& ws = eng.ws;
     FusedParams p{};
@@ -693,7 +694,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.desc_cap = (uint32_t)(n_bytes / 33 + 16);
     CK(ws.get(9, (uint64_t)p.desc_cap * sizeof(LongDesc), (void**)&p.desc));
     CK(ws.get(41, (uint64_t)p.desc_cap * sizeof(XlEntry), (void**)&p.xl_list));
-    CK(ws.get(44, 3ull * p.desc_cap * 4, (void**)&p.work_list));
+    CK(ws.get(44, (uint64_t)MID_LISTS * p.desc_cap * 4, (void**)&p.work_list));
     CK(ws.get(42, (p.n_slices + 2) * 2, (void**)&p.slice_first));
     CK(ws.get(43, (n_docs + 1) * 8, (void**)&p.ids_off_rel));
     p.xl_enabled = n_ids_host != nullptr && eng.model.merges_monotone && eng.model.max_token_span <= XL_MAX_WINDOW &&
@@ -708,7 +709,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.n_inline = 96 / p.id_bits;
     if (p.n_inline > MAXINLINE) p.n_inline = MAXINLINE;
     // ctrl words: [0] err flags, [2] desc cursor, [3] ovf cursor, [4..5] long cursor, [6..7] xlong cursor, [8] holes, [9] round size,
-    //             [10..12] work-list lengths
+    //             [10..14] work-list lengths
     p.work_count = ctrl + 10;
     p.xl_cursor = reinterpret_cast<unsigned long long*>(ctrl + 6);
     p.err = ctrl; p.desc_cursor = ctrl + 2; p.ovf_cursor = ctrl + 3; p.long_cursor = reinterpret_cast<unsigned long long*>(ctrl + 4);
@@ -721,7 +722,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         eng.cache_valid = true;
     } else {
         CK(cudaMemsetAsync(ctrl, 0, 12, st));                          // keep the overflow cursor
-        CK(cudaMemsetAsync(ctrl + 4, 0, 36, st));
+        CK(cudaMemsetAsync(ctrl + 4, 0, 48, st));
     }
     eng.mark("memset(cache)", st);
     unsigned doc_grid = (unsigned)((n_docs + 1 + 255) / 256);
@@ -732,9 +733,11 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     eng.launched(1); eng.mark("k_encode_slices", st);
     k_long_prep<<<eng.long_grid, 256, 0, st>>>(p);
     if (p.mid_enabled) {
-        k_encode_mid<MID_A><<<eng.mid_grid_a, 32, (2 * MID_A * 32 + MID_A * 4 + 256) * 4, st>>>(p, 0);
-        k_encode_mid<MID_B><<<eng.mid_grid_b, 32, (2 * MID_B * 32 + MID_B * 4 + 256) * 4, st>>>(p, 1);
-        eng.launched(2);
+        k_encode_mid<MID_N0><<<eng.mid_grid[0], 32, mid_smem(MID_N0), st>>>(p, 0);
+        k_encode_mid<MID_N1><<<eng.mid_grid[1], 32, mid_smem(MID_N1), st>>>(p, 1);
+        k_encode_mid<MID_N2><<<eng.mid_grid[2], 32, mid_smem(MID_N2), st>>>(p, 2);
+        k_encode_mid<MID_N3><<<eng.mid_grid[3], 32, mid_smem(MID_N3), st>>>(p, 3);
+        eng.launched(4);
     }
     k_encode_long<<<eng.long_grid, 256, 0, st>>>(p);
     eng.launched(2); eng.mark("k_long_prep+mid+long", st);

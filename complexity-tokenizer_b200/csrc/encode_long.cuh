@@ -251,8 +251,10 @@ __device__ __forceinline__ uint32_t long_piece(const FusedParams& p, const uint8
 // ------------------------------------------------------------------------------------------------
 // k_long_prep: one thread per long pre-token.  Resolves the length of those that run past their chunk (the next
 // owned start of a later slice, or the end of the text), reserves room in the long pool (one atomic per warp) and
-// sorts the pre-token into a work list: MID_A (<= 64 bytes), MID_B (<= 128 bytes), REST.
-constexpr int MID_A = 64, MID_B = 128;
+// sorts the pre-token into a work list by length class (<= 48, 64, 96, 128 bytes: batches of similar pre-tokens, and
+// more warps per SM for the short classes) or the rest.
+constexpr int MID_N0 = 48, MID_N1 = 64, MID_N2 = 96, MID_N3 = 128;   // one k_encode_mid instantiation and one work list per class
+constexpr int MID_LISTS = 5;                         // the four classes + the rest (k_encode_long)
 __global__ void __launch_bounds__(256) k_long_prep(const FusedParams p) {
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -286,9 +288,12 @@ __global__ void __launch_bounds__(256) k_long_prep(const FusedParams p) {
     bool ok = have && (xl || po + len <= p.long_cap);
     if (have && !ok) atomicOr(p.err, ERRF_POOL);
     if (have) { p.desc[i].pool = xl ? kNone : (uint32_t)po; p.desc[i].cnt = 0; }
-    const int which = !ok ? 3 : (!xl && p.mid_enabled && len <= MID_A) ? 0 : (!xl && p.mid_enabled && len <= MID_B) ? 1 : 2;
+    int which = !ok ? MID_LISTS : MID_LISTS - 1;
+    if (ok && !xl && p.mid_enabled) {
+        which = len <= (uint64_t)MID_N0 ? 0 : len <= (uint64_t)MID_N1 ? 1 : len <= (uint64_t)MID_N2 ? 2 : len <= (uint64_t)MID_N3 ? 3 : which;
+    }
 #pragma unroll
-    for (int w = 0; w < 3; ++w) {
+    for (int w = 0; w < MID_LISTS; ++w) {
         const unsigned m = __ballot_sync(full, which == w);
         if (!m) continue;
         uint32_t b0 = 0;
@@ -408,8 +413,8 @@ __global__ void __launch_bounds__(256) k_encode_long(const FusedParams p) {
     const int lane = threadIdx.x & 31;
     __shared__ RoundBuf s_rb[8];
     RoundBuf* const rb = (p.t.round_parallel && !p.no_rounds) ? &s_rb[threadIdx.x >> 5] : nullptr;
-    const uint32_t count = min(p.work_count[2], p.desc_cap);
-    const uint32_t* list = p.work_list + 2ull * p.desc_cap;
+    const uint32_t count = min(p.work_count[MID_LISTS - 1], p.desc_cap);
+    const uint32_t* list = p.work_list + (uint64_t)(MID_LISTS - 1) * p.desc_cap;
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += n_warps) {
         const uint32_t i = list[w];

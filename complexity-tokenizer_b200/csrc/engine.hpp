@@ -75,7 +75,7 @@ struct Engine {
     bool cache_valid = false;           // the pre-token cache holds entries of earlier calls
     bool use_general = false;           // debug: run the multi-kernel pipeline instead of the fused kernel
     int long_grid = 0;
-    int mid_grid_a = 0, mid_grid_b = 0; // co-resident single-warp CTAs of k_encode_mid<64> / <128>
+    int mid_grid[4] = {};               // co-resident single-warp CTAs of the four k_encode_mid instantiations
     uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // bytes the last host-buffer encode call moved over PCIe
     int xl_last_rounds = 0;             // rounds the last very-long-pre-token pass took (diagnostics)
     int fused_grid = 0;                 // co-resident CTAs of k_encode_fused (SMs x occupancy), computed once
