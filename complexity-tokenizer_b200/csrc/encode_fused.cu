@@ -678,10 +678,13 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.text = d_text; p.n_bytes = n_bytes; p.off = d_off; p.n_docs = n_docs;
     p.n_slices = (n_bytes + SLICE - 1) / SLICE;
     p.n_tiles = (uint32_t)((p.n_slices + FW - 1) / FW);
-    const uint32_t cache_slots = 1u << 20, ovf_cap = 1u << 18;
+    // small inputs: a small cache (the clear is part of every call) and the plain long path (fewer launches)
+    uint32_t cache_slots = 1u << 20;
+    while (cache_slots > 1024 && (uint64_t)cache_slots * 4 > n_bytes) cache_slots >>= 1;   // ~one slot per 4-8 input bytes
+    const uint32_t ovf_cap = 1u << 18;
     uint32_t *first_doc, *ctrl, *slice_base;
     CK(ws.get(0, (p.n_slices + 1) * 4, (void**)&first_doc));
-    CK(ws.get(18, (uint64_t)cache_slots * sizeof(CacheSlot), (void**)&p.cache));
+    CK(ws.get(18, (uint64_t)(1u << 20) * sizeof(CacheSlot), (void**)&p.cache));       // always the full table; a call uses a prefix
     CK(ws.get(19, (uint64_t)ovf_cap * 64, (void**)&p.ovf_pool));
     CK(ws.get(4, 256, (void**)&ctrl));
     CK(ws.get(1, (p.n_slices + 2) * 4, (void**)&p.slice_cnt));
@@ -700,7 +703,7 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.xl_enabled = n_ids_host != nullptr && eng.model.merges_monotone && eng.model.max_token_span <= XL_MAX_WINDOW &&
                    eng.tables.n_added == 0 && !getenv("CTK_NO_XLONG");
     p.no_rounds = getenv("CTK_NO_ROUNDS") != nullptr;
-    p.mid_enabled = eng.tables.n_added == 0 && (eng.model.pairs.empty() || eng.model.pairs.back().rank < (1u << 24)) && !getenv("CTK_NO_MID");   // rank << 8 | slot keys
+    p.mid_enabled = n_bytes > (256u << 10) && eng.tables.n_added == 0 && (eng.model.pairs.empty() || eng.model.pairs.back().rank < (1u << 24)) && !getenv("CTK_NO_MID");   // rank << 8 | slot keys
     p.check_nfc = check_nfc ? 1 : 0;
     p.first_doc = first_doc; p.cache_mask = cache_slots - 1; p.ovf_cap = ovf_cap;
     uint32_t max_id = eng.model.id_present.empty() ? 1u : (uint32_t)eng.model.id_present.size() - 1;
@@ -720,7 +723,12 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
         CK(cudaMemsetAsync(p.cache, 0xFF, (uint64_t)cache_slots * sizeof(CacheSlot), st));
         CK(cudaMemsetAsync(ctrl, 0, 256, st));
         eng.cache_valid = true;
+        eng.cache_init_slots = cache_slots;
     } else {
+        if (cache_slots > eng.cache_init_slots) {                      // kept cache, larger prefix than ever cleared: clear the new part
+            CK(cudaMemsetAsync(p.cache + eng.cache_init_slots, 0xFF, (uint64_t)(cache_slots - eng.cache_init_slots) * sizeof(CacheSlot), st));
+            eng.cache_init_slots = cache_slots;
+        }
         CK(cudaMemsetAsync(ctrl, 0, 12, st));                          // keep the overflow cursor
         CK(cudaMemsetAsync(ctrl + 4, 0, 48, st));
     }

@@ -73,6 +73,7 @@ struct Engine {
     std::mutex mu;                      // serialises device work issued through this tokenizer
     bool cache_persistent = false;
     bool cache_valid = false;           // the pre-token cache holds entries of earlier calls
+    uint32_t cache_init_slots = 0;      // slots [0, this) hold entries or EMPTY; the rest of the table was never cleared since the last full clear
     bool use_general = false;           // debug: run the multi-kernel pipeline instead of the fused kernel
     int long_grid = 0;
     int mid_grid[4] = {};               // co-resident single-warp CTAs of the four k_encode_mid instantiations
