@@ -142,3 +142,27 @@ def test_hypothesis_differential(built_lib, tok_paths):
         assert tok.decode_batch_with_options(got, True, False) == orc.decode_batch(got, True, False)
 
     check()
+
+
+def test_persistent_cache_across_calls_of_different_sizes(built_lib, tok_paths):
+    """ctk_set_cache_persistent(1) keeps the pre-token cache between calls; a call uses a prefix of the table sized to
+    its input, so small and large calls alternate over differently sized prefixes (parts never cleared before must be
+    cleared when first used).  Ids stay the oracle's whatever the order; turning persistence off again clears."""
+    import synth
+    tok, orc = _tok(tok_paths['config2']), _oracle(tok_paths['config2'])
+    small = ['a few words only', 'another short text, with punctuation!', '']
+    mid_text, mid_offs = synth.gen_corpus('ascii', 77, 300 << 10, doc_median=1024)
+    big_text, big_offs = synth.gen_corpus('ascii', 78, 6 << 20, doc_median=2048)
+    want_small = orc.encode_batch(small)
+    want_mid, want_big = orc.encode_packed(mid_text, mid_offs), orc.encode_packed(big_text, big_offs)
+    tok.set_cache_persistent(True)
+    for rnd in range(2):
+        assert tok.encode_batch(small) == want_small
+        ids, off = tok.encode_packed(mid_text, mid_offs)
+        assert np.array_equal(ids, want_mid[0]) and np.array_equal(off, want_mid[1])
+        ids, off = tok.encode_packed(big_text, big_offs)
+        assert np.array_equal(ids, want_big[0]) and np.array_equal(off, want_big[1])
+        assert tok.encode_batch(small) == want_small
+    tok.set_cache_persistent(False)
+    ids, off = tok.encode_packed(mid_text, mid_offs)
+    assert np.array_equal(ids, want_mid[0]) and np.array_equal(off, want_mid[1])
