@@ -100,6 +100,44 @@ def _pack_texts(texts):
     return buf, off
 
 
+def arrow_strings_to_packed(strings):
+    """(uint8 text view, uint64[n+1] offsets) of a pyarrow string array, zero-copy for the text; nulls are rejected
+    (the reference takes list[str]).  Sliced and chunked arrays are handled."""
+    import pyarrow as pa
+    if isinstance(strings, pa.ChunkedArray):
+        strings = strings.combine_chunks() if strings.num_chunks != 1 else strings.chunk(0)
+    if not (pa.types.is_string(strings.type) or pa.types.is_large_string(strings.type)):
+        raise TypeError('expected an Arrow string array, got %s' % strings.type)
+    if strings.null_count:
+        raise ValueError('null strings cannot be encoded')
+    n = len(strings)
+    _, off_buf, data_buf = strings.buffers()
+    odt = np.int64 if pa.types.is_large_string(strings.type) else np.int32
+    offs = np.frombuffer(off_buf, dtype=odt)[strings.offset:strings.offset + n + 1] if n or off_buf is not None else np.zeros(1, odt)
+    if len(offs) == 0:
+        offs = np.zeros(1, odt)
+    lo, hi = int(offs[0]), int(offs[-1])
+    text = np.frombuffer(data_buf, dtype=np.uint8)[lo:hi] if data_buf is not None and hi > lo else np.zeros(0, np.uint8)
+    return text, (offs.astype(np.int64) - lo).astype(np.uint64)
+
+
+def arrow_lists_to_packed(id_lists):
+    """(uint32 ids, uint64[n+1] offsets) of a pyarrow (Large)ListArray of integer ids."""
+    import pyarrow as pa
+    if isinstance(id_lists, pa.ChunkedArray):
+        id_lists = id_lists.combine_chunks() if id_lists.num_chunks != 1 else id_lists.chunk(0)
+    if not (pa.types.is_list(id_lists.type) or pa.types.is_large_list(id_lists.type)):
+        raise TypeError('expected an Arrow list array, got %s' % id_lists.type)
+    if id_lists.null_count:
+        raise ValueError('null id lists cannot be decoded')
+    offs = id_lists.offsets.to_numpy().astype(np.int64)
+    lo = int(offs[0]) if len(offs) else 0
+    vals = id_lists.values.to_numpy(zero_copy_only=False)
+    hi = int(offs[-1]) if len(offs) else 0
+    ids = np.ascontiguousarray(vals[lo:hi]).astype(np.uint32, copy=False)
+    return ids, (offs - lo).astype(np.uint64) if len(offs) else np.zeros(1, np.uint64)
+
+
 class Tokenizer:
     """HuggingFace tokenizer.json byte-level BPE tokenizer; encode/decode run on the GPU."""
 
@@ -176,6 +214,22 @@ class Tokenizer:
         finally:
             lib.ctk_result_free(res)
         return b, off
+
+    # ---- Arrow in / Arrow out (host ingestion without per-string Python objects)
+    def encode_arrow(self, strings):
+        """pyarrow StringArray / LargeStringArray / ChunkedArray of strings -> LargeListArray<uint32> of ids.
+        The Arrow data and offsets buffers ARE the packed batch the C ABI takes; nothing is copied per string."""
+        text, offs = arrow_strings_to_packed(strings)
+        ids, ioff = self.encode_packed(text, offs)
+        import pyarrow as pa
+        return pa.LargeListArray.from_arrays(pa.array(ioff.astype(np.int64)), pa.array(ids))
+
+    def decode_arrow(self, id_lists, skip_special_tokens=False, clean_up_tokenization_spaces=True):
+        """pyarrow ListArray / LargeListArray of unsigned ids -> LargeStringArray (decode_batch_with_options semantics)."""
+        import pyarrow as pa
+        ids, offs = arrow_lists_to_packed(id_lists)
+        b, boff = self.decode_packed(ids, offs, skip_special_tokens, clean_up_tokenization_spaces)
+        return pa.LargeStringArray.from_buffers(len(offs) - 1, pa.py_buffer(boff.astype(np.int64)), pa.py_buffer(b))
 
     # ---- reference API (bindings/tokenizer.rs:203-238, 655-663)
     def encode(self, text):

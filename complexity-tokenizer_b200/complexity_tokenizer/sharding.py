@@ -62,3 +62,29 @@ def encode_batch_sharded(tok, text, offsets, rank, world, group=None):
     ids, ioff = tok.encode_packed(t, o)
     meta = exchange_shard_metadata(d0, len(o) - 1, int(ioff[-1]), group)
     return ids, ioff + np.uint64(meta[rank]['ids_base']), meta
+
+
+def gather_ids(ids, meta, rank, dst=0, group=None):
+    """Optional: bring every shard's ids to ONE rank.  `ids` is this rank's torch tensor of ids
+    (on its GPU with NCCL -- the copies then go GPU to GPU over NVLink/NVSwitch -- or on the CPU with gloo); `meta` is
+    exchange_shard_metadata()'s result.  Returns on `dst` one tensor holding all ids in document order (shard r at
+    meta[r]['ids_base']), elsewhere None.  Point-to-point sends: no collective, nothing moves that is not needed."""
+    import torch
+    import torch.distributed as dist
+    world = len(meta)
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return ids
+    total = meta[-1]['ids_base'] + meta[-1]['n_ids']
+    if rank == dst:
+        out = torch.empty(total, dtype=ids.dtype, device=ids.device)
+        base = meta[rank]['ids_base']
+        out[base:base + meta[rank]['n_ids']].copy_(ids[:meta[rank]['n_ids']])
+        ops = [dist.P2POp(dist.irecv, out[m['ids_base']:m['ids_base'] + m['n_ids']], r, group)
+               for r, m in enumerate(meta) if r != dst and m['n_ids']]
+        for req in (dist.batch_isend_irecv(ops) if ops else []):
+            req.wait()
+        return out
+    if meta[rank]['n_ids']:
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, ids[:meta[rank]['n_ids']].contiguous(), dst, group)]):
+            req.wait()
+    return None

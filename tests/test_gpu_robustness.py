@@ -166,3 +166,23 @@ def test_persistent_cache_across_calls_of_different_sizes(built_lib, tok_paths):
     tok.set_cache_persistent(False)
     ids, off = tok.encode_packed(mid_text, mid_offs)
     assert np.array_equal(ids, want_mid[0]) and np.array_equal(off, want_mid[1])
+
+
+def test_arrow_in_arrow_out(built_lib, tok_paths):
+    """encode_arrow / decode_arrow: same ids and strings as the list API, for plain, large-offset,
+    sliced and chunked Arrow arrays."""
+    import pyarrow as pa
+    import synth
+    tok, orc = _tok(tok_paths['config3']), _oracle(tok_paths['config3'])
+    text, offs = synth.gen_corpus('mixed', 4711, 2 << 20, doc_median=700)
+    docs = [d.decode() for d in synth.split_docs(text, offs)]
+    want = orc.encode_batch(docs)
+    for arr in (pa.array(docs), pa.array(docs, type=pa.large_string()), pa.array(['x'] + docs)[1:],
+                pa.chunked_array([pa.array(docs[:100]), pa.array(docs[100:])])):
+        got = tok.encode_arrow(arr)
+        assert pa.types.is_large_list(got.type) and got.type.value_type == pa.uint32()
+        assert got.to_pylist() == want
+    back = tok.decode_arrow(tok.encode_arrow(pa.array(docs)), False, False)
+    import unicodedata
+    assert back.to_pylist() == [unicodedata.normalize('NFC', d) for d in docs]
+    assert tok.decode_arrow(pa.array(want[:50], type=pa.list_(pa.uint32()))).to_pylist() == orc.decode_batch(want[:50])

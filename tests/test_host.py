@@ -188,3 +188,28 @@ def test_round_parallel_rule_matches_sequential_order():
         b, _r = vwm.trial(rng, rng.choice([1, 2, 3, 4]), rng.choice([2, 3, 4, 5, 6]), rng.choice([3, 6, 12, 30, 60]), 100, True)
         bad += b
     assert bad == 0
+
+
+def test_arrow_packing_is_zero_copy_and_handles_slices():
+    """Arrow string arrays are already the packed batch (offsets + bytes); slices, chunks, large
+    offsets and empty arrays map to (text view, uint64 offsets) without per-string work."""
+    import pyarrow as pa
+    from complexity_tokenizer import arrow_lists_to_packed, arrow_strings_to_packed
+    texts = ['hello', '', 'wörld ✓', 'x' * 70000, 'last']
+    for arr in (pa.array(texts), pa.array(texts, type=pa.large_string()), pa.array(['skip me'] + texts)[1:],
+                pa.chunked_array([pa.array(texts[:2]), pa.array(texts[2:])])):
+        text, offs = arrow_strings_to_packed(arr)
+        assert offs.dtype == np.uint64 and offs[0] == 0 and len(offs) == len(texts) + 1
+        raw = text.tobytes()
+        assert [raw[int(offs[i]):int(offs[i + 1])].decode() for i in range(len(texts))] == texts
+    arr = pa.array(texts)
+    text, _ = arrow_strings_to_packed(arr)
+    assert text.ctypes.data == arr.buffers()[2].address                   # a view of Arrow's data buffer, not a copy
+    text, offs = arrow_strings_to_packed(pa.array([], type=pa.string()))
+    assert text.size == 0 and offs.tolist() == [0]
+    with pytest.raises(ValueError):
+        arrow_strings_to_packed(pa.array(['a', None]))
+    with pytest.raises(TypeError):
+        arrow_strings_to_packed(pa.array([1, 2]))
+    ids, offs = arrow_lists_to_packed(pa.array([[1, 2, 3], [], [70000]], type=pa.list_(pa.uint32()))[1:])
+    assert ids.tolist() == [70000] and offs.tolist() == [0, 0, 1]

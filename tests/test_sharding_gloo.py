@@ -36,7 +36,8 @@ def _worker(rank, world, port, tok_json, result_path):
     import torch.distributed as dist
     import c_oracle
     import synth
-    from complexity_tokenizer.sharding import encode_batch_sharded, shard_ranges
+    import torch
+    from complexity_tokenizer.sharding import encode_batch_sharded, gather_ids, shard_ranges
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         orc = c_oracle.COracle.from_str(tok_json)
@@ -46,6 +47,11 @@ def _worker(rank, world, port, tok_json, result_path):
         assert meta[rank]['first_doc'] == d0 and meta[rank]['n_docs'] == d1 - d0 and meta[rank]['n_ids'] == ids.size
         assert sum(m['n_docs'] for m in meta) == len(offs) - 1
         np.savez(result_path % rank, ids=ids, gioff=gioff, d0=d0, d1=d1)
+        allids = gather_ids(torch.from_numpy(ids.astype(np.int64)), meta, rank, dst=0)      # optional gather of the ids to rank 0
+        if rank == 0:
+            np.save(result_path % 99, allids.numpy())
+        else:
+            assert allids is None
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -65,3 +71,4 @@ def test_two_rank_gloo_sharded_encode_equals_whole_batch(tmp_path, small_tok_jso
     assert np.array_equal(np.concatenate([p['ids'] for p in parts]), wids)
     goff = np.concatenate([p['gioff'][:-1] for p in parts] + [parts[-1]['gioff'][-1:]])
     assert np.array_equal(goff, woff)
+    assert np.array_equal(np.load((result_path % 99) + '.npy').astype(np.uint32), wids)   # gather_ids: all ids on rank 0, in document order
