@@ -99,3 +99,25 @@ def test_getters(built_lib, tok_paths):
     assert tok.id_to_token(300) == orc.twin.id_to_token_str(300)
     assert tok.id_to_token(10 ** 9) is None
     assert tok.special_tokens == orc.twin.special_tokens == {'</s>': 0, '<pad>': 1, '<s>': 2, '<unk>': 3}
+
+
+def test_golden_hf_vectors_on_the_gpu(built_lib):
+    """The committed golden vectors (tests/golden/hf_crosscheck.json: ids from HuggingFace tokenizers 0.22.2 set up to
+    coincide with the reference's semantics, tools/make_golden.py) straight against the CUDA path: 222 texts incl.
+    pre-tokens of 12 .. 5000 bytes (cache, mid, warp-round and grid-round merge paths), as one batch and one by one."""
+    import json
+    import os
+    import complexity_tokenizer as ct
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'hf_crosscheck.json'), encoding='utf-8') as f:
+        g = json.load(f)
+    tok = ct.Tokenizer.from_str(json.dumps(g['tokenizer'], ensure_ascii=False))
+    got = tok.encode_batch(g['texts'])
+    bad = [i for i, (a, b) in enumerate(zip(got, g['ids'])) if a != b]
+    assert not bad, (bad[:5], g['texts'][bad[0]][:60])
+    for t, want in list(zip(g['texts'], g['ids']))[::7]:
+        assert tok.encode(t) == want
+    assert sum(len(t.encode()) for t in g['texts']) * 5 > (256 << 10)          # large enough for the per-class mid kernels
+    assert tok.encode_batch(g['texts'] * 5) == g['ids'] * 5
+    # decode of the golden ids gives the NFC text back (ByteLevel round trip, decoders.rs:94-119)
+    back = tok.decode_batch_with_options(g['ids'], False, False)
+    assert back == [unicodedata.normalize('NFC', t) for t in g['texts']]

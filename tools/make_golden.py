@@ -42,6 +42,19 @@ def main():
     texts += ["", " ", "Hello, world!", "don't", "'sup", "!'s", "a  b", "a b", "x ", " 's", "  's", "I'll've been",
               "été été", "Å 豈 각", "tab\tnew\n\nline  two   spaces",
               "<s>hi</s> <pad> <unk>", "　full　width　", "1234 5.67 8,900 x2 3rd", "\U0001F600\U0001F44D\U0001F3FD ok"]
+    # long pre-tokens: the mid (33..128 B, one lane each), warp-round (129..256 B) and grid-round (> 256 B) device paths
+    import numpy as np
+    rng = np.random.default_rng(4245)
+    han = [chr(0x4E00 + int(i)) for i in rng.integers(0, 3500 * 5, size=400)]
+    letters = 'etaoinshrdlucmfwypvbgkqjxz'
+    def run(alpha, n):
+        return ''.join(alpha[int(i)] for i in rng.integers(0, len(alpha), size=n))
+    for n in (12, 17, 22, 33, 40, 43, 64, 86, 100, 129, 200, 257, 300, 1000, 5000):
+        texts.append('start ' + run(letters, n) + ' end.')
+        texts.append(run(han, max(4, n // 3)) + '。' + run(han, 5))
+    texts += ['x' * 700, 'ab' * 400, ' ' * 300 + 'w', 'w' + ' ' * 300, '=' * 257, '-=' * 200, '9' * 129, 'é' * 150,
+              ' '.join(run(letters, int(k)) for k in rng.integers(30, 140, size=12)),
+              run(han, 43) + 'mixed' + run(han, 30) + ' tail ' + '\U0001F600' * 40]
     tk = hf_tokenizer(tj)
     ids = [e.ids for e in tk.encode_batch(texts, add_special_tokens=False)]
     out = {'generator': 'tools/make_golden.py', 'hf_tokenizers_version': tokenizers.__version__,
