@@ -588,19 +588,19 @@ static int xlong_rounds(Engine& eng, const FusedParams& p, uint64_t cursor, uint
     const uint32_t n_list = (uint32_t)n_list64;
     Workspace& ws = eng.ws;
     eng.mark(nullptr, st);
-    uint32_t *xa, *xb, *rank, *newid, *flags, *pos, *sep_pos;
-    unsigned long long* sv;
+    uint32_t *xa, *xb, *rank, *newid, *pos, *sep_pos;
+    uint8_t* sv;
     void* tmp;
     CK(ws.get(32, (total + 2) * 4, (void**)&xa));
     CK(ws.get(33, (total + 2) * 4, (void**)&xb));
     CK(ws.get(34, total * 4, (void**)&rank));
     CK(ws.get(35, total * 4, (void**)&newid));
-    CK(ws.get(36, total * 8, (void**)&sv));
-    CK(ws.get(37, total * 4, (void**)&flags));
+    CK(ws.get(36, total + 16, (void**)&sv));
     CK(ws.get(38, total * 4, (void**)&pos));
     CK(ws.get(39, (uint64_t)n_list * 4 + 16, (void**)&sep_pos));
     size_t t1 = 0, t2 = 0;
-    cub::TransformInputIterator<uint32_t, XlKeep, const uint32_t*> keep_it(flags, XlKeep());
+    cub::CountingInputIterator<uint32_t> idx_it(0);
+    cub::TransformInputIterator<uint32_t, XlKeepFn, cub::CountingInputIterator<uint32_t>> keep_it(idx_it, XlKeepFn{xa, rank, sv});
     CK(cub::DeviceScan::InclusiveScan(nullptr, t1, sv, sv, XlSegOp(), (int)total, st));
     CK(cub::DeviceScan::ExclusiveSum(nullptr, t2, keep_it, pos, (int)total, st));
     const size_t tmp_bytes = (t1 > t2 ? t1 : t2) + 16;
@@ -626,11 +626,11 @@ static int xlong_rounds(Engine& eng, const FusedParams& p, uint64_t cursor, uint
         k_xl_rank<<<(n + XL_TILE - 1) / XL_TILE, XL_THREADS, smem, st>>>(p.t, xa, n, W, drop_holes ? 1 : 0, rank, newid, sv);
         size_t tb = tmp_bytes;
         CK(cub::DeviceScan::InclusiveScan(tmp, tb, sv, sv, XlSegOp(), (int)n, st));
-        k_xl_flags<<<g256, 256, 0, st>>>(xa, rank, sv, n, flags);
         tb = tmp_bytes;
-        CK(cub::DeviceScan::ExclusiveSum(tmp, tb, keep_it, pos, (int)n, st));
-        k_xl_scatter<<<g256, 256, 0, st>>>(xa, newid, flags, pos, n, xb, n_out);
-        eng.launched(5);
+        cub::TransformInputIterator<uint32_t, XlKeepFn, cub::CountingInputIterator<uint32_t>> keep_now(idx_it, XlKeepFn{xa, rank, sv});
+        CK(cub::DeviceScan::ExclusiveSum(tmp, tb, keep_now, pos, (int)n, st));
+        k_xl_scatter<<<g256, 256, 0, st>>>(xa, rank, newid, sv, pos, n, xb, n_out);
+        eng.launched(4);
         CK(eng.publish({{n_out, 1, 6}}, st));
         CK(cudaStreamSynchronize(st));
         const uint32_t n_new = eng.h_flags[6];

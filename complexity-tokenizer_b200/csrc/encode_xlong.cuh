@@ -18,13 +18,14 @@
 //
 // All very long pre-tokens of a call are laid out in ONE symbol array X (each followed by a separator that
 // carries its list index) and every round is a handful of grid-wide kernels:
-//     k_xl_rank    pair ranks (merge-table probes), windowed minimum in shared memory -> blocked, run heads
-//     scan 1       segmented scan: run start and "blocked so far in the run"
-//     k_xl_flags   selected / kept symbols;  scan 2: new positions;  k_xl_scatter: the next X
+//     k_xl_rank    pair ranks (merge-table probes), window test in shared memory -> blocked, run heads (1 byte per pair)
+//     scan 1       segmented scan of those bytes: parity of the run's start and "blocked so far in the run"
+//     scan 2       new positions (the kept flag is computed on the fly);  k_xl_scatter: the next X
 // until a round selects nothing.  k_xl_count then gives every region's id count to its slice, and after the
 // scan of the slice counts k_xl_place writes the ids straight to their place in the packed output.
 #pragma once
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
 namespace ctk {
@@ -56,12 +57,12 @@ __global__ void __launch_bounds__(256) k_xl_init(const FusedParams p, const XlEn
     if (hole) atomicOr(holes, 1u);
 }
 
-// per pair: rank, new id, and the scan element  hi = (run head ? index + 1 : 0), lo = blocked
+// per pair: rank, new id, and the one-byte scan element: bit 2 = run head, bit 1 = parity of the head's index, bit 0 = blocked
 // shared memory: two arrays of XL_TILE + 2 W ranks (tile + halo of W pairs on each side), ping-ponged by the
 // window-minimum doubling
 __global__ void __launch_bounds__(XL_THREADS) k_xl_rank(const DevTables t, const uint32_t* __restrict__ xs, uint32_t n, uint32_t W,
                                                         int no_merge, uint32_t* __restrict__ rank, uint32_t* __restrict__ newid,
-                                                        unsigned long long* __restrict__ scanv) {
+                                                        uint8_t* __restrict__ scanv) {
     extern __shared__ uint32_t sm[];
     const int iW = (int)W, span = XL_TILE + 2 * iW, tid = threadIdx.x;
     uint32_t* A = sm;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(XL_THREADS) k_xl_rank(const DevTables t, const
             }
             const bool head = r == kNone || left_r[q] != r;
             rank[i] = r; newid[i] = my_v[q];
-            scanv[i] = ((unsigned long long)(head ? (uint32_t)i + 1u : 0u) << 32) | (blocked ? 1u : 0u);
+            scanv[i] = (uint8_t)((head ? 4u | (((uint32_t)i & 1u) << 1) : 0u) | (blocked ? 1u : 0u));
         }
         return;
     }
@@ -138,43 +139,41 @@ __global__ void __launch_bounds__(XL_THREADS) k_xl_rank(const DevTables t, const
         const bool blocked = wmin < r;
         const bool head = r == kNone || left_r[q] != r;
         rank[i] = r; newid[i] = my_v[q];
-        scanv[i] = ((unsigned long long)(head ? (uint32_t)i + 1u : 0u) << 32) | (blocked ? 1u : 0u);
+        scanv[i] = (uint8_t)((head ? 4u | (((uint32_t)i & 1u) << 1) : 0u) | (blocked ? 1u : 0u));
     }
 }
 
-struct XlSegOp {                                               // segmented (run start, blocked-so-far)
-    __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const {
-        return (b >> 32) ? b : ((a & 0xFFFFFFFF00000000ull) | ((a | b) & 1ull));
+struct XlSegOp {                                               // segmented scan: (head seen, parity of the run's first index, blocked so far)
+    __device__ __forceinline__ uint8_t operator()(uint8_t a, uint8_t b) const {
+        return (b & 4u) ? b : (uint8_t)((a & 6u) | ((a | b) & 1u));
     }
 };
 
-__device__ __forceinline__ bool xl_selected(uint32_t i, uint32_t r, unsigned long long sv) {
-    if (r == kNone || (sv & 1ull)) return false;
-    const uint32_t start = (uint32_t)(sv >> 32) - 1u;          // a pair with a rank always has a head at or before it
-    return ((i - start) & 1u) == 0;
+__device__ __forceinline__ bool xl_selected(uint32_t i, uint32_t r, uint32_t sv) {
+    if (r == kNone || (sv & 1u)) return false;
+    return ((i ^ (sv >> 1)) & 1u) == 0;                        // even distance from the first pair of its run
 }
 
-// flags[i]: bit 0 = symbol i survives, bit 1 = it becomes newid[i]
-__global__ void __launch_bounds__(256) k_xl_flags(const uint32_t* __restrict__ xs, const uint32_t* __restrict__ rank,
-                                                  const unsigned long long* __restrict__ sv, uint32_t n, uint32_t* __restrict__ flags) {
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n) return;
-    const bool sel = xl_selected(i, rank[i], sv[i]);
-    const bool eaten = i > 0 && xl_selected(i - 1, rank[i - 1], sv[i - 1]);
-    const bool keep = !eaten && xs[i] != kNone;
-    flags[i] = (keep ? 1u : 0u) | (sel ? 2u : 0u);
-}
+// symbol i survives the round unless the pair to its left was selected (or it is a hole); computed on the fly for the
+// position scan, so that no per-symbol flag array goes through HBM
+struct XlKeepFn {
+    const uint32_t* xs; const uint32_t* rank; const uint8_t* sv;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        if (xs[i] == kNone) return 0u;
+        return (i > 0 && xl_selected(i - 1, rank[i - 1], sv[i - 1])) ? 0u : 1u;
+    }
+};
 
-struct XlKeep { __device__ __forceinline__ uint32_t operator()(uint32_t f) const { return f & 1u; } };
-
-__global__ void __launch_bounds__(256) k_xl_scatter(const uint32_t* __restrict__ xs, const uint32_t* __restrict__ newid,
-                                                    const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, uint32_t n,
+__global__ void __launch_bounds__(256) k_xl_scatter(const uint32_t* __restrict__ xs, const uint32_t* __restrict__ rank,
+                                                    const uint32_t* __restrict__ newid, const uint8_t* __restrict__ sv,
+                                                    const uint32_t* __restrict__ pos, uint32_t n,
                                                     uint32_t* __restrict__ out, uint32_t* __restrict__ n_out) {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i >= n) return;
-    const uint32_t f = flags[i];
-    if (f & 1u) out[pos[i]] = (f & 2u) ? newid[i] : xs[i];
-    if (i == n - 1) *n_out = pos[i] + (f & 1u);
+    const uint32_t x = xs[i];
+    const bool keep = x != kNone && !(i > 0 && xl_selected(i - 1, rank[i - 1], sv[i - 1]));
+    if (keep) out[pos[i]] = xl_selected(i, rank[i], sv[i]) ? newid[i] : x;
+    if (i == n - 1) *n_out = pos[i] + (keep ? 1u : 0u);
 }
 
 // after the last round: separator positions (via their rank among separators), then every id to the long pool
