@@ -5,6 +5,10 @@
 //   k_encode_slices  ALL of normalised-text -> ids: classes, pre-token boundaries, pre-token cache, BPE.
 //                    One warp per slice, warps fully independent (no barrier, no inter-warp order).
 //                    Writes the slice's ids to a fixed-stride scratch run and its count.
+//   k_long_prep      sorts the pre-tokens longer than 32 bytes into work lists       (encode_long.cuh)
+//   k_encode_mid<N>  33..128 bytes: one LANE per pre-token, the reference's loop verbatim
+//   k_encode_long    129..256 bytes: one warp per pre-token (round-parallel, or registers)
+//   k_xl_*           > 256 bytes: grid-wide round-parallel merging, only when one occurs (encode_xlong.cuh)
 //   (device scan of the per-slice counts)
 //   k_compact        moves every slice's run to its final place in the packed output
 //   k_doc_fixup      ids_off[d] (written slice-relative by k_encode_slices) += base of its slice
@@ -23,7 +27,8 @@
 //     batch's pre-token cache slot (BPE of a pre-token is a pure function of its bytes, so each distinct
 //     pre-token of a batch is merged once and every other occurrence copies the ids), unpack the ids.
 //     Everything else (cache miss, 17..32 bytes, ids that do not fit inline, > 32 bytes) takes the
-//     warp-cooperative slow path: bpe_warp32 [bpe.rs:104-153] or, for long ones, global scratch.
+//     warp-cooperative slow path: bpe_warp32 [bpe.rs:104-153]; pre-tokens > 32 bytes are only DESCRIBED here
+//     (LongDesc) and merged by the kernels above.  NFC-suspect code points are reported, not handled (engine.hpp).
 //   5 ids leave in pre-token order (mod.rs:562-612 `result.extend`)
 #include <cub/device/device_scan.cuh>
 

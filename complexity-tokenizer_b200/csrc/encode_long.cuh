@@ -1,5 +1,10 @@
-// k_encode_long: BPE of the pre-tokens that are longer than 32 bytes (CJK runs, URLs, long digit or
-// punctuation runs), one warp per pre-token.  Included by encode_fused.cu after FusedParams.
+// BPE of the pre-tokens that are longer than 32 bytes (CJK runs, URLs, long digit or punctuation runs).
+// Included by encode_fused.cu after FusedParams.
+//   k_long_prep      length of those that run past their chunk, room in the long pool, work lists by length class
+//   k_encode_mid<N>  33 .. 128 bytes, one LANE per pre-token (32 per warp): exact for every merge table
+//   k_encode_long    the rest up to 256 bytes (and everything when k_encode_mid is off), one WARP per pre-token:
+//                    round-parallel merging in shared memory (bpe_warp_rounds) when the table allows, else
+//                    bpe_warp_regs / bpe_warp_long as described next; > 256 bytes are handed to encode_xlong.cuh
 //
 // Same order as the reference (bpe.rs:104-153): every iteration applies ONE merge, the lowest rank,
 // leftmost on ties.  Up to 256 symbols live in registers, blocked K per lane, together with the cached
