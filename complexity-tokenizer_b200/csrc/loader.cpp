@@ -8,6 +8,7 @@
 #include "model.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/ctk.h"
@@ -163,6 +164,7 @@ void token_reach(HostModel& m) {
     m.round_parallel = false;
     m.reach.clear();
     if (!m.merges_monotone || m.pairs.empty()) return;
+    if (getenv("CTK_NO_REACH")) return;                           // debug/tests: keep the uniform-window rounds
     if (m.vocab.size() != (size_t)std::count(m.id_present.begin(), m.id_present.end(), (uint8_t)1)) return;   // two tokens, one id
     for (const PairEntry& p : m.pairs) {
         if (p.a >= m.id_to_token.size() || p.b >= m.id_to_token.size() || p.new_id >= m.id_to_token.size()) return;

@@ -247,6 +247,23 @@ def test_xlong_rounds_match_oracle(built_lib, tok_paths):
         assert ct._lib().ctk_debug_xlong_rounds(tok._h) > 0          # the rounds did run
 
 
+def test_xlong_rounds_with_the_uniform_window(built_lib, tok_paths):
+    """A monotone table without per-token reach windows (forced here with CTK_NO_REACH; in the field: a table whose
+    merge products are not the concatenation of their parts) uses the uniform window W = longest token in the grid-wide
+    rounds and the register path in k_encode_long.  Same ids as the oracle."""
+    import os
+    import complexity_tokenizer as ct
+    os.environ['CTK_NO_REACH'] = '1'
+    try:
+        tok = _tok(tok_paths['config2'])
+    finally:
+        del os.environ['CTK_NO_REACH']
+    orc = _oracle(tok_paths['config2'])
+    docs = _xlong_docs()
+    assert tok.encode_batch(docs) == orc.encode_batch(docs)
+    assert ct._lib().ctk_debug_xlong_rounds(tok._h) > 0
+
+
 def test_xlong_rounds_equal_sequential_device_path(built_lib, tok_paths):
     """Same inputs through the sequential warp path (CTK_NO_XLONG) and the rounds: identical ids."""
     import os
