@@ -129,6 +129,105 @@ __device__ __forceinline__ uint32_t dec_cp(const uint8_t* s, uint64_t n, uint64_
     return r;
 }
 
+// ---- exact NFC of a segment with ANY number of combining marks per starter, in O(1) memory ----------------------
+// The streaming pass above keeps a starter and its marks in a 48-entry buffer.  "Zalgo" text stacks more marks than
+// that on one base; such a segment is redone here.  The fully decomposed stream is read through a restartable
+// iterator; a block = [starter] + its run of marks.  Canonical order of the run = ascending combining class, stable
+// inside a class, so it is produced by one pass over the run PER CLASS that occurs in it (<= 55 classes exist); the
+// composition rule of UAX #15 (a mark composes with the starter unless a kept mark of an equal or higher class
+// precedes it) only needs the current starter and the class of the last kept mark.  A dry pass finds the final
+// starter, a second pass writes it and the marks that stay.  A starter whose marks all vanished is held back: the
+// next starter may still compose with it (Hangul L+V+T, and a few others).
+constexpr uint32_t kNoCp = 0xFFFFFFFFu;
+struct NfcDIter {                       // iterator over the full canonical decomposition of text[i, end)
+    const uint8_t* s; uint64_t i, end;
+    uint32_t q[8]; int qn, qi;
+    __device__ void init(const uint8_t* s_, uint64_t a, uint64_t b) { s = s_; i = a; end = b; qn = qi = 0; }
+    __device__ bool next(const NfcTables& t, uint32_t& out) {
+        if (qi < qn) { out = q[qi++]; return true; }
+        if (i >= end) return false;
+        const uint32_t cp = dec_cp(s, end, i);
+        qn = 0; qi = 0;
+        if (cp >= 0xAC00 && cp < 0xD7A4) {
+            const uint32_t x = cp - 0xAC00;
+            q[qn++] = 0x1100 + x / 588; q[qn++] = 0x1161 + (x % 588) / 28;
+            if (x % 28) q[qn++] = 0x11A7 + x % 28;
+        } else {
+            uint32_t stack[8]; int sp = 0;
+            stack[sp++] = cp;
+            while (sp) {
+                const uint32_t c = stack[--sp];
+                const int di = nfc_decomp_idx(t, c);
+                if (di < 0) { if (qn < 8) q[qn++] = c; continue; }
+                const uint32_t a = t.da[di], b = t.db[di];
+                if (b && sp < 7) stack[sp++] = b;
+                if (sp < 8) stack[sp++] = a;
+            }
+        }
+        out = q[qi++];
+        return true;
+    }
+};
+
+__device__ void nfc_segment_slow(const NfcTables& t, const uint8_t* text, uint64_t a, uint64_t b, NfcSink& sink) {
+    NfcDIter it;
+    it.init(text, a, b);
+    uint32_t P = kNoCp;                  // starter held back (all of its marks composed into it)
+    uint32_t c = 0;
+    bool have = it.next(t, c);
+    while (have) {
+        uint32_t base = kNoCp;
+        if (nfc_ccc(t, c) == 0) {
+            base = c;
+            if (P != kNoCp) { const uint32_t comp = nfc_compose(t, P, c); if (comp) base = comp; else sink.put(P); }
+            P = kNoCp;
+            have = it.next(t, c);
+        }
+        // the run of marks: `c` is its first element (if any), `run` re-reads what follows it
+        const NfcDIter run = it;
+        const uint32_t first = c;
+        uint32_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint64_t cnt = 0;
+        while (have) {
+            const int cc = nfc_ccc(t, c);
+            if (cc == 0) break;
+            present[cc >> 5] |= 1u << (cc & 31);
+            ++cnt;
+            have = it.next(t, c);
+        }
+        if (cnt == 0) { P = base; continue; }
+        uint32_t sfin = base;
+        uint64_t left = 0;
+        for (int pass = 0; pass < 2; ++pass) {                       // 0: dry run, 1: write
+            uint32_t st = base;
+            int prev_cc = 0;
+            if (pass == 1) {
+                if (left == 0) break;
+                if (base != kNoCp) sink.put(sfin);
+            }
+            for (int v = 1; v < 256; ++v) {
+                if (!((present[v >> 5] >> (v & 31)) & 1u)) continue;
+                NfcDIter r = run;
+                uint32_t m = first;
+                for (uint64_t k = 0; k < cnt; ++k) {
+                    if (nfc_ccc(t, m) == v) {
+                        bool composed = false;
+                        if (st != kNoCp && (prev_cc == 0 || prev_cc < v)) {
+                            const uint32_t x = nfc_compose(t, st, m);
+                            if (x) { st = x; composed = true; }
+                        }
+                        if (!composed) { prev_cc = v; if (pass == 0) ++left; else sink.put(m); }
+                    }
+                    if (k + 1 < cnt) r.next(t, m);
+                }
+            }
+            if (pass == 0) sfin = st;
+        }
+        if (left == 0) P = sfin;                                     // may still compose with the next starter
+    }
+    if (P != kNoCp) sink.put(P);
+}
+
 // one thread per 16 bytes: any suspect code point -> set its bit in `susp` and mark its document
 __global__ void __launch_bounds__(256) k_nfc_flag(NfcTables t, const uint8_t* __restrict__ text, uint64_t n,
                                                   const uint64_t* __restrict__ off, uint64_t n_docs,
@@ -207,7 +306,7 @@ __global__ void __launch_bounds__(256) k_nfc_doc(NfcTables t, const uint8_t* __r
                     st.push(dec_cp(text, hi, i));                        // the base (or the first suspect one at a document start)
                     while (i < hi && ((susp[i >> 5] >> (i & 31)) & 1u)) st.push(dec_cp(text, hi, i));
                     st.flush();
-                    overflow = overflow || st.overflow;
+                    if (st.overflow) { sink.n = 0; nfc_segment_slow(t, text, s0, i, sink); }   // more marks on one base than the buffer holds
                     seg_end = i; seg_out = sink.n;
                 }
                 seg_end = __shfl_sync(full, seg_end, 0);

@@ -360,3 +360,29 @@ def test_optimistic_nfc_switches_back_and_forth(built_lib, tok_paths):
         assert tok.encode_batch(batch) == orc.encode_batch(batch)
         for t in batch[:2]:
             assert tok.encode(t) == orc.twin.encode(t)
+
+
+def test_nfc_with_long_combining_sequences(built_lib, tok_paths):
+    """"Zalgo" text: far more combining marks on one base than the normaliser's streaming buffer holds (48).  Such
+    segments are redone by the O(1)-memory multi-pass routine (nfc.cu: nfc_segment_slow): canonical reordering over the
+    whole run, composition with the base, Hangul chains.  Ids equal the oracle's; the raw decode equals
+    unicodedata.normalize('NFC', text) (normalizers.rs:45-47)."""
+    rng = np.random.default_rng(99)
+    marks = [chr(c) for c in list(range(0x300, 0x34F)) + list(range(0x591, 0x5BE)) + list(range(0x64B, 0x653)) + [0x0F71, 0x0F72, 0x0F74, 0x1DC0, 0x20D0, 0x302A, 0x3099]]
+    bases = ['a', 'e', 'o', 'A', 'x', 'ᄀ', '가', 'क', 'α', ' ', '中']
+    docs = []
+    for n in (40, 47, 48, 49, 50, 60, 100, 257, 1000):
+        for _ in range(3):
+            s = 'start '
+            for _ in range(int(rng.integers(1, 4))):
+                s += bases[int(rng.integers(0, len(bases)))] + ''.join(marks[int(i)] for i in rng.integers(0, len(marks), size=n))
+                s += ['', ' ', 'ᅡᆨ', 'b'][int(rng.integers(0, 4))]
+            docs.append(s + ' end')
+    docs.append('́' * 300)                                         # marks with no base at the start of a document
+    docs.append('a' + '̧́' * 200 + 'z')                              # two classes alternating: stable order inside each class
+    for cfg in ('config1', 'config3'):
+        tok, orc = _tok(tok_paths[cfg]), _oracle(tok_paths[cfg])
+        got, want = tok.encode_batch(docs), orc.encode_batch(docs)
+        bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+        assert not bad, bad[:5]
+        assert tok.decode_batch_with_options(got, False, False) == [unicodedata.normalize('NFC', d) for d in docs]
