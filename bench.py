@@ -338,9 +338,13 @@ def main():
                     'all_kernels_ms_per_step': {k: v[0] / args.steps for k, v in sorted(prof.items())}}
     if roofline:                      # DRAM bytes of the dominant kernel from the committed ncu --set full capture of this workload
         try:
-            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-                tr = json.load(f)
-            ent = tr.get(roofline['kernel'])
+            tr = None
+            for cand in (os.path.join(ROOT, 'profiles', 'traffic.json'), os.path.join(ROOT, 'bench_traffic.json')):   # profiles/ may not travel to the GPU box
+                if os.path.exists(cand):
+                    with open(cand) as f:
+                        tr = json.load(f)
+                    break
+            ent = (tr or {}).get(roofline['kernel'])
             if ent and int(ent['input_bytes']) == int(B):
                 roofline['traffic'] = int(ent['dram_bytes_per_launch'])
                 roofline['traffic_source'] = ent.get('source')

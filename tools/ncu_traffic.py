@@ -13,4 +13,5 @@ path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 d = json.load(open(path)) if os.path.exists(path) else {}
 d[kernel] = {'dram_bytes_per_launch': int(tot), 'input_bytes': nbytes, 'source': note}
 json.dump(d, open(path, 'w'), indent=1)
+json.dump(d, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bench_traffic.json'), 'w'), indent=1)   # copy that travels with the repo snapshot
 print(kernel, int(tot), 'bytes per launch')
