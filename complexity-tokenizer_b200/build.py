@@ -31,6 +31,7 @@ def needs_build():
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
+        build_marshal()
         return OUT
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     objs = []
@@ -52,7 +53,19 @@ def build(force=False, verbose=False):
     if verbose:
         print('\n'.join(log))
     subprocess.check_call([NVCC, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    build_marshal()
     return OUT
+
+
+def build_marshal():
+    """_ctk_marshal: CPython helpers for list[str] <-> packed buffers (csrc/marshal.c); marshalling only."""
+    import sysconfig
+    out = os.path.join(HERE, 'complexity_tokenizer', '_ctk_marshal' + (sysconfig.get_config_var('EXT_SUFFIX') or '.so'))
+    src = os.path.join(CSRC, 'marshal.c')
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    subprocess.check_call([os.environ.get('CC', 'gcc'), '-O2', '-shared', '-fPIC', '-Wall', '-I' + sysconfig.get_paths()['include'], src, '-o', out])
+    return out
 
 
 if __name__ == '__main__':

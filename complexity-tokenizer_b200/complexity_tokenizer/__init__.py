@@ -78,6 +78,12 @@ def _lib():
     return lib
 
 
+try:                                    # compiled list <-> packed-buffer conversions (csrc/marshal.c); marshalling only
+    from . import _ctk_marshal as _marshal
+except ImportError:                     # not built: the NumPy conversions below do the same, slower
+    _marshal = None
+
+
 def _raise(rc):
     msg = (_lib().ctk_last_error() or b'').decode('utf-8', 'replace')
     if rc == CTK_ERR_IO:
@@ -238,6 +244,18 @@ class Tokenizer:
     def encode_batch(self, texts):
         if isinstance(texts, str):
             raise TypeError("argument 'texts': Can't extract `str` to `Vec`")
+        if _marshal is not None:
+            lib = _lib()
+            text, off = _marshal.pack_strs(texts if isinstance(texts, (list, tuple)) else list(texts))
+            n = len(off) // 8 - 1
+            res = ctypes.c_void_p()
+            rc = lib.ctk_encode_batch(self._h, text if text else None, off, n, ctypes.byref(res))
+            if rc != CTK_OK:
+                _raise(rc)
+            try:
+                return _marshal.unpack_ids(lib.ctk_result_ids(res) or 0, lib.ctk_result_offsets(res), n)
+            finally:
+                lib.ctk_result_free(res)
         buf, off = _pack_texts(list(texts))
         ids, ioff = self.encode_packed(buf, off)
         lst = ids.tolist()
@@ -254,6 +272,19 @@ class Tokenizer:
         return self.decode_batch_with_options(batch, False, True)
 
     def decode_batch_with_options(self, batch, skip_special_tokens=False, clean_up_tokenization_spaces=True):
+        if _marshal is not None:
+            lib = _lib()
+            ids, off = _marshal.pack_id_lists(batch if isinstance(batch, (list, tuple)) else list(batch))
+            n = len(off) // 8 - 1
+            res = ctypes.c_void_p()
+            rc = lib.ctk_decode_batch(self._h, ids if ids else None, off, n, int(bool(skip_special_tokens)),
+                                      int(bool(clean_up_tokenization_spaces)), ctypes.byref(res))
+            if rc != CTK_OK:
+                _raise(rc)
+            try:
+                return _marshal.unpack_strs(lib.ctk_result_bytes(res) or 0, lib.ctk_result_offsets(res), n)
+            finally:
+                lib.ctk_result_free(res)
         batch = [list(b) for b in batch]
         off = np.zeros(len(batch) + 1, dtype=np.uint64)
         if batch:

@@ -213,3 +213,34 @@ def test_arrow_packing_is_zero_copy_and_handles_slices():
         arrow_strings_to_packed(pa.array([1, 2]))
     ids, offs = arrow_lists_to_packed(pa.array([[1, 2, 3], [], [70000]], type=pa.list_(pa.uint32()))[1:])
     assert ids.tolist() == [70000] and offs.tolist() == [0, 0, 1]
+
+
+def test_marshal_extension_round_trips(built_lib):
+    """csrc/marshal.c: the compiled list <-> packed-buffer conversions of the shim (what PyO3 does for the reference,
+    bindings/tokenizer.rs:203-238).  Same buffers as the NumPy conversions, same exceptions as PyO3's extraction."""
+    import ctypes
+    from complexity_tokenizer import _marshal, _pack_texts
+    assert _marshal is not None, '_ctk_marshal is not built'
+    texts = ['hello', '', 'wörld ✓ \U0001F600', 'x' * 5000, '\x00nul']
+    text, off = _marshal.pack_strs(texts)
+    buf, o = _pack_texts(texts)
+    assert text == buf.tobytes() and np.frombuffer(off, dtype=np.uint64).tolist() == o.tolist()
+    assert _marshal.pack_strs([]) == (b'', (0).to_bytes(8, 'little'))
+    assert _marshal.pack_strs(tuple(texts))[0] == text                            # any sequence
+    with pytest.raises(TypeError):
+        _marshal.pack_strs(['ok', 5])
+    with pytest.raises(UnicodeEncodeError):
+        _marshal.pack_strs(['lone surrogate \ud800'])
+    rows = [[1, 2, 3], [], [4294967295], list(range(1000))]
+    ids, off = _marshal.pack_id_lists(rows)
+    assert np.frombuffer(ids, dtype=np.uint32).tolist() == [x for r in rows for x in r]
+    assert np.frombuffer(off, dtype=np.uint64).tolist() == [0, 3, 3, 4, 1004]
+    for bad in ([[1, -1]], [[1 << 32]], [[1.5]], [['a']]):
+        with pytest.raises((OverflowError, TypeError)):
+            _marshal.pack_id_lists(bad)
+    a_ids = ctypes.cast(ctypes.c_char_p(ids), ctypes.c_void_p).value
+    a_off = ctypes.cast(ctypes.c_char_p(off), ctypes.c_void_p).value
+    assert _marshal.unpack_ids(a_ids, a_off, len(rows)) == rows
+    a_txt = ctypes.cast(ctypes.c_char_p(text), ctypes.c_void_p).value
+    toff = _marshal.pack_strs(texts)[1]
+    assert _marshal.unpack_strs(a_txt, ctypes.cast(ctypes.c_char_p(toff), ctypes.c_void_p).value, len(texts)) == texts
