@@ -69,6 +69,7 @@ def _lib():
         'ctk_debug_merge_props': (I, [P, S, ctypes.POINTER(I), ctypes.POINTER(ctypes.c_uint32)]),
         'ctk_debug_xlong_rounds': (I, [P]),
         'ctk_last_transfer_bytes': (None, [P, ctypes.POINTER(U64), ctypes.POINTER(U64)]),
+        'ctk_debug_parallel_copy': (I, [P, P, S, I, I]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

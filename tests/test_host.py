@@ -244,3 +244,34 @@ def test_marshal_extension_round_trips(built_lib):
     a_txt = ctypes.cast(ctypes.c_char_p(text), ctypes.c_void_p).value
     toff = _marshal.pack_strs(texts)[1]
     assert _marshal.unpack_strs(a_txt, ctypes.cast(ctypes.c_char_p(toff), ctypes.c_void_p).value, len(texts)) == texts
+
+
+def test_staging_worker_pool(built_lib):
+    """host_api.cu: TaskPool, the persistent workers that copy pageable input into page-locked staging buffers.
+    Exercised here as a parallel memcpy: many jobs back to back, more parts than threads, from several caller threads."""
+    import threading
+    lib = built_lib
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, 256, size=(8 << 20) + 123, dtype=np.uint8)
+    for threads, parts in ((1, 1), (2, 7), (4, 16), (4, 1), (3, 64)):
+        for _ in range(20):
+            dst = np.zeros_like(src)
+            assert lib.ctk_debug_parallel_copy(dst.ctypes.data, src.ctypes.data, src.size, threads, parts) == 0
+            assert np.array_equal(dst, src)
+    errs = []
+
+    def hammer():
+        try:
+            for _ in range(30):
+                d = np.zeros(1 << 20, dtype=np.uint8)
+                assert lib.ctk_debug_parallel_copy(d.ctypes.data, src.ctypes.data, d.size, 4, 9) == 0
+                assert np.array_equal(d, src[:d.size])
+        except Exception as e:                                        # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=hammer) for _ in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs[:2]
