@@ -261,8 +261,11 @@ __global__ void __launch_bounds__(256) k_nfc_flag(NfcTables t, const uint8_t* __
 // suspect code points change: a segment is the code point before a run of suspect code points (a
 // starter with NFC_QC=Yes, so nothing before it can interact) plus the run; lane 0 normalises it with
 // the streaming UAX #15 pass, the whole warp copies the unchanged stretches in between.
+// SLOW = false: the common kernel; a document in which a segment overflows the streaming buffer is only MARKED
+// (doc_flag = 2) and left to the SLOW = true instantiation, which carries nfc_segment_slow (and its registers).
+template <bool SLOW>
 __global__ void __launch_bounds__(256) k_nfc_doc(NfcTables t, const uint8_t* __restrict__ text, const uint64_t* __restrict__ off,
-                                                 uint64_t n_docs, const uint8_t* __restrict__ doc_flag,
+                                                 uint64_t n_docs, uint8_t* __restrict__ doc_flag,
                                                  const uint32_t* __restrict__ susp, const uint64_t* __restrict__ new_off, uint8_t* out,
                                                  uint64_t* __restrict__ new_len, uint32_t* __restrict__ err) {
     const unsigned full = 0xFFFFFFFFu;
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(256) k_nfc_doc(NfcTables t, const uint8_t* __r
     const int lane = threadIdx.x & 31;
     const uint64_t lo = off[d], hi = off[d + 1];
     uint8_t* o = out ? out + new_off[d] : nullptr;
+    if (SLOW ? doc_flag[d] != 2 : doc_flag[d] == 2) return;
     if (!doc_flag[d]) {
         if (!out) { if (lane == 0) new_len[d] = hi - lo; return; }
         for (uint64_t i = lo + lane; i < hi; i += 32) o[i - lo] = text[i];
@@ -306,7 +310,8 @@ __global__ void __launch_bounds__(256) k_nfc_doc(NfcTables t, const uint8_t* __r
                     st.push(dec_cp(text, hi, i));                        // the base (or the first suspect one at a document start)
                     while (i < hi && ((susp[i >> 5] >> (i & 31)) & 1u)) st.push(dec_cp(text, hi, i));
                     st.flush();
-                    if (st.overflow) { sink.n = 0; nfc_segment_slow(t, text, s0, i, sink); }   // more marks on one base than the buffer holds
+                    if (SLOW) { if (st.overflow) { sink.n = 0; nfc_segment_slow(t, text, s0, i, sink); } }   // more marks on one base than the buffer holds
+                    else overflow = overflow || st.overflow;
                     seg_end = i; seg_out = sink.n;
                 }
                 seg_end = __shfl_sync(full, seg_end, 0);
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(256) k_nfc_doc(NfcTables t, const uint8_t* __r
     if (o) for (uint64_t i = cur_in + lane; i < hi; i += 32) o[cur_out + (i - cur_in)] = text[i];
     cur_out += hi - cur_in;
     if (lane == 0) {
-        if (overflow) atomicOr(err, ERRF_NFC_LONG);
+        if (overflow) { atomicOr(err, ERRF_NFC_LONG); doc_flag[d] = 2; }      // its length / bytes come from the SLOW kernel
         if (!out) new_len[d] = cur_out;
     }
 }
@@ -355,7 +360,7 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
     CK(ws.get(29, (n_docs + 2) * 8, (void**)&new_off));
     unsigned grid = (unsigned)((n_docs * 32 + 255) / 256);
     eng.mark(nullptr, st);
-    k_nfc_doc<<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, susp, nullptr, nullptr, new_len, any + 1);
+    k_nfc_doc<false><<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, susp, nullptr, nullptr, new_len, any + 1);
     eng.launched(1); eng.mark("k_nfc_doc(count)", st);
     CK(cudaMemsetAsync(new_len + n_docs, 0, 8, st));
     size_t cub_bytes = 0; void* cub_tmp;
@@ -364,19 +369,24 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
     CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, new_len, new_off, n_docs + 1, st));
     eng.launched(1);
     uint64_t total = 0;
-    CK(eng.publish({{new_off + n_docs, 2, 10}}, st));
+    CK(eng.publish({{new_off + n_docs, 2, 10}, {any + 1, 1, 8}}, st));
     CK(cudaStreamSynchronize(st));
+    const bool long_runs = (eng.h_flags[8] & ERRF_NFC_LONG) != 0;    // "Zalgo" documents: counted (and later written) by the SLOW kernel
+    if (long_runs) {
+        k_nfc_doc<true><<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, susp, nullptr, nullptr, new_len, any + 1);
+        CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, new_len, new_off, n_docs + 1, st));
+        eng.launched(2);
+        CK(eng.publish({{new_off + n_docs, 2, 10}}, st));
+        CK(cudaStreamSynchronize(st));
+    }
     memcpy(&total, eng.h_flags + 10, 8);
     uint8_t* out;
     CK(ws.get(30, total + 64, (void**)&out));
     CK(cudaMemsetAsync(out + total, 0, 64, st));
     eng.mark(nullptr, st);
-    k_nfc_doc<<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, susp, new_off, out, nullptr, any + 1);
+    k_nfc_doc<false><<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, susp, new_off, out, nullptr, any + 1);
+    if (long_runs) { k_nfc_doc<true><<<grid, 256, 0, st>>>(t, d_text, d_off, n_docs, flag, susp, new_off, out, nullptr, any + 1); eng.launched(1); }
     eng.launched(1); eng.mark("k_nfc_doc(write)", st);
-    CK(eng.publish({{any + 1, 1, 8}}, st));
-    CK(cudaStreamSynchronize(st));
-    if (eng.h_flags[8] & ERRF_NFC_LONG)
-        return eng.fail(CTK_ERR_UNSUPPORTED, "a combining sequence longer than 48 code points needs NFC; not supported");
     *o_text = out; *o_off = new_off; *o_bytes = total;
     return CTK_OK;
 }
