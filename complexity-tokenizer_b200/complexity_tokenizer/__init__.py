@@ -14,12 +14,37 @@ import os
 import numpy as np
 
 __version__ = '0.3.3+b200'
-__all__ = ['Tokenizer', 'Trainer', '__version__']
+__all__ = ['Tokenizer', 'Encoding', 'BatchEncoding', 'Trainer', 'PanicException', '__version__']
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-CTK_OK, CTK_ERR_IO, CTK_ERR_INVALID_DATA, CTK_ERR_UNSUPPORTED, CTK_ERR_CUDA, CTK_ERR_ARG = range(6)
+CTK_OK, CTK_ERR_IO, CTK_ERR_INVALID_DATA, CTK_ERR_UNSUPPORTED, CTK_ERR_CUDA, CTK_ERR_ARG, CTK_ERR_PANIC = range(7)
+
+
+class PanicException(BaseException):
+    """The reference panics on this input; PyO3 surfaces a Rust panic as pyo3_runtime.PanicException (a BaseException)."""
+
+
+class _ResultOwner:
+    """Frees a ctk_encodings result when the last NumPy view of it is gone."""
+
+    def __init__(self, res):
+        self._res = res
+
+    def __del__(self):
+        res, self._res = self._res, None
+        if res and _LIB is not None:
+            try:
+                _LIB.ctk_encodings_free(res)
+            except Exception:
+                pass
+
+
+class _EncodingOptions(ctypes.Structure):       # include/ctk.h: ctk_encoding_options
+    _fields_ = [('add_special_tokens', ctypes.c_int), ('pair', ctypes.c_int), ('truncation', ctypes.c_int),
+                ('max_length', ctypes.c_uint64), ('padding', ctypes.c_int), ('pad_to', ctypes.c_uint64),
+                ('pad_left', ctypes.c_int), ('want_offsets', ctypes.c_int)]
 
 
 class UnsupportedTokenizerError(IOError):
@@ -70,6 +95,21 @@ def _lib():
         'ctk_debug_xlong_rounds': (I, [P]),
         'ctk_last_transfer_bytes': (None, [P, ctypes.POINTER(U64), ctypes.POINTER(U64)]),
         'ctk_debug_parallel_copy': (I, [P, P, S, I, I]),
+        'ctk_encode_batch_to_encoding': (I, [P, P, P, S, ctypes.POINTER(_EncodingOptions), ctypes.POINTER(P)]),
+        'ctk_encodings_rows': (S, [P]),
+        'ctk_encodings_row_offsets': (P, [P]),
+        'ctk_encodings_row_full_lengths': (P, [P]),
+        'ctk_encodings_input_ids': (P, [P]),
+        'ctk_encodings_attention_mask': (P, [P]),
+        'ctk_encodings_type_ids': (P, [P]),
+        'ctk_encodings_special_tokens_mask': (P, [P]),
+        'ctk_encodings_token_offsets': (P, [P]),
+        'ctk_encodings_token_ids': (P, [P]),
+        'ctk_encodings_offsets': (P, [P]),
+        'ctk_encodings_word_ids': (P, [P]),
+        'ctk_encodings_free': (None, [P]),
+        'ctk_post_processor_items': (S, [P, ctypes.POINTER(ctypes.c_int64), S]),
+        'ctk_pad_token': (ctypes.c_uint32, [P, ctypes.POINTER(P), ctypes.POINTER(S)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -95,6 +135,8 @@ def _raise(rc):
         raise UnsupportedTokenizerError(msg)
     if rc == CTK_ERR_ARG:
         raise ValueError(msg)
+    if rc == CTK_ERR_PANIC:
+        raise PanicException(msg)
     raise RuntimeError(msg)
 
 
@@ -150,6 +192,9 @@ class Tokenizer:
 
     def __init__(self, handle):
         self._h = handle
+        self._model_max_length = 512        # mod.rs:243-245 (from_file)
+        self._padding_side = 'right'        # mod.rs:325
+        self._truncation_side = 'right'     # mod.rs:326
 
     # ---- constructors
     @staticmethod
@@ -299,6 +344,165 @@ class Tokenizer:
     def batch_decode(self, sequences, skip_special_tokens=False, clean_up_tokenization_spaces=True):
         return self.decode_batch_with_options(sequences, skip_special_tokens, clean_up_tokenization_spaces)
 
+    # ---- rich Encoding outputs (bindings/tokenizer.rs:33-201, :259-368), computed in csrc/encoding.cu
+    def _encode_rows(self, text_buf, text_off, pair=False, add_special_tokens=True, truncation=False, max_length=0, padding=0,
+                     pad_to=0, pad_left=False, want_offsets=False, overflow_mode='single', stride=0):
+        """Packed texts -> PackedEncodings (NumPy copies of every array the device produced)."""
+        from .encoding import PackedEncodings
+        lib = _lib()
+        text_buf = np.ascontiguousarray(text_buf, dtype=np.uint8)
+        text_off = np.ascontiguousarray(text_off, dtype=np.uint64)
+        n = len(text_off) - 1
+        opt = _EncodingOptions(int(bool(add_special_tokens)), int(bool(pair)), int(bool(truncation)), int(max_length), int(padding),
+                               int(pad_to), int(bool(pad_left)), int(bool(want_offsets)))
+        res = ctypes.c_void_p()
+        rc = lib.ctk_encode_batch_to_encoding(self._h, text_buf.ctypes.data if text_buf.size else None, text_off.ctypes.data, n,
+                                              ctypes.byref(opt), ctypes.byref(res))
+        if rc != CTK_OK:
+            _raise(rc)
+        owner = _ResultOwner(res)                   # the arrays below are VIEWS of the library's page-locked result block
+
+        def arr(fn, ctype, count, shape=None):
+            p = fn(res)
+            if not p or count == 0:
+                return np.zeros(shape or (0,), dtype=ctype)
+            raw = (ctypes.c_uint8 * (count * np.dtype(ctype).itemsize)).from_address(p)
+            raw._owner = owner                      # keeps the result alive as long as any view of it
+            a = np.frombuffer(raw, dtype=ctype)
+            return a.reshape(shape) if shape else a
+        rows = int(lib.ctk_encodings_rows(res))
+        row_off = arr(lib.ctk_encodings_row_offsets, np.uint64, rows + 1)
+        tok_off = arr(lib.ctk_encodings_token_offsets, np.uint64, n + 1)
+        total, n_tok = int(row_off[-1]), int(tok_off[-1])
+        ptok, plen = ctypes.c_void_p(), ctypes.c_size_t()
+        pad_id = lib.ctk_pad_token(self._h, ctypes.byref(ptok), ctypes.byref(plen))
+        offs = arr(lib.ctk_encodings_offsets, np.uint32, 2 * n_tok, (n_tok, 2)) if want_offsets else None
+        wids = arr(lib.ctk_encodings_word_ids, np.uint32, n_tok) if want_offsets else None
+        return PackedEncodings(
+            self, pair=bool(pair), add_special_tokens=bool(add_special_tokens), truncation=bool(truncation),
+            max_length=int(max_length), pad_left=bool(pad_left), overflow_mode=overflow_mode, stride=int(stride),
+            pad_id=int(pad_id), pad_token=ctypes.string_at(ptok, plen.value).decode('utf-8'),
+            text_buf=text_buf, text_off=text_off, row_off=row_off, tok_off=tok_off,
+            row_full=arr(lib.ctk_encodings_row_full_lengths, np.uint64, rows),
+            input_ids=arr(lib.ctk_encodings_input_ids, np.uint32, total),
+            attention_mask=arr(lib.ctk_encodings_attention_mask, np.uint8, total),
+            token_type_ids=arr(lib.ctk_encodings_type_ids, np.uint8, total),
+            special_tokens_mask=arr(lib.ctk_encodings_special_tokens_mask, np.uint8, total),
+            raw_ids=arr(lib.ctk_encodings_token_ids, np.uint32, n_tok), offsets=offs, word_ids=wids)
+
+    @staticmethod
+    def _interleave(texts, pairs):
+        flat = []
+        for a, b in zip(texts, pairs):
+            flat.append(a)
+            flat.append(b)
+        return flat
+
+    def __call__(self, text, text_pair=None, add_special_tokens=True, padding=None, truncation=False, max_length=None, stride=0,
+                 return_attention_mask=True, return_token_type_ids=True, return_offsets_mapping=False,
+                 return_special_tokens_mask=False):
+        """bindings/tokenizer.rs:33-201"""
+        from .encoding import BatchEncoding
+        if isinstance(text, (list, tuple)) and all(isinstance(t, str) for t in text):
+            texts = list(text)
+            pairs = list(text_pair) if isinstance(text_pair, (list, tuple)) and all(isinstance(t, str) for t in text_pair) else None
+        elif isinstance(text, str):
+            texts = [text]
+            pairs = [text_pair] if isinstance(text_pair, str) else None
+        else:
+            raise TypeError('Expected str or List[str]')
+        flat = self._interleave(texts, pairs) if pairs is not None else texts
+        max_len = self._model_max_length if max_length is None else int(max_length)
+        if max_len < 0 or stride < 0:
+            raise OverflowError("can't convert negative int to unsigned")
+        if truncation and stride > 0 and stride >= max_len:
+            raise ValueError('stride >= max_length: the reference loops forever (encoding.rs:190-193)')
+        pad_mode = 0 if padding is None else 2 if padding == 'max_length' else 1
+        pad_left = padding == 'left' or self._padding_side == 'left'
+        buf, off = _pack_texts(flat)
+        p = self._encode_rows(buf, off, pair=pairs is not None, add_special_tokens=add_special_tokens, truncation=truncation,
+                              max_length=max_len, padding=pad_mode, pad_to=max_len, pad_left=pad_left,
+                              overflow_mode='stride' if stride > 0 else 'single', stride=stride)
+        return BatchEncoding(p, return_attention_mask, return_token_type_ids, return_offsets_mapping, return_special_tokens_mask)
+
+    def encode_to_encoding(self, text):
+        return self.encode_batch_to_encoding([text])[0]
+
+    def encode_pair_to_encoding(self, text, text_pair):
+        return self.encode_batch_pairs_to_encoding([(text, text_pair)])[0]
+
+    def encode_with_truncation(self, text, text_pair=None, max_length=512, stride=0):
+        """mod.rs:349-357: truncate_with_stride whenever the row is longer than max_length (also for stride = 0)"""
+        if stride >= max_length > 0 or (max_length == 0):
+            raise ValueError('stride >= max_length: the reference loops forever (encoding.rs:190-193)')
+        flat = [text] if text_pair is None else [text, text_pair]
+        buf, off = _pack_texts(flat)
+        p = self._encode_rows(buf, off, pair=text_pair is not None, truncation=True, max_length=max_length,
+                              overflow_mode='stride', stride=stride)
+        return p.encoding(0)
+
+    def encode_batch_to_encoding(self, texts):
+        if isinstance(texts, str):
+            raise TypeError("argument 'texts': Can't extract `str` to `Vec`")
+        buf, off = _pack_texts(list(texts))
+        p = self._encode_rows(buf, off)
+        return [p.encoding(r) for r in range(p.n_rows)]
+
+    def encode_batch_pairs_to_encoding(self, pairs):
+        flat = self._interleave([a for a, _ in pairs], [b for _, b in pairs])
+        buf, off = _pack_texts(flat)
+        p = self._encode_rows(buf, off, pair=True)
+        return [p.encoding(r) for r in range(p.n_rows)]
+
+    def encode_batch_with_padding(self, texts, max_length=None, pad_left=False):
+        """mod.rs:490-516: pad to max_length, or to the longest row; rows longer than that stay as they are"""
+        buf, off = _pack_texts(list(texts))
+        p = self._encode_rows(buf, off, padding=1 if max_length is None else 2, pad_to=max_length or 0, pad_left=pad_left)
+        return [p.encoding(r) for r in range(p.n_rows)]
+
+    def encode_batch_pairs_with_padding(self, pairs, max_length=None, pad_left=False):
+        flat = self._interleave([a for a, _ in pairs], [b for _, b in pairs])
+        buf, off = _pack_texts(flat)
+        p = self._encode_rows(buf, off, pair=True, padding=1 if max_length is None else 2, pad_to=max_length or 0, pad_left=pad_left)
+        return [p.encoding(r) for r in range(p.n_rows)]
+
+    def encode_plus(self, text):
+        return self.encode_to_encoding(text)
+
+    def batch_encode_plus(self, texts):
+        return self.encode_batch_to_encoding(texts)
+
+    @property
+    def model_max_length(self):
+        return self._model_max_length
+
+    @model_max_length.setter
+    def model_max_length(self, value):
+        self._model_max_length = int(value)
+
+    @property
+    def padding_side(self):
+        return self._padding_side
+
+    @padding_side.setter
+    def padding_side(self, value):
+        self._padding_side = str(value)
+
+    @property
+    def truncation_side(self):
+        return self._truncation_side
+
+    @truncation_side.setter
+    def truncation_side(self, value):
+        self._truncation_side = str(value)
+
+    @property
+    def post_processor_items(self):
+        """What the loaded post-processor does to one sequence: list of items, -1 = the ids, else a literal id."""
+        buf = (ctypes.c_int64 * 64)()
+        k = _lib().ctk_post_processor_items(self._h, buf, 64)
+        return [int(buf[i]) for i in range(min(k, 64))]
+
     # ---- getters (bindings/tokenizer.rs:271-289)
     @property
     def vocab_size(self):
@@ -364,6 +568,9 @@ class Tokenizer:
 
     def set_cache_persistent(self, flag):
         _lib().ctk_set_cache_persistent(self._h, int(bool(flag)))
+
+
+from .encoding import BatchEncoding, Encoding  # noqa: E402
 
 
 class Trainer:

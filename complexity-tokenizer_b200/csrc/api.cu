@@ -118,6 +118,29 @@ static int upload(Engine& eng) {
         UP(15, eng.tables.added_meta, meta.data(), meta.size() * sizeof(uint4));
         UP(16, eng.tables.mapped_alnum, CTK_MAPPED_ALNUM, sizeof(CTK_MAPPED_ALNUM));
     }
+    {   // rich Encoding outputs (encoding.cu)
+        const size_t nid = m.dec_special.size();
+        std::vector<uint32_t> info(nid + 1, 0);
+        for (size_t id = 0; id < nid; ++id) {
+            const uint32_t L = m.dec_off[id + 1] - m.dec_off[id], S = id < m.token_str_len.size() ? m.token_str_len[id] : 0u;
+            info[id] = (L < 0xFFFFu ? L : 0xFFFFu) | ((S < 0xFFFFu ? S : 0xFFFFu) << 16);
+        }
+        UP(21, eng.rich.tok_info, info.data(), info.size() * 4);
+        uint32_t max_sp = 0;
+        for (auto& kv : m.specials) if (kv.second < (1u << 27) && kv.second > max_sp) max_sp = kv.second;
+        std::vector<uint32_t> bits(max_sp / 32 + 1, 0);
+        for (auto& kv : m.specials) if (kv.second < (1u << 27)) bits[kv.second >> 5] |= 1u << (kv.second & 31);
+        eng.rich.n_special_words = m.specials.empty() ? 0u : (uint32_t)bits.size();
+        UP(22, eng.rich.special_bits, bits.data(), bits.size() * 4);
+        uint32_t b2c[256];
+        byte_map(b2c);
+        uint16_t map2[256];
+        for (int b = 0; b < 256; ++b) {
+            const uint32_t cp = b2c[b];
+            map2[b] = cp < 0x80u ? (uint16_t)cp : (uint16_t)((0xC0u | (cp >> 6)) | ((0x80u | (cp & 63u)) << 8));
+        }
+        UP(23, eng.rich.byte_map2, map2, sizeof map2);
+    }
     eng.tables.round_parallel = m.round_parallel ? 1u : 0u;
     UP(17, eng.tables.reach, m.reach.data(), m.reach.size() * 4);
 #undef UP
@@ -349,6 +372,17 @@ int ctk_debug_load_only(const uint8_t* json, size_t len, uint64_t* n_pairs, uint
     if (vocab_size) *vocab_size = m.vocab.size();
     if (nfc) *nfc = m.nfc;
     if (may_match) *may_match = m.any_added_may_match;
+    return CTK_OK;
+}
+
+// model-only load: the post-processor reduced to items (-1 = the ids, else a literal id), for CPU tests of the load rules
+int ctk_debug_post_processor(const uint8_t* json, size_t len, int64_t* items, size_t cap, size_t* n) {
+    HostModel m;
+    std::string err;
+    int rc = load_model(json, len, m, err);
+    if (rc != CTK_OK) { set_last_error(err); return rc; }
+    for (size_t i = 0; i < m.pp_items.size() && i < cap; ++i) items[i] = m.pp_items[i];
+    if (n) *n = m.pp_items.size();
     return CTK_OK;
 }
 

@@ -141,6 +141,22 @@ __global__ void k_doc_offsets(const uint64_t* __restrict__ text_off, uint64_t n_
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
 
+// Pre-token start bitmap of a batch (one bit per byte) + the number of starts per block of 256 words (8 KiB);
+// used by the rich `Encoding` path (encoding.cu), which needs the words themselves and not only their ids.
+// ds: (n_words + 1) words of scratch for the document-start bits.
+int starts_bitmap(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes, uint32_t* ds,
+                  uint32_t* start_bits, uint32_t* block_counts, uint32_t* err, cudaStream_t st) {
+    const uint64_t n_words = (n_bytes + 31) / 32;
+    const uint32_t n_blocks = (uint32_t)((n_words + 255) / 256);
+    CK(cudaMemsetAsync(ds, 0, (n_words + 1) * 4, st));
+    k_docstart<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_off, n_docs, n_bytes, ds, err);
+    TextView tv{d_text, n_bytes, ds, eng.tables.trie_index, eng.tables.trie_blocks};
+    k_starts<<<n_blocks, 256, 0, st>>>(tv, start_bits, block_counts);
+    eng.launched(2);
+    CK(cudaGetLastError());
+    return CTK_OK;
+}
+
 int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                    uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st) {
     if (n_bytes >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_ARG, "one device call handles less than 4 GiB of text");

@@ -16,7 +16,8 @@
 namespace ctk {
 
 // device-side error flags (OR-ed into a word the host reads back)
-enum : uint32_t { ERRF_OFFSETS = 1, ERRF_CAPACITY = 2, ERRF_UTF8 = 4, ERRF_POOL = 8, ERRF_NFC_LONG = 16, ERRF_NFC_SUSPECT = 32 };
+enum : uint32_t { ERRF_OFFSETS = 1, ERRF_CAPACITY = 2, ERRF_UTF8 = 4, ERRF_POOL = 8, ERRF_NFC_LONG = 16, ERRF_NFC_SUSPECT = 32,
+                  ERRF_ALIGN = 64, ERRF_PANIC = 128 };
 constexpr int CTK_RETRY_NFC = 100;     // internal: the optimistic encode met a code point that needs NFC; run the normaliser and encode again
 
 void set_last_error(const std::string& s);
@@ -25,7 +26,7 @@ extern std::atomic<uint64_t> g_kernel_launches;
 // Grow-only device scratch, one buffer per slot.  Growing frees the old buffer (cudaFree
 // synchronises the device, so nothing in flight can still be using it).
 struct Workspace {
-    static constexpr int kSlots = 48;
+    static constexpr int kSlots = 80;
     void* p[kSlots] = {};
     size_t cap[kSlots] = {};
     cudaError_t get(int slot, size_t bytes, void** out) {
@@ -62,13 +63,21 @@ struct NfcTables {                      // canonical decomposition / composition
     const uint8_t *trie_index, *trie_blocks;
 };
 
+struct RichTables {
+    const uint32_t* tok_info = nullptr;     // [n ids] decoded byte length | vocabulary-string byte length << 16
+    const uint32_t* special_bits = nullptr; // bit per id: id is a value of the special_tokens map (encoding.rs:77-83)
+    uint32_t n_special_words = 0;
+    const uint16_t* byte_map2 = nullptr;    // [256] UTF-8 of the byte-mapped char: low byte first, high byte 0 for one-byte chars
+};
+
 struct Engine {
     HostModel model;
     int device = 0;
     DevTables tables{};
     DecodeTables dec{};
     NfcTables nfc{};
-    void* d_table_mem[24] = {};
+    RichTables rich{};
+    void* d_table_mem[32] = {};
     Workspace ws;
     std::mutex mu;                      // serialises device work issued through this tokenizer
     bool cache_persistent = false;
@@ -146,6 +155,26 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
                  uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st, bool check_nfc = false);
 int encode_general(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                    uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
+int starts_bitmap(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes, uint32_t* ds,
+                  uint32_t* start_bits, uint32_t* block_counts, uint32_t* err, cudaStream_t st);
+cudaError_t pinned_get(size_t bytes, void** out, size_t* cap);      // process-wide pool of page-locked buffers (host_api.cu)
+void pinned_put(void* p, size_t cap);
+
+// ---- rich `Encoding` outputs (encoding.cu) ------------------------------------------------------
+struct RichOut {                            // device pointers into the engine's workspace, valid until its next call
+    uint64_t n_rows = 0, total = 0, n_tokens = 0, max_row = 0;
+    const uint64_t* row_off = nullptr;      // n_rows + 1
+    const uint64_t* row_full = nullptr;     // n_rows: length before truncation and padding
+    const uint32_t* ids = nullptr;          // total
+    const uint8_t *attention = nullptr, *type_ids = nullptr, *special = nullptr;   // total each
+    const uint64_t* tok_off = nullptr;      // n_texts + 1: tokens of each text before post-processing
+    const uint32_t* raw_ids = nullptr;      // n_tokens
+    const uint2* offsets = nullptr;         // n_tokens (byte start, byte end) in the original text; NULL if not asked for
+    const uint32_t* word_ids = nullptr;     // n_tokens
+};
+int encode_rich_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_texts, uint64_t n_bytes,
+                       const ctk_encoding_options& opt, RichOut* out, cudaStream_t st);
+
 int clean_parallel(Engine& eng, const uint8_t* raw, const uint64_t* raw_off, size_t n_docs, uint64_t n, uint8_t* d_out,
                    uint64_t out_cap, uint64_t* d_out_off, uint32_t* err, cudaStream_t st);
 int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off, size_t n, uint64_t total_ids,

@@ -58,6 +58,8 @@ struct PinnedPool {
     }
 };
 static PinnedPool g_pinned;
+cudaError_t pinned_get(size_t bytes, void** out, size_t* cap) { return g_pinned.get(bytes, out, cap); }
+void pinned_put(void* p, size_t cap) { g_pinned.put(p, cap); }
 
 struct Result {
     size_t n = 0;

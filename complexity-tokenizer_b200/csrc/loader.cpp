@@ -121,6 +121,85 @@ int parse_pre(const JValue* v, std::vector<bool>& stages, std::string& err) {
     return 1;                                                   // unknown type => None
 }
 
+// parsing.rs:253-270
+std::string template_from_array(const JValue& arr) {
+    std::string out;
+    bool first = true;
+    for (auto& item : arr.arr) {
+        if (!item.is_obj()) continue;
+        std::string part;
+        bool have = false;
+        if (const JValue* sp = item.get("SpecialToken")) {
+            const JValue* id = sp->get("id");
+            if (id && id->is_str()) { part = id->s; have = true; }
+        } else if (const JValue* sq = item.get("Sequence")) {
+            const JValue* id = sq->get("id");
+            if (id && id->is_str()) { part = "$" + id->s; have = true; }
+        }
+        if (!have) continue;
+        if (!first) out += ' ';
+        out += part;
+        first = false;
+    }
+    return out;
+}
+
+bool rust_is_whitespace(uint32_t c) {
+    return (c >= 9 && c <= 13) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) ||
+           c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+
+// The template walk of postprocessors.rs:88-148 with pair_ids = None, recorded instead of executed.
+void template_items(const std::string& tpl, const std::unordered_map<std::string, uint32_t>& specials, std::vector<int64_t>& items) {
+    std::vector<uint32_t> ch;
+    for (size_t i = 0; i < tpl.size();) ch.push_back(next_cp(tpl, i));
+    size_t i = 0;
+    while (i < ch.size()) {
+        if (ch[i] == '$' && i + 1 < ch.size()) {
+            if (ch[i + 1] == 'A') { items.push_back(-1); i += 2; }
+            else if (ch[i + 1] == 'B') { i += 2; }
+            else i += 1;
+        } else if (ch[i] == '<' || ch[i] == '[') {
+            const uint32_t endc = ch[i] == '<' ? '>' : ']';
+            size_t start = i;
+            while (i < ch.size() && ch[i] != endc) ++i;
+            if (i < ch.size()) ++i;
+            size_t a = start, b = i;                            // str::trim
+            while (a < b && rust_is_whitespace(ch[a])) ++a;
+            while (b > a && rust_is_whitespace(ch[b - 1])) --b;
+            std::string tok;
+            for (size_t k = a; k < b; ++k) put_utf8(tok, ch[k]);
+            auto it = specials.find(tok);
+            if (it != specials.end()) items.push_back((int64_t)it->second);
+        } else {
+            i += 1;
+        }
+    }
+}
+
+// parsing.rs:193-250
+void parse_post_processor(const JValue* v, const std::unordered_map<std::string, uint32_t>& specials, HostModel& m) {
+    m.pp_items.clear();
+    m.has_post_processor = false;
+    auto get = [&](const char* k, uint32_t dflt) { auto it = specials.find(k); return it == specials.end() ? dflt : it->second; };
+    const char* t = type_of(v);
+    std::string ty = t ? t : "";
+    if (ty == "TemplateProcessing") {
+        const JValue* s = v->get("single");
+        std::string single = (s && s->is_arr()) ? template_from_array(*s) : "<s> $A </s>";
+        template_items(single, specials, m.pp_items);
+        m.has_post_processor = true;
+    } else if (ty == "RobertaProcessing") {
+        m.pp_items = {(int64_t)get("<s>", 0), -1, (int64_t)get("</s>", 2)};
+        m.has_post_processor = true;
+    } else if (ty == "BertProcessing") {
+        m.pp_items = {(int64_t)get("[CLS]", 101), -1, (int64_t)get("[SEP]", 102)};
+        m.has_post_processor = true;
+    } else {
+        m.pp_items = {-1};
+    }
+}
+
 int klass_ascii(uint8_t c) {   // 0 other, 1 letter, 2 number, 3 whitespace
     if ((c | 0x20) >= 'a' && (c | 0x20) <= 'z') return 1;
     if (c >= '0' && c <= '9') return 2;
@@ -376,6 +455,17 @@ int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err) 
         if (special_map.count(tok)) m.dec_special[id] = 1;
     }
     m.dec_off[nid] = (uint32_t)m.dec_blob.size();
+    // ---- rich Encoding outputs
+    {
+        std::unordered_map<std::string, uint32_t> smap(special_map.begin(), special_map.end());
+        const JValue* ppj = root.get("post_processor");
+        parse_post_processor(ppj && ppj->t != JValue::Null ? ppj : nullptr, smap, m);
+        m.token_str_len.assign(nid, 0);
+        for (size_t id = 0; id < nid; ++id) if (m.id_present[id]) m.token_str_len[id] = (uint32_t)m.id_to_token[id].size();
+        auto p1 = smap.find("[PAD]"), p2 = smap.find("<pad>");
+        m.pad_id = p1 != smap.end() ? p1->second : p2 != smap.end() ? p2->second : 0u;
+        m.pad_token = (m.pad_id < nid && m.id_present[m.pad_id]) ? m.id_to_token[m.pad_id] : std::string("<pad>");
+    }
     token_reach(m);
     return CTK_OK;
 }

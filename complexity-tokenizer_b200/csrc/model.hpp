@@ -45,6 +45,14 @@ struct HostModel {
     // `round_parallel` holds: monotone table, every merge product is the concatenation of its parts, ids unique.
     std::vector<uint32_t> reach;
     bool round_parallel = false;
+    // ---- rich `Encoding` outputs (loader.cpp: parse_post_processor)
+    // The post-processor reduced to what `process(ids, None)` does (postprocessors.rs:34-55 with pair_ids = None,
+    // which is the only way mod.rs:372-375 calls it): an ordered list of items, -1 = "the ids" ($A), else a literal id.
+    std::vector<int64_t> pp_items;                         // {-1} when the file has no (parsable) post_processor
+    bool has_post_processor = false;
+    std::vector<uint32_t> token_str_len;                   // byte length of the vocabulary string of each id (0: absent), mod.rs:421-425
+    uint32_t pad_id = 0;                                   // special_tokens["[PAD]"] or ["<pad>"] or 0 (mod.rs:504-507)
+    std::string pad_token;                                 // id_to_token(pad_id) or "<pad>"
 };
 
 // Returns a CTK_* code; on failure `err` holds the message.

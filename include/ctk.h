@@ -31,6 +31,7 @@ extern "C" {
 #define CTK_ERR_UNSUPPORTED 3   /* pipeline outside the hot path (non-ByteLevel, NFKC, ...)            */
 #define CTK_ERR_CUDA 4          /* CUDA failure, no device, out of memory                              */
 #define CTK_ERR_ARG 5           /* bad argument (null pointer, unaligned device buffer, ...)           */
+#define CTK_ERR_PANIC 6         /* the reference panics on this input (pyo3 PanicException); message says where */
 
 typedef struct ctk_tokenizer ctk_tokenizer;   /* opaque */
 typedef struct ctk_result ctk_result;         /* opaque, owns host (pinned) result buffers */
@@ -96,6 +97,51 @@ int ctk_decode_batch_device(const ctk_tokenizer* tok, const uint32_t* d_ids, con
                             int clean_up_tokenization_spaces, uint8_t* d_text_out, uint64_t text_cap,
                             uint64_t* d_text_off_out, uint64_t* n_bytes_host, void* stream);
 size_t ctk_decode_max_bytes(const ctk_tokenizer* tok);   /* longest decoded token, in bytes */
+
+/* ---- rich `Encoding` outputs ----------------------------------------
+ * Replaces, for a whole batch and on the GPU,
+ *   HuggingFaceTokenizer::encode_to_encoding / encode_pair_to_encoding / encode_batch_to_encoding /
+ *   encode_batch_pairs_to_encoding                       (src/huggingface/mod.rs:340-395, :481-488)
+ *   encode_batch_with_padding / encode_batch_pairs_with_padding            (mod.rs:490-545)
+ *   PyTokenizer::__call__ (truncate + pad of a batch)     (src/bindings/tokenizer.rs:33-201)
+ * with the arithmetic of Encoding::{from_ids, merge, mark_special_tokens, truncate, pad} (src/encoding.rs:44-267)
+ * and PostProcessor::process(ids, None) (src/postprocessors.rs:34-188).
+ *
+ * A ROW is one Encoding: one text, or (pair != 0) texts 2r and 2r+1 merged.  All rows come back packed: `row_off`
+ * (n_rows + 1) indexes input_ids / attention_mask / token_type_ids / special_tokens_mask; with padding every row has
+ * the same length and the arrays are a dense row-major matrix.  Offsets and word ids exist per token BEFORE
+ * post-processing (the reference neither shifts nor pads them, mod.rs:372-383, encoding.rs:86-129) and are indexed by
+ * `token_off` (n_texts + 1).  Offsets are BYTE positions in the original text, found the way
+ * pre_tokenize_with_offsets does (mod.rs:447-478: str::find of the byte-mapped word from a running position). */
+typedef struct ctk_encoding_options {
+    int add_special_tokens;   /* 1: encode_to_encoding (no added-token scan, post-processor, special mask);
+                                 0: encode + Encoding::from_ids (bindings/tokenizer.rs:88-96), no offsets */
+    int pair;                 /* 1: texts 2r, 2r+1 are (text, text_pair) of row r (Encoding::merge, type id 1) */
+    int truncation;           /* 1: rows longer than max_length keep their first max_length entries (encoding.rs:132-232) */
+    uint64_t max_length;
+    int padding;              /* 0 none; 1 to the longest row of the batch; 2 to pad_to (encoding.rs:86-129) */
+    uint64_t pad_to;
+    int pad_left;
+    int want_offsets;         /* 1: also compute offsets + word ids (only with add_special_tokens = 1) */
+} ctk_encoding_options;
+typedef struct ctk_encodings ctk_encodings;   /* opaque, owns host (pinned) result buffers */
+int ctk_encode_batch_to_encoding(const ctk_tokenizer* tok, const uint8_t* text, const uint64_t* text_off, size_t n_texts,
+                                 const ctk_encoding_options* opt, ctk_encodings** res);
+size_t ctk_encodings_rows(const ctk_encodings* res);
+const uint64_t* ctk_encodings_row_offsets(const ctk_encodings* res);       /* n_rows + 1 */
+const uint64_t* ctk_encodings_row_full_lengths(const ctk_encodings* res);  /* n_rows: before truncation / padding */
+const uint32_t* ctk_encodings_input_ids(const ctk_encodings* res);
+const uint8_t* ctk_encodings_attention_mask(const ctk_encodings* res);
+const uint8_t* ctk_encodings_type_ids(const ctk_encodings* res);
+const uint8_t* ctk_encodings_special_tokens_mask(const ctk_encodings* res);
+const uint64_t* ctk_encodings_token_offsets(const ctk_encodings* res);     /* n_texts + 1 */
+const uint32_t* ctk_encodings_token_ids(const ctk_encodings* res);         /* ids before post-processing */
+const uint32_t* ctk_encodings_offsets(const ctk_encodings* res);           /* 2 per token: start, end; NULL if not computed */
+const uint32_t* ctk_encodings_word_ids(const ctk_encodings* res);          /* NULL if not computed */
+void ctk_encodings_free(ctk_encodings* res);
+/* What the loaded post-processor does to one sequence: writes up to cap items (-1 = the ids, else a literal id), returns the count. */
+size_t ctk_post_processor_items(const ctk_tokenizer* tok, int64_t* items, size_t cap);
+uint32_t ctk_pad_token(const ctk_tokenizer* tok, const uint8_t** token, size_t* len);   /* mod.rs:504-509 */
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char* ctk_last_error(void);
