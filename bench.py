@@ -173,6 +173,8 @@ def main():
     ap.add_argument('--bytes', type=int, default=1 << 30, help='corpus bytes per GPU')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-encodings', action='store_true')
+    ap.add_argument('--encodings-bytes', type=int, default=256 << 20)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -321,6 +323,34 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- rich Encoding outputs on a bounded sample of the same corpus, through the C ABI with host buffers:
+    #      (a) the tokenizer(texts, padding='max_length', truncation=True, max_length=1024) shape: dense ids + masks
+    #      (b) encode_batch_to_encoding with byte offsets and word ids
+    encodings = None
+    if not args.no_encodings:
+        n_s = int(np.searchsorted(offs, min(B, args.encodings_bytes), side='right')) - 1
+        s_off = offs[:n_s + 1].copy()
+        s_B = int(s_off[-1])
+        s_text = h_np[:s_B]
+        encodings = {'sample': 'first %d docs (%.1f MiB) of the same corpus, host buffers in, page-locked result out' % (n_s, s_B / 2**20)}
+        for key, kw in (('call_padded_1024', dict(add_special_tokens=True, truncation=True, max_length=1024, padding=2, pad_to=1024)),
+                        ('to_encoding_offsets', dict(add_special_tokens=True, want_offsets=True))):
+            r_ = tok._encode_rows(s_text, s_off, **kw)
+            del r_
+            tok.profile_enable(True)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                r_ = tok._encode_rows(s_text, s_off, **kw)
+                n_out = int(r_.input_ids.size)
+                del r_
+            ms_ = (time.perf_counter() - t0) * 1e3 / 2
+            pr = tok.profile_report()
+            tok.profile_enable(False)
+            encodings[key] = {'e2e_ms': ms_, 'e2e_MB_per_s': s_B / (ms_ * 1e-3) / 1e6, 'out_elements': n_out,
+                              'device_ms': sum(v[0] / v[1] for v in pr.values()),
+                              'device_MB_per_s': s_B / (sum(v[0] / v[1] for v in pr.values()) * 1e-3) / 1e6,
+                              'kernels_ms': {k: v[0] / v[1] for k, v in sorted(pr.items())}}
+
     # ---- roofline of the dominant kernel (CUDA events inside the library, same timed region)
     peak, peak_src = peaks()
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
@@ -361,7 +391,7 @@ def main():
                    'lexicon_words': 50000, 'vocab': 50257, 'l2': 'inputs (1 GiB) larger than L2 (126 MB); no flush needed',
                    'pretoken_cache': 'cleared inside every step', 'parallelism': 'documents sharded over %d GPU(s), no collective on the data path' % world},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
-        'decode_batch': decode}
+        'decode_batch': decode, 'encodings': encodings}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

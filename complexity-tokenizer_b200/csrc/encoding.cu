@@ -99,18 +99,79 @@ __global__ void k_tok_check(const uint64_t* __restrict__ pos, const uint32_t* __
 }
 
 // ---- word spans: the find chain of mod.rs:447-478 ------------------------------------------------------------------
+// Per word, data-parallel: {length, leading U+0020 count, bytes outside 0x21..0x7E (each becomes a two-byte mapped char),
+// first byte of the mapped string that will be searched for}.  One lane per word; words longer than 64 bytes are
+// scanned by the whole warp.
+__global__ void __launch_bounds__(256) k_word_meta(const uint8_t* __restrict__ N, uint64_t n_bytes, const uint32_t* __restrict__ starts,
+                                                   uint32_t n_words, const uint16_t* __restrict__ map2, uint4* __restrict__ meta) {
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = k < n_words;
+    const uint32_t ws = valid ? starts[k] : 0u;
+    const uint32_t we = valid ? (k + 1 < n_words ? starts[k + 1] : (uint32_t)n_bytes) : 0u;
+    const uint32_t wlen = we - ws;
+    uint32_t nsp = 0, np = 0;
+    constexpr uint32_t kShort = 64;
+    if (valid && wlen <= kShort) {
+        bool lead = true;
+        for (uint32_t i = 0; i < wlen; ++i) {
+            const uint32_t b = N[ws + i];
+            lead = lead && b == 0x20u;
+            nsp += lead ? 1u : 0u;
+            np += (b < 0x21u || b > 0x7Eu) ? 1u : 0u;
+        }
+    }
+    unsigned longm = __ballot_sync(kFull, valid && wlen > kShort);
+    while (longm) {
+        const int src = __ffs(longm) - 1;
+        longm &= longm - 1;
+        const uint32_t lws = __shfl_sync(kFull, ws, src), lwlen = __shfl_sync(kFull, wlen, src);
+        uint32_t tn = 0, tp = 0;
+        bool lead = true;
+        for (uint32_t base = 0; base < lwlen; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t b = i < lwlen ? N[lws + i] : (uint32_t)'a';         // padding lanes: printable, not a space
+            const unsigned sp = __ballot_sync(kFull, b == 0x20u);
+            tp += __popc(__ballot_sync(kFull, b < 0x21u || b > 0x7Eu));
+            if (lead) {
+                const uint32_t t = ~sp ? (uint32_t)(__ffs(~sp) - 1) : 32u;
+                tn += t;
+                lead = t == 32u;
+            }
+        }
+        if (lane == src) { nsp = tn; np = tp; }
+    }
+    if (valid) {
+        const bool all_space = nsp == wlen;                                      // trim_start_matches('Ġ') left nothing: the word itself is searched
+        const uint32_t ts = all_space ? 0u : nsp;
+        const uint32_t np_trim = all_space ? np : np - nsp;
+        // first two bytes of the needle (the mapped string of the word from ts on); second byte 0 when the needle has one byte
+        const uint32_t v0 = map2[N[ws + ts]];
+        uint32_t b1 = v0 >> 8;
+        if (!b1 && wlen - ts > 1) b1 = map2[N[ws + ts + 1]] & 0xFFu;
+        meta[k] = make_uint4(wlen, nsp, np, (v0 & 0xFFu) | (b1 << 8));
+    }
+}
+
 struct SpanArgs {
     const uint8_t* O; const uint64_t* o_off;         // the original batch (what str::find searches)
     const uint8_t* N; const uint64_t* n_off;         // the normalised batch (what the words are cut from)
     uint64_t n_docs;
     WordIndex wi;
     const uint32_t* starts;
+    const uint4* meta;
     const uint16_t* map2;
-    uint2* wspan;
-    uint32_t* wdoc0;
+    uint4* wspan;                                    // {start, end, first word of the text, -}
     uint32_t* err;                                   // err[0] flags, err[8] first panicking text
+    int same;                                        // N is O (nothing was normalised or prepended)
 };
 
+// One warp per text walks its words in order (the position each search starts from is the previous result).
+//  * on the rails: the text is its own normalised form, the word is printable ASCII after its leading spaces and the
+//    running position lies inside those spaces: str::find returns the word's own position (the bytes in between are
+//    spaces, the needle does not start with one).  No byte of the text is read.
+//  * a needle with a two-byte mapped char cannot occur in a text that has no byte C2..C5: not found, no search.
+//  * otherwise 32 candidate positions per step, first byte first.
 __global__ void __launch_bounds__(128) k_word_spans(SpanArgs a) {
     const uint64_t d = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     if (d >= a.n_docs) return;
@@ -124,63 +185,90 @@ __global__ void __launch_bounds__(128) k_word_spans(SpanArgs a) {
     for (uint32_t i = lane; i < olen; i += 32) { const uint32_t b = od[i]; hh |= (b - 0xC2u) <= 3u; }
     const bool has_hi = __any_sync(kFull, hh);
     uint32_t ss = 0;
+    bool boundary = true;                                                        // ss is known to be a char boundary of the text
+    uint4 mt = a.meta[k0];
+    uint32_t ws_next = a.starts[k0];
     for (uint32_t k = k0; k < k1; ++k) {
-        const uint64_t ws = a.starts[k];
-        const uint64_t we = (k + 1 < k1) ? (uint64_t)a.starts[k + 1] : ne;
-        const uint32_t wlen = (uint32_t)(we - ws);
-        const uint8_t* __restrict__ wp = a.N + ws;
-        uint32_t nsp = 0, np = 0;
-        bool lead = true;
-        for (uint32_t base = 0; base < wlen; base += 32) {
-            const uint32_t i = base + lane;
-            const uint32_t b = i < wlen ? wp[i] : (uint32_t)'a';
-            const unsigned sp = __ballot_sync(kFull, b == 0x20u);
-            np += __popc(__ballot_sync(kFull, b < 0x21u || b > 0x7Eu));
-            if (lead) {
-                const uint32_t t = ~sp ? (uint32_t)(__ffs(~sp) - 1) : 32u;      // padding lanes read 'a': never a space
-                nsp += t;
-                lead = t == 32u;
-            }
-        }
-        const bool all_space = nsp == wlen;                                      // trim_start_matches('Ġ') left nothing: search the word
+        const uint4 me = mt;
+        const uint64_t ws = ws_next;
+        if (k + 1 < k1) { mt = a.meta[k + 1]; ws_next = a.starts[k + 1]; }      // independent of the chain: in flight during this word
+        const uint32_t wlen = me.x, nsp = me.y, np = me.z, fb = me.w & 0xFFu, sb = me.w >> 8;
+        const bool all_space = nsp == wlen;
         const uint32_t ts = all_space ? 0u : nsp;
         const uint32_t np_trim = all_space ? np : np - nsp;
         const uint32_t tl = wlen - ts;
         const uint64_t m = (uint64_t)tl + np_trim;                               // bytes of the mapped string searched for
         const uint64_t mword = (uint64_t)wlen + np;                              // word.len()
         const bool pure = np_trim == 0;
-        if (ss < olen && (od[ss] & 0xC0u) == 0x80u) {                            // original[search_start..] panics
-            if (lane == 0) { atomicOr(a.err, ERRF_PANIC); atomicMin(a.err + 8, (uint32_t)(d < 0xFFFFFFFFull ? d : 0xFFFFFFFFull)); }
-            return;
-        }
+        const uint64_t rel = ws - nb;                                            // the word's own position when N is O
         int64_t found = -1;
-        if (m <= (uint64_t)(olen - ss) && (pure || has_hi)) {
-            const uint8_t* __restrict__ tp = wp + ts;
-            const uint32_t fb = pure ? (uint32_t)tp[0] : (uint32_t)(a.map2[tp[0]] & 0xFFu);
-            for (uint64_t base = ss; base + m <= olen; base += 32) {
-                const uint64_t p = base + lane;
-                bool ok = p + m <= olen && od[p] == fb;
-                if (ok) {
-                    if (pure) {
-                        for (uint32_t j = 1; j < tl; ++j) if (od[p + j] != tp[j]) { ok = false; break; }
-                    } else {
-                        uint64_t q = p;
-                        for (uint32_t j = 0; j < tl; ++j) {
-                            const uint32_t v = a.map2[tp[j]];
-                            if (od[q] != (v & 0xFFu)) { ok = false; break; }
-                            ++q;
-                            if (v >> 8) { if (od[q] != (v >> 8)) { ok = false; break; } ++q; }
+        if (a.same && pure && ss >= rel && ss <= rel + ts) {
+            found = (int64_t)(rel + ts);
+        } else {
+            if (!boundary && ss < olen && (od[ss] & 0xC0u) == 0x80u) {           // original[search_start..] panics
+                if (lane == 0) { atomicOr(a.err, ERRF_PANIC); atomicMin(a.err + 8, (uint32_t)(d < 0xFFFFFFFFull ? d : 0xFFFFFFFFull)); }
+                return;
+            }
+            if (m <= (uint64_t)(olen - ss) && (pure || has_hi)) {
+                // 16 candidate positions per lane and step: one aligned 16-byte load (+4 bytes for the second-byte test),
+                // byte-wise compares of the needle's first two bytes, survivors verified in ascending order
+                const uint8_t* __restrict__ tp = a.N + ws + ts;
+                const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(od) & 15u);
+                const uint8_t* __restrict__ ab = od - mis;                       // aligned; the bytes before od belong to the same buffer
+                const int64_t last = (int64_t)olen - (int64_t)m;                 // last position a match can start at
+                const uint32_t f4 = fb * 0x01010101u, s4 = sb * 0x01010101u;
+                for (int64_t c = (int64_t)((mis + ss) >> 4) + lane;; c += 32) {
+                    const int64_t cs = c * 16 - (int64_t)mis;                    // position of the chunk's first byte in the text
+                    const int64_t cs0 = cs - 16 * lane;                          // lane 0's chunk: uniform loop exit
+                    if (cs0 > last) break;
+                    uint32_t cand = 0;
+                    if (cs <= last) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(ab + c * 16);
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        uint32_t e1 = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) e1 |= (((__vcmpeq4(w[q], f4) & 0x01010101u) * 0x10204080u) >> 28) << (4 * q);
+                        cand = e1;
+                        if (m > 1) {
+                            const uint32_t nx = *reinterpret_cast<const uint32_t*>(ab + c * 16 + 16);
+                            uint32_t e2 = 0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) e2 |= (((__vcmpeq4(w[q], s4) & 0x01010101u) * 0x10204080u) >> 28) << (4 * q);
+                            e2 |= (((__vcmpeq4(nx, s4) & 0x01010101u) * 0x10204080u) >> 28) << 16;
+                            cand &= e2 >> 1;
                         }
+                        const int64_t lo = (int64_t)ss - cs, hi = last - cs;     // valid bit range [lo, hi]
+                        if (lo > 0) cand &= lo >= 16 ? 0u : ~((1u << lo) - 1u);
+                        if (hi < 15) cand &= (2u << hi) - 1u;
                     }
+                    int64_t hit = -1;
+                    while (cand) {
+                        const int j = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        const uint64_t p = (uint64_t)(cs + j);
+                        bool ok = true;
+                        if (pure) {
+                            for (uint32_t i = 2; i < tl; ++i) if (od[p + i] != tp[i]) { ok = false; break; }
+                        } else {
+                            uint64_t q = p;
+                            for (uint32_t i = 0; i < tl; ++i) {
+                                const uint32_t mv = a.map2[tp[i]];
+                                if (od[q] != (mv & 0xFFu)) { ok = false; break; }
+                                ++q;
+                                if (mv >> 8) { if (od[q] != (mv >> 8)) { ok = false; break; } ++q; }
+                            }
+                        }
+                        if (ok) { hit = (int64_t)p; break; }
+                    }
+                    const unsigned mask = __ballot_sync(kFull, hit >= 0);
+                    if (mask) { found = __shfl_sync(kFull, hit, __ffs(mask) - 1); break; }
                 }
-                const unsigned mask = __ballot_sync(kFull, ok);
-                if (mask) { found = (int64_t)(base + (uint64_t)(__ffs(mask) - 1)); break; }
             }
         }
         uint32_t start, end;
-        if (found >= 0) { start = (uint32_t)found; end = (uint32_t)(found + (int64_t)m); }
-        else { start = ss; const uint64_t e = (uint64_t)ss + mword; end = e < olen ? (uint32_t)e : olen; }
-        if (lane == 0) { a.wspan[k] = make_uint2(start, end); a.wdoc0[k] = k0; }
+        if (found >= 0) { start = (uint32_t)found; end = (uint32_t)(found + (int64_t)m); boundary = true; }
+        else { start = ss; const uint64_t e = (uint64_t)ss + mword; end = e < olen ? (uint32_t)e : olen; boundary = end == olen; }
+        if (lane == 0) a.wspan[k] = make_uint4(start, end, k0, 0u);
         ss = end;
     }
 }
@@ -197,19 +285,19 @@ __global__ void __launch_bounds__(256) k_tok_first(const uint64_t* __restrict__ 
 
 __global__ void __launch_bounds__(256) k_tok_offsets(const uint64_t* __restrict__ pos, const uint32_t* __restrict__ ids, TokLen tl,
                                                      uint64_t n_tokens, WordIndex wi, const uint32_t* __restrict__ wfirst,
-                                                     const uint2* __restrict__ wspan, const uint32_t* __restrict__ wdoc0,
+                                                     const uint4* __restrict__ wspan,
                                                      uint2* __restrict__ offsets, uint32_t* __restrict__ word_ids) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n_tokens) return;
     const uint64_t v = pos[i];
     const uint64_t g = (uint32_t)v;
     const uint32_t w = wi.before(g + 1) - 1u;                                   // the word that holds byte g
-    const uint2 sp = wspan[w];
+    const uint4 sp = wspan[w];
     const uint64_t before = (uint32_t)((uint32_t)(v >> 32) - wfirst[w]);         // string bytes of the word's earlier tokens
     const uint64_t slen = (uint32_t)(tl(ids[i]) >> 32);
     const uint64_t s = (uint64_t)sp.x + before, e = s + slen;                    // mod.rs:421-428: end = min(off + len, word_end)
     offsets[i] = make_uint2((uint32_t)(s < sp.y ? s : sp.y), (uint32_t)(e < sp.y ? e : sp.y));
-    word_ids[i] = w - wdoc0[w];
+    word_ids[i] = w - sp.z;
 }
 
 // ---- rows ----------------------------------------------------------------------------------------------------------------
@@ -382,12 +470,13 @@ int encode_rich_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off
         uint32_t n_words = 0;
         CK(cudaMemcpyAsync(&n_words, bb + n_blocks, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        uint32_t *wrank, *starts, *wdoc0, *wfirst, *word_ids;
-        uint2 *wspan, *offs;
+        uint32_t *wrank, *starts, *wfirst, *word_ids;
+        uint4 *wspan, *wmeta;
+        uint2* offs;
         CK(ws.get(S_WRANK, (n_w32 + 1) * 4, (void**)&wrank));
         CK(ws.get(S_STARTS, ((uint64_t)n_words + 2) * 4, (void**)&starts));
-        CK(ws.get(S_WSPAN, ((uint64_t)n_words + 1) * 8, (void**)&wspan));
-        CK(ws.get(S_WDOC0, ((uint64_t)n_words + 1) * 4, (void**)&wdoc0));
+        CK(ws.get(S_WSPAN, ((uint64_t)n_words + 1) * 16, (void**)&wspan));
+        CK(ws.get(S_WDOC0, ((uint64_t)n_words + 1) * 16, (void**)&wmeta));
         CK(ws.get(S_WFIRST, ((uint64_t)n_words + 1) * 4, (void**)&wfirst));
         CK(ws.get(S_OFFS, (n_tokens + 1) * 8, (void**)&offs));
         CK(ws.get(S_WIDS, (n_tokens + 1) * 4, (void**)&word_ids));
@@ -398,14 +487,16 @@ int encode_rich_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off
         eng.mark("rich:scan_token_lengths", st);
         k_tok_check<<<(unsigned)((n_texts + 1 + 255) / 256), 256, 0, st>>>(pos, raw, tl, tok_off, noff, n_texts, n_tokens, nbytes, err);
         WordIndex wi{sb, wrank, nbytes, n_words};
-        SpanArgs sa{d_text, d_off, nt, noff, n_texts, wi, starts, eng.rich.byte_map2, wspan, wdoc0, err};
+        k_word_meta<<<(n_words + 255) / 256, 256, 0, st>>>(nt, nbytes, starts, n_words, eng.rich.byte_map2, wmeta);
+        eng.mark("rich:k_word_meta", st);
+        SpanArgs sa{d_text, d_off, nt, noff, n_texts, wi, starts, wmeta, eng.rich.byte_map2, wspan, err, nt == d_text ? 1 : 0};
         k_word_spans<<<(unsigned)((n_texts * 32 + 127) / 128), 128, 0, st>>>(sa);
         eng.mark("rich:k_word_spans", st);
         const unsigned tg = (unsigned)((n_tokens + 255) / 256);
         k_tok_first<<<tg, 256, 0, st>>>(pos, n_tokens, wi, wfirst);
-        k_tok_offsets<<<tg, 256, 0, st>>>(pos, raw, tl, n_tokens, wi, wfirst, wspan, wdoc0, offs, word_ids);
+        k_tok_offsets<<<tg, 256, 0, st>>>(pos, raw, tl, n_tokens, wi, wfirst, wspan, offs, word_ids);
         eng.mark("rich:k_tok_offsets", st);
-        eng.launched(7);
+        eng.launched(8);
         CK(cudaGetLastError());
         out->offsets = offs; out->word_ids = word_ids;
     }
