@@ -11,6 +11,7 @@
 
 #include "device_common.cuh"
 #include "engine.hpp"
+#include "start_window.cuh"
 
 namespace ctk {
 
@@ -141,6 +142,60 @@ __global__ void k_doc_offsets(const uint64_t* __restrict__ text_off, uint64_t n_
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
 
+// The same bitmap through the bit-parallel window logic of the fused kernel (start_window.cuh): one thread per 16-byte group,
+// one CTA per 8 KiB (512 groups + one halo group on each side, masks exchanged through shared memory).  Output layout
+// identical to k_starts: one word per 32 bytes + the number of starts per 8 KiB block.
+constexpr int kFastGroups = 512;
+__global__ void __launch_bounds__(kFastGroups + 32) k_starts_window(const uint8_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ ds,
+                                                                    const uint8_t* __restrict__ trie_index, const uint8_t* __restrict__ trie_blocks,
+                                                                    uint32_t* __restrict__ start_bits, uint32_t* __restrict__ block_counts) {
+    __shared__ Masks16 sm[kFastGroups + 2];
+    __shared__ uint32_t sds[kFastGroups + 2];
+    __shared__ int scount;
+    const int t = threadIdx.x;
+    const int64_t g = (int64_t)blockIdx.x * kFastGroups + t - 1;               // t = 0 and t = 513 are the halo groups
+    const int64_t n_groups = (int64_t)((n + 15) / 16);
+    if (t == 0) scount = 0;
+    if (t < kFastGroups + 2) {
+        Masks16 m{};
+        uint32_t d16 = 0;
+        if (g >= 0 && g <= n_groups) {                                          // group n_groups: only zero padding, but position n is a document start
+            const uint4 v = *reinterpret_cast<const uint4*>(text + g * 16);
+            m = classify16(text + g * 16, 0, v.x, v.y, v.z, v.w, trie_index, trie_blocks);
+            d16 = (ds[g >> 1] >> (16 * (g & 1))) & 0xFFFFu;
+            const int64_t past = (int64_t)n - g * 16;                           // positions >= n count as document starts
+            if (past < 16) d16 |= past <= 0 ? 0xFFFFu : (0xFFFFu << past) & 0xFFFFu;
+        }
+        sm[t] = m;
+        sds[t] = d16;
+    }
+    __syncthreads();
+    uint32_t s16 = 0;
+    if (t >= 1 && t <= kFastGroups && g < n_groups) {
+        const Masks16 &a = sm[t - 1], &b = sm[t], &c = sm[t + 1];
+        const uint32_t S = start_window(window(a.L, b.L, c.L), window(a.N, b.N, c.N), window(a.W, b.W, c.W), window(a.SP, b.SP, c.SP),
+                                        window(a.AP, b.AP, c.AP), window(a.CONT, b.CONT, c.CONT), window(sds[t - 1], sds[t], sds[t + 1]),
+                                        text + g * 16 - 8);
+        s16 = (S >> 8) & 0xFFFFu;
+        const int64_t past = (int64_t)n - g * 16;
+        if (past < 16) s16 &= (1u << past) - 1u;
+    }
+    // groups (t = 1, 2), (3, 4), ... share an output word: the odd t holds the low half
+    __shared__ uint32_t sout[kFastGroups + 2];
+    if (t < kFastGroups + 2) sout[t] = s16;
+    __syncthreads();
+    if (t >= 1 && t <= kFastGroups && (t & 1)) {
+        const uint64_t w = ((uint64_t)blockIdx.x * kFastGroups + (t - 1)) >> 1;
+        if (w * 32 < n) {
+            const uint32_t bits = sout[t] | (sout[t + 1] << 16);
+            start_bits[w] = bits;
+            atomicAdd(&scount, __popc(bits));
+        }
+    }
+    __syncthreads();
+    if (t == 0) block_counts[blockIdx.x] = (uint32_t)scount;
+}
+
 // Pre-token start bitmap of a batch (one bit per byte) + the number of starts per block of 256 words (8 KiB);
 // used by the rich `Encoding` path (encoding.cu), which needs the words themselves and not only their ids.
 // ds: (n_words + 1) words of scratch for the document-start bits.
@@ -150,8 +205,13 @@ int starts_bitmap(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, siz
     const uint32_t n_blocks = (uint32_t)((n_words + 255) / 256);
     CK(cudaMemsetAsync(ds, 0, (n_words + 1) * 4, st));
     k_docstart<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_off, n_docs, n_bytes, ds, err);
-    TextView tv{d_text, n_bytes, ds, eng.tables.trie_index, eng.tables.trie_blocks};
-    k_starts<<<n_blocks, 256, 0, st>>>(tv, start_bits, block_counts);
+    if (getenv("CTK_SCALAR_STARTS") || (reinterpret_cast<uintptr_t>(d_text) & 15)) {   // debug / unaligned text: the scalar predicate
+        TextView tv{d_text, n_bytes, ds, eng.tables.trie_index, eng.tables.trie_blocks};
+        k_starts<<<n_blocks, 256, 0, st>>>(tv, start_bits, block_counts);
+    } else {
+        k_starts_window<<<n_blocks, kFastGroups + 32, 0, st>>>(d_text, n_bytes, ds, eng.tables.trie_index, eng.tables.trie_blocks,
+                                                               start_bits, block_counts);
+    }
     eng.launched(2);
     CK(cudaGetLastError());
     return CTK_OK;

@@ -153,6 +153,19 @@ __global__ void __launch_bounds__(256) k_word_meta(const uint8_t* __restrict__ N
     }
 }
 
+// has_hi[d] = text d holds a byte C2..C5 (the only lead bytes byte-mapped two-byte chars have).  One warp per text.
+__global__ void __launch_bounds__(256) k_doc_has_hi(const uint8_t* __restrict__ O, const uint64_t* __restrict__ o_off, uint64_t n_docs,
+                                                    uint8_t* __restrict__ has_hi) {
+    const uint64_t d = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_docs) return;
+    const int lane = threadIdx.x & 31;
+    const uint64_t lo = o_off[d], hi = o_off[d + 1];
+    bool hh = false;
+    for (uint64_t i = lo + lane; i < hi; i += 32) hh |= (uint32_t)(O[i] - 0xC2u) <= 3u;
+    hh = __any_sync(kFull, hh);
+    if (lane == 0) has_hi[d] = hh ? 1 : 0;
+}
+
 struct SpanArgs {
     const uint8_t* O; const uint64_t* o_off;         // the original batch (what str::find searches)
     const uint8_t* N; const uint64_t* n_off;         // the normalised batch (what the words are cut from)
@@ -161,6 +174,7 @@ struct SpanArgs {
     const uint32_t* starts;
     const uint4* meta;
     const uint16_t* map2;
+    const uint8_t* has_hi;
     uint4* wspan;                                    // {start, end, first word of the text, -}
     uint32_t* err;                                   // err[0] flags, err[8] first panicking text
     int same;                                        // N is O (nothing was normalised or prepended)
@@ -169,9 +183,12 @@ struct SpanArgs {
 // One warp per text walks its words in order (the position each search starts from is the previous result).
 //  * on the rails: the text is its own normalised form, the word is printable ASCII after its leading spaces and the
 //    running position lies inside those spaces: str::find returns the word's own position (the bytes in between are
-//    spaces, the needle does not start with one).  No byte of the text is read.
+//    spaces, the needle does not start with one), and the next word is entered exactly at its start.  A RUN of such words
+//    is settled 32 at a time, one lane per word, without reading a byte of the text.
+//  * saturated: once the position has reached the end of the text nothing can be found any more: the remaining words all get
+//    the empty span at the end, 32 at a time.
 //  * a needle with a two-byte mapped char cannot occur in a text that has no byte C2..C5: not found, no search.
-//  * otherwise 32 candidate positions per step, first byte first.
+//  * otherwise the warp searches: 16 candidate positions per lane and step.
 __global__ void __launch_bounds__(128) k_word_spans(SpanArgs a) {
     const uint64_t d = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     if (d >= a.n_docs) return;
@@ -181,17 +198,39 @@ __global__ void __launch_bounds__(128) k_word_spans(SpanArgs a) {
     const uint8_t* __restrict__ od = a.O + a.o_off[d];
     const uint32_t olen = (uint32_t)(a.o_off[d + 1] - a.o_off[d]);
     const uint32_t k0 = a.wi.before(nb), k1 = a.wi.before(ne);
-    bool hh = false;
-    for (uint32_t i = lane; i < olen; i += 32) { const uint32_t b = od[i]; hh |= (b - 0xC2u) <= 3u; }
-    const bool has_hi = __any_sync(kFull, hh);
+    const bool has_hi = a.has_hi[d] != 0;
     uint32_t ss = 0;
     bool boundary = true;                                                        // ss is known to be a char boundary of the text
-    uint4 mt = a.meta[k0];
-    uint32_t ws_next = a.starts[k0];
-    for (uint32_t k = k0; k < k1; ++k) {
-        const uint4 me = mt;
-        const uint64_t ws = ws_next;
-        if (k + 1 < k1) { mt = a.meta[k + 1]; ws_next = a.starts[k + 1]; }      // independent of the chain: in flight during this word
+    uint32_t k = k0;
+    while (k < k1) {
+        if (ss == olen) {                                                        // saturated (mod.rs:470-474 with nothing left to search)
+            for (uint32_t kk = k + lane; kk < k1; kk += 32) a.wspan[kk] = make_uint4(olen, olen, k0, 0u);
+            break;
+        }
+        // lane j looks at word k + j
+        const uint32_t kj = k + lane;
+        const bool valid = kj < k1;
+        const uint4 mj = valid ? a.meta[kj] : make_uint4(1u, 0u, 1u, 0u);
+        const uint32_t wsj = valid ? a.starts[kj] : 0u;
+        if (a.same) {
+            const bool all_sp = mj.y == mj.x;
+            const bool pure_j = valid && !all_sp && mj.z == mj.y;                // every byte after the leading spaces is printable ASCII
+            const uint64_t rel0 = (uint64_t)__shfl_sync(kFull, wsj, 0) - nb;
+            const uint32_t ts0 = __shfl_sync(kFull, mj.y, 0);
+            const unsigned pm = __ballot_sync(kFull, pure_j);
+            const int run = (ss >= rel0 && ss <= rel0 + ts0) ? (~pm ? __ffs(~pm) - 1 : 32) : 0;
+            if (run > 0) {
+                const uint32_t relj = (uint32_t)(wsj - nb);
+                if (lane < run) a.wspan[kj] = make_uint4(relj + mj.y, relj + mj.x, k0, 0u);
+                ss = __shfl_sync(kFull, relj + mj.x, run - 1);
+                boundary = true;
+                k += run;
+                continue;
+            }
+        }
+        // one word, sequentially: word k (lane 0's)
+        const uint4 me = make_uint4(__shfl_sync(kFull, mj.x, 0), __shfl_sync(kFull, mj.y, 0), __shfl_sync(kFull, mj.z, 0), __shfl_sync(kFull, mj.w, 0));
+        const uint64_t ws = __shfl_sync(kFull, wsj, 0);
         const uint32_t wlen = me.x, nsp = me.y, np = me.z, fb = me.w & 0xFFu, sb = me.w >> 8;
         const bool all_space = nsp == wlen;
         const uint32_t ts = all_space ? 0u : nsp;
@@ -270,6 +309,7 @@ __global__ void __launch_bounds__(128) k_word_spans(SpanArgs a) {
         else { start = ss; const uint64_t e = (uint64_t)ss + mword; end = e < olen ? (uint32_t)e : olen; boundary = end == olen; }
         if (lane == 0) a.wspan[k] = make_uint4(start, end, k0, 0u);
         ss = end;
+        ++k;
     }
 }
 
@@ -392,7 +432,7 @@ __global__ void __launch_bounds__(256) k_rows_fill(RowArgs a, const uint64_t* __
 
 // slots 48.. of the workspace belong to this file
 enum { S_RAW = 48, S_TOKOFF, S_DS, S_SB, S_BC, S_BB, S_ERR, S_WRANK, S_STARTS, S_POS, S_CUB, S_WSPAN, S_WDOC0, S_WFIRST, S_OFFS, S_WIDS,
-       S_CUT, S_FIN, S_ROWOFF, S_FULL, S_OIDS, S_OATTN, S_OTYPE, S_OSPEC };
+       S_CUT, S_FIN, S_ROWOFF, S_FULL, S_OIDS, S_OATTN, S_OTYPE, S_OSPEC, S_HASHI };
 
 int encode_rich_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_texts, uint64_t n_bytes,
                        const ctk_encoding_options& opt, RichOut* out, cudaStream_t st) {
@@ -489,14 +529,17 @@ int encode_rich_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off
         WordIndex wi{sb, wrank, nbytes, n_words};
         k_word_meta<<<(n_words + 255) / 256, 256, 0, st>>>(nt, nbytes, starts, n_words, eng.rich.byte_map2, wmeta);
         eng.mark("rich:k_word_meta", st);
-        SpanArgs sa{d_text, d_off, nt, noff, n_texts, wi, starts, wmeta, eng.rich.byte_map2, wspan, err, nt == d_text ? 1 : 0};
+        uint8_t* has_hi;
+        CK(ws.get(S_HASHI, n_texts + 16, (void**)&has_hi));
+        k_doc_has_hi<<<(unsigned)((n_texts * 32 + 255) / 256), 256, 0, st>>>(d_text, d_off, n_texts, has_hi);
+        SpanArgs sa{d_text, d_off, nt, noff, n_texts, wi, starts, wmeta, eng.rich.byte_map2, has_hi, wspan, err, nt == d_text ? 1 : 0};
         k_word_spans<<<(unsigned)((n_texts * 32 + 127) / 128), 128, 0, st>>>(sa);
         eng.mark("rich:k_word_spans", st);
         const unsigned tg = (unsigned)((n_tokens + 255) / 256);
         k_tok_first<<<tg, 256, 0, st>>>(pos, n_tokens, wi, wfirst);
         k_tok_offsets<<<tg, 256, 0, st>>>(pos, raw, tl, n_tokens, wi, wfirst, wspan, offs, word_ids);
         eng.mark("rich:k_tok_offsets", st);
-        eng.launched(8);
+        eng.launched(9);
         CK(cudaGetLastError());
         out->offsets = offs; out->word_ids = word_ids;
     }
@@ -584,8 +627,8 @@ int ctk_encode_batch_to_encoding(const ctk_tokenizer* tok, const uint8_t* text, 
     if (n_bytes && !text) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
     cudaStream_t st = eng.st_comp;
     uint8_t* d_text; uint64_t* d_off;
-    CK(eng.ws.get(72, n_bytes + 128, (void**)&d_text));
-    CK(eng.ws.get(73, (n_texts + 2) * 8, (void**)&d_off));
+    CK(eng.ws.get(78, n_bytes + 128, (void**)&d_text));
+    CK(eng.ws.get(79, (n_texts + 2) * 8, (void**)&d_off));
     if (n_bytes) CK(cudaMemcpyAsync(d_text, text, n_bytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_text + n_bytes, 0, 64, st));
     CK(cudaMemcpyAsync(d_off, text_off, (n_texts + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -635,6 +678,33 @@ const uint32_t* ctk_encodings_token_ids(const ctk_encodings* res) { return (cons
 const uint32_t* ctk_encodings_offsets(const ctk_encodings* res) { return (const uint32_t*)ENC(res)->offs; }
 const uint32_t* ctk_encodings_word_ids(const ctk_encodings* res) { return (const uint32_t*)ENC(res)->wids; }
 void ctk_encodings_free(ctk_encodings* res) { delete reinterpret_cast<Encodings*>(res); }
+
+// debug/test hook: the pre-token start bitmap of a batch as the device computes it for the Encoding path (one bit per byte;
+// out_bits: (n + 31) / 32 words).  CTK_SCALAR_STARTS=1 selects the scalar predicate instead of the bit-parallel kernel.
+int ctk_debug_starts_device(const ctk_tokenizer* tok, const uint8_t* text, uint64_t n, const uint64_t* off, size_t n_docs, uint32_t* out_bits) {
+    Engine& eng = *const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
+    std::lock_guard<std::mutex> lk(eng.mu);
+    CK(cudaSetDevice(eng.device));
+    cudaStream_t st = eng.st_comp;
+    const uint64_t n_w32 = (n + 31) / 32;
+    const uint32_t n_blocks = (uint32_t)((n_w32 + 255) / 256);
+    uint8_t* d_text; uint64_t* d_off; uint32_t *ds, *sb, *bc, *err;
+    CK(eng.ws.get(78, n + 128, (void**)&d_text));
+    CK(eng.ws.get(79, (n_docs + 2) * 8, (void**)&d_off));
+    CK(eng.ws.get(S_DS, (n_w32 + 1) * 4, (void**)&ds));
+    CK(eng.ws.get(S_SB, (n_w32 + 1) * 4, (void**)&sb));
+    CK(eng.ws.get(S_BC, ((uint64_t)n_blocks + 1) * 4, (void**)&bc));
+    CK(eng.ws.get(S_ERR, 256, (void**)&err));
+    CK(cudaMemsetAsync(d_text, 0, n + 128, st));
+    if (n) CK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_off, off, (n_docs + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(err, 0, 256, st));
+    int rc = n ? starts_bitmap(eng, d_text, d_off, n_docs, n, ds, sb, bc, err, st) : CTK_OK;
+    if (rc != CTK_OK) return rc;
+    if (n) CK(cudaMemcpyAsync(out_bits, sb, n_w32 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return CTK_OK;
+}
 
 size_t ctk_post_processor_items(const ctk_tokenizer* tok, int64_t* items, size_t cap) {
     const HostModel& m = reinterpret_cast<const Engine*>(tok)->model;

@@ -173,3 +173,36 @@ def test_ids_ignore_added_tokens_on_this_path(built_lib, small_tok_json):
     assert 70000 not in tok.encode_to_encoding(t).ids
     assert 70000 in tok(t, add_special_tokens=False)[0].ids
     assert tok.encode(t) == orc.tok.encode(t)                 # the switch does not leak into later encode calls
+
+
+def test_bit_parallel_start_bitmap_equals_the_scalar_predicate(built_lib, tok_paths):
+    """k_starts_window (16 bytes per thread, the fused kernel's window logic) == k_starts (scalar, per byte) == the host's scalar
+    predicate, on mixed French / CJK / emoji text with document boundaries at arbitrary bytes and ragged sizes."""
+    import ctypes
+    import os
+    import complexity_tokenizer as ct
+    import synth
+    lib = built_lib
+    lib.ctk_debug_starts_device.restype = ctypes.c_int
+    lib.ctk_debug_starts_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    tok = ct.Tokenizer.from_file(tok_paths['config3'])
+    for kind, seed, size in (('mixed', 3003, 3 << 20), ('english', 1001, (1 << 20) + 12345), ('mixed', 7, 8191), ('mixed', 8, 16), ('ascii', 9, 1)):
+        text, offs = synth.gen_corpus(kind, seed, size, doc_median=700)
+        text = np.ascontiguousarray(text[:int(offs[-1])])
+        n, nd = int(text.size), len(offs) - 1
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        nw = (n + 31) // 32
+        got = {}
+        for mode in ('window', 'scalar'):
+            if mode == 'scalar':
+                os.environ['CTK_SCALAR_STARTS'] = '1'
+            try:
+                out = np.zeros(nw + 1, dtype=np.uint32)
+                assert lib.ctk_debug_starts_device(tok._h, text.ctypes.data, n, offs.ctypes.data, nd, out.ctypes.data) == 0
+                got[mode] = out[:nw].copy()
+            finally:
+                os.environ.pop('CTK_SCALAR_STARTS', None)
+        host = np.zeros(nw + 2, dtype=np.uint32)
+        assert lib.ctk_debug_starts_host(text.ctypes.data, n, offs.ctypes.data, nd, host.ctypes.data) == 0
+        assert np.array_equal(got['scalar'], host[:nw]), (kind, size)
+        assert np.array_equal(got['window'], host[:nw]), (kind, size)

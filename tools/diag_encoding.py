@@ -4,7 +4,7 @@
   (c) encode_batch_to_encoding with offsets + word ids
 Per-kernel device times come from the library's CUDA-event marks (ctk_profile_enable).
 usage: python tools/diag_encoding.py [MiB=256] [max_length=1024]"""
-import sys, time
+import os, sys, time
 sys.path.insert(0, 'complexity-tokenizer_b200'); sys.path.insert(0, 'fixtures'); sys.path.insert(0, 'oracle')
 import numpy as np
 import complexity_tokenizer as ct, synth
@@ -17,7 +17,7 @@ B, D = text.size, len(offs) - 1
 print('corpus: %.1f MiB, %d docs' % (B / 2**20, D))
 
 
-def run(name, reps=3, **kw):
+def run(name, reps=int(os.environ.get('DIAG_REPS', '3')), **kw):
     tok._encode_rows(text, offs, **kw)                       # warm-up (workspace growth, pinned pool)
     tok.profile_enable(True)
     t = time.perf_counter()
