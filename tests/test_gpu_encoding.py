@@ -206,3 +206,60 @@ def test_bit_parallel_start_bitmap_equals_the_scalar_predicate(built_lib, tok_pa
         assert lib.ctk_debug_starts_host(text.ctypes.data, n, offs.ctypes.data, nd, host.ctypes.data) == 0
         assert np.array_equal(got['scalar'], host[:nw]), (kind, size)
         assert np.array_equal(got['window'], host[:nw]), (kind, size)
+
+
+def test_edges_errors_and_threads(built_lib, small_tok_json):
+    """Empty batches, empty texts, argument errors of the C entry point, and concurrent use of one tokenizer from host threads."""
+    import ctypes
+    import threading
+    import complexity_tokenizer as ct
+    tok, orc = _both(_tj(small_tok_json, TEMPLATE))
+    assert len(tok([])) == 0 and tok([]).input_ids == [] and tok.encode_batch_to_encoding([]) == []
+    for g, w in zip(tok(['', '', ''], padding=True).encodings(), orc.call(['', '', ''], padding=True)):
+        _same(g, w)
+    for g, w in zip(tok(['', ''], add_special_tokens=False, padding='max_length', max_length=3).encodings(),
+                    orc.call(['', ''], add_special_tokens=False, padding='max_length', max_length=3)):
+        _same(g, w)
+    with pytest.raises(TypeError):
+        tok(123)
+    lib = built_lib
+    opt = ct._EncodingOptions(1, 1, 0, 0, 0, 0, 0, 0)            # pair mode with an odd number of texts
+    off = np.array([0, 1, 2, 3], dtype=np.uint64)
+    buf = np.frombuffer(b'abc', dtype=np.uint8)
+    res = ctypes.c_void_p()
+    assert lib.ctk_encode_batch_to_encoding(tok._h, buf.ctypes.data, off.ctypes.data, 3, ctypes.byref(opt), ctypes.byref(res)) == ct.CTK_ERR_ARG
+    assert lib.ctk_encode_batch_to_encoding(tok._h, buf.ctypes.data, off.ctypes.data, 3, None, ctypes.byref(res)) == ct.CTK_ERR_ARG
+    bad = np.array([1, 2, 3, 3], dtype=np.uint64)                # offsets must start at 0
+    opt.pair = 0
+    assert lib.ctk_encode_batch_to_encoding(tok._h, buf.ctypes.data, bad.ctypes.data, 3, ctypes.byref(opt), ctypes.byref(res)) == ct.CTK_ERR_ARG
+    # a template without $A: the reference underflows at mod.rs:377
+    tj = _tj(small_tok_json, {'type': 'TemplateProcessing', 'single': [{'SpecialToken': {'id': '<s>', 'type_id': 0}}]})
+    t2, _ = _both(tj)
+    with pytest.raises(ct.PanicException):
+        t2.encode_to_encoding('abc')
+    assert t2('abc', add_special_tokens=False)[0].ids == t2.encode('abc')
+    # threads: the engine serialises calls; results must not mix
+    ok, _ = _split_panics(orc, TEXTS)
+    want_call = [e.ids for e in orc.call(ok, padding=True)]
+    want_ids = orc.tok.encode_batch(ok)
+    want_off = [e.offsets for e in (orc.encode_to_encoding(t) for t in ok)]
+    errs = []
+
+    def work(kind):
+        try:
+            for _ in range(6):
+                if kind == 0:
+                    assert tok(ok, padding=True).input_ids == want_call
+                elif kind == 1:
+                    assert tok.encode_batch(ok) == want_ids
+                else:
+                    assert [e.offsets for e in tok.encode_batch_to_encoding(ok)] == [[tuple(o) for o in w] for w in want_off]
+        except BaseException as e:       # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(k % 3,)) for k in range(6)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
