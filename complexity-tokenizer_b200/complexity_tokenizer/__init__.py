@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 __version__ = '0.3.3+b200'
-__all__ = ['Tokenizer', 'Encoding', 'BatchEncoding', 'Trainer', 'PanicException', '__version__']
+__all__ = ['Tokenizer', 'Encoding', 'BatchEncoding', 'Trainer', 'BpeTrainer', 'PanicException', '__version__']
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -45,6 +45,19 @@ class _EncodingOptions(ctypes.Structure):       # include/ctk.h: ctk_encoding_op
     _fields_ = [('add_special_tokens', ctypes.c_int), ('pair', ctypes.c_int), ('truncation', ctypes.c_int),
                 ('max_length', ctypes.c_uint64), ('padding', ctypes.c_int), ('pad_to', ctypes.c_uint64),
                 ('pad_left', ctypes.c_int), ('want_offsets', ctypes.c_int)]
+
+
+class _TrainerConfig(ctypes.Structure):        # include/ctk.h: ctk_bpe_trainer_config
+    _fields_ = [('vocab_size', ctypes.c_uint64), ('min_frequency', ctypes.c_uint32), ('special_tokens', ctypes.c_void_p),
+                ('special_off', ctypes.c_void_p), ('n_special', ctypes.c_size_t), ('initial_alphabet', ctypes.c_void_p),
+                ('n_alphabet', ctypes.c_size_t), ('limit_alphabet', ctypes.c_int64), ('continuing_subword_prefix', ctypes.c_void_p),
+                ('prefix_len', ctypes.c_size_t), ('end_of_word_suffix', ctypes.c_void_p), ('suffix_len', ctypes.c_size_t)]
+
+
+class _TrainStats(ctypes.Structure):           # include/ctk.h: ctk_train_stats
+    _fields_ = [('n_bytes', ctypes.c_uint64), ('n_words', ctypes.c_uint64), ('n_unique_words', ctypes.c_uint64),
+                ('n_symbols', ctypes.c_uint64), ('n_merges', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint64),
+                ('stop_reason', ctypes.c_uint32), ('ms_words', ctypes.c_double), ('ms_merges', ctypes.c_double)]
 
 
 class UnsupportedTokenizerError(IOError):
@@ -110,6 +123,11 @@ def _lib():
         'ctk_encodings_free': (None, [P]),
         'ctk_post_processor_items': (S, [P, ctypes.POINTER(ctypes.c_int64), S]),
         'ctk_pad_token': (ctypes.c_uint32, [P, ctypes.POINTER(P), ctypes.POINTER(S)]),
+        'ctk_train_bpe': (I, [ctypes.POINTER(_TrainerConfig), I, P, P, S, ctypes.POINTER(P)]),
+        'ctk_trained_symbols': (S, [P, ctypes.POINTER(P), ctypes.POINTER(P), ctypes.POINTER(P)]),
+        'ctk_trained_merges': (S, [P, ctypes.POINTER(P)]),
+        'ctk_trained_stats': (None, [P, ctypes.POINTER(_TrainStats)]),
+        'ctk_trained_free': (None, [P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -578,3 +596,76 @@ class Trainer:
 
     def __init__(self, *a, **k):
         raise NotImplementedError('Trainer is outside the B200 encode/decode hot path (SURVEY.md section 2, rows 13-15)')
+
+
+class BpeTrainer:
+    """BPE training on the GPU; mirrors the reference's PyO3 `BpeTrainer` (src/bindings/trainers.rs:218-280: same
+    constructor arguments and defaults, `train(texts) -> (vocab, merges)`, getters) over `ctk_train_bpe`.
+    `initial_alphabet` / `limit_alphabet` are the Rust-API knobs of BpeTrainerConfig (bpe_trainer.rs:24-26).
+    Where the reference decides in hash-iteration order the choice is fixed (include/ctk.h)."""
+
+    def __init__(self, vocab_size=30000, min_frequency=2, special_tokens=None, show_progress=True, end_of_word_suffix=None,
+                 continuing_subword_prefix=None, initial_alphabet=None, limit_alphabet=None, device=None):
+        self._vocab_size = int(vocab_size)
+        self._min_frequency = int(min_frequency)
+        self._special = list(special_tokens) if special_tokens is not None else ['<unk>', '<pad>', '<s>', '</s>']
+        self._show_progress = bool(show_progress)      # accepted; nothing is printed
+        self._suffix = end_of_word_suffix
+        self._prefix = continuing_subword_prefix
+        self._alphabet = None if initial_alphabet is None else [ord(c) for c in initial_alphabet]
+        self._limit = limit_alphabet
+        self._device = int(os.environ.get('LOCAL_RANK', 0)) if device is None else int(device)
+        self.last_stats = None
+
+    @property
+    def vocab_size(self):
+        return self._vocab_size
+
+    @property
+    def min_frequency(self):
+        return self._min_frequency
+
+    def train(self, texts):
+        """-> (dict token -> id, list of (left, right)); bpe_trainer.rs:100."""
+        buf, off = _pack_texts(texts)
+        return self.train_packed(buf, off)
+
+    def train_packed(self, buf, off):
+        lib = _lib()
+        sp, sp_off = _pack_texts(self._special)
+        keep = [np.ascontiguousarray(buf, dtype=np.uint8), np.ascontiguousarray(off, dtype=np.uint64), sp, sp_off]
+        cfg = _TrainerConfig()
+        cfg.vocab_size, cfg.min_frequency = self._vocab_size, self._min_frequency
+        cfg.special_tokens, cfg.special_off, cfg.n_special = sp.ctypes.data, sp_off.ctypes.data, len(self._special)
+        if self._alphabet is not None:
+            al = np.asarray(self._alphabet, dtype=np.uint32)
+            keep.append(al)
+            cfg.initial_alphabet, cfg.n_alphabet = (al.ctypes.data if len(al) else sp_off.ctypes.data), len(al)
+        cfg.limit_alphabet = -1 if self._limit is None else int(self._limit)
+        for name, ln, val in (('continuing_subword_prefix', 'prefix_len', self._prefix), ('end_of_word_suffix', 'suffix_len', self._suffix)):
+            if val is not None:
+                b = np.frombuffer(val.encode('utf-8') + b'\0', dtype=np.uint8)
+                keep.append(b)
+                setattr(cfg, name, b.ctypes.data)
+                setattr(cfg, ln, len(b) - 1)
+        h = ctypes.c_void_p()
+        rc = lib.ctk_train_bpe(ctypes.byref(cfg), self._device, keep[0].ctypes.data, keep[1].ctypes.data, len(keep[1]) - 1, ctypes.byref(h))
+        if rc != CTK_OK:
+            _raise(rc)
+        try:
+            pb, po, pv, pm = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+            ns = lib.ctk_trained_symbols(h, ctypes.byref(pb), ctypes.byref(po), ctypes.byref(pv))
+            so = np.ctypeslib.as_array(ctypes.cast(po, ctypes.POINTER(ctypes.c_uint64)), (ns + 1,)).copy() if ns else np.zeros(1, np.uint64)
+            sb = ctypes.string_at(pb, int(so[-1])) if ns else b''
+            vid = np.ctypeslib.as_array(ctypes.cast(pv, ctypes.POINTER(ctypes.c_int64)), (ns,)).copy() if ns else np.zeros(0, np.int64)
+            syms = [sb[int(so[i]):int(so[i + 1])].decode('utf-8') for i in range(ns)]
+            nm = lib.ctk_trained_merges(h, ctypes.byref(pm))
+            mp = np.ctypeslib.as_array(ctypes.cast(pm, ctypes.POINTER(ctypes.c_uint32)), (2 * nm,)).copy() if nm else np.zeros(0, np.uint32)
+            st = _TrainStats()
+            lib.ctk_trained_stats(h, ctypes.byref(st))
+            self.last_stats = {k: getattr(st, k) for k, _ in _TrainStats._fields_}
+        finally:
+            lib.ctk_trained_free(h)
+        vocab = {syms[i]: int(vid[i]) for i in range(ns) if vid[i] >= 0}
+        merges = [(syms[int(mp[2 * i])], syms[int(mp[2 * i + 1])]) for i in range(nm)]
+        return vocab, merges

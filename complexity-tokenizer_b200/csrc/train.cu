@@ -1,0 +1,713 @@
+// BPE training on the GPU.  Replaces BpeTrainer::train (src/bpe_trainer.rs:100-228) behind the
+// C ABI ctk_train_bpe; the reference's two hash-order decisions are fixed as oracle/py_trainer.py states them
+// (best pair: highest count, then smallest (left index, right index); characters of equal frequency: by code point).
+//
+// Stage W -- word histogram (bpe_trainer.rs:241-275), data-parallel over the text bytes, HBM-bound:
+//   k_mark_breaks     one bit per text start (words do not span texts)
+//   cub select        positions where a word starts (a non-White_Space char after White_Space / a text start)
+//   k_word_insert     one thread per word: walk it, 64-bit hash, insert into an open-addressing table
+//                     {hash, count, first position}
+//   k_word_verify     one thread per word: bytes == bytes of the slot's first occurrence (a 64-bit collision is
+//                     detected, never trusted; the call then repeats with another hash seed)
+//   k_unique_*        table -> packed unique words (bytes, offsets, counts) for the host
+// The host (train_host below) does what the reference does once per unique word: initial vocabulary
+// (:278-320), split into symbols (:323-338).  Stage M never leaves the device:
+// Stage M -- the merge loop (:141-183), two launches per merge, no host round trip inside a batch of merges:
+//   k_merge_count     thread per word (warp per long word): apply the previous merge in place (:379-401), then
+//                     add the word's count to every adjacent pair of the new sequence in a pair hash table
+//                     (:341-376, the reference's full recount)
+//   k_best_pair       scan + clear the pair table, lexicographic (count, pair) reduction; the last CTA decides:
+//                     stop (:147-165), or name the merged symbol -- symbols are STRINGS in the reference, so a
+//                     merged string that already exists must get the existing symbol.  The device keeps two
+//                     64-bit polynomial hashes per symbol (hash(ab) = hash(a) * p^len(b) + hash(b)) and a symbol
+//                     map; the host replays every merge on real strings afterwards and fails the call if a
+//                     single decision differs, so the result is exact, not probabilistic.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ctk.h"
+#include "engine.hpp"
+
+namespace ctk {
+namespace {
+
+constexpr uint32_t INVALID = 0xFFFFFFFFu;
+constexpr uint64_t EMPTY64 = ~0ull;
+constexpr uint64_t P1 = 0x100000001B3ull, P2 = 0x9E3779B97F4A7C15ull;
+constexpr int LONG_WORD = 64;          // words of more symbols than this get a warp
+constexpr int BATCH = 256;             // merges per host round trip
+
+// ------------------------------------------------------------------------------------------------ stage W
+__device__ __forceinline__ bool brk_at(const uint32_t* brk, uint64_t i) { return (brk[i >> 5] >> (i & 31)) & 1u; }
+
+// Is the char that contains byte i White_Space (what str::split_whitespace splits on)?  Valid UTF-8 assumed.
+__device__ __forceinline__ bool ws_at(const uint8_t* t, uint64_t n, uint64_t i) {
+    uint32_t c = t[i];
+    if (c < 0x80) return c == 0x20 || (c - 9u) < 5u;
+    uint64_t p = i;
+    if ((c & 0xC0) == 0x80) {
+        if (p > 0) --p;
+        if ((t[p] & 0xC0) == 0x80 && p > 0) --p;
+        if ((t[p] & 0xC0) == 0x80 && p > 0) --p;
+    }
+    uint32_t b0 = t[p];
+    if (b0 != 0xC2 && (b0 < 0xE1 || b0 > 0xE3)) return false;
+    uint32_t b1 = p + 1 < n ? t[p + 1] : 0, b2 = p + 2 < n ? t[p + 2] : 0;
+    if (b0 == 0xC2) return b1 == 0x85 || b1 == 0xA0;
+    if (b0 == 0xE1) return b1 == 0x9A && b2 == 0x80;
+    if (b0 == 0xE2) {
+        if (b1 == 0x80) return (b2 >= 0x80 && b2 <= 0x8A) || b2 == 0xA8 || b2 == 0xA9 || b2 == 0xAF;
+        return b1 == 0x81 && b2 == 0x9F;
+    }
+    return b1 == 0x80 && b2 == 0x80;   // U+3000
+}
+
+struct IsWordStart {
+    const uint8_t* t; const uint32_t* brk; uint64_t n;
+    __device__ bool operator()(uint32_t i) const {
+        uint32_t c = t[i];
+        if ((c & 0xC0) == 0x80) return false;
+        if (ws_at(t, n, i)) return false;
+        if (i == 0 || brk_at(brk, i)) return true;
+        return ws_at(t, n, i - 1);
+    }
+};
+
+__global__ void k_mark_breaks(const uint64_t* off, size_t n_texts, uint32_t* brk) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_texts) return;
+    uint64_t o = off[i];
+    atomicOr(&brk[o >> 5], 1u << (o & 31));
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+// end of the word that starts at s (first byte past it)
+__device__ __forceinline__ uint64_t word_end(const uint8_t* t, const uint32_t* brk, uint64_t n, uint64_t s) {
+    uint64_t j = s + 1;
+    while (j < n && !brk_at(brk, j) && !ws_at(t, n, j)) ++j;
+    return j;
+}
+
+struct WordTable { uint64_t* key; uint32_t* count; uint32_t* rep; uint32_t mask; };
+
+__global__ void k_word_insert(const uint8_t* t, const uint32_t* brk, uint64_t n, const uint32_t* starts, uint32_t n_words,
+                              uint64_t seed, WordTable tab, uint32_t* slot_of) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint64_t s = starts[w], j = s, h = seed;
+    do { h = h * P1 + t[j] + 1; ++j; } while (j < n && !brk_at(brk, j) && !ws_at(t, n, j));
+    h = mix64(h ^ ((j - s) * P2));
+    if (h == EMPTY64) h = 0;
+    uint32_t slot = (uint32_t)(h >> 20) & tab.mask;
+    for (;;) {
+        uint64_t k = tab.key[slot];
+        if (k == EMPTY64) k = atomicCAS((unsigned long long*)&tab.key[slot], EMPTY64, h), k = (k == EMPTY64) ? h : k;
+        if (k == h) break;
+        slot = (slot + 1) & tab.mask;
+    }
+    atomicAdd(&tab.count[slot], 1u);
+    atomicMin(&tab.rep[slot], (uint32_t)s);
+    slot_of[w] = slot;
+}
+
+__global__ void k_word_verify(const uint8_t* t, const uint32_t* brk, uint64_t n, const uint32_t* starts, uint32_t n_words,
+                              WordTable tab, const uint32_t* slot_of, uint32_t* collision) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint64_t s = starts[w], r = tab.rep[slot_of[w]];
+    if (r == s) return;
+    uint64_t j = 0;
+    bool ok = true;
+    do {
+        if (r + j >= n || t[r + j] != t[s + j] || (j > 0 && brk_at(brk, r + j))) { ok = false; break; }
+        ++j;
+    } while (s + j < n && !brk_at(brk, s + j) && !ws_at(t, n, s + j));
+    if (ok && r + j < n && !brk_at(brk, r + j) && !ws_at(t, n, r + j)) ok = false;   // the first occurrence is longer
+    if (!ok) *collision = 1;
+}
+
+struct U32ToU64 { __device__ uint64_t operator()(uint32_t v) const { return v; } };
+
+struct SlotUsed {
+    const uint64_t* key;
+    __device__ bool operator()(uint32_t i) const { return key[i] != EMPTY64; }
+};
+
+__global__ void k_unique_len(const uint8_t* t, const uint32_t* brk, uint64_t n, WordTable tab, const uint32_t* uslot,
+                             uint32_t n_unique, uint32_t* ulen, uint32_t* ucount, uint32_t* urep) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_unique) return;
+    uint32_t slot = uslot[u], r = tab.rep[slot];
+    ulen[u] = (uint32_t)(word_end(t, brk, n, r) - r);
+    ucount[u] = tab.count[slot];
+    urep[u] = r;
+}
+
+__global__ void k_unique_gather(const uint8_t* t, const uint32_t* urep, const uint32_t* ulen, const uint64_t* uoff,
+                                uint32_t n_unique, uint8_t* out) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_unique) return;
+    const uint8_t* s = t + urep[u];
+    uint8_t* d = out + uoff[u];
+    for (uint32_t k = 0, l = ulen[u]; k < l; ++k) d[k] = s[k];
+}
+
+// ------------------------------------------------------------------------------------------------ stage M
+struct TrainState {
+    uint32_t done, reason;               // reason: 1 no pairs, 2 below min_frequency, 3 vocabulary full, 4 symbol table full
+    uint32_t n_symbols, sym_cap;
+    uint32_t vocab_len, vocab_size, min_freq;
+    uint32_t cur_l, cur_r, cur_m;        // merge k_merge_count applies before it counts
+    uint32_t n_log, ticket;
+    uint32_t live_pairs;                 // diagnostics: pair-table entries seen by the last k_best_pair
+};
+
+struct PairTable { uint64_t* key; uint32_t* val; uint32_t mask; };
+
+__device__ __forceinline__ void pair_add(const PairTable& pt, uint32_t a, uint32_t b, uint32_t f) {
+    uint64_t key = ((uint64_t)a << 32) | b;
+    uint32_t slot = (uint32_t)(mix64(key) >> 24) & pt.mask;
+    for (;;) {
+        uint64_t k = pt.key[slot];
+        if (k == EMPTY64) k = atomicCAS((unsigned long long*)&pt.key[slot], EMPTY64, key), k = (k == EMPTY64) ? key : k;
+        if (k == key) break;
+        slot = (slot + 1) & pt.mask;
+    }
+    atomicAdd(&pt.val[slot], f);
+}
+
+// thread per word (words of at most LONG_WORD symbols at the start)
+__global__ void __launch_bounds__(128) k_merge_count(TrainState* st, uint32_t* sym, const uint32_t* woff, uint32_t* wlen,
+                                                     const uint32_t* wfreq, uint32_t n_words, PairTable pt) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words || st->done) return;
+    uint32_t len = wlen[w];
+    if (len < 2) return;
+    const uint32_t l = st->cur_l, r = st->cur_r, m = st->cur_m, f = wfreq[w];
+    uint32_t* s = sym + woff[w];
+    uint32_t i = 0, out = 0, prev = INVALID, nxt = s[0];
+    while (i < len) {
+        uint32_t v = nxt;
+        nxt = i + 1 < len ? s[i + 1] : INVALID;
+        if (v == l && nxt == r && nxt != INVALID) {
+            v = m; i += 2;
+            nxt = i < len ? s[i] : INVALID;
+        } else {
+            i += 1;
+        }
+        if (out != i - 1) s[out] = v;
+        if (out > 0) pair_add(pt, prev, v, f);
+        prev = v; ++out;
+    }
+    if (out != len) wlen[w] = out;
+}
+
+// warp per long word: chunks of 32 symbols, left to right, compacted in place
+__global__ void __launch_bounds__(128) k_merge_count_long(TrainState* st, uint32_t* sym, const uint32_t* woff, uint32_t* wlen,
+                                                          const uint32_t* wfreq, uint32_t n_words, PairTable pt) {
+    uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_words || st->done) return;
+    uint32_t len = wlen[w];
+    if (len < 2) return;
+    const uint32_t l = st->cur_l, r = st->cur_r, m = st->cur_m, f = wfreq[w];
+    uint32_t* s = sym + woff[w];
+    uint32_t out_base = 0, carry = 0, prev_last = INVALID;
+    for (uint32_t c = 0; c < len; c += 32) {
+        uint32_t i = c + lane;
+        bool valid = i < len;
+        uint32_t v = valid ? s[i] : INVALID;
+        uint32_t ahead = (c + 32 < len) ? s[c + 32] : INVALID;          // same address in every lane
+        uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, v, 1);
+        if (lane == 31) nx = ahead;
+        uint32_t M = __ballot_sync(0xFFFFFFFFu, valid && v == l && nx == r && nx != INVALID);
+        uint32_t merges = M;
+        if (l == r || carry) {                                          // overlapping candidates: leftmost first
+            merges = 0;
+            uint32_t skip = carry;
+            for (int b = 0; b < 32; ++b) {
+                if (skip) { skip = 0; continue; }
+                if ((M >> b) & 1u) { merges |= 1u << b; skip = 1; }
+            }
+        }
+        uint32_t consumed = (merges << 1) | carry;
+        carry = merges >> 31;
+        uint32_t validm = __ballot_sync(0xFFFFFFFFu, valid);
+        uint32_t kept = validm & ~consumed;
+        bool keep = (kept >> lane) & 1u;
+        if ((merges >> lane) & 1u) v = m;
+        uint32_t below = kept & ((1u << lane) - 1u);
+        int src = below ? 31 - __clz(below) : 0;
+        uint32_t pv = __shfl_sync(0xFFFFFFFFu, v, src);
+        if (!below) pv = prev_last;
+        __syncwarp();
+        if (keep) s[out_base + __popc(below)] = v;
+        // count (prev, v), one atomic per distinct pair in the chunk
+        bool has = keep && pv != INVALID;
+        uint64_t key = has ? (((uint64_t)pv << 32) | v) : EMPTY64 - 1 - lane;
+        uint32_t same = __match_any_sync(0xFFFFFFFFu, key);
+        if (has && (uint32_t)(__ffs(same) - 1) == lane) pair_add(pt, pv, v, f * (uint32_t)__popc(same));
+        if (kept) prev_last = __shfl_sync(0xFFFFFFFFu, v, 31 - __clz(kept));
+        out_base += __popc(kept);
+        __syncwarp();
+    }
+    if (lane == 0 && out_base != len) wlen[w] = out_base;
+}
+
+struct SymTab {                          // device copy of what the host knows about every symbol
+    uint64_t *h1, *h2, *pw1, *pw2;       // polynomial hashes of the symbol's string and p^length
+    uint8_t* in_vocab;
+    uint64_t* map_key; uint64_t* map_h2; uint32_t* map_id; uint32_t map_mask;   // hash -> symbol
+};
+
+struct Best { uint32_t count; uint64_t key; };
+__device__ __forceinline__ bool better(const Best& a, const Best& b) { return a.count > b.count || (a.count == b.count && a.key < b.key); }
+
+__global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt, Best* block_best, SymTab sy, uint4* log) {
+    if (st->done) return;
+    Best best{0u, EMPTY64};
+    uint32_t cap = pt.mask + 1, seen = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        uint64_t k = pt.key[i];
+        if (k == EMPTY64) continue;
+        Best c{pt.val[i], k};
+        if (better(c, best)) best = c;
+        pt.key[i] = EMPTY64; pt.val[i] = 0; ++seen;
+    }
+    __shared__ Best sb[8];
+    __shared__ uint32_t s_seen[8];
+    __shared__ bool s_last;
+    for (int d = 16; d > 0; d >>= 1) {
+        Best o{__shfl_down_sync(0xFFFFFFFFu, best.count, d), __shfl_down_sync(0xFFFFFFFFu, best.key, d)};
+        if (better(o, best)) best = o;
+        seen += __shfl_down_sync(0xFFFFFFFFu, seen, d);
+    }
+    if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; s_seen[threadIdx.x >> 5] = seen; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) { if (better(sb[k], best)) best = sb[k]; seen += s_seen[k]; }
+        block_best[blockIdx.x] = best;
+        atomicAdd(&st->live_pairs, seen);
+        __threadfence();
+        s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    best = Best{0u, EMPTY64};
+    for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+        Best c = ((volatile Best*)block_best)[i].count ? Best{((volatile Best*)block_best)[i].count, ((volatile Best*)block_best)[i].key} : Best{0u, EMPTY64};
+        if (better(c, best)) best = c;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        Best o{__shfl_down_sync(0xFFFFFFFFu, best.count, d), __shfl_down_sync(0xFFFFFFFFu, best.key, d)};
+        if (better(o, best)) best = o;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int k = 1; k < 8; ++k) if (better(sb[k], best)) best = sb[k];
+    st->ticket = 0;
+    st->cur_l = INVALID;
+    if (best.key == EMPTY64 || best.count == 0) { st->done = 1; st->reason = 1; return; }     // bpe_trainer.rs:147-149
+    if (best.count < st->min_freq) { st->done = 1; st->reason = 2; return; }                  // :162-165
+    uint32_t l = (uint32_t)(best.key >> 32), r = (uint32_t)best.key;
+    uint64_t h1 = sy.h1[l] * sy.pw1[r] + sy.h1[r], h2 = sy.h2[l] * sy.pw2[r] + sy.h2[r];
+    uint64_t mk = h1 == EMPTY64 ? 0 : h1;
+    uint32_t slot = (uint32_t)(mix64(mk) >> 24) & sy.map_mask, id = INVALID;
+    for (;;) {
+        uint64_t k = sy.map_key[slot];
+        if (k == EMPTY64) break;
+        if (k == mk && sy.map_h2[slot] == h2) { id = sy.map_id[slot]; break; }
+        slot = (slot + 1) & sy.map_mask;
+    }
+    if (id == INVALID) {                                                                      // a new string
+        if (st->n_symbols >= st->sym_cap) { st->done = 1; st->reason = 4; return; }
+        id = st->n_symbols++;
+        sy.map_key[slot] = mk; sy.map_h2[slot] = h2; sy.map_id[slot] = id;
+        sy.h1[id] = h1; sy.h2[id] = h2; sy.pw1[id] = sy.pw1[l] * sy.pw1[r]; sy.pw2[id] = sy.pw2[l] * sy.pw2[r];
+        sy.in_vocab[id] = 0;
+    }
+    if (!sy.in_vocab[id]) { sy.in_vocab[id] = 1; st->vocab_len++; }                           // :168-169
+    log[st->n_log++] = make_uint4(l, r, id, best.count);
+    st->cur_l = l; st->cur_r = r; st->cur_m = id;
+    if (st->vocab_len >= st->vocab_size) { st->done = 1; st->reason = 3; }                    // :141
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct DevBuf {
+    std::vector<void*> all;
+    template <class T> cudaError_t get(T** p, size_t n) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) { all.push_back(q); *p = (T*)q; }
+        return e;
+    }
+    ~DevBuf() { for (void* q : all) cudaFree(q); }
+};
+
+uint32_t pow2_at_least(uint64_t x) { uint64_t p = 1024; while (p < x) p <<= 1; return (uint32_t)std::min<uint64_t>(p, 1ull << 31); }
+
+void hash_string(const std::string& s, uint64_t* h1, uint64_t* h2, uint64_t* pw1, uint64_t* pw2) {
+    uint64_t a = 0, b = 0, pa = 1, pb = 1;
+    for (unsigned char c : s) { a = a * P1 + c + 1; b = b * P2 + c + 1; pa *= P1; pb *= P2; }
+    *h1 = a; *h2 = b; *pw1 = pa; *pw2 = pb;
+}
+uint64_t mix64_host(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+void put_utf8(std::string& s, uint32_t cp) {
+    if (cp < 0x80) s += (char)cp;
+    else if (cp < 0x800) { s += (char)(0xC0 | (cp >> 6)); s += (char)(0x80 | (cp & 63)); }
+    else if (cp < 0x10000) { s += (char)(0xE0 | (cp >> 12)); s += (char)(0x80 | ((cp >> 6) & 63)); s += (char)(0x80 | (cp & 63)); }
+    else { s += (char)(0xF0 | (cp >> 18)); s += (char)(0x80 | ((cp >> 12) & 63)); s += (char)(0x80 | ((cp >> 6) & 63)); s += (char)(0x80 | (cp & 63)); }
+}
+
+}  // namespace
+
+struct Trained {
+    std::vector<std::string> symbols;        // every symbol string, by symbol index
+    std::vector<int64_t> vocab_id;           // per symbol: id in the vocabulary map, -1 = not in it
+    std::vector<uint32_t> merges;            // 2 per merge: symbol indices
+    // packed views for the C ABI
+    std::vector<uint8_t> sym_bytes; std::vector<uint64_t> sym_off;
+    double ms_words = 0, ms_merges = 0, ms_host = 0;
+    uint64_t n_words = 0, n_unique = 0, n_bytes = 0, n_symbols0 = 0, kernels = 0;
+    uint32_t stop_reason = 0;
+};
+
+#define TCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); return CTK_ERR_CUDA; } } while (0)
+
+static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8_t* text, const uint64_t* off, size_t n_texts, Trained& out) {
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev == 0) {
+        set_last_error(std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e0));
+        return CTK_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_last_error("bad device index"); return CTK_ERR_ARG; }
+    TCK(cudaSetDevice(device));
+    const uint64_t n = n_texts ? off[n_texts] : 0;
+    if (n >= (1ull << 32) - 64) { set_last_error("ctk_train_bpe: one call takes less than 4 GiB of text"); return CTK_ERR_UNSUPPORTED; }
+    for (size_t i = 0; i < n_texts; ++i) if (off[i] > off[i + 1]) { set_last_error("text offsets are not monotone"); return CTK_ERR_ARG; }
+    out.n_bytes = n;
+    cudaStream_t st;
+    TCK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{st};
+    cudaEvent_t ev[4];
+    for (auto& e : ev) TCK(cudaEventCreate(&e));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } eg{ev};
+    uint64_t launches = 0;
+
+    // ---------------- stage W
+    std::vector<uint8_t> ubytes; std::vector<uint64_t> uoff_h; std::vector<uint32_t> ucount_h;
+    uint32_t n_words = 0, n_unique = 0;
+    {
+        DevBuf db;
+        uint8_t* d_text; uint64_t* d_off; uint32_t* d_brk; uint32_t* d_starts; uint32_t* d_num; uint32_t* d_collision;
+        TCK(db.get(&d_text, n + 16)); TCK(db.get(&d_off, n_texts + 1)); TCK(db.get(&d_brk, (n >> 5) + 2));
+        TCK(db.get(&d_num, 4)); TCK(db.get(&d_collision, 1));
+        TCK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st));
+        if (n_texts) TCK(cudaMemcpyAsync(d_off, off, (n_texts + 1) * 8, cudaMemcpyHostToDevice, st));
+        TCK(cudaEventRecord(ev[0], st));
+        if (n > 0) {
+            TCK(cudaMemsetAsync(d_brk, 0, ((n >> 5) + 2) * 4, st));
+            k_mark_breaks<<<(unsigned)((n_texts + 256) / 256), 256, 0, st>>>(d_off, n_texts, d_brk); ++launches;
+            // an upper bound of the number of words is (n + 1) / 2; count first, then select
+            cub::CountingInputIterator<uint32_t> it(0);
+            IsWordStart pred{d_text, d_brk, n};
+            TCK(db.get(&d_starts, (size_t)(n + 1) / 2 + 1));
+            size_t tmp_bytes = 0;
+            TCK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_starts, d_num, (int64_t)n, pred, st));
+            uint8_t* d_tmp; TCK(db.get(&d_tmp, tmp_bytes));
+            TCK(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_starts, d_num, (int64_t)n, pred, st)); launches += 2;
+            TCK(cudaMemcpyAsync(&n_words, d_num, 4, cudaMemcpyDeviceToHost, st));
+            TCK(cudaStreamSynchronize(st));
+        }
+        if (n_words > 0) {
+            WordTable tab; uint32_t cap = pow2_at_least(2ull * n_words); tab.mask = cap - 1;
+            uint32_t* d_slot; uint32_t* d_uslot;
+            TCK(db.get(&tab.key, cap)); TCK(db.get(&tab.count, cap)); TCK(db.get(&tab.rep, cap)); TCK(db.get(&d_slot, n_words));
+            uint32_t collision = 1;
+            for (int attempt = 0; attempt < 4 && collision; ++attempt) {
+                TCK(cudaMemsetAsync(tab.key, 0xFF, (size_t)cap * 8, st));
+                TCK(cudaMemsetAsync(tab.count, 0, (size_t)cap * 4, st));
+                TCK(cudaMemsetAsync(tab.rep, 0xFF, (size_t)cap * 4, st));
+                TCK(cudaMemsetAsync(d_collision, 0, 4, st));
+                unsigned g = (n_words + 127) / 128;
+                k_word_insert<<<g, 128, 0, st>>>(d_text, d_brk, n, d_starts, n_words, 0x9E37ull + 0x51ED27ull * attempt, tab, d_slot);
+                k_word_verify<<<g, 128, 0, st>>>(d_text, d_brk, n, d_starts, n_words, tab, d_slot, d_collision); launches += 2;
+                TCK(cudaMemcpyAsync(&collision, d_collision, 4, cudaMemcpyDeviceToHost, st));
+                TCK(cudaStreamSynchronize(st));
+            }
+            if (collision) { set_last_error("ctk_train_bpe: word hash collisions under four seeds"); return CTK_ERR_UNSUPPORTED; }
+            TCK(db.get(&d_uslot, n_words));
+            cub::CountingInputIterator<uint32_t> it(0);
+            SlotUsed used{tab.key};
+            size_t tmp_bytes = 0;
+            TCK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_uslot, d_num, (int64_t)cap, used, st));
+            uint8_t* d_tmp; TCK(db.get(&d_tmp, tmp_bytes));
+            TCK(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_uslot, d_num, (int64_t)cap, used, st)); launches += 2;
+            TCK(cudaMemcpyAsync(&n_unique, d_num, 4, cudaMemcpyDeviceToHost, st));
+            TCK(cudaStreamSynchronize(st));
+            uint32_t *d_ulen, *d_ucount, *d_urep; uint64_t* d_uoff; uint8_t* d_ubytes;
+            TCK(db.get(&d_ulen, n_unique + 1)); TCK(db.get(&d_ucount, n_unique)); TCK(db.get(&d_urep, n_unique)); TCK(db.get(&d_uoff, n_unique + 1));
+            TCK(cudaMemsetAsync(d_ulen + n_unique, 0, 4, st));
+            unsigned g = (n_unique + 127) / 128;
+            k_unique_len<<<g, 128, 0, st>>>(d_text, d_brk, n, tab, d_uslot, n_unique, d_ulen, d_ucount, d_urep); ++launches;
+            cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> lens(d_ulen, U32ToU64());
+            size_t tb2 = 0;
+            TCK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, lens, d_uoff, (int64_t)n_unique + 1, st));
+            uint8_t* d_tmp2; TCK(db.get(&d_tmp2, tb2));
+            TCK(cub::DeviceScan::ExclusiveSum(d_tmp2, tb2, lens, d_uoff, (int64_t)n_unique + 1, st)); launches += 2;
+            uoff_h.resize(n_unique + 1); ucount_h.resize(n_unique);
+            TCK(cudaMemcpyAsync(uoff_h.data(), d_uoff, (n_unique + 1) * 8ull, cudaMemcpyDeviceToHost, st));
+            TCK(cudaStreamSynchronize(st));
+            ubytes.resize(uoff_h[n_unique]);
+            TCK(db.get(&d_ubytes, ubytes.size()));
+            k_unique_gather<<<g, 128, 0, st>>>(d_text, d_urep, d_ulen, d_uoff, n_unique, d_ubytes); ++launches;
+            TCK(cudaEventRecord(ev[1], st));
+            TCK(cudaMemcpyAsync(ubytes.data(), d_ubytes, ubytes.size(), cudaMemcpyDeviceToHost, st));
+            TCK(cudaMemcpyAsync(ucount_h.data(), d_ucount, n_unique * 4ull, cudaMemcpyDeviceToHost, st));
+            TCK(cudaStreamSynchronize(st));
+        } else {
+            TCK(cudaEventRecord(ev[1], st));
+            TCK(cudaStreamSynchronize(st));
+            uoff_h.assign(1, 0);
+        }
+        float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); out.ms_words = ms;
+    }
+    out.n_words = n_words; out.n_unique = n_unique;
+
+    // ---------------- host: initial vocabulary and symbol sequences (once per unique word)
+    std::string suffix = cfg.end_of_word_suffix ? std::string((const char*)cfg.end_of_word_suffix, cfg.suffix_len) : std::string();
+    std::string prefix = cfg.continuing_subword_prefix ? std::string((const char*)cfg.continuing_subword_prefix, cfg.prefix_len) : std::string();
+    const bool has_prefix = cfg.continuing_subword_prefix != nullptr;
+    std::unordered_map<std::string, uint32_t> index;                   // symbol string -> symbol index
+    std::vector<std::string>& symbols = out.symbols;
+    std::vector<int64_t>& vocab_id = out.vocab_id;
+    auto sym = [&](const std::string& s) -> uint32_t {
+        auto it = index.find(s);
+        if (it != index.end()) return it->second;
+        uint32_t id = (uint32_t)symbols.size();
+        index.emplace(s, id); symbols.push_back(s); vocab_id.push_back(-1);
+        return id;
+    };
+    uint64_t next_id = 0, vocab_len = 0;
+    auto vocab_insert = [&](uint32_t s, uint64_t id) { if (vocab_id[s] < 0) ++vocab_len; vocab_id[s] = (int64_t)id; };
+    for (size_t i = 0; i < cfg.n_special; ++i) {                        // bpe_trainer.rs:283-286
+        std::string t((const char*)cfg.special_tokens + cfg.special_off[i], cfg.special_off[i + 1] - cfg.special_off[i]);
+        vocab_insert(sym(t), next_id++);
+    }
+    if (cfg.initial_alphabet) {                                         // :289-297
+        for (size_t i = 0; i < cfg.n_alphabet; ++i) {
+            std::string c; put_utf8(c, cfg.initial_alphabet[i]);
+            uint32_t s = sym(c);
+            if (vocab_id[s] < 0) vocab_insert(s, next_id++);
+        }
+    }
+    // chars of the data with their frequencies (:300-306); a word is its bytes + the suffix
+    std::unordered_map<uint32_t, uint32_t> char_freq;
+    auto for_chars = [](const uint8_t* p, size_t len, auto&& fn) {
+        for (size_t i = 0; i < len;) {
+            uint32_t c = p[i], cp; size_t l;
+            if (c < 0x80) { cp = c; l = 1; }
+            else if (c < 0xE0) { cp = c & 31; l = 2; }
+            else if (c < 0xF0) { cp = c & 15; l = 3; }
+            else { cp = c & 7; l = 4; }
+            for (size_t k = 1; k < l && i + k < len; ++k) cp = (cp << 6) | (p[i + k] & 63);
+            fn(cp);
+            i += l;
+        }
+    };
+    for (uint32_t u = 0; u < n_unique; ++u) {
+        uint32_t f = ucount_h[u];
+        for_chars(ubytes.data() + uoff_h[u], uoff_h[u + 1] - uoff_h[u], [&](uint32_t cp) { char_freq[cp] += f; });
+        for_chars((const uint8_t*)suffix.data(), suffix.size(), [&](uint32_t cp) { char_freq[cp] += f; });
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> chars(char_freq.begin(), char_freq.end());
+    std::sort(chars.begin(), chars.end(), [](auto& a, auto& b) { return a.second != b.second ? a.second > b.second : a.first < b.first; });
+    const uint64_t limit = cfg.limit_alphabet >= 0 ? (uint64_t)cfg.limit_alphabet : chars.size();
+    std::unordered_map<uint32_t, uint32_t> char_sym, char_sym_cont;
+    for (size_t k = 0; k < chars.size(); ++k) {                         // :309-317
+        std::string c; put_utf8(c, chars[k].first);
+        uint32_t s = sym(c);
+        if (k < limit && vocab_id[s] < 0) vocab_insert(s, next_id++);
+        char_sym[chars[k].first] = s;
+    }
+    if (has_prefix) for (auto& ch : chars) { std::string c = prefix; put_utf8(c, ch.first); char_sym_cont[ch.first] = sym(c); }
+    // symbol sequences (:323-338); words of one symbol have no pairs and are left out
+    struct W { uint32_t off, len, freq; };
+    std::vector<uint32_t> seq; std::vector<W> ws;
+    seq.reserve(ubytes.size() + 16);
+    for (uint32_t u = 0; u < n_unique; ++u) {
+        uint32_t o = (uint32_t)seq.size();
+        auto push = [&](uint32_t cp) { seq.push_back(cp); };
+        for_chars(ubytes.data() + uoff_h[u], uoff_h[u + 1] - uoff_h[u], push);
+        for_chars((const uint8_t*)suffix.data(), suffix.size(), push);
+        uint32_t len = (uint32_t)seq.size() - o;
+        for (uint32_t k = 0; k < len; ++k) seq[o + k] = (has_prefix && len > 1 && k > 0) ? char_sym_cont[seq[o + k]] : char_sym[seq[o + k]];
+        if (len < 2 || ucount_h[u] == 0) { seq.resize(o); continue; }
+        ws.push_back({o, len, ucount_h[u]});
+    }
+    std::stable_sort(ws.begin(), ws.end(), [](const W& a, const W& b) { return a.len > b.len; });   // similar lengths share a warp
+    size_t n_long = 0;
+    while (n_long < ws.size() && ws[n_long].len > (uint32_t)LONG_WORD) ++n_long;
+    const size_t n_short = ws.size() - n_long;
+    uint64_t n_pairs = 0;
+    for (auto& w : ws) n_pairs += w.len - 1;
+    out.n_symbols0 = seq.size();
+    const uint32_t n_sym0 = (uint32_t)symbols.size();
+
+    // ---------------- stage M
+    const uint64_t vocab_size = cfg.vocab_size;
+    if (vocab_len < vocab_size && !ws.empty()) {
+        DevBuf db;
+        const uint64_t grow = std::min<uint64_t>(vocab_size - vocab_len, n_pairs);   // every new symbol takes a vocabulary slot
+        const uint32_t sym_cap = (uint32_t)std::min<uint64_t>(n_sym0 + grow + 1, 0xFFFFFFF0ull);
+        TrainState hs{}; hs.n_symbols = n_sym0; hs.sym_cap = sym_cap; hs.vocab_len = (uint32_t)vocab_len;
+        hs.vocab_size = (uint32_t)std::min<uint64_t>(vocab_size, 0xFFFFFFFFull); hs.min_freq = cfg.min_frequency;
+        hs.cur_l = hs.cur_r = hs.cur_m = INVALID;
+        TrainState* d_st; uint32_t *d_sym, *d_woff, *d_wlen, *d_wfreq; Best* d_bb; uint4* d_log;
+        PairTable pt; SymTab sy;
+        const uint32_t pcap = pow2_at_least(2 * n_pairs); pt.mask = pcap - 1;
+        const uint32_t mcap = pow2_at_least(2ull * sym_cap); sy.map_mask = mcap - 1;
+        TCK(db.get(&d_st, 1)); TCK(db.get(&d_sym, seq.size())); TCK(db.get(&d_woff, ws.size())); TCK(db.get(&d_wlen, ws.size()));
+        TCK(db.get(&d_wfreq, ws.size())); TCK(db.get(&d_bb, 2048)); TCK(db.get(&d_log, BATCH));
+        TCK(db.get(&pt.key, pcap)); TCK(db.get(&pt.val, pcap));
+        TCK(db.get(&sy.h1, sym_cap)); TCK(db.get(&sy.h2, sym_cap)); TCK(db.get(&sy.pw1, sym_cap)); TCK(db.get(&sy.pw2, sym_cap));
+        TCK(db.get(&sy.in_vocab, sym_cap)); TCK(db.get(&sy.map_key, mcap)); TCK(db.get(&sy.map_h2, mcap)); TCK(db.get(&sy.map_id, mcap));
+        {
+            std::vector<uint64_t> h1(n_sym0), h2(n_sym0), p1(n_sym0), p2(n_sym0), mk(mcap, EMPTY64), mh(mcap, 0);
+            std::vector<uint32_t> mi(mcap, 0); std::vector<uint8_t> iv(n_sym0);
+            for (uint32_t s = 0; s < n_sym0; ++s) {
+                hash_string(symbols[s], &h1[s], &h2[s], &p1[s], &p2[s]);
+                iv[s] = vocab_id[s] >= 0;
+                uint64_t k = h1[s] == EMPTY64 ? 0 : h1[s];
+                uint32_t slot = (uint32_t)(mix64_host(k) >> 24) & sy.map_mask;
+                while (mk[slot] != EMPTY64) {
+                    if (mk[slot] == k && mh[slot] == h2[s]) { set_last_error("ctk_train_bpe: symbol hash collision"); return CTK_ERR_UNSUPPORTED; }
+                    slot = (slot + 1) & sy.map_mask;
+                }
+                mk[slot] = k; mh[slot] = h2[s]; mi[slot] = s;
+            }
+            std::vector<uint32_t> woff(ws.size()), wlen(ws.size()), wfreq(ws.size());
+            for (size_t i = 0; i < ws.size(); ++i) { woff[i] = ws[i].off; wlen[i] = ws[i].len; wfreq[i] = ws[i].freq; }
+            TCK(cudaMemcpyAsync(sy.h1, h1.data(), n_sym0 * 8ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(sy.h2, h2.data(), n_sym0 * 8ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(sy.pw1, p1.data(), n_sym0 * 8ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(sy.pw2, p2.data(), n_sym0 * 8ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(sy.in_vocab, iv.data(), n_sym0, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(sy.map_key, mk.data(), mcap * 8ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(sy.map_h2, mh.data(), mcap * 8ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(sy.map_id, mi.data(), mcap * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_sym, seq.data(), seq.size() * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_woff, woff.data(), ws.size() * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_wlen, wlen.data(), ws.size() * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_wfreq, wfreq.data(), ws.size() * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_st, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemsetAsync(pt.key, 0xFF, pcap * 8ull, st));
+            TCK(cudaMemsetAsync(pt.val, 0, pcap * 4ull, st));
+            TCK(cudaStreamSynchronize(st));
+        }
+        TCK(cudaEventRecord(ev[2], st));
+        const unsigned g_short = (unsigned)((n_short + 127) / 128), g_long = (unsigned)((n_long * 32 + 127) / 128);
+        const unsigned g_best = std::max(1u, std::min(1024u, pcap / 2048u));
+        std::vector<uint4> log(BATCH);
+        TrainState back{};
+        for (;;) {
+            for (int it = 0; it < BATCH; ++it) {
+                if (n_long) k_merge_count_long<<<g_long, 128, 0, st>>>(d_st, d_sym, d_woff, d_wlen, d_wfreq, (uint32_t)n_long, pt);
+                if (n_short) k_merge_count<<<g_short, 128, 0, st>>>(d_st, d_sym, d_woff + n_long, d_wlen + n_long, d_wfreq + n_long, (uint32_t)n_short, pt);
+                k_best_pair<<<g_best, 256, 0, st>>>(d_st, pt, d_bb, sy, d_log);
+                launches += 1 + (n_long ? 1 : 0) + (n_short ? 1 : 0);
+            }
+            TCK(cudaMemcpyAsync(&back, d_st, sizeof back, cudaMemcpyDeviceToHost, st));
+            TCK(cudaMemcpyAsync(log.data(), d_log, BATCH * sizeof(uint4), cudaMemcpyDeviceToHost, st));
+            TCK(cudaMemsetAsync(&d_st->n_log, 0, 4, st));
+            TCK(cudaStreamSynchronize(st));
+            // replay on strings: every decision of the device must be the one the reference's string logic takes
+            for (uint32_t i = 0; i < back.n_log; ++i) {
+                uint32_t l = log[i].x, r = log[i].y, m = log[i].z;
+                if (l >= symbols.size() || r >= symbols.size()) { set_last_error("ctk_train_bpe: corrupt merge log"); return CTK_ERR_CUDA; }
+                std::string merged = symbols[l] + symbols[r];
+                auto f = index.find(merged);
+                uint32_t expect = f != index.end() ? f->second : (uint32_t)symbols.size();
+                if (expect != m) { set_last_error("ctk_train_bpe: symbol hash collision (device and string replay disagree)"); return CTK_ERR_UNSUPPORTED; }
+                uint32_t s = sym(merged);
+                uint64_t id = vocab_len;                                    // :168-169: id = vocab.len() before the insert
+                vocab_insert(s, id);
+                out.merges.push_back(l); out.merges.push_back(r);
+            }
+            if (back.done) break;
+        }
+        if (back.reason == 4) { set_last_error("ctk_train_bpe: symbol table full"); return CTK_ERR_CUDA; }
+        out.stop_reason = back.reason;
+        TCK(cudaEventRecord(ev[3], st));
+        TCK(cudaStreamSynchronize(st));
+        float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); out.ms_merges = ms;
+    }
+    out.kernels = launches;
+    g_kernel_launches.fetch_add(launches, std::memory_order_relaxed);
+    out.sym_off.assign(1, 0);
+    for (auto& s : symbols) { out.sym_bytes.insert(out.sym_bytes.end(), s.begin(), s.end()); out.sym_off.push_back(out.sym_bytes.size()); }
+    return CTK_OK;
+}
+
+}  // namespace ctk
+
+extern "C" {
+
+struct ctk_trained { ctk::Trained t; };
+
+int ctk_train_bpe(const ctk_bpe_trainer_config* cfg, int device, const uint8_t* text, const uint64_t* text_off, size_t n_texts,
+                  ctk_trained** out) {
+    if (!cfg || !out || (n_texts && (!text_off || (!text && text_off[n_texts])))) { ctk::set_last_error("null argument"); return CTK_ERR_ARG; }
+    if (cfg->n_special && (!cfg->special_tokens || !cfg->special_off)) { ctk::set_last_error("special tokens missing"); return CTK_ERR_ARG; }
+    *out = nullptr;
+    ctk_trained* res = new (std::nothrow) ctk_trained();
+    if (!res) { ctk::set_last_error("out of memory"); return CTK_ERR_CUDA; }
+    int rc;
+    try { rc = ctk::train_impl(*cfg, device, text, text_off, n_texts, res->t); }
+    catch (const std::bad_alloc&) { ctk::set_last_error("out of host memory"); rc = CTK_ERR_CUDA; }
+    if (rc != CTK_OK) { delete res; return rc; }
+    *out = res;
+    return CTK_OK;
+}
+
+size_t ctk_trained_symbols(const ctk_trained* t, const uint8_t** bytes, const uint64_t** off, const int64_t** vocab_id) {
+    if (bytes) *bytes = t->t.sym_bytes.data();
+    if (off) *off = t->t.sym_off.data();
+    if (vocab_id) *vocab_id = t->t.vocab_id.data();
+    return t->t.symbols.size();
+}
+
+size_t ctk_trained_merges(const ctk_trained* t, const uint32_t** pairs) {
+    if (pairs) *pairs = t->t.merges.data();
+    return t->t.merges.size() / 2;
+}
+
+void ctk_trained_stats(const ctk_trained* t, ctk_train_stats* s) {
+    s->n_bytes = t->t.n_bytes; s->n_words = t->t.n_words; s->n_unique_words = t->t.n_unique; s->n_symbols = t->t.n_symbols0;
+    s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason;
+    s->ms_words = t->t.ms_words; s->ms_merges = t->t.ms_merges;
+}
+
+void ctk_trained_free(ctk_trained* t) { delete t; }
+
+}  // extern "C"

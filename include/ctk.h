@@ -143,6 +143,42 @@ void ctk_encodings_free(ctk_encodings* res);
 size_t ctk_post_processor_items(const ctk_tokenizer* tok, int64_t* items, size_t cap);
 uint32_t ctk_pad_token(const ctk_tokenizer* tok, const uint8_t** token, size_t* len);   /* mod.rs:504-509 */
 
+/* ---- BPE training ----------------------------------------------------------
+ * Replaces BpeTrainer::train (src/bpe_trainer.rs:100-228; Python: BpeTrainer.train, src/bindings/trainers.rs:261-269).
+ * texts are packed like everywhere else; words are split on Unicode White_Space (:248).  The word histogram and the
+ * whole merge loop run on `device`.  Where the reference decides in hash-iteration order (:152-155 best pair,
+ * :305-306 characters of equal frequency) this library decides by (count, left symbol index, right symbol index) and
+ * by code point -- every output is one the reference can produce; oracle/py_trainer.py states the rule.
+ * Fields mirror BpeTrainerConfig (:13-31). */
+typedef struct ctk_bpe_trainer_config {
+    uint64_t vocab_size;                       /* :16 */
+    uint32_t min_frequency;                    /* :18 */
+    const uint8_t* special_tokens;             /* :20, packed UTF-8 */
+    const uint64_t* special_off;               /* n_special + 1 */
+    size_t n_special;
+    const uint32_t* initial_alphabet;          /* :24, code points; NULL = None */
+    size_t n_alphabet;
+    int64_t limit_alphabet;                    /* :26; -1 = None */
+    const uint8_t* continuing_subword_prefix;  /* :28; NULL = None */
+    size_t prefix_len;
+    const uint8_t* end_of_word_suffix;         /* :30; NULL = None */
+    size_t suffix_len;
+} ctk_bpe_trainer_config;
+typedef struct ctk_trained ctk_trained;        /* opaque: the (vocab, merges) pair train() returns */
+typedef struct ctk_train_stats {
+    uint64_t n_bytes, n_words, n_unique_words, n_symbols, n_merges, kernel_launches;
+    uint32_t stop_reason;                      /* 0 none, 1 no pairs left (:147), 2 below min_frequency (:162), 3 vocabulary full (:141) */
+    double ms_words, ms_merges;                /* device time of the word histogram / of the merge loop (CUDA events) */
+} ctk_train_stats;
+int ctk_train_bpe(const ctk_bpe_trainer_config* cfg, int device, const uint8_t* text, const uint64_t* text_off, size_t n_texts,
+                  ctk_trained** out);
+/* Every symbol string the training knows, by symbol index, and its id in the returned vocabulary map (-1: not in it).  Returns the count. */
+size_t ctk_trained_symbols(const ctk_trained* t, const uint8_t** bytes, const uint64_t** off, const int64_t** vocab_id);
+/* Merges in order, two symbol indices each.  Returns the count. */
+size_t ctk_trained_merges(const ctk_trained* t, const uint32_t** pairs);
+void ctk_trained_stats(const ctk_trained* t, ctk_train_stats* stats);
+void ctk_trained_free(ctk_trained* t);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char* ctk_last_error(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
