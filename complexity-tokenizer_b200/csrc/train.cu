@@ -12,11 +12,13 @@
 //   k_unique_*        table -> packed unique words (bytes, offsets, counts) for the host
 // The host (train_host below) does what the reference does once per unique word: initial vocabulary
 // (:278-320), split into symbols (:323-338).  Stage M never leaves the device:
-// Stage M -- the merge loop (:141-183), two launches per merge, no host round trip inside a batch of merges:
-//   k_merge_count     thread per word (warp per long word): apply the previous merge in place (:379-401), then
-//                     add the word's count to every adjacent pair of the new sequence in a pair hash table
-//                     (:341-376, the reference's full recount)
-//   k_best_pair       scan + clear the pair table, lexicographic (count, pair) reduction; the last CTA decides:
+// Stage M -- the merge loop (:141-183), three launches per merge, no host round trip inside a batch of merges:
+//   k_count_all       the reference's full recount (:341-376), one thread per symbol: builds the pair hash table once
+//                     (and again when the table has to grow); afterwards the same sums are kept up to date
+//   k_detect          one thread per symbol: which words contain the pair -> list
+//   k_apply           warp per listed word: merge in place, left to right (:379-401); pairs that disappear are
+//                     subtracted from the table and the new ones added (sums mod 2^32, as the reference's u32)
+//   k_best_pair       scan the pair table, lexicographic (count, pair) reduction; the last CTA decides:
 //                     stop (:147-165), or name the merged symbol -- symbols are STRINGS in the reference, so a
 //                     merged string that already exists must get the existing symbol.  The device keeps two
 //                     64-bit polynomial hashes per symbol (hash(ab) = hash(a) * p^len(b) + hash(b)) and a symbol
@@ -43,7 +45,6 @@ namespace {
 constexpr uint32_t INVALID = 0xFFFFFFFFu;
 constexpr uint64_t EMPTY64 = ~0ull;
 constexpr uint64_t P1 = 0x100000001B3ull, P2 = 0x9E3779B97F4A7C15ull;
-constexpr int LONG_WORD = 64;          // words of more symbols than this get a warp
 constexpr int BATCH = 256;             // merges per host round trip
 
 // ------------------------------------------------------------------------------------------------ stage W
@@ -168,102 +169,128 @@ __global__ void k_unique_gather(const uint8_t* t, const uint32_t* urep, const ui
 // ------------------------------------------------------------------------------------------------ stage M
 struct TrainState {
     uint32_t done, reason;               // reason: 1 no pairs, 2 below min_frequency, 3 vocabulary full, 4 symbol table full
+    uint32_t pause;                      // the pair table needs to grow (or overflowed): the host rebuilds it from the words
+    uint32_t overflow, fill;             // pair table: an insert found no slot / number of keys in it
     uint32_t n_symbols, sym_cap;
     uint32_t vocab_len, vocab_size, min_freq;
-    uint32_t cur_l, cur_r, cur_m;        // merge k_merge_count applies before it counts
+    uint32_t cur_l, cur_r, cur_m;        // the merge k_detect / k_apply carry out
     uint32_t n_log, ticket;
-    uint32_t live_pairs;                 // diagnostics: pair-table entries seen by the last k_best_pair
+    uint32_t iter, n_dirty;              // merge number; words that contain the current pair
 };
 
 struct PairTable { uint64_t* key; uint32_t* val; uint32_t mask; };
 
-__device__ __forceinline__ void pair_add(const PairTable& pt, uint32_t a, uint32_t b, uint32_t f) {
+// count[(a, b)] += f (mod 2^32, like the reference's u32 sums; f may be "negative")
+__device__ __forceinline__ void pair_add(const PairTable& pt, TrainState* st, uint32_t a, uint32_t b, uint32_t f) {
     uint64_t key = ((uint64_t)a << 32) | b;
     uint32_t slot = (uint32_t)(mix64(key) >> 24) & pt.mask;
-    for (;;) {
+    for (uint32_t probes = 0; probes <= pt.mask; ++probes) {
         uint64_t k = pt.key[slot];
-        if (k == EMPTY64) k = atomicCAS((unsigned long long*)&pt.key[slot], EMPTY64, key), k = (k == EMPTY64) ? key : k;
-        if (k == key) break;
+        if (k == EMPTY64) {
+            k = atomicCAS((unsigned long long*)&pt.key[slot], EMPTY64, key);
+            if (k == EMPTY64) { atomicAdd(&st->fill, 1u); k = key; }
+        }
+        if (k == key) { atomicAdd(&pt.val[slot], f); return; }
         slot = (slot + 1) & pt.mask;
     }
-    atomicAdd(&pt.val[slot], f);
+    st->overflow = 1;
 }
 
-// thread per word (words of at most LONG_WORD symbols at the start)
-__global__ void __launch_bounds__(128) k_merge_count(TrainState* st, uint32_t* sym, const uint32_t* woff, uint32_t* wlen,
-                                                     const uint32_t* wfreq, uint32_t n_words, PairTable pt) {
-    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_words || st->done) return;
-    uint32_t len = wlen[w];
-    if (len < 2) return;
-    const uint32_t l = st->cur_l, r = st->cur_r, m = st->cur_m, f = wfreq[w];
-    uint32_t* s = sym + woff[w];
-    uint32_t i = 0, out = 0, prev = INVALID, nxt = s[0];
-    while (i < len) {
-        uint32_t v = nxt;
-        nxt = i + 1 < len ? s[i + 1] : INVALID;
-        if (v == l && nxt == r && nxt != INVALID) {
-            v = m; i += 2;
-            nxt = i < len ? s[i] : INVALID;
-        } else {
-            i += 1;
-        }
-        if (out != i - 1) s[out] = v;
-        if (out > 0) pair_add(pt, prev, v, f);
-        prev = v; ++out;
-    }
-    if (out != len) wlen[w] = out;
+struct Words {                           // every word keeps its slot range [woff, woff + initial length); wlen shrinks
+    uint32_t* sym; const uint32_t* slot_word; const uint32_t* woff; uint32_t* wlen; const uint32_t* wfreq;
+    uint32_t* dirty_stamp; uint32_t* dirty_list; uint32_t n_slots, n_words;
+};
+
+// The reference's full recount (bpe_trainer.rs:341-376), one thread per symbol slot.  Runs before the first merge and
+// whenever the pair table is rebuilt; between merges the counts are kept up to date by k_apply (same sums).
+__global__ void __launch_bounds__(256) k_count_all(TrainState* st, Words W, PairTable pt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W.n_slots) return;
+    uint32_t w = W.slot_word[i], k = i - W.woff[w];
+    if (k + 1 >= W.wlen[w]) return;
+    pair_add(pt, st, W.sym[i], W.sym[i + 1], W.wfreq[w]);
 }
 
-// warp per long word: chunks of 32 symbols, left to right, compacted in place
-__global__ void __launch_bounds__(128) k_merge_count_long(TrainState* st, uint32_t* sym, const uint32_t* woff, uint32_t* wlen,
-                                                          const uint32_t* wfreq, uint32_t n_words, PairTable pt) {
-    uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n_words || st->done) return;
-    uint32_t len = wlen[w];
-    if (len < 2) return;
-    const uint32_t l = st->cur_l, r = st->cur_r, m = st->cur_m, f = wfreq[w];
-    uint32_t* s = sym + woff[w];
-    uint32_t out_base = 0, carry = 0, prev_last = INVALID;
-    for (uint32_t c = 0; c < len; c += 32) {
-        uint32_t i = c + lane;
-        bool valid = i < len;
-        uint32_t v = valid ? s[i] : INVALID;
-        uint32_t ahead = (c + 32 < len) ? s[c + 32] : INVALID;          // same address in every lane
-        uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, v, 1);
-        if (lane == 31) nx = ahead;
-        uint32_t M = __ballot_sync(0xFFFFFFFFu, valid && v == l && nx == r && nx != INVALID);
-        uint32_t merges = M;
-        if (l == r || carry) {                                          // overlapping candidates: leftmost first
-            merges = 0;
-            uint32_t skip = carry;
-            for (int b = 0; b < 32; ++b) {
-                if (skip) { skip = 0; continue; }
-                if ((M >> b) & 1u) { merges |= 1u << b; skip = 1; }
+// Which words contain the pair (cur_l, cur_r)?  One thread per symbol slot.
+__global__ void __launch_bounds__(256) k_detect(TrainState* st, Words W) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W.n_slots) return;
+    const uint32_t l = st->cur_l;
+    if (l == INVALID || st->done || st->pause) return;
+    if (W.sym[i] != l) return;
+    uint32_t w = W.slot_word[i], k = i - W.woff[w];
+    if (k + 1 >= W.wlen[w] || W.sym[i + 1] != st->cur_r) return;
+    uint32_t stamp = st->iter + 1;
+    if (atomicExch(&W.dirty_stamp[w], stamp) != stamp) W.dirty_list[atomicAdd(&st->n_dirty, 1u)] = w;
+}
+
+// Apply the merge to the listed words (bpe_trainer.rs:379-401: left to right, so "aaa" -> "aa a"), a warp per word,
+// 32 symbols at a time, compacted in place; pairs that disappear are subtracted from the table, new ones added.
+__global__ void __launch_bounds__(128) k_apply(TrainState* st, Words W, PairTable pt) {
+    const uint32_t l = st->cur_l;
+    if (l == INVALID || st->done || st->pause) return;
+    const uint32_t r = st->cur_r, m = st->cur_m, n_dirty = st->n_dirty, lane = threadIdx.x & 31;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; d < n_dirty; d += n_warps) {
+        const uint32_t w = W.dirty_list[d], len = W.wlen[w], f = W.wfreq[w];
+        uint32_t* s = W.sym + W.woff[w];
+        uint32_t out_base = 0, carry = 0, new_last = INVALID, new_last_m = 0, old_last = INVALID, old_last_inv = 0;
+        for (uint32_t c = 0; c < len; c += 32) {
+            const uint32_t i = c + lane;
+            const bool valid = i < len;
+            const uint32_t o = valid ? s[i] : INVALID;
+            const uint32_t ahead = (c + 32 < len) ? s[c + 32] : INVALID;
+            uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, o, 1);
+            if (lane == 31) nx = ahead;
+            const uint32_t M = __ballot_sync(0xFFFFFFFFu, valid && o == l && nx == r && nx != INVALID);
+            uint32_t merges = M;
+            if (l == r) {                                               // overlapping candidates: leftmost first
+                merges = 0;
+                uint32_t skip = carry;
+                for (int b = 0; b < 32; ++b) {
+                    if (skip) { skip = 0; continue; }
+                    if ((M >> b) & 1u) { merges |= 1u << b; skip = 1; }
+                }
             }
+            const uint32_t consumed = (merges << 1) | carry;
+            carry = merges >> 31;
+            const uint32_t validm = __ballot_sync(0xFFFFFFFFu, valid);
+            const uint32_t kept = validm & ~consumed, inv = merges | consumed;
+            // pairs of the old sequence that disappear: (old[i-1], old[i]) with either end merged or consumed
+            uint32_t op = __shfl_up_sync(0xFFFFFFFFu, o, 1);
+            bool op_inv = (inv >> ((lane + 31) & 31)) & 1u;
+            if (lane == 0) { op = old_last; op_inv = old_last_inv; }
+            {
+                const bool has = valid && op != INVALID && (((inv >> lane) & 1u) || op_inv);
+                const uint64_t key = has ? (((uint64_t)op << 32) | o) : EMPTY64 - 1 - lane;
+                const uint32_t same = __match_any_sync(0xFFFFFFFFu, key);
+                if (has && (uint32_t)(__ffs(same) - 1) == lane) pair_add(pt, st, op, o, 0u - f * (uint32_t)__popc(same));
+            }
+            old_last = __shfl_sync(0xFFFFFFFFu, o, 31); old_last_inv = inv >> 31;   // only read again if the word goes on
+            // the new sequence
+            const bool keep = (kept >> lane) & 1u, mg = (merges >> lane) & 1u;
+            const uint32_t v = mg ? m : o;
+            const uint32_t below = kept & ((1u << lane) - 1u);
+            const int src = below ? 31 - __clz(below) : 0;
+            uint32_t pv = __shfl_sync(0xFFFFFFFFu, v, src);
+            bool pm = (merges >> src) & 1u;
+            if (!below) { pv = new_last; pm = new_last_m; }
+            if (keep && (mg || out_base + __popc(below) != i)) s[out_base + __popc(below)] = v;
+            {
+                const bool has = keep && pv != INVALID && (mg || pm);
+                const uint64_t key = has ? (((uint64_t)pv << 32) | v) : EMPTY64 - 1 - lane;
+                const uint32_t same = __match_any_sync(0xFFFFFFFFu, key);
+                if (has && (uint32_t)(__ffs(same) - 1) == lane) pair_add(pt, st, pv, v, f * (uint32_t)__popc(same));
+            }
+            if (kept) {
+                const int top = 31 - __clz(kept);
+                new_last = __shfl_sync(0xFFFFFFFFu, v, top); new_last_m = (merges >> top) & 1u;
+            }
+            out_base += __popc(kept);
+            __syncwarp();
         }
-        uint32_t consumed = (merges << 1) | carry;
-        carry = merges >> 31;
-        uint32_t validm = __ballot_sync(0xFFFFFFFFu, valid);
-        uint32_t kept = validm & ~consumed;
-        bool keep = (kept >> lane) & 1u;
-        if ((merges >> lane) & 1u) v = m;
-        uint32_t below = kept & ((1u << lane) - 1u);
-        int src = below ? 31 - __clz(below) : 0;
-        uint32_t pv = __shfl_sync(0xFFFFFFFFu, v, src);
-        if (!below) pv = prev_last;
-        __syncwarp();
-        if (keep) s[out_base + __popc(below)] = v;
-        // count (prev, v), one atomic per distinct pair in the chunk
-        bool has = keep && pv != INVALID;
-        uint64_t key = has ? (((uint64_t)pv << 32) | v) : EMPTY64 - 1 - lane;
-        uint32_t same = __match_any_sync(0xFFFFFFFFu, key);
-        if (has && (uint32_t)(__ffs(same) - 1) == lane) pair_add(pt, pv, v, f * (uint32_t)__popc(same));
-        if (kept) prev_last = __shfl_sync(0xFFFFFFFFu, v, 31 - __clz(kept));
-        out_base += __popc(kept);
-        __syncwarp();
+        if (lane == 0) W.wlen[w] = out_base;
     }
-    if (lane == 0 && out_base != len) wlen[w] = out_base;
 }
 
 struct SymTab {                          // device copy of what the host knows about every symbol
@@ -275,31 +302,28 @@ struct SymTab {                          // device copy of what the host knows a
 struct Best { uint32_t count; uint64_t key; };
 __device__ __forceinline__ bool better(const Best& a, const Best& b) { return a.count > b.count || (a.count == b.count && a.key < b.key); }
 
+// Best pair of the table (bpe_trainer.rs:152-155 with the tie rule of oracle/py_trainer.py); the last CTA decides.
 __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt, Best* block_best, SymTab sy, uint4* log) {
-    if (st->done) return;
+    if (st->done || st->pause) return;
     Best best{0u, EMPTY64};
-    uint32_t cap = pt.mask + 1, seen = 0;
+    const uint32_t cap = pt.mask + 1;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        uint64_t k = pt.key[i];
-        if (k == EMPTY64) continue;
-        Best c{pt.val[i], k};
-        if (better(c, best)) best = c;
-        pt.key[i] = EMPTY64; pt.val[i] = 0; ++seen;
+        const uint32_t c = pt.val[i];
+        if (c == 0) continue;                                          // empty slot, or a pair that no longer occurs
+        Best b{c, pt.key[i]};
+        if (better(b, best)) best = b;
     }
     __shared__ Best sb[8];
-    __shared__ uint32_t s_seen[8];
     __shared__ bool s_last;
     for (int d = 16; d > 0; d >>= 1) {
         Best o{__shfl_down_sync(0xFFFFFFFFu, best.count, d), __shfl_down_sync(0xFFFFFFFFu, best.key, d)};
         if (better(o, best)) best = o;
-        seen += __shfl_down_sync(0xFFFFFFFFu, seen, d);
     }
-    if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; s_seen[threadIdx.x >> 5] = seen; }
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; ++k) { if (better(sb[k], best)) best = sb[k]; seen += s_seen[k]; }
+        for (int k = 1; k < 8; ++k) if (better(sb[k], best)) best = sb[k];
         block_best[blockIdx.x] = best;
-        atomicAdd(&st->live_pairs, seen);
         __threadfence();
         s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
     }
@@ -308,7 +332,8 @@ __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt,
     __threadfence();
     best = Best{0u, EMPTY64};
     for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-        Best c = ((volatile Best*)block_best)[i].count ? Best{((volatile Best*)block_best)[i].count, ((volatile Best*)block_best)[i].key} : Best{0u, EMPTY64};
+        const volatile Best* p = block_best + i;
+        Best c{p->count, p->key};
         if (better(c, best)) best = c;
     }
     for (int d = 16; d > 0; d >>= 1) {
@@ -322,7 +347,9 @@ __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt,
     for (int k = 1; k < 8; ++k) if (better(sb[k], best)) best = sb[k];
     st->ticket = 0;
     st->cur_l = INVALID;
-    if (best.key == EMPTY64 || best.count == 0) { st->done = 1; st->reason = 1; return; }     // bpe_trainer.rs:147-149
+    st->n_dirty = 0;
+    if (st->overflow || st->fill > (cap >> 1) + (cap >> 3)) { st->pause = 1; return; }        // host rebuilds, then this step repeats
+    if (best.count == 0) { st->done = 1; st->reason = 1; return; }                            // bpe_trainer.rs:147-149
     if (best.count < st->min_freq) { st->done = 1; st->reason = 2; return; }                  // :162-165
     uint32_t l = (uint32_t)(best.key >> 32), r = (uint32_t)best.key;
     uint64_t h1 = sy.h1[l] * sy.pw1[r] + sy.h1[r], h2 = sy.h2[l] * sy.pw2[r] + sy.h2[r];
@@ -344,8 +371,10 @@ __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt,
     if (!sy.in_vocab[id]) { sy.in_vocab[id] = 1; st->vocab_len++; }                           // :168-169
     log[st->n_log++] = make_uint4(l, r, id, best.count);
     st->cur_l = l; st->cur_r = r; st->cur_m = id;
+    st->iter++;
     if (st->vocab_len >= st->vocab_size) { st->done = 1; st->reason = 3; }                    // :141
 }
+
 
 // ------------------------------------------------------------------------------------------------ host side
 struct DevBuf {
@@ -388,7 +417,7 @@ struct Trained {
     std::vector<uint8_t> sym_bytes; std::vector<uint64_t> sym_off;
     double ms_words = 0, ms_merges = 0, ms_host = 0;
     uint64_t n_words = 0, n_unique = 0, n_bytes = 0, n_symbols0 = 0, kernels = 0;
-    uint32_t stop_reason = 0;
+    uint32_t stop_reason = 0, rebuilds = 0;
 };
 
 #define TCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); return CTK_ERR_CUDA; } } while (0)
@@ -565,10 +594,6 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         if (len < 2 || ucount_h[u] == 0) { seq.resize(o); continue; }
         ws.push_back({o, len, ucount_h[u]});
     }
-    std::stable_sort(ws.begin(), ws.end(), [](const W& a, const W& b) { return a.len > b.len; });   // similar lengths share a warp
-    size_t n_long = 0;
-    while (n_long < ws.size() && ws[n_long].len > (uint32_t)LONG_WORD) ++n_long;
-    const size_t n_short = ws.size() - n_long;
     uint64_t n_pairs = 0;
     for (auto& w : ws) n_pairs += w.len - 1;
     out.n_symbols0 = seq.size();
@@ -583,13 +608,15 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         TrainState hs{}; hs.n_symbols = n_sym0; hs.sym_cap = sym_cap; hs.vocab_len = (uint32_t)vocab_len;
         hs.vocab_size = (uint32_t)std::min<uint64_t>(vocab_size, 0xFFFFFFFFull); hs.min_freq = cfg.min_frequency;
         hs.cur_l = hs.cur_r = hs.cur_m = INVALID;
-        TrainState* d_st; uint32_t *d_sym, *d_woff, *d_wlen, *d_wfreq; Best* d_bb; uint4* d_log;
-        PairTable pt; SymTab sy;
-        const uint32_t pcap = pow2_at_least(2 * n_pairs); pt.mask = pcap - 1;
+        TrainState* d_st; Best* d_bb; uint4* d_log; uint32_t *d_sym, *d_slot_word, *d_woff, *d_wlen, *d_wfreq, *d_stamp, *d_list;
+        PairTable pt{}; SymTab sy;
+        const uint32_t n_slots = (uint32_t)seq.size(), nw = (uint32_t)ws.size();
+        const uint32_t pcap_max = pow2_at_least(4ull * n_slots + 1024);
+        uint32_t pcap = std::min<uint32_t>(pcap_max, std::max<uint32_t>(1u << 16, pow2_at_least(n_pairs / 8)));
         const uint32_t mcap = pow2_at_least(2ull * sym_cap); sy.map_mask = mcap - 1;
-        TCK(db.get(&d_st, 1)); TCK(db.get(&d_sym, seq.size())); TCK(db.get(&d_woff, ws.size())); TCK(db.get(&d_wlen, ws.size()));
-        TCK(db.get(&d_wfreq, ws.size())); TCK(db.get(&d_bb, 2048)); TCK(db.get(&d_log, BATCH));
-        TCK(db.get(&pt.key, pcap)); TCK(db.get(&pt.val, pcap));
+        TCK(db.get(&d_st, 1)); TCK(db.get(&d_sym, (size_t)n_slots + 1)); TCK(db.get(&d_slot_word, n_slots)); TCK(db.get(&d_woff, nw));
+        TCK(db.get(&d_wlen, nw)); TCK(db.get(&d_wfreq, nw)); TCK(db.get(&d_stamp, nw)); TCK(db.get(&d_list, nw));
+        TCK(db.get(&d_bb, 2048)); TCK(db.get(&d_log, BATCH));
         TCK(db.get(&sy.h1, sym_cap)); TCK(db.get(&sy.h2, sym_cap)); TCK(db.get(&sy.pw1, sym_cap)); TCK(db.get(&sy.pw2, sym_cap));
         TCK(db.get(&sy.in_vocab, sym_cap)); TCK(db.get(&sy.map_key, mcap)); TCK(db.get(&sy.map_h2, mcap)); TCK(db.get(&sy.map_id, mcap));
         {
@@ -606,8 +633,11 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
                 }
                 mk[slot] = k; mh[slot] = h2[s]; mi[slot] = s;
             }
-            std::vector<uint32_t> woff(ws.size()), wlen(ws.size()), wfreq(ws.size());
-            for (size_t i = 0; i < ws.size(); ++i) { woff[i] = ws[i].off; wlen[i] = ws[i].len; wfreq[i] = ws[i].freq; }
+            std::vector<uint32_t> woff(nw), wlen(nw), wfreq(nw), slot_word(n_slots);
+            for (uint32_t i = 0; i < nw; ++i) {
+                woff[i] = ws[i].off; wlen[i] = ws[i].len; wfreq[i] = ws[i].freq;
+                for (uint32_t k = 0; k < ws[i].len; ++k) slot_word[ws[i].off + k] = i;
+            }
             TCK(cudaMemcpyAsync(sy.h1, h1.data(), n_sym0 * 8ull, cudaMemcpyHostToDevice, st));
             TCK(cudaMemcpyAsync(sy.h2, h2.data(), n_sym0 * 8ull, cudaMemcpyHostToDevice, st));
             TCK(cudaMemcpyAsync(sy.pw1, p1.data(), n_sym0 * 8ull, cudaMemcpyHostToDevice, st));
@@ -616,27 +646,44 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             TCK(cudaMemcpyAsync(sy.map_key, mk.data(), mcap * 8ull, cudaMemcpyHostToDevice, st));
             TCK(cudaMemcpyAsync(sy.map_h2, mh.data(), mcap * 8ull, cudaMemcpyHostToDevice, st));
             TCK(cudaMemcpyAsync(sy.map_id, mi.data(), mcap * 4ull, cudaMemcpyHostToDevice, st));
-            TCK(cudaMemcpyAsync(d_sym, seq.data(), seq.size() * 4ull, cudaMemcpyHostToDevice, st));
-            TCK(cudaMemcpyAsync(d_woff, woff.data(), ws.size() * 4ull, cudaMemcpyHostToDevice, st));
-            TCK(cudaMemcpyAsync(d_wlen, wlen.data(), ws.size() * 4ull, cudaMemcpyHostToDevice, st));
-            TCK(cudaMemcpyAsync(d_wfreq, wfreq.data(), ws.size() * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_sym, seq.data(), n_slots * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_slot_word, slot_word.data(), n_slots * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_woff, woff.data(), nw * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_wlen, wlen.data(), nw * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemcpyAsync(d_wfreq, wfreq.data(), nw * 4ull, cudaMemcpyHostToDevice, st));
+            TCK(cudaMemsetAsync(d_stamp, 0, nw * 4ull, st));
             TCK(cudaMemcpyAsync(d_st, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
-            TCK(cudaMemsetAsync(pt.key, 0xFF, pcap * 8ull, st));
-            TCK(cudaMemsetAsync(pt.val, 0, pcap * 4ull, st));
             TCK(cudaStreamSynchronize(st));
         }
+        Words W{d_sym, d_slot_word, d_woff, d_wlen, d_wfreq, d_stamp, d_list, n_slots, nw};
         TCK(cudaEventRecord(ev[2], st));
-        const unsigned g_short = (unsigned)((n_short + 127) / 128), g_long = (unsigned)((n_long * 32 + 127) / 128);
-        const unsigned g_best = std::max(1u, std::min(1024u, pcap / 2048u));
+        const unsigned g_slots = (n_slots + 255) / 256;
+        int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const unsigned g_apply = (unsigned)std::min<uint64_t>((nw + 3) / 4, (uint64_t)sms * 8);
         std::vector<uint4> log(BATCH);
         TrainState back{};
+        void *old_key = nullptr, *old_val = nullptr;
+        // (re)build the pair table from the words: a full recount into a fresh table of `pcap` slots
+        auto rebuild = [&]() -> int {
+            if (old_key) { cudaFree(old_key); cudaFree(old_val); }
+            TCK(cudaMalloc(&old_key, pcap * 8ull)); TCK(cudaMalloc(&old_val, pcap * 4ull));
+            pt.key = (uint64_t*)old_key; pt.val = (uint32_t*)old_val; pt.mask = pcap - 1;
+            TCK(cudaMemsetAsync(pt.key, 0xFF, pcap * 8ull, st));
+            TCK(cudaMemsetAsync(pt.val, 0, pcap * 4ull, st));
+            TCK(cudaMemsetAsync(&d_st->pause, 0, 12, st));               // pause, overflow, fill
+            k_count_all<<<g_slots, 256, 0, st>>>(d_st, W, pt); ++launches;
+            return CTK_OK;
+        };
+        struct TableGuard { void** a; void** b; ~TableGuard() { if (*a) cudaFree(*a); if (*b) cudaFree(*b); } } tg{&old_key, &old_val};
+        { int rc = rebuild(); if (rc != CTK_OK) return rc; }
         for (;;) {
+            const unsigned g_best = std::max(1u, std::min(1024u, pcap / 2048u));
             for (int it = 0; it < BATCH; ++it) {
-                if (n_long) k_merge_count_long<<<g_long, 128, 0, st>>>(d_st, d_sym, d_woff, d_wlen, d_wfreq, (uint32_t)n_long, pt);
-                if (n_short) k_merge_count<<<g_short, 128, 0, st>>>(d_st, d_sym, d_woff + n_long, d_wlen + n_long, d_wfreq + n_long, (uint32_t)n_short, pt);
+                k_detect<<<g_slots, 256, 0, st>>>(d_st, W);
+                k_apply<<<g_apply, 128, 0, st>>>(d_st, W, pt);
                 k_best_pair<<<g_best, 256, 0, st>>>(d_st, pt, d_bb, sy, d_log);
-                launches += 1 + (n_long ? 1 : 0) + (n_short ? 1 : 0);
             }
+            launches += 3 * BATCH;
             TCK(cudaMemcpyAsync(&back, d_st, sizeof back, cudaMemcpyDeviceToHost, st));
             TCK(cudaMemcpyAsync(log.data(), d_log, BATCH * sizeof(uint4), cudaMemcpyDeviceToHost, st));
             TCK(cudaMemsetAsync(&d_st->n_log, 0, 4, st));
@@ -655,6 +702,12 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
                 out.merges.push_back(l); out.merges.push_back(r);
             }
             if (back.done) break;
+            if (back.pause) {
+                // At the largest size a recount alone makes room: live pairs <= slots <= pcap_max / 4.
+                pcap = pcap < pcap_max / 4 ? pcap * 4 : pcap_max;
+                ++out.rebuilds;
+                int rc = rebuild(); if (rc != CTK_OK) return rc;
+            }
         }
         if (back.reason == 4) { set_last_error("ctk_train_bpe: symbol table full"); return CTK_ERR_CUDA; }
         out.stop_reason = back.reason;
@@ -704,7 +757,7 @@ size_t ctk_trained_merges(const ctk_trained* t, const uint32_t** pairs) {
 
 void ctk_trained_stats(const ctk_trained* t, ctk_train_stats* s) {
     s->n_bytes = t->t.n_bytes; s->n_words = t->t.n_words; s->n_unique_words = t->t.n_unique; s->n_symbols = t->t.n_symbols0;
-    s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason;
+    s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason; s->table_rebuilds = t->t.rebuilds;
     s->ms_words = t->t.ms_words; s->ms_merges = t->t.ms_merges;
 }
 

@@ -122,4 +122,15 @@ def test_trained_table_feeds_the_encode_path(built_lib, tmp_path):
     ids, ioff = tok.encode_packed(text, offs)
     wids, woff = orc.encode_packed(text, offs)
     assert np.array_equal(ioff, woff) and np.array_equal(ids, wids)
-    assert ids.size < text.size / 2                       # the trained merges are in use
+    assert ids.size < text.size * 0.6                       # the trained merges are in use
+
+
+@pytest.mark.parametrize('n_words', [60000, 130000])
+def test_pair_table_growth(built_lib, n_words):
+    """More distinct pairs than the first pair table holds: fill guard (60K) and overflow (130K) -> recount into a larger table."""
+    rng = random.Random(n_words)
+    alpha = [chr(0x4E00 + k) for k in range(400)]
+    words = ["".join(rng.choice(alpha) for _ in range(2)) for _ in range(n_words)]
+    texts = [" ".join(words[i:i + 50]) for i in range(0, n_words, 50)]
+    _, stats = both(texts, vocab_size=4 + 400 + 25, min_frequency=1)
+    assert stats['table_rebuilds'] >= 1
