@@ -5,8 +5,8 @@
 // Stage W -- word histogram (bpe_trainer.rs:241-275), data-parallel over the text bytes, HBM-bound:
 //   k_mark_breaks     one bit per text start (words do not span texts)
 //   cub select        positions where a word starts (a non-White_Space char after White_Space / a text start)
-//   k_word_insert     one thread per word: walk it, 64-bit hash, insert into an open-addressing table
-//                     {hash, count, first position}
+//   k_word_insert     one thread per word: walk it, 64-bit hash; equal hashes of a CTA's 512 words are merged in
+//                     shared memory, then inserted into an open-addressing table {hash, count, first position}
 //   k_word_verify     one thread per word: bytes == bytes of the slot's first occurrence (a 64-bit collision is
 //                     detected, never trusted; the call then repeats with another hash seed)
 //   k_unique_*        table -> packed unique words (bytes, offsets, counts) for the host
@@ -104,28 +104,61 @@ __device__ __forceinline__ uint64_t word_end(const uint8_t* t, const uint32_t* b
 
 struct WordTable { uint64_t* key; uint32_t* count; uint32_t* rep; uint32_t mask; };
 
-__global__ void k_word_insert(const uint8_t* t, const uint32_t* brk, uint64_t n, const uint32_t* starts, uint32_t n_words,
-                              uint64_t seed, WordTable tab, uint32_t* slot_of) {
-    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_words) return;
-    uint64_t s = starts[w], j = s, h = seed;
-    do { h = h * P1 + t[j] + 1; ++j; } while (j < n && !brk_at(brk, j) && !ws_at(t, n, j));
-    h = mix64(h ^ ((j - s) * P2));
-    if (h == EMPTY64) h = 0;
-    uint32_t slot = (uint32_t)(h >> 20) & tab.mask;
-    for (;;) {
-        uint64_t k = tab.key[slot];
-        if (k == EMPTY64) k = atomicCAS((unsigned long long*)&tab.key[slot], EMPTY64, h), k = (k == EMPTY64) ? h : k;
-        if (k == h) break;
-        slot = (slot + 1) & tab.mask;
+// A CTA takes 512 consecutive words: each thread walks and hashes one, equal hashes are merged in a shared-memory
+// table first (the most frequent word of a text is ~5 % of all words: without this every one of its occurrences is an
+// atomic on the same global address), then one thread per distinct hash updates the global table.
+constexpr int WI_THREADS = 512, WI_SLOTS = 1024;
+struct WordFlags { uint32_t collision, overflow, fill; };
+
+__global__ void __launch_bounds__(WI_THREADS) k_word_insert(const uint8_t* t, const uint32_t* brk, uint64_t n, const uint32_t* starts,
+                                                            uint32_t n_words, uint64_t seed, WordTable tab, uint32_t* slot_of, WordFlags* fl) {
+    __shared__ unsigned long long s_key[WI_SLOTS];
+    __shared__ uint32_t s_count[WI_SLOTS], s_rep[WI_SLOTS], s_gslot[WI_SLOTS];
+    for (int k = threadIdx.x; k < WI_SLOTS; k += WI_THREADS) { s_key[k] = EMPTY64; s_count[k] = 0; s_rep[k] = INVALID; }
+    __syncthreads();
+    const uint32_t w = blockIdx.x * WI_THREADS + threadIdx.x;
+    uint32_t mine = INVALID;
+    if (w < n_words) {
+        uint64_t s = starts[w], j = s, h = seed;
+        do { h = h * P1 + t[j] + 1; ++j; } while (j < n && !brk_at(brk, j) && !ws_at(t, n, j));
+        h = mix64(h ^ ((j - s) * P2));
+        if (h == EMPTY64) h = 0;
+        uint32_t slot = (uint32_t)(h >> 40) & (WI_SLOTS - 1);
+        for (;;) {                                                       // 512 words, 1024 slots: always ends
+            unsigned long long k = s_key[slot];
+            if (k == EMPTY64) k = atomicCAS(&s_key[slot], EMPTY64, h), k = (k == EMPTY64) ? h : k;
+            if (k == h) break;
+            slot = (slot + 1) & (WI_SLOTS - 1);
+        }
+        atomicAdd(&s_count[slot], 1u);
+        atomicMin(&s_rep[slot], (uint32_t)s);
+        mine = slot;
     }
-    atomicAdd(&tab.count[slot], 1u);
-    atomicMin(&tab.rep[slot], (uint32_t)s);
-    slot_of[w] = slot;
+    __syncthreads();
+    for (int k = threadIdx.x; k < WI_SLOTS; k += WI_THREADS) {
+        const uint64_t h = s_key[k];
+        if (h == EMPTY64) continue;
+        uint32_t slot = (uint32_t)(h >> 20) & tab.mask, probes = 0;
+        for (;; ++probes) {
+            if (probes > tab.mask) { fl->overflow = 1; slot = 0; break; }
+            uint64_t g = tab.key[slot];
+            if (g == EMPTY64) {
+                g = atomicCAS((unsigned long long*)&tab.key[slot], EMPTY64, h);
+                if (g == EMPTY64) { atomicAdd(&fl->fill, 1u); g = h; }
+            }
+            if (g == h) break;
+            slot = (slot + 1) & tab.mask;
+        }
+        atomicAdd(&tab.count[slot], s_count[k]);
+        atomicMin(&tab.rep[slot], s_rep[k]);
+        s_gslot[k] = slot;
+    }
+    __syncthreads();
+    if (mine != INVALID) slot_of[w] = s_gslot[mine];
 }
 
 __global__ void k_word_verify(const uint8_t* t, const uint32_t* brk, uint64_t n, const uint32_t* starts, uint32_t n_words,
-                              WordTable tab, const uint32_t* slot_of, uint32_t* collision) {
+                              WordTable tab, const uint32_t* slot_of, WordFlags* fl) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     uint64_t s = starts[w], r = tab.rep[slot_of[w]];
@@ -137,7 +170,7 @@ __global__ void k_word_verify(const uint8_t* t, const uint32_t* brk, uint64_t n,
         ++j;
     } while (s + j < n && !brk_at(brk, s + j) && !ws_at(t, n, s + j));
     if (ok && r + j < n && !brk_at(brk, r + j) && !ws_at(t, n, r + j)) ok = false;   // the first occurrence is longer
-    if (!ok) *collision = 1;
+    if (!ok) fl->collision = 1;
 }
 
 struct U32ToU64 { __device__ uint64_t operator()(uint32_t v) const { return v; } };
@@ -448,9 +481,9 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
     uint32_t n_words = 0, n_unique = 0;
     {
         DevBuf db;
-        uint8_t* d_text; uint64_t* d_off; uint32_t* d_brk; uint32_t* d_starts; uint32_t* d_num; uint32_t* d_collision;
+        uint8_t* d_text; uint64_t* d_off; uint32_t* d_brk; uint32_t* d_starts; uint32_t* d_num;
         TCK(db.get(&d_text, n + 16)); TCK(db.get(&d_off, n_texts + 1)); TCK(db.get(&d_brk, (n >> 5) + 2));
-        TCK(db.get(&d_num, 4)); TCK(db.get(&d_collision, 1));
+        TCK(db.get(&d_num, 4));
         TCK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st));
         if (n_texts) TCK(cudaMemcpyAsync(d_off, off, (n_texts + 1) * 8, cudaMemcpyHostToDevice, st));
         TCK(cudaEventRecord(ev[0], st));
@@ -469,22 +502,39 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             TCK(cudaStreamSynchronize(st));
         }
         if (n_words > 0) {
-            WordTable tab; uint32_t cap = pow2_at_least(2ull * n_words); tab.mask = cap - 1;
-            uint32_t* d_slot; uint32_t* d_uslot;
-            TCK(db.get(&tab.key, cap)); TCK(db.get(&tab.count, cap)); TCK(db.get(&tab.rep, cap)); TCK(db.get(&d_slot, n_words));
-            uint32_t collision = 1;
-            for (int attempt = 0; attempt < 4 && collision; ++attempt) {
+            // The table starts small (distinct words are a few per cent of the words of a text) and is rebuilt four times
+            // larger when it fills beyond 5/8 -- at most up to 2 slots per word; a 64-bit collision repeats with a new seed.
+            WordTable tab{}; uint32_t* d_slot; uint32_t* d_uslot; WordFlags* d_fl;
+            const uint32_t cap_max = pow2_at_least(2ull * n_words);
+            uint32_t cap = std::min<uint32_t>(cap_max, std::max<uint32_t>(1u << 16, pow2_at_least(n_words / 8)));
+            TCK(db.get(&d_slot, n_words)); TCK(db.get(&d_fl, 1));
+            void* tab_mem = nullptr;
+            struct MemGuard { void** p; ~MemGuard() { if (*p) cudaFree(*p); } } mg{&tab_mem};
+            WordFlags fl{1, 0, 0};
+            for (int attempt = 0, seed_no = 0; attempt < 24; ++attempt) {
+                if (!tab_mem) {
+                    TCK(cudaMalloc(&tab_mem, (size_t)cap * 16));
+                    tab.key = (uint64_t*)tab_mem; tab.count = (uint32_t*)(tab.key + cap); tab.rep = tab.count + cap; tab.mask = cap - 1;
+                }
                 TCK(cudaMemsetAsync(tab.key, 0xFF, (size_t)cap * 8, st));
                 TCK(cudaMemsetAsync(tab.count, 0, (size_t)cap * 4, st));
                 TCK(cudaMemsetAsync(tab.rep, 0xFF, (size_t)cap * 4, st));
-                TCK(cudaMemsetAsync(d_collision, 0, 4, st));
-                unsigned g = (n_words + 127) / 128;
-                k_word_insert<<<g, 128, 0, st>>>(d_text, d_brk, n, d_starts, n_words, 0x9E37ull + 0x51ED27ull * attempt, tab, d_slot);
-                k_word_verify<<<g, 128, 0, st>>>(d_text, d_brk, n, d_starts, n_words, tab, d_slot, d_collision); launches += 2;
-                TCK(cudaMemcpyAsync(&collision, d_collision, 4, cudaMemcpyDeviceToHost, st));
+                TCK(cudaMemsetAsync(d_fl, 0, sizeof(WordFlags), st));
+                k_word_insert<<<(n_words + WI_THREADS - 1) / WI_THREADS, WI_THREADS, 0, st>>>(d_text, d_brk, n, d_starts, n_words,
+                                                                                           0x9E37ull + 0x51ED27ull * seed_no, tab, d_slot, d_fl);
+                k_word_verify<<<(n_words + 127) / 128, 128, 0, st>>>(d_text, d_brk, n, d_starts, n_words, tab, d_slot, d_fl); launches += 2;
+                TCK(cudaMemcpyAsync(&fl, d_fl, sizeof fl, cudaMemcpyDeviceToHost, st));
                 TCK(cudaStreamSynchronize(st));
+                if (fl.overflow || (fl.fill > cap / 8 * 5 && cap < cap_max)) {      // grow and repeat
+                    cudaFree(tab_mem); tab_mem = nullptr;
+                    cap = cap < cap_max / 4 ? cap * 4 : cap_max;
+                    fl.collision = 1;
+                    continue;
+                }
+                if (!fl.collision) break;
+                ++seed_no;
             }
-            if (collision) { set_last_error("ctk_train_bpe: word hash collisions under four seeds"); return CTK_ERR_UNSUPPORTED; }
+            if (fl.collision) { set_last_error("ctk_train_bpe: word hash collisions under every seed"); return CTK_ERR_UNSUPPORTED; }
             TCK(db.get(&d_uslot, n_words));
             cub::CountingInputIterator<uint32_t> it(0);
             SlotUsed used{tab.key};
@@ -677,7 +727,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         struct TableGuard { void** a; void** b; ~TableGuard() { if (*a) cudaFree(*a); if (*b) cudaFree(*b); } } tg{&old_key, &old_val};
         { int rc = rebuild(); if (rc != CTK_OK) return rc; }
         for (;;) {
-            const unsigned g_best = std::max(1u, std::min(1024u, pcap / 2048u));
+            const unsigned g_best = std::max(1u, std::min(1024u, pcap / 256u));
             for (int it = 0; it < BATCH; ++it) {
                 k_detect<<<g_slots, 256, 0, st>>>(d_st, W);
                 k_apply<<<g_apply, 128, 0, st>>>(d_st, W, pt);

@@ -20,6 +20,7 @@ def main():
     ap.add_argument('--mib', type=int, default=256)
     ap.add_argument('--vocab', type=int, default=32000)
     ap.add_argument('--oracle-merges', type=int, default=300)
+    ap.add_argument('--skip-config1', action='store_true')
     a = ap.parse_args()
     import complexity_tokenizer as ct
     import synth
@@ -31,10 +32,10 @@ def main():
     tr = ct.BpeTrainer(vocab_size=a.vocab, min_frequency=2, show_progress=False)
     tr.train_packed(text[:4096], np.array([0, 4096], dtype=np.uint64))          # warm-up (context, module load)
     t0 = time.perf_counter()
-    vocab, merges = tr.train_packed(text, offs)
+    vocab, merges = tr.train_packed(text, offs) if not a.skip_config1 else ({}, [])
     wall = time.perf_counter() - t0
     s = tr.last_stats
-    out['config1_sample'] = dict(s, wall_s=wall, vocab=len(vocab), merges=len(merges),
+    out['config1_sample'] = None if a.skip_config1 else dict(s, wall_s=wall, vocab=len(vocab), merges=len(merges),
                                  us_per_merge=1e3 * s['ms_merges'] / max(1, len(merges)),
                                  words_GBps=s['n_bytes'] / max(s['ms_words'], 1e-9) / 1e6)
     # (2) word histogram at scale: a few merges only
