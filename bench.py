@@ -175,6 +175,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-encodings', action='store_true')
     ap.add_argument('--encodings-bytes', type=int, default=256 << 20)
+    ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--train-bytes', type=int, default=3 << 20)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -351,6 +353,25 @@ def main():
                               'device_MB_per_s': s_B / (sum(v[0] / v[1] for v in pr.values()) * 1e-3) / 1e6,
                               'kernels_ms': {k: v[0] / v[1] for k, v in sorted(pr.items())}}
 
+    # ---- BPE training on the GPU on the trainer's own shape: the first documents of the same corpus
+    #      (config 1 trains on a ~3 MB sample), vocabulary of 32 000, through the C ABI with host buffers
+    train = None
+    if not args.no_train and rank == 0:
+        import complexity_tokenizer as ct
+        n_t = int(np.searchsorted(offs, min(B, args.train_bytes), side='right')) - 1
+        t_off = offs[:n_t + 1].copy()
+        trn = ct.BpeTrainer(vocab_size=32000, min_frequency=2, show_progress=False, device=local)
+        trn.train_packed(h_np[:4096], np.array([0, 4096], dtype=np.uint64))
+        t0 = time.perf_counter()
+        tv, tm = trn.train_packed(h_np[:int(t_off[-1])], t_off)
+        wall_ = time.perf_counter() - t0
+        ts_ = trn.last_stats
+        train = {'sample': 'first %d docs (%.1f MiB) of the same corpus, split on White_Space' % (n_t, int(t_off[-1]) / 2**20),
+                 'vocab_size': len(tv), 'merges': len(tm), 'wall_s': wall_, 'device_ms_word_histogram': ts_['ms_words'],
+                 'device_ms_merge_loop': ts_['ms_merges'], 'us_per_merge': 1e3 * ts_['ms_merges'] / max(1, len(tm)),
+                 'words': ts_['n_words'], 'unique_words': ts_['n_unique_words'], 'symbols': ts_['n_symbols'],
+                 'kernel_launches': ts_['kernel_launches'], 'table_rebuilds': ts_['table_rebuilds']}
+
     # ---- roofline of the dominant kernel (CUDA events inside the library, same timed region)
     peak, peak_src = peaks()
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
@@ -391,7 +412,7 @@ def main():
                    'lexicon_words': 50000, 'vocab': 50257, 'l2': 'inputs (1 GiB) larger than L2 (126 MB); no flush needed',
                    'pretoken_cache': 'cleared inside every step', 'parallelism': 'documents sharded over %d GPU(s), no collective on the data path' % world},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
-        'decode_batch': decode, 'encodings': encodings}
+        'decode_batch': decode, 'encodings': encodings, 'train_bpe': train}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

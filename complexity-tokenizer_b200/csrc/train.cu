@@ -27,6 +27,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
@@ -82,6 +85,26 @@ struct IsWordStart {
         return ws_at(t, n, i - 1);
     }
 };
+
+// number of word starts (so that the list of starts is allocated at its exact size: device allocation is what a
+// training call waits for most, ~0.14 ms per MB on the B200 box)
+__global__ void __launch_bounds__(256) k_count_starts(IsWordStart pred, uint64_t n, unsigned long long* total) {
+    const uint64_t base = (uint64_t)blockIdx.x * 4096;
+    uint32_t mine = 0;
+    for (int k = 0; k < 16; ++k) {
+        uint64_t i = base + k * 256 + threadIdx.x;
+        if (i < n && pred((uint32_t)i)) ++mine;
+    }
+    mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+    __shared__ uint32_t s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; ++k) t += s[k];
+        if (t) atomicAdd(total, (unsigned long long)t);
+    }
+}
 
 __global__ void k_mark_breaks(const uint64_t* off, size_t n_texts, uint32_t* brk) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -453,6 +476,18 @@ struct Trained {
     uint32_t stop_reason = 0, rebuilds = 0;
 };
 
+struct PhaseTrace {                       // CTK_TRAIN_TRACE=1: host-timed phases (each ends with the stream idle) on stderr
+    bool on = getenv("CTK_TRAIN_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char* what, cudaStream_t st) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ctk train] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 #define TCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); return CTK_ERR_CUDA; } } while (0)
 
 static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8_t* text, const uint64_t* off, size_t n_texts, Trained& out) {
@@ -487,19 +522,26 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         TCK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st));
         if (n_texts) TCK(cudaMemcpyAsync(d_off, off, (n_texts + 1) * 8, cudaMemcpyHostToDevice, st));
         TCK(cudaEventRecord(ev[0], st));
+        PhaseTrace tr; tr.mark("alloc + copy in", st);
         if (n > 0) {
             TCK(cudaMemsetAsync(d_brk, 0, ((n >> 5) + 2) * 4, st));
             k_mark_breaks<<<(unsigned)((n_texts + 256) / 256), 256, 0, st>>>(d_off, n_texts, d_brk); ++launches;
-            // an upper bound of the number of words is (n + 1) / 2; count first, then select
             cub::CountingInputIterator<uint32_t> it(0);
             IsWordStart pred{d_text, d_brk, n};
-            TCK(db.get(&d_starts, (size_t)(n + 1) / 2 + 1));
+            unsigned long long* d_total; unsigned long long total = 0;
+            TCK(db.get(&d_total, 1));
+            TCK(cudaMemsetAsync(d_total, 0, 8, st));
+            k_count_starts<<<(unsigned)((n + 4095) / 4096), 256, 0, st>>>(pred, n, d_total); ++launches;
+            TCK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+            TCK(cudaStreamSynchronize(st));
+            TCK(db.get(&d_starts, (size_t)total + 1));
             size_t tmp_bytes = 0;
             TCK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_starts, d_num, (int64_t)n, pred, st));
             uint8_t* d_tmp; TCK(db.get(&d_tmp, tmp_bytes));
             TCK(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_starts, d_num, (int64_t)n, pred, st)); launches += 2;
             TCK(cudaMemcpyAsync(&n_words, d_num, 4, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
+            tr.mark("breaks + word starts", st);
         }
         if (n_words > 0) {
             // The table starts small (distinct words are a few per cent of the words of a text) and is rebuilt four times
@@ -525,6 +567,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
                 k_word_verify<<<(n_words + 127) / 128, 128, 0, st>>>(d_text, d_brk, n, d_starts, n_words, tab, d_slot, d_fl); launches += 2;
                 TCK(cudaMemcpyAsync(&fl, d_fl, sizeof fl, cudaMemcpyDeviceToHost, st));
                 TCK(cudaStreamSynchronize(st));
+                tr.mark("table: insert + verify", st);
                 if (fl.overflow || (fl.fill > cap / 8 * 5 && cap < cap_max)) {      // grow and repeat
                     cudaFree(tab_mem); tab_mem = nullptr;
                     cap = cap < cap_max / 4 ? cap * 4 : cap_max;
@@ -544,6 +587,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             TCK(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_uslot, d_num, (int64_t)cap, used, st)); launches += 2;
             TCK(cudaMemcpyAsync(&n_unique, d_num, 4, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
+            tr.mark("unique slots", st);
             uint32_t *d_ulen, *d_ucount, *d_urep; uint64_t* d_uoff; uint8_t* d_ubytes;
             TCK(db.get(&d_ulen, n_unique + 1)); TCK(db.get(&d_ucount, n_unique)); TCK(db.get(&d_urep, n_unique)); TCK(db.get(&d_uoff, n_unique + 1));
             TCK(cudaMemsetAsync(d_ulen + n_unique, 0, 4, st));
@@ -564,6 +608,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             TCK(cudaMemcpyAsync(ubytes.data(), d_ubytes, ubytes.size(), cudaMemcpyDeviceToHost, st));
             TCK(cudaMemcpyAsync(ucount_h.data(), d_ucount, n_unique * 4ull, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
+            tr.mark("unique words out", st);
         } else {
             TCK(cudaEventRecord(ev[1], st));
             TCK(cudaStreamSynchronize(st));
