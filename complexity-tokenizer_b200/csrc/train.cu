@@ -24,6 +24,7 @@
 //                     64-bit polynomial hashes per symbol (hash(ab) = hash(a) * p^len(b) + hash(b)) and a symbol
 //                     map; the host replays every merge on real strings afterwards and fails the call if a
 //                     single decision differs, so the result is exact, not probabilistic.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -41,6 +42,8 @@
 
 #include "../../include/ctk.h"
 #include "engine.hpp"
+
+namespace cg = cooperative_groups;
 
 namespace ctk {
 namespace {
@@ -267,27 +270,31 @@ __global__ void __launch_bounds__(256) k_count_all(TrainState* st, Words W, Pair
     pair_add(pt, st, W.sym[i], W.sym[i + 1], W.wfreq[w]);
 }
 
-// Which words contain the pair (cur_l, cur_r)?  One thread per symbol slot.
-__global__ void __launch_bounds__(256) k_detect(TrainState* st, Words W) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= W.n_slots) return;
+// Which words contain the pair (cur_l, cur_r)?  One thread per symbol slot (grid-stride in the persistent kernel).
+__device__ __forceinline__ void detect_range(TrainState* st, const Words& W, uint32_t tid, uint32_t n_threads) {
     const uint32_t l = st->cur_l;
-    if (l == INVALID || st->done || st->pause) return;
-    if (W.sym[i] != l) return;
-    uint32_t w = W.slot_word[i], k = i - W.woff[w];
-    if (k + 1 >= W.wlen[w] || W.sym[i + 1] != st->cur_r) return;
-    uint32_t stamp = st->iter + 1;
-    if (atomicExch(&W.dirty_stamp[w], stamp) != stamp) W.dirty_list[atomicAdd(&st->n_dirty, 1u)] = w;
+    if (l == INVALID) return;
+    const uint32_t r = st->cur_r, stamp = st->iter + 1;
+    for (uint32_t i = tid; i < W.n_slots; i += n_threads) {
+        if (W.sym[i] != l) continue;
+        uint32_t w = W.slot_word[i], k = i - W.woff[w];
+        if (k + 1 >= W.wlen[w] || W.sym[i + 1] != r) continue;
+        if (atomicExch(&W.dirty_stamp[w], stamp) != stamp) W.dirty_list[atomicAdd(&st->n_dirty, 1u)] = w;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_detect(TrainState* st, Words W) {
+    if (st->done || st->pause) return;
+    detect_range(st, W, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // Apply the merge to the listed words (bpe_trainer.rs:379-401: left to right, so "aaa" -> "aa a"), a warp per word,
 // 32 symbols at a time, compacted in place; pairs that disappear are subtracted from the table, new ones added.
-__global__ void __launch_bounds__(128) k_apply(TrainState* st, Words W, PairTable pt) {
+__device__ __forceinline__ void apply_range(TrainState* st, const Words& W, const PairTable& pt, uint32_t warp, uint32_t n_warps) {
     const uint32_t l = st->cur_l;
-    if (l == INVALID || st->done || st->pause) return;
+    if (l == INVALID) return;
     const uint32_t r = st->cur_r, m = st->cur_m, n_dirty = st->n_dirty, lane = threadIdx.x & 31;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; d < n_dirty; d += n_warps) {
+    for (uint32_t d = warp; d < n_dirty; d += n_warps) {
         const uint32_t w = W.dirty_list[d], len = W.wlen[w], f = W.wfreq[w];
         uint32_t* s = W.sym + W.woff[w];
         uint32_t out_base = 0, carry = 0, new_last = INVALID, new_last_m = 0, old_last = INVALID, old_last_inv = 0;
@@ -349,6 +356,11 @@ __global__ void __launch_bounds__(128) k_apply(TrainState* st, Words W, PairTabl
     }
 }
 
+__global__ void __launch_bounds__(128) k_apply(TrainState* st, Words W, PairTable pt) {
+    if (st->done || st->pause) return;
+    apply_range(st, W, pt, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5);
+}
+
 struct SymTab {                          // device copy of what the host knows about every symbol
     uint64_t *h1, *h2, *pw1, *pw2;       // polynomial hashes of the symbol's string and p^length
     uint8_t* in_vocab;
@@ -359,8 +371,7 @@ struct Best { uint32_t count; uint64_t key; };
 __device__ __forceinline__ bool better(const Best& a, const Best& b) { return a.count > b.count || (a.count == b.count && a.key < b.key); }
 
 // Best pair of the table (bpe_trainer.rs:152-155 with the tie rule of oracle/py_trainer.py); the last CTA decides.
-__global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt, Best* block_best, SymTab sy, uint4* log) {
-    if (st->done || st->pause) return;
+__device__ __forceinline__ void best_phase(TrainState* st, const PairTable& pt, Best* block_best, const SymTab& sy, uint4* log) {
     Best best{0u, EMPTY64};
     const uint32_t cap = pt.mask + 1;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
@@ -369,8 +380,9 @@ __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt,
         Best b{c, pt.key[i]};
         if (better(b, best)) best = b;
     }
-    __shared__ Best sb[8];
+    __shared__ Best sb[32];
     __shared__ bool s_last;
+    const int n_warps = blockDim.x >> 5;
     for (int d = 16; d > 0; d >>= 1) {
         Best o{__shfl_down_sync(0xFFFFFFFFu, best.count, d), __shfl_down_sync(0xFFFFFFFFu, best.key, d)};
         if (better(o, best)) best = o;
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt,
     if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; ++k) if (better(sb[k], best)) best = sb[k];
+        for (int k = 1; k < n_warps; ++k) if (better(sb[k], best)) best = sb[k];
         block_best[blockIdx.x] = best;
         __threadfence();
         s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt,
     if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
     __syncthreads();
     if (threadIdx.x != 0) return;
-    for (int k = 1; k < 8; ++k) if (better(sb[k], best)) best = sb[k];
+    for (int k = 1; k < n_warps; ++k) if (better(sb[k], best)) best = sb[k];
     st->ticket = 0;
     st->cur_l = INVALID;
     st->n_dirty = 0;
@@ -429,6 +441,29 @@ __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt,
     st->cur_l = l; st->cur_r = r; st->cur_m = id;
     st->iter++;
     if (st->vocab_len >= st->vocab_size) { st->done = 1; st->reason = 3; }                    // :141
+}
+
+__global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt, Best* block_best, SymTab sy, uint4* log) {
+    if (st->done || st->pause) return;
+    best_phase(st, pt, block_best, sy, log);
+}
+
+// The same three phases for up to `iters` merges in ONE cooperative launch (a CTA per SM, grid-wide barriers instead
+// of kernel boundaries): the loop is a chain of short dependent steps over L2-resident state, so launch gaps matter.
+__global__ void __launch_bounds__(1024, 1) k_train_loop(TrainState* st, Words W, PairTable pt, Best* block_best, SymTab sy, uint4* log, int iters) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; ++it) {
+        if (*(volatile uint32_t*)&st->cur_l != INVALID) {               // uniform: written before the last barrier
+            detect_range(st, W, tid, n_threads);
+            grid.sync();
+            apply_range(st, W, pt, tid >> 5, n_threads >> 5);
+            grid.sync();
+        }
+        best_phase(st, pt, block_best, sy, log);
+        grid.sync();
+        if (*(volatile uint32_t*)&st->done || *(volatile uint32_t*)&st->pause) break;
+    }
 }
 
 
@@ -473,7 +508,7 @@ struct Trained {
     std::vector<uint8_t> sym_bytes; std::vector<uint64_t> sym_off;
     double ms_words = 0, ms_merges = 0, ms_host = 0;
     uint64_t n_words = 0, n_unique = 0, n_bytes = 0, n_symbols0 = 0, kernels = 0;
-    uint32_t stop_reason = 0, rebuilds = 0;
+    uint32_t stop_reason = 0, rebuilds = 0; int cooperative = 0;
 };
 
 struct PhaseTrace {                       // CTK_TRAIN_TRACE=1: host-timed phases (each ends with the stream idle) on stderr
@@ -771,14 +806,30 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         };
         struct TableGuard { void** a; void** b; ~TableGuard() { if (*a) cudaFree(*a); if (*b) cudaFree(*b); } } tg{&old_key, &old_val};
         { int rc = rebuild(); if (rc != CTK_OK) return rc; }
+        // One cooperative launch per batch of merges (a CTA per SM); CTK_TRAIN_STEPWISE=1 or a device without
+        // cooperative launch: three kernels per merge.
+        int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        int loop_threads = 1024, per_sm = 0;
+        if (coop) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_train_loop, loop_threads, 0) != cudaSuccess || per_sm < 1) coop = 0;
+        }
+        if (getenv("CTK_TRAIN_STEPWISE")) coop = 0;
+        out.cooperative = coop;
         for (;;) {
             const unsigned g_best = std::max(1u, std::min(1024u, pcap / 256u));
-            for (int it = 0; it < BATCH; ++it) {
-                k_detect<<<g_slots, 256, 0, st>>>(d_st, W);
-                k_apply<<<g_apply, 128, 0, st>>>(d_st, W, pt);
-                k_best_pair<<<g_best, 256, 0, st>>>(d_st, pt, d_bb, sy, d_log);
+            if (coop) {
+                int iters = BATCH;
+                void* args[] = {&d_st, &W, &pt, &d_bb, &sy, &d_log, &iters};
+                TCK(cudaLaunchCooperativeKernel((void*)k_train_loop, dim3(sms), dim3(loop_threads), args, 0, st));
+                launches += 1;
+            } else {
+                for (int it = 0; it < BATCH; ++it) {
+                    k_detect<<<g_slots, 256, 0, st>>>(d_st, W);
+                    k_apply<<<g_apply, 128, 0, st>>>(d_st, W, pt);
+                    k_best_pair<<<g_best, 256, 0, st>>>(d_st, pt, d_bb, sy, d_log);
+                }
+                launches += 3 * BATCH;
             }
-            launches += 3 * BATCH;
             TCK(cudaMemcpyAsync(&back, d_st, sizeof back, cudaMemcpyDeviceToHost, st));
             TCK(cudaMemcpyAsync(log.data(), d_log, BATCH * sizeof(uint4), cudaMemcpyDeviceToHost, st));
             TCK(cudaMemsetAsync(&d_st->n_log, 0, 4, st));
@@ -852,7 +903,7 @@ size_t ctk_trained_merges(const ctk_trained* t, const uint32_t** pairs) {
 
 void ctk_trained_stats(const ctk_trained* t, ctk_train_stats* s) {
     s->n_bytes = t->t.n_bytes; s->n_words = t->t.n_words; s->n_unique_words = t->t.n_unique; s->n_symbols = t->t.n_symbols0;
-    s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason; s->table_rebuilds = t->t.rebuilds;
+    s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason; s->table_rebuilds = t->t.rebuilds; s->cooperative = (uint32_t)t->t.cooperative;
     s->ms_words = t->t.ms_words; s->ms_merges = t->t.ms_merges;
 }
 
