@@ -24,7 +24,6 @@
 //                     64-bit polynomial hashes per symbol (hash(ab) = hash(a) * p^len(b) + hash(b)) and a symbol
 //                     map; the host replays every merge on real strings afterwards and fails the call if a
 //                     single decision differs, so the result is exact, not probabilistic.
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -42,8 +41,6 @@
 
 #include "../../include/ctk.h"
 #include "engine.hpp"
-
-namespace cg = cooperative_groups;
 
 namespace ctk {
 namespace {
@@ -270,7 +267,7 @@ __global__ void __launch_bounds__(256) k_count_all(TrainState* st, Words W, Pair
     pair_add(pt, st, W.sym[i], W.sym[i + 1], W.wfreq[w]);
 }
 
-// Which words contain the pair (cur_l, cur_r)?  One thread per symbol slot (grid-stride in the persistent kernel).
+// Which words contain the pair (cur_l, cur_r)?  One thread per symbol slot .
 __device__ __forceinline__ void detect_range(TrainState* st, const Words& W, uint32_t tid, uint32_t n_threads) {
     const uint32_t l = st->cur_l;
     if (l == INVALID) return;
@@ -448,25 +445,6 @@ __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt,
     best_phase(st, pt, block_best, sy, log);
 }
 
-// The same three phases for up to `iters` merges in ONE cooperative launch (a CTA per SM, grid-wide barriers instead
-// of kernel boundaries): the loop is a chain of short dependent steps over L2-resident state, so launch gaps matter.
-__global__ void __launch_bounds__(1024, 1) k_train_loop(TrainState* st, Words W, PairTable pt, Best* block_best, SymTab sy, uint4* log, int iters) {
-    cg::grid_group grid = cg::this_grid();
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
-    for (int it = 0; it < iters; ++it) {
-        if (*(volatile uint32_t*)&st->cur_l != INVALID) {               // uniform: written before the last barrier
-            detect_range(st, W, tid, n_threads);
-            grid.sync();
-            apply_range(st, W, pt, tid >> 5, n_threads >> 5);
-            grid.sync();
-        }
-        best_phase(st, pt, block_best, sy, log);
-        grid.sync();
-        if (*(volatile uint32_t*)&st->done || *(volatile uint32_t*)&st->pause) break;
-    }
-}
-
-
 // ------------------------------------------------------------------------------------------------ host side
 struct DevBuf {
     std::vector<void*> all;
@@ -508,7 +486,7 @@ struct Trained {
     std::vector<uint8_t> sym_bytes; std::vector<uint64_t> sym_off;
     double ms_words = 0, ms_merges = 0, ms_host = 0;
     uint64_t n_words = 0, n_unique = 0, n_bytes = 0, n_symbols0 = 0, kernels = 0;
-    uint32_t stop_reason = 0, rebuilds = 0; int cooperative = 0;
+    uint32_t stop_reason = 0, rebuilds = 0;
 };
 
 struct PhaseTrace {                       // CTK_TRAIN_TRACE=1: host-timed phases (each ends with the stream idle) on stderr
@@ -806,30 +784,14 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         };
         struct TableGuard { void** a; void** b; ~TableGuard() { if (*a) cudaFree(*a); if (*b) cudaFree(*b); } } tg{&old_key, &old_val};
         { int rc = rebuild(); if (rc != CTK_OK) return rc; }
-        // One cooperative launch per batch of merges (a CTA per SM); CTK_TRAIN_STEPWISE=1 or a device without
-        // cooperative launch: three kernels per merge.
-        int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        int loop_threads = 1024, per_sm = 0;
-        if (coop) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_train_loop, loop_threads, 0) != cudaSuccess || per_sm < 1) coop = 0;
-        }
-        if (getenv("CTK_TRAIN_STEPWISE")) coop = 0;
-        out.cooperative = coop;
         for (;;) {
             const unsigned g_best = std::max(1u, std::min(1024u, pcap / 256u));
-            if (coop) {
-                int iters = BATCH;
-                void* args[] = {&d_st, &W, &pt, &d_bb, &sy, &d_log, &iters};
-                TCK(cudaLaunchCooperativeKernel((void*)k_train_loop, dim3(sms), dim3(loop_threads), args, 0, st));
-                launches += 1;
-            } else {
-                for (int it = 0; it < BATCH; ++it) {
-                    k_detect<<<g_slots, 256, 0, st>>>(d_st, W);
-                    k_apply<<<g_apply, 128, 0, st>>>(d_st, W, pt);
-                    k_best_pair<<<g_best, 256, 0, st>>>(d_st, pt, d_bb, sy, d_log);
-                }
-                launches += 3 * BATCH;
+            for (int it = 0; it < BATCH; ++it) {
+                k_detect<<<g_slots, 256, 0, st>>>(d_st, W);
+                k_apply<<<g_apply, 128, 0, st>>>(d_st, W, pt);
+                k_best_pair<<<g_best, 256, 0, st>>>(d_st, pt, d_bb, sy, d_log);
             }
+            launches += 3 * BATCH;
             TCK(cudaMemcpyAsync(&back, d_st, sizeof back, cudaMemcpyDeviceToHost, st));
             TCK(cudaMemcpyAsync(log.data(), d_log, BATCH * sizeof(uint4), cudaMemcpyDeviceToHost, st));
             TCK(cudaMemsetAsync(&d_st->n_log, 0, 4, st));
@@ -903,7 +865,7 @@ size_t ctk_trained_merges(const ctk_trained* t, const uint32_t** pairs) {
 
 void ctk_trained_stats(const ctk_trained* t, ctk_train_stats* s) {
     s->n_bytes = t->t.n_bytes; s->n_words = t->t.n_words; s->n_unique_words = t->t.n_unique; s->n_symbols = t->t.n_symbols0;
-    s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason; s->table_rebuilds = t->t.rebuilds; s->cooperative = (uint32_t)t->t.cooperative;
+    s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason; s->table_rebuilds = t->t.rebuilds;
     s->ms_words = t->t.ms_words; s->ms_merges = t->t.ms_merges;
 }
 

@@ -275,3 +275,15 @@ def test_staging_worker_pool(built_lib):
     for t in ts:
         t.join()
     assert not errs, errs[:2]
+
+
+def test_trainer_has_no_cpu_fallback(built_lib):
+    """ctk_train_bpe fails loudly without a device (same rule as the encode path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a device is present')
+    import complexity_tokenizer as ct
+    with pytest.raises(RuntimeError, match='no CUDA device'):
+        ct.BpeTrainer(vocab_size=100, min_frequency=1).train(['hello world'])
+    assert ct.BpeTrainer(vocab_size=123, min_frequency=5).vocab_size == 123      # getters of src/bindings/trainers.rs:271-279
+    assert ct.BpeTrainer(vocab_size=123, min_frequency=5).min_frequency == 5
