@@ -127,10 +127,10 @@ __device__ __forceinline__ uint64_t word_end(const uint8_t* t, const uint32_t* b
 
 struct WordTable { uint64_t* key; uint32_t* count; uint32_t* rep; uint32_t mask; };
 
-// A CTA takes 512 consecutive words: each thread walks and hashes one, equal hashes are merged in a shared-memory
+// A CTA takes 256 consecutive words: each thread walks and hashes one, equal hashes are merged in a shared-memory
 // table first (the most frequent word of a text is ~5 % of all words: without this every one of its occurrences is an
 // atomic on the same global address), then one thread per distinct hash updates the global table.
-constexpr int WI_THREADS = 512, WI_SLOTS = 1024;
+constexpr int WI_THREADS = 256, WI_SLOTS = 512;
 struct WordFlags { uint32_t collision, overflow, fill; };
 
 __global__ void __launch_bounds__(WI_THREADS) k_word_insert(const uint8_t* t, const uint32_t* brk, uint64_t n, const uint32_t* starts,
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(WI_THREADS) k_word_insert(const uint8_t* t, co
         h = mix64(h ^ ((j - s) * P2));
         if (h == EMPTY64) h = 0;
         uint32_t slot = (uint32_t)(h >> 40) & (WI_SLOTS - 1);
-        for (;;) {                                                       // 512 words, 1024 slots: always ends
+        for (;;) {                                                       // 256 words, 512 slots: always ends
             unsigned long long k = s_key[slot];
             if (k == EMPTY64) k = atomicCAS(&s_key[slot], EMPTY64, h), k = (k == EMPTY64) ? h : k;
             if (k == h) break;
@@ -234,19 +234,20 @@ struct TrainState {
     uint32_t iter, n_dirty;              // merge number; words that contain the current pair
 };
 
-struct PairTable { uint64_t* key; uint32_t* val; uint32_t mask; };
+struct __align__(16) TrainPair { unsigned long long key; uint32_t val, pad; };   // one 16-byte access reads key and count
+struct PairTable { TrainPair* e; uint32_t mask; };
 
 // count[(a, b)] += f (mod 2^32, like the reference's u32 sums; f may be "negative")
 __device__ __forceinline__ void pair_add(const PairTable& pt, TrainState* st, uint32_t a, uint32_t b, uint32_t f) {
     uint64_t key = ((uint64_t)a << 32) | b;
     uint32_t slot = (uint32_t)(mix64(key) >> 24) & pt.mask;
     for (uint32_t probes = 0; probes <= pt.mask; ++probes) {
-        uint64_t k = pt.key[slot];
+        uint64_t k = pt.e[slot].key;
         if (k == EMPTY64) {
-            k = atomicCAS((unsigned long long*)&pt.key[slot], EMPTY64, key);
+            k = atomicCAS(&pt.e[slot].key, EMPTY64, key);
             if (k == EMPTY64) { atomicAdd(&st->fill, 1u); k = key; }
         }
-        if (k == key) { atomicAdd(&pt.val[slot], f); return; }
+        if (k == key) { atomicAdd(&pt.e[slot].val, f); return; }
         slot = (slot + 1) & pt.mask;
     }
     st->overflow = 1;
@@ -254,11 +255,16 @@ __device__ __forceinline__ void pair_add(const PairTable& pt, TrainState* st, ui
 
 struct Words {                           // every word keeps its slot range [woff, woff + initial length); wlen shrinks
     uint32_t* sym; const uint32_t* slot_word; const uint32_t* woff; uint32_t* wlen; const uint32_t* wfreq;
-    uint32_t* dirty_stamp; uint32_t* dirty_list; uint32_t n_slots, n_words;
+    uint32_t* dirty_stamp; uint4* dirty_list; uint32_t n_slots, n_words;   // list entry: word, first slot, length, count
 };
 
 // The reference's full recount (bpe_trainer.rs:341-376), one thread per symbol slot.  Runs before the first merge and
 // whenever the pair table is rebuilt; between merges the counts are kept up to date by k_apply (same sums).
+__global__ void k_table_clear(PairTable pt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= pt.mask) *reinterpret_cast<uint4*>(pt.e + i) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+}
+
 __global__ void __launch_bounds__(256) k_count_all(TrainState* st, Words W, PairTable pt) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= W.n_slots) return;
@@ -269,14 +275,13 @@ __global__ void __launch_bounds__(256) k_count_all(TrainState* st, Words W, Pair
 
 // Which words contain the pair (cur_l, cur_r)?  One thread per symbol slot .
 __device__ __forceinline__ void detect_range(TrainState* st, const Words& W, uint32_t tid, uint32_t n_threads) {
-    const uint32_t l = st->cur_l;
-    if (l == INVALID) return;
-    const uint32_t r = st->cur_r, stamp = st->iter + 1;
     for (uint32_t i = tid; i < W.n_slots; i += n_threads) {
-        if (W.sym[i] != l) continue;
-        uint32_t w = W.slot_word[i], k = i - W.woff[w];
-        if (k + 1 >= W.wlen[w] || W.sym[i + 1] != r) continue;
-        if (atomicExch(&W.dirty_stamp[w], stamp) != stamp) W.dirty_list[atomicAdd(&st->n_dirty, 1u)] = w;
+        const uint32_t v = W.sym[i], nx = W.sym[i + 1], w = W.slot_word[i];     // independent loads first: the step is latency-bound
+        const uint32_t l = st->cur_l, r = st->cur_r, stamp = st->iter + 1;
+        if (l == INVALID || v != l || nx != r) continue;
+        const uint32_t o = W.woff[w], len = W.wlen[w], f = W.wfreq[w];
+        if (i - o + 1 >= len) continue;
+        if (atomicExch(&W.dirty_stamp[w], stamp) != stamp) W.dirty_list[atomicAdd(&st->n_dirty, 1u)] = make_uint4(w, o, len, f);
     }
 }
 
@@ -288,12 +293,14 @@ __global__ void __launch_bounds__(256) k_detect(TrainState* st, Words W) {
 // Apply the merge to the listed words (bpe_trainer.rs:379-401: left to right, so "aaa" -> "aa a"), a warp per word,
 // 32 symbols at a time, compacted in place; pairs that disappear are subtracted from the table, new ones added.
 __device__ __forceinline__ void apply_range(TrainState* st, const Words& W, const PairTable& pt, uint32_t warp, uint32_t n_warps) {
+    const uint4 first = W.dirty_list[warp < W.n_words ? warp : 0];      // issued together with the state loads
     const uint32_t l = st->cur_l;
     if (l == INVALID) return;
     const uint32_t r = st->cur_r, m = st->cur_m, n_dirty = st->n_dirty, lane = threadIdx.x & 31;
     for (uint32_t d = warp; d < n_dirty; d += n_warps) {
-        const uint32_t w = W.dirty_list[d], len = W.wlen[w], f = W.wfreq[w];
-        uint32_t* s = W.sym + W.woff[w];
+        const uint4 ent = d == warp ? first : W.dirty_list[d];
+        const uint32_t w = ent.x, len = ent.z, f = ent.w;
+        uint32_t* s = W.sym + ent.y;
         uint32_t out_base = 0, carry = 0, new_last = INVALID, new_last_m = 0, old_last = INVALID, old_last_inv = 0;
         for (uint32_t c = 0; c < len; c += 32) {
             const uint32_t i = c + lane;
@@ -372,9 +379,9 @@ __device__ __forceinline__ void best_phase(TrainState* st, const PairTable& pt, 
     Best best{0u, EMPTY64};
     const uint32_t cap = pt.mask + 1;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const uint32_t c = pt.val[i];
-        if (c == 0) continue;                                          // empty slot, or a pair that no longer occurs
-        Best b{c, pt.key[i]};
+        const uint4 e = *reinterpret_cast<const uint4*>(pt.e + i);
+        if (e.z == 0) continue;                                        // empty slot, or a pair that no longer occurs
+        Best b{e.z, ((uint64_t)e.y << 32) | e.x};
         if (better(b, best)) best = b;
     }
     __shared__ Best sb[32];
@@ -716,7 +723,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         TrainState hs{}; hs.n_symbols = n_sym0; hs.sym_cap = sym_cap; hs.vocab_len = (uint32_t)vocab_len;
         hs.vocab_size = (uint32_t)std::min<uint64_t>(vocab_size, 0xFFFFFFFFull); hs.min_freq = cfg.min_frequency;
         hs.cur_l = hs.cur_r = hs.cur_m = INVALID;
-        TrainState* d_st; Best* d_bb; uint4* d_log; uint32_t *d_sym, *d_slot_word, *d_woff, *d_wlen, *d_wfreq, *d_stamp, *d_list;
+        TrainState* d_st; Best* d_bb; uint4* d_log; uint32_t *d_sym, *d_slot_word, *d_woff, *d_wlen, *d_wfreq, *d_stamp; uint4* d_list;
         PairTable pt{}; SymTab sy;
         const uint32_t n_slots = (uint32_t)seq.size(), nw = (uint32_t)ws.size();
         const uint32_t pcap_max = pow2_at_least(4ull * n_slots + 1024);
@@ -770,19 +777,18 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         const unsigned g_apply = (unsigned)std::min<uint64_t>((nw + 3) / 4, (uint64_t)sms * 8);
         std::vector<uint4> log(BATCH);
         TrainState back{};
-        void *old_key = nullptr, *old_val = nullptr;
+        void* tab_mem = nullptr;
         // (re)build the pair table from the words: a full recount into a fresh table of `pcap` slots
         auto rebuild = [&]() -> int {
-            if (old_key) { cudaFree(old_key); cudaFree(old_val); }
-            TCK(cudaMalloc(&old_key, pcap * 8ull)); TCK(cudaMalloc(&old_val, pcap * 4ull));
-            pt.key = (uint64_t*)old_key; pt.val = (uint32_t*)old_val; pt.mask = pcap - 1;
-            TCK(cudaMemsetAsync(pt.key, 0xFF, pcap * 8ull, st));
-            TCK(cudaMemsetAsync(pt.val, 0, pcap * 4ull, st));
+            if (tab_mem) { cudaFree(tab_mem); tab_mem = nullptr; }
+            TCK(cudaMalloc(&tab_mem, pcap * sizeof(TrainPair)));
+            pt.e = (TrainPair*)tab_mem; pt.mask = pcap - 1;
+            k_table_clear<<<(pcap + 255) / 256, 256, 0, st>>>(pt); ++launches;
             TCK(cudaMemsetAsync(&d_st->pause, 0, 12, st));               // pause, overflow, fill
             k_count_all<<<g_slots, 256, 0, st>>>(d_st, W, pt); ++launches;
             return CTK_OK;
         };
-        struct TableGuard { void** a; void** b; ~TableGuard() { if (*a) cudaFree(*a); if (*b) cudaFree(*b); } } tg{&old_key, &old_val};
+        struct TableGuard { void** a; ~TableGuard() { if (*a) cudaFree(*a); } } tg{&tab_mem};
         { int rc = rebuild(); if (rc != CTK_OK) return rc; }
         for (;;) {
             const unsigned g_best = std::max(1u, std::min(1024u, pcap / 256u));
