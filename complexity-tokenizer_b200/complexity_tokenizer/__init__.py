@@ -57,7 +57,7 @@ class _TrainerConfig(ctypes.Structure):        # include/ctk.h: ctk_bpe_trainer_
 class _TrainStats(ctypes.Structure):           # include/ctk.h: ctk_train_stats
     _fields_ = [('n_bytes', ctypes.c_uint64), ('n_words', ctypes.c_uint64), ('n_unique_words', ctypes.c_uint64),
                 ('n_symbols', ctypes.c_uint64), ('n_merges', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint64),
-                ('table_rebuilds', ctypes.c_uint32), ('stop_reason', ctypes.c_uint32), ('ms_words', ctypes.c_double), ('ms_merges', ctypes.c_double)]
+                ('table_rebuilds', ctypes.c_uint32), ('cluster_size', ctypes.c_uint32), ('stop_reason', ctypes.c_uint32), ('ms_words', ctypes.c_double), ('ms_merges', ctypes.c_double)]
 
 
 class UnsupportedTokenizerError(IOError):

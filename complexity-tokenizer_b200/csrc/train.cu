@@ -24,6 +24,7 @@
 //                     64-bit polynomial hashes per symbol (hash(ab) = hash(a) * p^len(b) + hash(b)) and a symbol
 //                     map; the host replays every merge on real strings afterwards and fails the call if a
 //                     single decision differs, so the result is exact, not probabilistic.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -41,6 +42,8 @@
 
 #include "../../include/ctk.h"
 #include "engine.hpp"
+
+namespace cg = cooperative_groups;
 
 namespace ctk {
 namespace {
@@ -232,6 +235,7 @@ struct TrainState {
     uint32_t cur_l, cur_r, cur_m;        // the merge k_detect / k_apply carry out
     uint32_t n_log, ticket;
     uint32_t iter, n_dirty;              // merge number; words that contain the current pair
+    unsigned long long t_phase[4];       // cluster kernel: nanoseconds in detect / apply / best pair / barriers (CTA 0's view)
 };
 
 struct __align__(16) TrainPair { unsigned long long key; uint32_t val, pad; };   // one 16-byte access reads key and count
@@ -274,14 +278,25 @@ __global__ void __launch_bounds__(256) k_count_all(TrainState* st, Words W, Pair
 }
 
 // Which words contain the pair (cur_l, cur_r)?  One thread per symbol slot .
+__device__ __forceinline__ void detect_hit(TrainState* st, const Words& W, uint32_t i, uint32_t w, uint32_t stamp) {
+    const uint32_t o = W.woff[w], len = __ldcg(W.wlen + w), f = W.wfreq[w];
+    if (i - o + 1 >= len) return;                                               // a dead slot, or the word's last symbol
+    if (atomicExch(&W.dirty_stamp[w], stamp) != stamp) W.dirty_list[atomicAdd(&st->n_dirty, 1u)] = make_uint4(w, o, len, f);
+}
+
+// four slots per thread, all loads issued before the first compare (the step is latency-bound, not bandwidth-bound)
 __device__ __forceinline__ void detect_range(TrainState* st, const Words& W, uint32_t tid, uint32_t n_threads) {
-    for (uint32_t i = tid; i < W.n_slots; i += n_threads) {
-        const uint32_t v = W.sym[i], nx = W.sym[i + 1], w = W.slot_word[i];     // independent loads first: the step is latency-bound
-        const uint32_t l = st->cur_l, r = st->cur_r, stamp = st->iter + 1;
-        if (l == INVALID || v != l || nx != r) continue;
-        const uint32_t o = W.woff[w], len = W.wlen[w], f = W.wfreq[w];
-        if (i - o + 1 >= len) continue;
-        if (atomicExch(&W.dirty_stamp[w], stamp) != stamp) W.dirty_list[atomicAdd(&st->n_dirty, 1u)] = make_uint4(w, o, len, f);
+    for (uint32_t b = tid * 4; b < W.n_slots; b += n_threads * 4) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(W.sym + b));      // .cg: another CTA of the cluster may have rewritten the word
+        const uint32_t v4 = __ldcg(W.sym + b + 4);
+        const uint4 ws = *reinterpret_cast<const uint4*>(W.slot_word + b);
+        const volatile TrainState* vs = st;
+        const uint32_t l = vs->cur_l, r = vs->cur_r, stamp = vs->iter + 1;
+        if (l == INVALID) return;
+        if (v.x == l && v.y == r) detect_hit(st, W, b, ws.x, stamp);
+        if (v.y == l && v.z == r && b + 1 < W.n_slots) detect_hit(st, W, b + 1, ws.y, stamp);
+        if (v.z == l && v.w == r && b + 2 < W.n_slots) detect_hit(st, W, b + 2, ws.z, stamp);
+        if (v.w == l && v4 == r && b + 3 < W.n_slots) detect_hit(st, W, b + 3, ws.w, stamp);
     }
 }
 
@@ -293,20 +308,21 @@ __global__ void __launch_bounds__(256) k_detect(TrainState* st, Words W) {
 // Apply the merge to the listed words (bpe_trainer.rs:379-401: left to right, so "aaa" -> "aa a"), a warp per word,
 // 32 symbols at a time, compacted in place; pairs that disappear are subtracted from the table, new ones added.
 __device__ __forceinline__ void apply_range(TrainState* st, const Words& W, const PairTable& pt, uint32_t warp, uint32_t n_warps) {
-    const uint4 first = W.dirty_list[warp < W.n_words ? warp : 0];      // issued together with the state loads
-    const uint32_t l = st->cur_l;
+    const uint4 first = __ldcg(W.dirty_list + (warp < W.n_words ? warp : 0));   // issued together with the state loads
+    const volatile TrainState* vs = st;
+    const uint32_t l = vs->cur_l;
     if (l == INVALID) return;
-    const uint32_t r = st->cur_r, m = st->cur_m, n_dirty = st->n_dirty, lane = threadIdx.x & 31;
+    const uint32_t r = vs->cur_r, m = vs->cur_m, n_dirty = vs->n_dirty, lane = threadIdx.x & 31;
     for (uint32_t d = warp; d < n_dirty; d += n_warps) {
-        const uint4 ent = d == warp ? first : W.dirty_list[d];
+        const uint4 ent = d == warp ? first : __ldcg(W.dirty_list + d);
         const uint32_t w = ent.x, len = ent.z, f = ent.w;
         uint32_t* s = W.sym + ent.y;
         uint32_t out_base = 0, carry = 0, new_last = INVALID, new_last_m = 0, old_last = INVALID, old_last_inv = 0;
         for (uint32_t c = 0; c < len; c += 32) {
             const uint32_t i = c + lane;
             const bool valid = i < len;
-            const uint32_t o = valid ? s[i] : INVALID;
-            const uint32_t ahead = (c + 32 < len) ? s[c + 32] : INVALID;
+            const uint32_t o = valid ? __ldcg(s + i) : INVALID;
+            const uint32_t ahead = (c + 32 < len) ? __ldcg(s + c + 32) : INVALID;
             uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, o, 1);
             if (lane == 31) nx = ahead;
             const uint32_t M = __ballot_sync(0xFFFFFFFFu, valid && o == l && nx == r && nx != INVALID);
@@ -378,8 +394,9 @@ __device__ __forceinline__ bool better(const Best& a, const Best& b) { return a.
 __device__ __forceinline__ void best_phase(TrainState* st, const PairTable& pt, Best* block_best, const SymTab& sy, uint4* log) {
     Best best{0u, EMPTY64};
     const uint32_t cap = pt.mask + 1;
+#pragma unroll 4
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const uint4 e = *reinterpret_cast<const uint4*>(pt.e + i);
+        const uint4 e = __ldcg(reinterpret_cast<const uint4*>(pt.e + i));
         if (e.z == 0) continue;                                        // empty slot, or a pair that no longer occurs
         Best b{e.z, ((uint64_t)e.y << 32) | e.x};
         if (better(b, best)) best = b;
@@ -420,36 +437,62 @@ __device__ __forceinline__ void best_phase(TrainState* st, const PairTable& pt, 
     st->ticket = 0;
     st->cur_l = INVALID;
     st->n_dirty = 0;
-    if (st->overflow || st->fill > (cap >> 1) + (cap >> 3)) { st->pause = 1; return; }        // host rebuilds, then this step repeats
+    const volatile TrainState* vs = st;
+    if (vs->overflow || vs->fill > (cap >> 1) + (cap >> 3)) { st->pause = 1; return; }        // host rebuilds, then this step repeats
     if (best.count == 0) { st->done = 1; st->reason = 1; return; }                            // bpe_trainer.rs:147-149
-    if (best.count < st->min_freq) { st->done = 1; st->reason = 2; return; }                  // :162-165
+    if (best.count < vs->min_freq) { st->done = 1; st->reason = 2; return; }                  // :162-165
     uint32_t l = (uint32_t)(best.key >> 32), r = (uint32_t)best.key;
-    uint64_t h1 = sy.h1[l] * sy.pw1[r] + sy.h1[r], h2 = sy.h2[l] * sy.pw2[r] + sy.h2[r];
+    uint64_t h1 = __ldcg(sy.h1 + l) * __ldcg(sy.pw1 + r) + __ldcg(sy.h1 + r), h2 = __ldcg(sy.h2 + l) * __ldcg(sy.pw2 + r) + __ldcg(sy.h2 + r);
     uint64_t mk = h1 == EMPTY64 ? 0 : h1;
     uint32_t slot = (uint32_t)(mix64(mk) >> 24) & sy.map_mask, id = INVALID;
     for (;;) {
-        uint64_t k = sy.map_key[slot];
+        uint64_t k = __ldcg(sy.map_key + slot);
         if (k == EMPTY64) break;
-        if (k == mk && sy.map_h2[slot] == h2) { id = sy.map_id[slot]; break; }
+        if (k == mk && __ldcg(sy.map_h2 + slot) == h2) { id = __ldcg(sy.map_id + slot); break; }
         slot = (slot + 1) & sy.map_mask;
     }
     if (id == INVALID) {                                                                      // a new string
-        if (st->n_symbols >= st->sym_cap) { st->done = 1; st->reason = 4; return; }
-        id = st->n_symbols++;
+        if (vs->n_symbols >= vs->sym_cap) { st->done = 1; st->reason = 4; return; }
+        id = vs->n_symbols; st->n_symbols = id + 1;
         sy.map_key[slot] = mk; sy.map_h2[slot] = h2; sy.map_id[slot] = id;
-        sy.h1[id] = h1; sy.h2[id] = h2; sy.pw1[id] = sy.pw1[l] * sy.pw1[r]; sy.pw2[id] = sy.pw2[l] * sy.pw2[r];
+        sy.h1[id] = h1; sy.h2[id] = h2; sy.pw1[id] = __ldcg(sy.pw1 + l) * __ldcg(sy.pw1 + r); sy.pw2[id] = __ldcg(sy.pw2 + l) * __ldcg(sy.pw2 + r);
         sy.in_vocab[id] = 0;
     }
-    if (!sy.in_vocab[id]) { sy.in_vocab[id] = 1; st->vocab_len++; }                           // :168-169
-    log[st->n_log++] = make_uint4(l, r, id, best.count);
+    if (!__ldcg(sy.in_vocab + id)) { sy.in_vocab[id] = 1; st->vocab_len = vs->vocab_len + 1; }                           // :168-169
+    { const uint32_t nl = vs->n_log; log[nl] = make_uint4(l, r, id, best.count); st->n_log = nl + 1; }
     st->cur_l = l; st->cur_r = r; st->cur_m = id;
-    st->iter++;
-    if (st->vocab_len >= st->vocab_size) { st->done = 1; st->reason = 3; }                    // :141
+    st->iter = vs->iter + 1;
+    if (vs->vocab_len >= vs->vocab_size) { st->done = 1; st->reason = 3; }                    // :141
 }
 
 __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt, Best* block_best, SymTab sy, uint4* log) {
     if (st->done || st->pause) return;
     best_phase(st, pt, block_best, sy, log);
+}
+
+// The same three phases for up to `iters` merges inside ONE thread-block cluster: the hardware cluster barrier replaces
+// the kernel boundaries.  Everything one CTA writes and another reads afterwards is read with .cg / volatile loads
+// (L1 is per SM and not coherent); __threadfence() before each barrier orders the writes.
+__global__ void __launch_bounds__(1024, 1) k_train_cluster(TrainState* st, Words W, PairTable pt, Best* block_best, SymTab sy, uint4* log, int iters) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    const volatile TrainState* vs = st;
+    auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+    unsigned long long acc[4] = {0, 0, 0, 0}, t0 = now(), t1;
+    #define PHASE(k) t1 = now(); acc[k] += t1 - t0; t0 = t1;
+    for (int it = 0; it < iters; ++it) {
+        if (vs->cur_l != INVALID) {                                     // uniform: written before the last barrier
+            detect_range(st, W, tid, n_threads);
+            PHASE(0) __threadfence(); cluster.sync(); PHASE(3)
+            apply_range(st, W, pt, tid >> 5, n_threads >> 5);
+            PHASE(1) __threadfence(); cluster.sync(); PHASE(3)
+        }
+        best_phase(st, pt, block_best, sy, log);
+        PHASE(2) __threadfence(); cluster.sync(); PHASE(3)
+        if (vs->done || vs->pause) break;
+    }
+    #undef PHASE
+    if (tid == 0) for (int k = 0; k < 4; ++k) st->t_phase[k] += acc[k];
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -493,7 +536,7 @@ struct Trained {
     std::vector<uint8_t> sym_bytes; std::vector<uint64_t> sym_off;
     double ms_words = 0, ms_merges = 0, ms_host = 0;
     uint64_t n_words = 0, n_unique = 0, n_bytes = 0, n_symbols0 = 0, kernels = 0;
-    uint32_t stop_reason = 0, rebuilds = 0;
+    uint32_t stop_reason = 0, rebuilds = 0; int cluster = 0;
 };
 
 struct PhaseTrace {                       // CTK_TRAIN_TRACE=1: host-timed phases (each ends with the stream idle) on stderr
@@ -729,7 +772,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         const uint32_t pcap_max = pow2_at_least(4ull * n_slots + 1024);
         uint32_t pcap = std::min<uint32_t>(pcap_max, std::max<uint32_t>(1u << 16, pow2_at_least(n_pairs / 8)));
         const uint32_t mcap = pow2_at_least(2ull * sym_cap); sy.map_mask = mcap - 1;
-        TCK(db.get(&d_st, 1)); TCK(db.get(&d_sym, (size_t)n_slots + 1)); TCK(db.get(&d_slot_word, n_slots)); TCK(db.get(&d_woff, nw));
+        TCK(db.get(&d_st, 1)); TCK(db.get(&d_sym, (size_t)n_slots + 8)); TCK(db.get(&d_slot_word, (size_t)n_slots + 4)); TCK(db.get(&d_woff, nw));
         TCK(db.get(&d_wlen, nw)); TCK(db.get(&d_wfreq, nw)); TCK(db.get(&d_stamp, nw)); TCK(db.get(&d_list, nw));
         TCK(db.get(&d_bb, 2048)); TCK(db.get(&d_log, BATCH));
         TCK(db.get(&sy.h1, sym_cap)); TCK(db.get(&sy.h2, sym_cap)); TCK(db.get(&sy.pw1, sym_cap)); TCK(db.get(&sy.pw2, sym_cap));
@@ -772,9 +815,9 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         }
         Words W{d_sym, d_slot_word, d_woff, d_wlen, d_wfreq, d_stamp, d_list, n_slots, nw};
         TCK(cudaEventRecord(ev[2], st));
-        const unsigned g_slots = (n_slots + 255) / 256;
+        const unsigned g_slots = (n_slots + 255) / 256, g_detect = (n_slots / 4 + 256) / 256;
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        const unsigned g_apply = (unsigned)std::min<uint64_t>((nw + 3) / 4, (uint64_t)sms * 8);
+        const unsigned g_apply = (unsigned)std::min<uint64_t>((nw + 3) / 4, (uint64_t)sms * 2);
         std::vector<uint4> log(BATCH);
         TrainState back{};
         void* tab_mem = nullptr;
@@ -790,14 +833,41 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         };
         struct TableGuard { void** a; ~TableGuard() { if (*a) cudaFree(*a); } } tg{&tab_mem};
         { int rc = rebuild(); if (rc != CTK_OK) return rc; }
-        for (;;) {
-            const unsigned g_best = std::max(1u, std::min(1024u, pcap / 256u));
-            for (int it = 0; it < BATCH; ++it) {
-                k_detect<<<g_slots, 256, 0, st>>>(d_st, W);
-                k_apply<<<g_apply, 128, 0, st>>>(d_st, W, pt);
-                k_best_pair<<<g_best, 256, 0, st>>>(d_st, pt, d_bb, sy, d_log);
+        // Default: three kernels per merge.  CTK_TRAIN_CLUSTER=16 (or 8) runs a batch of merges inside ONE thread-block
+        // cluster instead (hardware cluster barrier between the phases, no kernel boundaries).  Measured on the config-1
+        // sample: 22-28 us per merge stepwise, 32-34 us in a cluster of 16 (each phase then has 16 SMs, not 148, for its
+        // ~9 MB of L2 traffic), 25.8 us as one cooperative grid, 41.7 us as a CUDA graph of the same 768 kernel nodes.
+        int cluster = getenv("CTK_TRAIN_CLUSTER") ? atoi(getenv("CTK_TRAIN_CLUSTER")) : 0;
+        if (cluster != 8 && cluster != 16) cluster = 0;
+        if (cluster) {
+            cudaFuncSetAttribute(k_train_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaLaunchConfig_t qc{}; cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = cluster; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.gridDim = dim3(cluster); qc.blockDim = dim3(1024); qc.attrs = qa; qc.numAttrs = 1;
+            int n_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&n_clusters, k_train_cluster, &qc) != cudaSuccess || n_clusters < 1) {
+                cluster = 8; qa[0].val.clusterDim.x = cluster; qc.gridDim = dim3(cluster);
+                if (cudaOccupancyMaxActiveClusters(&n_clusters, k_train_cluster, &qc) != cudaSuccess || n_clusters < 1) cluster = 0;
             }
-            launches += 3 * BATCH;
+            cudaGetLastError();
+        }
+        out.cluster = cluster;
+        for (;;) {
+            const unsigned g_best = std::max(1u, std::min((unsigned)sms * 2, pcap / 1024u));   // few CTAs: one ticket atomic and one candidate each
+            if (cluster) {
+                cudaLaunchConfig_t lc{}; cudaLaunchAttribute la[1];
+                la[0].id = cudaLaunchAttributeClusterDimension; la[0].val.clusterDim.x = cluster; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+                lc.gridDim = dim3(cluster); lc.blockDim = dim3(1024); lc.stream = st; lc.attrs = la; lc.numAttrs = 1;
+                TCK(cudaLaunchKernelEx(&lc, k_train_cluster, d_st, W, pt, d_bb, sy, d_log, (int)BATCH));
+                launches += 1;
+            } else {
+                for (int it = 0; it < BATCH; ++it) {
+                    k_detect<<<g_detect, 256, 0, st>>>(d_st, W);
+                    k_apply<<<g_apply, 128, 0, st>>>(d_st, W, pt);
+                    k_best_pair<<<g_best, 256, 0, st>>>(d_st, pt, d_bb, sy, d_log);
+                }
+                launches += 3 * BATCH;
+            }
             TCK(cudaMemcpyAsync(&back, d_st, sizeof back, cudaMemcpyDeviceToHost, st));
             TCK(cudaMemcpyAsync(log.data(), d_log, BATCH * sizeof(uint4), cudaMemcpyDeviceToHost, st));
             TCK(cudaMemsetAsync(&d_st->n_log, 0, 4, st));
@@ -823,6 +893,9 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
                 int rc = rebuild(); if (rc != CTK_OK) return rc;
             }
         }
+        if (getenv("CTK_TRAIN_TRACE") && cluster)
+            fprintf(stderr, "[ctk train] cluster of %d, thread 0: detect %.1f ms, apply %.1f ms, best pair %.1f ms, barriers (incl. waiting for the slowest CTA) %.1f ms\n", cluster,
+                    back.t_phase[0] * 1e-6, back.t_phase[1] * 1e-6, back.t_phase[2] * 1e-6, back.t_phase[3] * 1e-6);
         if (back.reason == 4) { set_last_error("ctk_train_bpe: symbol table full"); return CTK_ERR_CUDA; }
         out.stop_reason = back.reason;
         TCK(cudaEventRecord(ev[3], st));
@@ -871,7 +944,7 @@ size_t ctk_trained_merges(const ctk_trained* t, const uint32_t** pairs) {
 
 void ctk_trained_stats(const ctk_trained* t, ctk_train_stats* s) {
     s->n_bytes = t->t.n_bytes; s->n_words = t->t.n_words; s->n_unique_words = t->t.n_unique; s->n_symbols = t->t.n_symbols0;
-    s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason; s->table_rebuilds = t->t.rebuilds;
+    s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason; s->table_rebuilds = t->t.rebuilds; s->cluster_size = (uint32_t)t->t.cluster;
     s->ms_words = t->t.ms_words; s->ms_merges = t->t.ms_merges;
 }
 

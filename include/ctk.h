@@ -168,6 +168,7 @@ typedef struct ctk_trained ctk_trained;        /* opaque: the (vocab, merges) pa
 typedef struct ctk_train_stats {
     uint64_t n_bytes, n_words, n_unique_words, n_symbols, n_merges, kernel_launches;
     uint32_t table_rebuilds;                   /* times the pair table grew (full recount each time) */
+    uint32_t cluster_size;                     /* CTAs of the cluster the merge loop ran in; 0 = three kernels per merge */
     uint32_t stop_reason;                      /* 0 none, 1 no pairs left (:147), 2 below min_frequency (:162), 3 vocabulary full (:141) */
     double ms_words, ms_merges;                /* device time of the word histogram / of the merge loop (CUDA events) */
 } ctk_train_stats;

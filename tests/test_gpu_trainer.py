@@ -134,3 +134,13 @@ def test_pair_table_growth(built_lib, n_words):
     texts = [" ".join(words[i:i + 50]) for i in range(0, n_words, 50)]
     _, stats = both(texts, vocab_size=4 + 400 + 25, min_frequency=1)
     assert stats['table_rebuilds'] >= 1
+
+
+@pytest.mark.parametrize('size', ['8', '16'])
+def test_cluster_merge_loop(built_lib, monkeypatch, size):
+    """The opt-in single-cluster merge loop (CTK_TRAIN_CLUSTER) takes the same decisions as the three-kernel loop."""
+    monkeypatch.setenv('CTK_TRAIN_CLUSTER', size)
+    texts = _english(7, 64 << 10)
+    _, stats = both(texts, vocab_size=500, min_frequency=2)
+    assert stats['cluster_size'] in (8, 16)
+    both(["a" * 1000, "ab" * 333 + "a", "<s> <s> x<s>y"], vocab_size=60, min_frequency=1, special_tokens=['<s>'])
