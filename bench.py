@@ -370,7 +370,22 @@ def main():
                  'vocab_size': len(tv), 'merges': len(tm), 'wall_s': wall_, 'device_ms_word_histogram': ts_['ms_words'],
                  'device_ms_merge_loop': ts_['ms_merges'], 'us_per_merge': 1e3 * ts_['ms_merges'] / max(1, len(tm)),
                  'words': ts_['n_words'], 'unique_words': ts_['n_unique_words'], 'symbols': ts_['n_symbols'],
+                 'device_ms_word_histogram_kernels': ts_.get('ms_words_kernels'),
                  'kernel_launches': ts_['kernel_launches'], 'table_rebuilds': ts_['table_rebuilds']}
+        if not args.no_cpu:             # CPU arm on a bounded sample: the restated reference trainer (Python, strings, one core)
+            import py_trainer
+            raw_ = h_np[:int(t_off[min(n_t, 120)])].tobytes()
+            docs_ = [raw_[int(t_off[i]):int(t_off[i + 1])].decode() for i in range(min(n_t, 120))]
+            t0 = time.perf_counter()
+            want_ = py_trainer.train_bpe(docs_, vocab_size=4 + 80 + 200, min_frequency=2)
+            cpu_s_ = time.perf_counter() - t0
+            trn2 = ct.BpeTrainer(vocab_size=4 + 80 + 200, min_frequency=2, show_progress=False, device=local)
+            t0 = time.perf_counter()
+            got_ = trn2.train(docs_)
+            gpu_s_ = time.perf_counter() - t0
+            train['cpu_baseline'] = {'kind': 'port', 'cores': 1, 'sample': '%d docs, %d merges (oracle/py_trainer.py)' % (len(docs_), len(want_[1])),
+                                     'seconds': cpu_s_, 'gpu_wall_seconds': gpu_s_, 'gpu_device_ms_merge_loop': trn2.last_stats['ms_merges'],
+                                     'equal': got_ == want_}
 
     # ---- roofline of the dominant kernel (CUDA events inside the library, same timed region)
     peak, peak_src = peaks()

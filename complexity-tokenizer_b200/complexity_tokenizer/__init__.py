@@ -57,7 +57,7 @@ class _TrainerConfig(ctypes.Structure):        # include/ctk.h: ctk_bpe_trainer_
 class _TrainStats(ctypes.Structure):           # include/ctk.h: ctk_train_stats
     _fields_ = [('n_bytes', ctypes.c_uint64), ('n_words', ctypes.c_uint64), ('n_unique_words', ctypes.c_uint64),
                 ('n_symbols', ctypes.c_uint64), ('n_merges', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint64),
-                ('table_rebuilds', ctypes.c_uint32), ('cluster_size', ctypes.c_uint32), ('stop_reason', ctypes.c_uint32), ('ms_words', ctypes.c_double), ('ms_merges', ctypes.c_double)]
+                ('table_rebuilds', ctypes.c_uint32), ('cluster_size', ctypes.c_uint32), ('stop_reason', ctypes.c_uint32), ('ms_words', ctypes.c_double), ('ms_merges', ctypes.c_double), ('ms_words_kernels', ctypes.c_double)]
 
 
 class UnsupportedTokenizerError(IOError):
@@ -126,6 +126,7 @@ def _lib():
         'ctk_train_bpe': (I, [ctypes.POINTER(_TrainerConfig), I, P, P, S, ctypes.POINTER(P)]),
         'ctk_trained_symbols': (S, [P, ctypes.POINTER(P), ctypes.POINTER(P), ctypes.POINTER(P)]),
         'ctk_trained_merges': (S, [P, ctypes.POINTER(P)]),
+        'ctk_trained_merge_counts': (P, [P]),
         'ctk_trained_stats': (None, [P, ctypes.POINTER(_TrainStats)]),
         'ctk_trained_free': (None, [P]),
     }
@@ -616,6 +617,7 @@ class BpeTrainer:
         self._limit = limit_alphabet
         self._device = int(os.environ.get('LOCAL_RANK', 0)) if device is None else int(device)
         self.last_stats = None
+        self.last_merge_counts = None
 
     @property
     def vocab_size(self):
@@ -661,6 +663,8 @@ class BpeTrainer:
             syms = [sb[int(so[i]):int(so[i + 1])].decode('utf-8') for i in range(ns)]
             nm = lib.ctk_trained_merges(h, ctypes.byref(pm))
             mp = np.ctypeslib.as_array(ctypes.cast(pm, ctypes.POINTER(ctypes.c_uint32)), (2 * nm,)).copy() if nm else np.zeros(0, np.uint32)
+            pc = lib.ctk_trained_merge_counts(h)
+            self.last_merge_counts = np.ctypeslib.as_array(ctypes.cast(pc, ctypes.POINTER(ctypes.c_uint32)), (nm,)).copy() if nm else np.zeros(0, np.uint32)
             st = _TrainStats()
             lib.ctk_trained_stats(h, ctypes.byref(st))
             self.last_stats = {k: getattr(st, k) for k, _ in _TrainStats._fields_}

@@ -257,6 +257,11 @@ __device__ __forceinline__ void pair_add(const PairTable& pt, TrainState* st, ui
     st->overflow = 1;
 }
 
+// Loads of data another CTA may have written earlier in the SAME launch (cluster loop) must bypass the per-SM L1;
+// across kernel boundaries (the default three-kernel loop) plain loads are right and measurably faster (22.6 vs 26.7 us).
+template <bool CG, class T> __device__ __forceinline__ T ld(const T* p) { if (CG) return __ldcg(p); else return *p; }
+template <bool CG> __device__ __forceinline__ uint32_t lds(const uint32_t* p) { if (CG) return *(const volatile uint32_t*)p; else return *p; }   // state words
+
 struct Words {                           // every word keeps its slot range [woff, woff + initial length); wlen shrinks
     uint32_t* sym; const uint32_t* slot_word; const uint32_t* woff; uint32_t* wlen; const uint32_t* wfreq;
     uint32_t* dirty_stamp; uint4* dirty_list; uint32_t n_slots, n_words;   // list entry: word, first slot, length, count
@@ -278,51 +283,49 @@ __global__ void __launch_bounds__(256) k_count_all(TrainState* st, Words W, Pair
 }
 
 // Which words contain the pair (cur_l, cur_r)?  One thread per symbol slot .
-__device__ __forceinline__ void detect_hit(TrainState* st, const Words& W, uint32_t i, uint32_t w, uint32_t stamp) {
-    const uint32_t o = W.woff[w], len = __ldcg(W.wlen + w), f = W.wfreq[w];
+template <bool CG> __device__ __forceinline__ void detect_hit(TrainState* st, const Words& W, uint32_t i, uint32_t w, uint32_t stamp) {
+    const uint32_t o = W.woff[w], len = ld<CG>(W.wlen + w), f = W.wfreq[w];
     if (i - o + 1 >= len) return;                                               // a dead slot, or the word's last symbol
     if (atomicExch(&W.dirty_stamp[w], stamp) != stamp) W.dirty_list[atomicAdd(&st->n_dirty, 1u)] = make_uint4(w, o, len, f);
 }
 
 // four slots per thread, all loads issued before the first compare (the step is latency-bound, not bandwidth-bound)
-__device__ __forceinline__ void detect_range(TrainState* st, const Words& W, uint32_t tid, uint32_t n_threads) {
+template <bool CG> __device__ __forceinline__ void detect_range(TrainState* st, const Words& W, uint32_t tid, uint32_t n_threads) {
     for (uint32_t b = tid * 4; b < W.n_slots; b += n_threads * 4) {
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(W.sym + b));      // .cg: another CTA of the cluster may have rewritten the word
-        const uint32_t v4 = __ldcg(W.sym + b + 4);
+        const uint4 v = ld<CG>(reinterpret_cast<const uint4*>(W.sym + b));      // .cg: another CTA of the cluster may have rewritten the word
+        const uint32_t v4 = ld<CG>(W.sym + b + 4);
         const uint4 ws = *reinterpret_cast<const uint4*>(W.slot_word + b);
-        const volatile TrainState* vs = st;
-        const uint32_t l = vs->cur_l, r = vs->cur_r, stamp = vs->iter + 1;
+        const uint32_t l = lds<CG>(&st->cur_l), r = lds<CG>(&st->cur_r), stamp = lds<CG>(&st->iter) + 1;
         if (l == INVALID) return;
-        if (v.x == l && v.y == r) detect_hit(st, W, b, ws.x, stamp);
-        if (v.y == l && v.z == r && b + 1 < W.n_slots) detect_hit(st, W, b + 1, ws.y, stamp);
-        if (v.z == l && v.w == r && b + 2 < W.n_slots) detect_hit(st, W, b + 2, ws.z, stamp);
-        if (v.w == l && v4 == r && b + 3 < W.n_slots) detect_hit(st, W, b + 3, ws.w, stamp);
+        if (v.x == l && v.y == r) detect_hit<CG>(st, W, b, ws.x, stamp);
+        if (v.y == l && v.z == r && b + 1 < W.n_slots) detect_hit<CG>(st, W, b + 1, ws.y, stamp);
+        if (v.z == l && v.w == r && b + 2 < W.n_slots) detect_hit<CG>(st, W, b + 2, ws.z, stamp);
+        if (v.w == l && v4 == r && b + 3 < W.n_slots) detect_hit<CG>(st, W, b + 3, ws.w, stamp);
     }
 }
 
 __global__ void __launch_bounds__(256) k_detect(TrainState* st, Words W) {
     if (st->done || st->pause) return;
-    detect_range(st, W, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    detect_range<false>(st, W, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // Apply the merge to the listed words (bpe_trainer.rs:379-401: left to right, so "aaa" -> "aa a"), a warp per word,
 // 32 symbols at a time, compacted in place; pairs that disappear are subtracted from the table, new ones added.
-__device__ __forceinline__ void apply_range(TrainState* st, const Words& W, const PairTable& pt, uint32_t warp, uint32_t n_warps) {
-    const uint4 first = __ldcg(W.dirty_list + (warp < W.n_words ? warp : 0));   // issued together with the state loads
-    const volatile TrainState* vs = st;
-    const uint32_t l = vs->cur_l;
+template <bool CG> __device__ __forceinline__ void apply_range(TrainState* st, const Words& W, const PairTable& pt, uint32_t warp, uint32_t n_warps) {
+    const uint4 first = ld<CG>(W.dirty_list + (warp < W.n_words ? warp : 0));   // issued together with the state loads
+    const uint32_t l = lds<CG>(&st->cur_l);
     if (l == INVALID) return;
-    const uint32_t r = vs->cur_r, m = vs->cur_m, n_dirty = vs->n_dirty, lane = threadIdx.x & 31;
+    const uint32_t r = lds<CG>(&st->cur_r), m = lds<CG>(&st->cur_m), n_dirty = lds<CG>(&st->n_dirty), lane = threadIdx.x & 31;
     for (uint32_t d = warp; d < n_dirty; d += n_warps) {
-        const uint4 ent = d == warp ? first : __ldcg(W.dirty_list + d);
+        const uint4 ent = d == warp ? first : ld<CG>(W.dirty_list + d);
         const uint32_t w = ent.x, len = ent.z, f = ent.w;
         uint32_t* s = W.sym + ent.y;
         uint32_t out_base = 0, carry = 0, new_last = INVALID, new_last_m = 0, old_last = INVALID, old_last_inv = 0;
         for (uint32_t c = 0; c < len; c += 32) {
             const uint32_t i = c + lane;
             const bool valid = i < len;
-            const uint32_t o = valid ? __ldcg(s + i) : INVALID;
-            const uint32_t ahead = (c + 32 < len) ? __ldcg(s + c + 32) : INVALID;
+            const uint32_t o = valid ? ld<CG>(s + i) : INVALID;
+            const uint32_t ahead = (c + 32 < len) ? ld<CG>(s + c + 32) : INVALID;
             uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, o, 1);
             if (lane == 31) nx = ahead;
             const uint32_t M = __ballot_sync(0xFFFFFFFFu, valid && o == l && nx == r && nx != INVALID);
@@ -378,7 +381,7 @@ __device__ __forceinline__ void apply_range(TrainState* st, const Words& W, cons
 
 __global__ void __launch_bounds__(128) k_apply(TrainState* st, Words W, PairTable pt) {
     if (st->done || st->pause) return;
-    apply_range(st, W, pt, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5);
+    apply_range<false>(st, W, pt, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5);
 }
 
 struct SymTab {                          // device copy of what the host knows about every symbol
@@ -391,12 +394,12 @@ struct Best { uint32_t count; uint64_t key; };
 __device__ __forceinline__ bool better(const Best& a, const Best& b) { return a.count > b.count || (a.count == b.count && a.key < b.key); }
 
 // Best pair of the table (bpe_trainer.rs:152-155 with the tie rule of oracle/py_trainer.py); the last CTA decides.
-__device__ __forceinline__ void best_phase(TrainState* st, const PairTable& pt, Best* block_best, const SymTab& sy, uint4* log) {
+template <bool CG> __device__ __forceinline__ void best_phase(TrainState* st, const PairTable& pt, Best* block_best, const SymTab& sy, uint4* log) {
     Best best{0u, EMPTY64};
     const uint32_t cap = pt.mask + 1;
 #pragma unroll 4
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const uint4 e = __ldcg(reinterpret_cast<const uint4*>(pt.e + i));
+        const uint4 e = ld<CG>(reinterpret_cast<const uint4*>(pt.e + i));
         if (e.z == 0) continue;                                        // empty slot, or a pair that no longer occurs
         Best b{e.z, ((uint64_t)e.y << 32) | e.x};
         if (better(b, best)) best = b;
@@ -437,37 +440,36 @@ __device__ __forceinline__ void best_phase(TrainState* st, const PairTable& pt, 
     st->ticket = 0;
     st->cur_l = INVALID;
     st->n_dirty = 0;
-    const volatile TrainState* vs = st;
-    if (vs->overflow || vs->fill > (cap >> 1) + (cap >> 3)) { st->pause = 1; return; }        // host rebuilds, then this step repeats
+    if (lds<CG>(&st->overflow) || lds<CG>(&st->fill) > (cap >> 1) + (cap >> 3)) { st->pause = 1; return; }        // host rebuilds, then this step repeats
     if (best.count == 0) { st->done = 1; st->reason = 1; return; }                            // bpe_trainer.rs:147-149
-    if (best.count < vs->min_freq) { st->done = 1; st->reason = 2; return; }                  // :162-165
+    if (best.count < lds<CG>(&st->min_freq)) { st->done = 1; st->reason = 2; return; }                  // :162-165
     uint32_t l = (uint32_t)(best.key >> 32), r = (uint32_t)best.key;
-    uint64_t h1 = __ldcg(sy.h1 + l) * __ldcg(sy.pw1 + r) + __ldcg(sy.h1 + r), h2 = __ldcg(sy.h2 + l) * __ldcg(sy.pw2 + r) + __ldcg(sy.h2 + r);
+    uint64_t h1 = ld<CG>(sy.h1 + l) * ld<CG>(sy.pw1 + r) + ld<CG>(sy.h1 + r), h2 = ld<CG>(sy.h2 + l) * ld<CG>(sy.pw2 + r) + ld<CG>(sy.h2 + r);
     uint64_t mk = h1 == EMPTY64 ? 0 : h1;
     uint32_t slot = (uint32_t)(mix64(mk) >> 24) & sy.map_mask, id = INVALID;
     for (;;) {
-        uint64_t k = __ldcg(sy.map_key + slot);
+        uint64_t k = ld<CG>(sy.map_key + slot);
         if (k == EMPTY64) break;
-        if (k == mk && __ldcg(sy.map_h2 + slot) == h2) { id = __ldcg(sy.map_id + slot); break; }
+        if (k == mk && ld<CG>(sy.map_h2 + slot) == h2) { id = ld<CG>(sy.map_id + slot); break; }
         slot = (slot + 1) & sy.map_mask;
     }
     if (id == INVALID) {                                                                      // a new string
-        if (vs->n_symbols >= vs->sym_cap) { st->done = 1; st->reason = 4; return; }
-        id = vs->n_symbols; st->n_symbols = id + 1;
+        if (lds<CG>(&st->n_symbols) >= lds<CG>(&st->sym_cap)) { st->done = 1; st->reason = 4; return; }
+        id = lds<CG>(&st->n_symbols); st->n_symbols = id + 1;
         sy.map_key[slot] = mk; sy.map_h2[slot] = h2; sy.map_id[slot] = id;
-        sy.h1[id] = h1; sy.h2[id] = h2; sy.pw1[id] = __ldcg(sy.pw1 + l) * __ldcg(sy.pw1 + r); sy.pw2[id] = __ldcg(sy.pw2 + l) * __ldcg(sy.pw2 + r);
+        sy.h1[id] = h1; sy.h2[id] = h2; sy.pw1[id] = ld<CG>(sy.pw1 + l) * ld<CG>(sy.pw1 + r); sy.pw2[id] = ld<CG>(sy.pw2 + l) * ld<CG>(sy.pw2 + r);
         sy.in_vocab[id] = 0;
     }
-    if (!__ldcg(sy.in_vocab + id)) { sy.in_vocab[id] = 1; st->vocab_len = vs->vocab_len + 1; }                           // :168-169
-    { const uint32_t nl = vs->n_log; log[nl] = make_uint4(l, r, id, best.count); st->n_log = nl + 1; }
+    if (!ld<CG>(sy.in_vocab + id)) { sy.in_vocab[id] = 1; st->vocab_len = lds<CG>(&st->vocab_len) + 1; }                           // :168-169
+    { const uint32_t nl = lds<CG>(&st->n_log); log[nl] = make_uint4(l, r, id, best.count); st->n_log = nl + 1; }
     st->cur_l = l; st->cur_r = r; st->cur_m = id;
-    st->iter = vs->iter + 1;
-    if (vs->vocab_len >= vs->vocab_size) { st->done = 1; st->reason = 3; }                    // :141
+    st->iter = lds<CG>(&st->iter) + 1;
+    if (lds<CG>(&st->vocab_len) >= lds<CG>(&st->vocab_size)) { st->done = 1; st->reason = 3; }                    // :141
 }
 
 __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt, Best* block_best, SymTab sy, uint4* log) {
     if (st->done || st->pause) return;
-    best_phase(st, pt, block_best, sy, log);
+    best_phase<false>(st, pt, block_best, sy, log);
 }
 
 // The same three phases for up to `iters` merges inside ONE thread-block cluster: the hardware cluster barrier replaces
@@ -482,12 +484,12 @@ __global__ void __launch_bounds__(1024, 1) k_train_cluster(TrainState* st, Words
     #define PHASE(k) t1 = now(); acc[k] += t1 - t0; t0 = t1;
     for (int it = 0; it < iters; ++it) {
         if (vs->cur_l != INVALID) {                                     // uniform: written before the last barrier
-            detect_range(st, W, tid, n_threads);
+            detect_range<true>(st, W, tid, n_threads);
             PHASE(0) __threadfence(); cluster.sync(); PHASE(3)
-            apply_range(st, W, pt, tid >> 5, n_threads >> 5);
+            apply_range<true>(st, W, pt, tid >> 5, n_threads >> 5);
             PHASE(1) __threadfence(); cluster.sync(); PHASE(3)
         }
-        best_phase(st, pt, block_best, sy, log);
+        best_phase<true>(st, pt, block_best, sy, log);
         PHASE(2) __threadfence(); cluster.sync(); PHASE(3)
         if (vs->done || vs->pause) break;
     }
@@ -532,9 +534,10 @@ struct Trained {
     std::vector<std::string> symbols;        // every symbol string, by symbol index
     std::vector<int64_t> vocab_id;           // per symbol: id in the vocabulary map, -1 = not in it
     std::vector<uint32_t> merges;            // 2 per merge: symbol indices
+    std::vector<uint32_t> merge_counts;      // the pair's count when it was chosen
     // packed views for the C ABI
     std::vector<uint8_t> sym_bytes; std::vector<uint64_t> sym_off;
-    double ms_words = 0, ms_merges = 0, ms_host = 0;
+    double ms_words = 0, ms_words_kernels = 0, ms_merges = 0, ms_host = 0;
     uint64_t n_words = 0, n_unique = 0, n_bytes = 0, n_symbols0 = 0, kernels = 0;
     uint32_t stop_reason = 0, rebuilds = 0; int cluster = 0;
 };
@@ -549,6 +552,19 @@ struct PhaseTrace {                       // CTK_TRAIN_TRACE=1: host-timed phase
         fprintf(stderr, "[ctk train] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
         t = now;
     }
+};
+
+struct SegTimer {                         // device time of the kernel segments between the host's allocations and read-backs
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> v;
+    void begin(cudaStream_t s) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); v.push_back({a, b}); }
+    void end(cudaStream_t s) { cudaEventRecord(v.back().second, s); }
+    double total() {                                                      // after a synchronise
+        double t = 0;
+        for (auto& p : v) { float ms = 0; if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t += ms; cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        v.clear();
+        return t;
+    }
+    ~SegTimer() { total(); }
 };
 
 #define TCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); return CTK_ERR_CUDA; } } while (0)
@@ -586,7 +602,9 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         if (n_texts) TCK(cudaMemcpyAsync(d_off, off, (n_texts + 1) * 8, cudaMemcpyHostToDevice, st));
         TCK(cudaEventRecord(ev[0], st));
         PhaseTrace tr; tr.mark("alloc + copy in", st);
+        SegTimer seg;
         if (n > 0) {
+            seg.begin(st);
             TCK(cudaMemsetAsync(d_brk, 0, ((n >> 5) + 2) * 4, st));
             k_mark_breaks<<<(unsigned)((n_texts + 256) / 256), 256, 0, st>>>(d_off, n_texts, d_brk); ++launches;
             cub::CountingInputIterator<uint32_t> it(0);
@@ -595,13 +613,16 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             TCK(db.get(&d_total, 1));
             TCK(cudaMemsetAsync(d_total, 0, 8, st));
             k_count_starts<<<(unsigned)((n + 4095) / 4096), 256, 0, st>>>(pred, n, d_total); ++launches;
+            seg.end(st);
             TCK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
             TCK(db.get(&d_starts, (size_t)total + 1));
             size_t tmp_bytes = 0;
             TCK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_starts, d_num, (int64_t)n, pred, st));
             uint8_t* d_tmp; TCK(db.get(&d_tmp, tmp_bytes));
+            seg.begin(st);
             TCK(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_starts, d_num, (int64_t)n, pred, st)); launches += 2;
+            seg.end(st);
             TCK(cudaMemcpyAsync(&n_words, d_num, 4, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
             tr.mark("breaks + word starts", st);
@@ -621,6 +642,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
                     TCK(cudaMalloc(&tab_mem, (size_t)cap * 16));
                     tab.key = (uint64_t*)tab_mem; tab.count = (uint32_t*)(tab.key + cap); tab.rep = tab.count + cap; tab.mask = cap - 1;
                 }
+                seg.begin(st);
                 TCK(cudaMemsetAsync(tab.key, 0xFF, (size_t)cap * 8, st));
                 TCK(cudaMemsetAsync(tab.count, 0, (size_t)cap * 4, st));
                 TCK(cudaMemsetAsync(tab.rep, 0xFF, (size_t)cap * 4, st));
@@ -628,6 +650,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
                 k_word_insert<<<(n_words + WI_THREADS - 1) / WI_THREADS, WI_THREADS, 0, st>>>(d_text, d_brk, n, d_starts, n_words,
                                                                                            0x9E37ull + 0x51ED27ull * seed_no, tab, d_slot, d_fl);
                 k_word_verify<<<(n_words + 127) / 128, 128, 0, st>>>(d_text, d_brk, n, d_starts, n_words, tab, d_slot, d_fl); launches += 2;
+                seg.end(st);
                 TCK(cudaMemcpyAsync(&fl, d_fl, sizeof fl, cudaMemcpyDeviceToHost, st));
                 TCK(cudaStreamSynchronize(st));
                 tr.mark("table: insert + verify", st);
@@ -647,7 +670,9 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             size_t tmp_bytes = 0;
             TCK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_uslot, d_num, (int64_t)cap, used, st));
             uint8_t* d_tmp; TCK(db.get(&d_tmp, tmp_bytes));
+            seg.begin(st);
             TCK(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_uslot, d_num, (int64_t)cap, used, st)); launches += 2;
+            seg.end(st);
             TCK(cudaMemcpyAsync(&n_unique, d_num, 4, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
             tr.mark("unique slots", st);
@@ -655,18 +680,22 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             TCK(db.get(&d_ulen, n_unique + 1)); TCK(db.get(&d_ucount, n_unique)); TCK(db.get(&d_urep, n_unique)); TCK(db.get(&d_uoff, n_unique + 1));
             TCK(cudaMemsetAsync(d_ulen + n_unique, 0, 4, st));
             unsigned g = (n_unique + 127) / 128;
-            k_unique_len<<<g, 128, 0, st>>>(d_text, d_brk, n, tab, d_uslot, n_unique, d_ulen, d_ucount, d_urep); ++launches;
             cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> lens(d_ulen, U32ToU64());
             size_t tb2 = 0;
             TCK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, lens, d_uoff, (int64_t)n_unique + 1, st));
             uint8_t* d_tmp2; TCK(db.get(&d_tmp2, tb2));
+            seg.begin(st);
+            k_unique_len<<<g, 128, 0, st>>>(d_text, d_brk, n, tab, d_uslot, n_unique, d_ulen, d_ucount, d_urep); ++launches;
             TCK(cub::DeviceScan::ExclusiveSum(d_tmp2, tb2, lens, d_uoff, (int64_t)n_unique + 1, st)); launches += 2;
+            seg.end(st);
             uoff_h.resize(n_unique + 1); ucount_h.resize(n_unique);
             TCK(cudaMemcpyAsync(uoff_h.data(), d_uoff, (n_unique + 1) * 8ull, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
             ubytes.resize(uoff_h[n_unique]);
             TCK(db.get(&d_ubytes, ubytes.size()));
+            seg.begin(st);
             k_unique_gather<<<g, 128, 0, st>>>(d_text, d_urep, d_ulen, d_uoff, n_unique, d_ubytes); ++launches;
+            seg.end(st);
             TCK(cudaEventRecord(ev[1], st));
             TCK(cudaMemcpyAsync(ubytes.data(), d_ubytes, ubytes.size(), cudaMemcpyDeviceToHost, st));
             TCK(cudaMemcpyAsync(ucount_h.data(), d_ucount, n_unique * 4ull, cudaMemcpyDeviceToHost, st));
@@ -678,6 +707,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             uoff_h.assign(1, 0);
         }
         float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); out.ms_words = ms;
+        out.ms_words_kernels = seg.total();
     }
     out.n_words = n_words; out.n_unique = n_unique;
 
@@ -883,7 +913,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
                 uint32_t s = sym(merged);
                 uint64_t id = vocab_len;                                    // :168-169: id = vocab.len() before the insert
                 vocab_insert(s, id);
-                out.merges.push_back(l); out.merges.push_back(r);
+                out.merges.push_back(l); out.merges.push_back(r); out.merge_counts.push_back(log[i].w);
             }
             if (back.done) break;
             if (back.pause) {
@@ -937,6 +967,8 @@ size_t ctk_trained_symbols(const ctk_trained* t, const uint8_t** bytes, const ui
     return t->t.symbols.size();
 }
 
+const uint32_t* ctk_trained_merge_counts(const ctk_trained* t) { return t->t.merge_counts.data(); }
+
 size_t ctk_trained_merges(const ctk_trained* t, const uint32_t** pairs) {
     if (pairs) *pairs = t->t.merges.data();
     return t->t.merges.size() / 2;
@@ -945,7 +977,7 @@ size_t ctk_trained_merges(const ctk_trained* t, const uint32_t** pairs) {
 void ctk_trained_stats(const ctk_trained* t, ctk_train_stats* s) {
     s->n_bytes = t->t.n_bytes; s->n_words = t->t.n_words; s->n_unique_words = t->t.n_unique; s->n_symbols = t->t.n_symbols0;
     s->n_merges = t->t.merges.size() / 2; s->kernel_launches = t->t.kernels; s->stop_reason = t->t.stop_reason; s->table_rebuilds = t->t.rebuilds; s->cluster_size = (uint32_t)t->t.cluster;
-    s->ms_words = t->t.ms_words; s->ms_merges = t->t.ms_merges;
+    s->ms_words = t->t.ms_words; s->ms_words_kernels = t->t.ms_words_kernels; s->ms_merges = t->t.ms_merges;
 }
 
 void ctk_trained_free(ctk_trained* t) { delete t; }

@@ -170,7 +170,8 @@ typedef struct ctk_train_stats {
     uint32_t table_rebuilds;                   /* times the pair table grew (full recount each time) */
     uint32_t cluster_size;                     /* CTAs of the cluster the merge loop ran in; 0 = three kernels per merge */
     uint32_t stop_reason;                      /* 0 none, 1 no pairs left (:147), 2 below min_frequency (:162), 3 vocabulary full (:141) */
-    double ms_words, ms_merges;                /* device time of the word histogram / of the merge loop (CUDA events) */
+    double ms_words, ms_merges;                /* stream time of the word histogram (includes waiting for device allocations) / of the merge loop (CUDA events) */
+    double ms_words_kernels;                   /* word histogram: kernels only */
 } ctk_train_stats;
 int ctk_train_bpe(const ctk_bpe_trainer_config* cfg, int device, const uint8_t* text, const uint64_t* text_off, size_t n_texts,
                   ctk_trained** out);
@@ -178,6 +179,8 @@ int ctk_train_bpe(const ctk_bpe_trainer_config* cfg, int device, const uint8_t* 
 size_t ctk_trained_symbols(const ctk_trained* t, const uint8_t** bytes, const uint64_t** off, const int64_t** vocab_id);
 /* Merges in order, two symbol indices each.  Returns the count. */
 size_t ctk_trained_merges(const ctk_trained* t, const uint32_t** pairs);
+/* Count of each merge's pair at the moment it was chosen (bpe_trainer.rs:161); non-increasing along the list. */
+const uint32_t* ctk_trained_merge_counts(const ctk_trained* t);
 void ctk_trained_stats(const ctk_trained* t, ctk_train_stats* stats);
 void ctk_trained_free(ctk_trained* t);
 

