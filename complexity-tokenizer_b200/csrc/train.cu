@@ -577,7 +577,10 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         return CTK_ERR_CUDA;
     }
     if (device < 0 || device >= ndev) { set_last_error("bad device index"); return CTK_ERR_ARG; }
+    int prev_device = 0;
+    cudaGetDevice(&prev_device);
     TCK(cudaSetDevice(device));
+    struct DeviceGuard { int d; ~DeviceGuard() { cudaSetDevice(d); } } dguard{prev_device};   // the caller's current device is left as it was
     const uint64_t n = n_texts ? off[n_texts] : 0;
     if (n >= (1ull << 32) - 64) { set_last_error("ctk_train_bpe: one call takes less than 4 GiB of text"); return CTK_ERR_UNSUPPORTED; }
     for (size_t i = 0; i < n_texts; ++i) if (off[i] > off[i + 1]) { set_last_error("text offsets are not monotone"); return CTK_ERR_ARG; }
