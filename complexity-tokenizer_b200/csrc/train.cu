@@ -4,7 +4,8 @@
 //
 // Stage W -- word histogram (bpe_trainer.rs:241-275), data-parallel over the text bytes, HBM-bound:
 //   k_mark_breaks     one bit per text start (words do not span texts)
-//   cub select        positions where a word starts (a non-White_Space char after White_Space / a text start)
+//   k_word_bits       thread per 32 bytes: White_Space chars -> bitmaps S (a word starts) and E (a word continues)
+//   k_expand_starts   S -> list of word starts
 //   k_word_insert     one thread per word: walk it, 64-bit hash; equal hashes of a CTA's 512 words are merged in
 //                     shared memory, then inserted into an open-addressing table {hash, count, first position}
 //   k_word_verify     one thread per word: bytes == bytes of the slot's first occurrence (a 64-bit collision is
@@ -54,60 +55,107 @@ constexpr uint64_t P1 = 0x100000001B3ull, P2 = 0x9E3779B97F4A7C15ull;
 constexpr int BATCH = 256;             // merges per host round trip
 
 // ------------------------------------------------------------------------------------------------ stage W
-__device__ __forceinline__ bool brk_at(const uint32_t* brk, uint64_t i) { return (brk[i >> 5] >> (i & 31)) & 1u; }
-
-// Is the char that contains byte i White_Space (what str::split_whitespace splits on)?  Valid UTF-8 assumed.
-__device__ __forceinline__ bool ws_at(const uint8_t* t, uint64_t n, uint64_t i) {
-    uint32_t c = t[i];
-    if (c < 0x80) return c == 0x20 || (c - 9u) < 5u;
-    uint64_t p = i;
-    if ((c & 0xC0) == 0x80) {
-        if (p > 0) --p;
-        if ((t[p] & 0xC0) == 0x80 && p > 0) --p;
-        if ((t[p] & 0xC0) == 0x80 && p > 0) --p;
+// ---- word bitmaps.  One thread per 32 bytes decides, for each byte, whether it belongs to a White_Space char (what
+// str::split_whitespace splits on: 25 code points, 1..3 bytes each; valid UTF-8 assumed) and writes two bits per byte:
+//   S = a word starts here        E = this byte continues the word of the previous byte
+// Words do not span texts (brk has a bit at every text start).  Everything after this kernel works on the bitmaps:
+// a word's length is a run of E bits, no byte of the text is classified twice.
+__global__ void __launch_bounds__(256) k_word_bits(const uint8_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ brk,
+                                                   uint32_t n_groups, uint32_t* __restrict__ S, uint32_t* __restrict__ E,
+                                                   unsigned long long* total) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t starts = 0;
+    if (g < n_groups) {
+        // bytes [32g - 4, 32g + 36): window byte q is position 32g + q - 4 (the text is padded with zero bytes)
+        uint32_t w[10];
+        const uint4 a = reinterpret_cast<const uint4*>(text)[2 * (size_t)g], b = reinterpret_cast<const uint4*>(text)[2 * (size_t)g + 1];
+        w[0] = g ? reinterpret_cast<const uint32_t*>(text)[8 * (size_t)g - 1] : 0u;
+        w[1] = a.x; w[2] = a.y; w[3] = a.z; w[4] = a.w; w[5] = b.x; w[6] = b.y; w[7] = b.z; w[8] = b.w;
+        w[9] = reinterpret_cast<const uint32_t*>(text)[8 * (size_t)g + 8];
+        uint32_t hi = 0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) hi |= w[k];
+        unsigned long long A = 0, L2 = 0, L3 = 0;
+        #define WB(q) ((w[(q) >> 2] >> (((q) & 3) * 8)) & 0xFFu)
+        if (hi & 0x80808080u) {                                         // some non-ASCII byte: the multi-byte White_Space chars
+#pragma unroll
+            for (int q = 1; q <= 35; ++q) {
+                const uint32_t c0 = WB(q), c1 = WB(q + 1), c2 = WB(q + 2);
+                const bool as = c0 == 0x20 || (c0 - 9u) < 5u;
+                const bool l2 = c0 == 0xC2 && (c1 == 0x85 || c1 == 0xA0);
+                const bool l3 = (c0 == 0xE1 && c1 == 0x9A && c2 == 0x80) ||
+                                (c0 == 0xE2 && ((c1 == 0x80 && ((c2 - 0x80u) <= 0x0Au || c2 == 0xA8 || c2 == 0xA9 || c2 == 0xAF)) || (c1 == 0x81 && c2 == 0x9F))) ||
+                                (c0 == 0xE3 && c1 == 0x80 && c2 == 0x80);
+                A |= (unsigned long long)as << q; L2 |= (unsigned long long)l2 << q; L3 |= (unsigned long long)l3 << q;
+            }
+        } else {
+#pragma unroll
+            for (int q = 3; q <= 35; ++q) { const uint32_t c0 = WB(q); A |= (unsigned long long)(c0 == 0x20 || (c0 - 9u) < 5u) << q; }
+        }
+        #undef WB
+        const unsigned long long ws = A | L2 | (L2 << 1) | L3 | (L3 << 1) | (L3 << 2);
+        const uint64_t lo = 32ull * g;
+        const uint32_t vm = lo + 32 <= n ? 0xFFFFFFFFu : ((1u << (uint32_t)(n - lo)) - 1u);
+        const uint32_t W = ~(uint32_t)(ws >> 4) & vm;
+        const uint32_t Wprev = g ? (uint32_t)(~(ws >> 3) & 1ull) : 0u;
+        const uint32_t e = W & ((W << 1) | Wprev) & ~brk[g];
+        const uint32_t st = W & ~e;
+        S[g] = st; E[g] = e;
+        starts = __popc(st);
     }
-    uint32_t b0 = t[p];
-    if (b0 != 0xC2 && (b0 < 0xE1 || b0 > 0xE3)) return false;
-    uint32_t b1 = p + 1 < n ? t[p + 1] : 0, b2 = p + 2 < n ? t[p + 2] : 0;
-    if (b0 == 0xC2) return b1 == 0x85 || b1 == 0xA0;
-    if (b0 == 0xE1) return b1 == 0x9A && b2 == 0x80;
-    if (b0 == 0xE2) {
-        if (b1 == 0x80) return (b2 >= 0x80 && b2 <= 0x8A) || b2 == 0xA8 || b2 == 0xA9 || b2 == 0xAF;
-        return b1 == 0x81 && b2 == 0x9F;
-    }
-    return b1 == 0x80 && b2 == 0x80;   // U+3000
-}
-
-struct IsWordStart {
-    const uint8_t* t; const uint32_t* brk; uint64_t n;
-    __device__ bool operator()(uint32_t i) const {
-        uint32_t c = t[i];
-        if ((c & 0xC0) == 0x80) return false;
-        if (ws_at(t, n, i)) return false;
-        if (i == 0 || brk_at(brk, i)) return true;
-        return ws_at(t, n, i - 1);
-    }
-};
-
-// number of word starts (so that the list of starts is allocated at its exact size: device allocation is what a
-// training call waits for most, ~0.14 ms per MB on the B200 box)
-__global__ void __launch_bounds__(256) k_count_starts(IsWordStart pred, uint64_t n, unsigned long long* total) {
-    const uint64_t base = (uint64_t)blockIdx.x * 4096;
-    uint32_t mine = 0;
-    for (int k = 0; k < 16; ++k) {
-        uint64_t i = base + k * 256 + threadIdx.x;
-        if (i < n && pred((uint32_t)i)) ++mine;
-    }
-    mine = __reduce_add_sync(0xFFFFFFFFu, mine);
-    __shared__ uint32_t s[8];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = mine;
+    starts = __reduce_add_sync(0xFFFFFFFFu, starts);
+    __shared__ uint32_t sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = starts;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t t = 0;
-        for (int k = 0; k < 8; ++k) t += s[k];
+        for (int k = 0; k < 8; ++k) t += sh[k];
         if (t) atomicAdd(total, (unsigned long long)t);
     }
 }
+
+// S bitmap -> list of word-start positions (the order of the list does not matter: counts are sums)
+__global__ void __launch_bounds__(256) k_expand_starts(const uint32_t* __restrict__ S, uint32_t n_groups, uint32_t* __restrict__ starts,
+                                                       unsigned int* cursor) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    uint32_t bits = g < n_groups ? S[g] : 0u;
+    const uint32_t c = __popc(bits);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += u; }
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t base;
+    if (lane == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; ++k) { uint32_t v = wsum[k]; wsum[k] = t; t += v; }
+        base = t ? atomicAdd(cursor, t) : 0u;
+    }
+    __syncthreads();
+    uint32_t o = base + wsum[threadIdx.x >> 5] + incl - c;
+    while (bits) { starts[o++] = 32u * g + (uint32_t)__ffs(bits) - 1u; bits &= bits - 1; }
+}
+
+// length of the word that starts at s: 1 + the run of E bits after it (E is zero past the end of the text)
+__device__ __forceinline__ uint32_t word_len(const uint32_t* __restrict__ E, uint64_t s) {
+    uint64_t p = s + 1;
+    uint32_t len = 1;
+    for (;;) {
+        const uint32_t sh = (uint32_t)p & 31u, avail = 32u - sh;
+        const uint32_t stop = ~(E[p >> 5] >> sh);                       // the shifted-in top bits read as "stop"
+        const uint32_t run = (uint32_t)__ffs(stop) - 1u;                // stop != 0 whenever sh > 0
+        if (stop != 0 && run < avail) return len + run;
+        len += avail; p += avail;
+    }
+}
+
+// four text bytes starting at byte position p (aligned loads; the text is padded)
+struct Bytes4 {
+    const uint32_t* t32; uint32_t idx, sh, cur;
+    __device__ __forceinline__ Bytes4(const uint8_t* text, uint64_t p) : t32(reinterpret_cast<const uint32_t*>(text)), idx((uint32_t)(p >> 2)), sh(((uint32_t)p & 3u) * 8u) { cur = t32[idx]; }
+    __device__ __forceinline__ uint32_t next() { const uint32_t nx = t32[++idx]; const uint32_t v = __funnelshift_r(cur, nx, sh); cur = nx; return v; }
+};
 
 __global__ void k_mark_breaks(const uint64_t* off, size_t n_texts, uint32_t* brk) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,13 +169,6 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     return x;
 }
 
-// end of the word that starts at s (first byte past it)
-__device__ __forceinline__ uint64_t word_end(const uint8_t* t, const uint32_t* brk, uint64_t n, uint64_t s) {
-    uint64_t j = s + 1;
-    while (j < n && !brk_at(brk, j) && !ws_at(t, n, j)) ++j;
-    return j;
-}
-
 struct WordTable { uint64_t* key; uint32_t* count; uint32_t* rep; uint32_t mask; };
 
 // A CTA takes 256 consecutive words: each thread walks and hashes one, equal hashes are merged in a shared-memory
@@ -136,7 +177,7 @@ struct WordTable { uint64_t* key; uint32_t* count; uint32_t* rep; uint32_t mask;
 constexpr int WI_THREADS = 256, WI_SLOTS = 512;
 struct WordFlags { uint32_t collision, overflow, fill; };
 
-__global__ void __launch_bounds__(WI_THREADS) k_word_insert(const uint8_t* t, const uint32_t* brk, uint64_t n, const uint32_t* starts,
+__global__ void __launch_bounds__(WI_THREADS) k_word_insert(const uint8_t* __restrict__ t, const uint32_t* __restrict__ E, const uint32_t* __restrict__ starts,
                                                             uint32_t n_words, uint64_t seed, WordTable tab, uint32_t* slot_of, WordFlags* fl) {
     __shared__ unsigned long long s_key[WI_SLOTS];
     __shared__ uint32_t s_count[WI_SLOTS], s_rep[WI_SLOTS], s_gslot[WI_SLOTS];
@@ -145,9 +186,16 @@ __global__ void __launch_bounds__(WI_THREADS) k_word_insert(const uint8_t* t, co
     const uint32_t w = blockIdx.x * WI_THREADS + threadIdx.x;
     uint32_t mine = INVALID;
     if (w < n_words) {
-        uint64_t s = starts[w], j = s, h = seed;
-        do { h = h * P1 + t[j] + 1; ++j; } while (j < n && !brk_at(brk, j) && !ws_at(t, n, j));
-        h = mix64(h ^ ((j - s) * P2));
+        const uint64_t s = starts[w];
+        const uint32_t len = word_len(E, s);
+        uint64_t h = seed;
+        Bytes4 rd(t, s);
+        for (uint32_t o = 0; o < len; o += 4) {                          // four bytes per step, the tail masked
+            uint32_t v = rd.next();
+            if (len - o < 4) v &= (1u << (8 * (len - o))) - 1u;
+            h = (h ^ v) * P1; h ^= h >> 29;
+        }
+        h = mix64(h ^ (len * P2));
         if (h == EMPTY64) h = 0;
         uint32_t slot = (uint32_t)(h >> 40) & (WI_SLOTS - 1);
         for (;;) {                                                       // 256 words, 512 slots: always ends
@@ -183,19 +231,22 @@ __global__ void __launch_bounds__(WI_THREADS) k_word_insert(const uint8_t* t, co
     if (mine != INVALID) slot_of[w] = s_gslot[mine];
 }
 
-__global__ void k_word_verify(const uint8_t* t, const uint32_t* brk, uint64_t n, const uint32_t* starts, uint32_t n_words,
-                              WordTable tab, const uint32_t* slot_of, WordFlags* fl) {
+__global__ void k_word_verify(const uint8_t* __restrict__ t, const uint32_t* __restrict__ E, const uint32_t* __restrict__ starts, uint32_t n_words,
+                              WordTable tab, const uint32_t* __restrict__ slot_of, WordFlags* fl) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
-    uint64_t s = starts[w], r = tab.rep[slot_of[w]];
+    const uint64_t s = starts[w], r = tab.rep[slot_of[w]];
     if (r == s) return;
-    uint64_t j = 0;
-    bool ok = true;
-    do {
-        if (r + j >= n || t[r + j] != t[s + j] || (j > 0 && brk_at(brk, r + j))) { ok = false; break; }
-        ++j;
-    } while (s + j < n && !brk_at(brk, s + j) && !ws_at(t, n, s + j));
-    if (ok && r + j < n && !brk_at(brk, r + j) && !ws_at(t, n, r + j)) ok = false;   // the first occurrence is longer
+    const uint32_t len = word_len(E, s);
+    bool ok = word_len(E, r) == len;
+    if (ok) {
+        Bytes4 a(t, s), b(t, r);
+        for (uint32_t o = 0; o < len; o += 4) {
+            uint32_t d = a.next() ^ b.next();
+            if (len - o < 4) d &= (1u << (8 * (len - o))) - 1u;
+            if (d) { ok = false; break; }
+        }
+    }
     if (!ok) fl->collision = 1;
 }
 
@@ -206,12 +257,12 @@ struct SlotUsed {
     __device__ bool operator()(uint32_t i) const { return key[i] != EMPTY64; }
 };
 
-__global__ void k_unique_len(const uint8_t* t, const uint32_t* brk, uint64_t n, WordTable tab, const uint32_t* uslot,
+__global__ void k_unique_len(const uint32_t* __restrict__ E, WordTable tab, const uint32_t* uslot,
                              uint32_t n_unique, uint32_t* ulen, uint32_t* ucount, uint32_t* urep) {
     uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_unique) return;
     uint32_t slot = uslot[u], r = tab.rep[slot];
-    ulen[u] = (uint32_t)(word_end(t, brk, n, r) - r);
+    ulen[u] = word_len(E, r);
     ucount[u] = tab.count[slot];
     urep[u] = r;
 }
@@ -599,36 +650,36 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
     {
         DevBuf db;
         uint8_t* d_text; uint64_t* d_off; uint32_t* d_brk; uint32_t* d_starts; uint32_t* d_num;
-        TCK(db.get(&d_text, n + 16)); TCK(db.get(&d_off, n_texts + 1)); TCK(db.get(&d_brk, (n >> 5) + 2));
+        TCK(db.get(&d_text, n + 64)); TCK(db.get(&d_off, n_texts + 1)); TCK(db.get(&d_brk, (n >> 5) + 2));
         TCK(db.get(&d_num, 4));
         TCK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st));
         if (n_texts) TCK(cudaMemcpyAsync(d_off, off, (n_texts + 1) * 8, cudaMemcpyHostToDevice, st));
         TCK(cudaEventRecord(ev[0], st));
         PhaseTrace tr; tr.mark("alloc + copy in", st);
         SegTimer seg;
+        uint32_t *d_S = nullptr, *d_E = nullptr;
+        const uint32_t n_groups = (uint32_t)((n + 31) / 32);
         if (n > 0) {
-            seg.begin(st);
-            TCK(cudaMemsetAsync(d_brk, 0, ((n >> 5) + 2) * 4, st));
-            k_mark_breaks<<<(unsigned)((n_texts + 256) / 256), 256, 0, st>>>(d_off, n_texts, d_brk); ++launches;
-            cub::CountingInputIterator<uint32_t> it(0);
-            IsWordStart pred{d_text, d_brk, n};
             unsigned long long* d_total; unsigned long long total = 0;
-            TCK(db.get(&d_total, 1));
+            unsigned int* d_cursor;
+            TCK(db.get(&d_total, 1)); TCK(db.get(&d_cursor, 1)); TCK(db.get(&d_S, (size_t)n_groups + 2)); TCK(db.get(&d_E, (size_t)n_groups + 2));
+            seg.begin(st);
+            TCK(cudaMemsetAsync(d_text + n, 0, 64, st));                 // the kernels read whole words past the end
+            TCK(cudaMemsetAsync(d_brk, 0, ((n >> 5) + 2) * 4, st));
+            TCK(cudaMemsetAsync(d_E + n_groups, 0, 8, st));
             TCK(cudaMemsetAsync(d_total, 0, 8, st));
-            k_count_starts<<<(unsigned)((n + 4095) / 4096), 256, 0, st>>>(pred, n, d_total); ++launches;
+            TCK(cudaMemsetAsync(d_cursor, 0, 4, st));
+            k_mark_breaks<<<(unsigned)((n_texts + 256) / 256), 256, 0, st>>>(d_off, n_texts, d_brk);
+            k_word_bits<<<(n_groups + 255) / 256, 256, 0, st>>>(d_text, n, d_brk, n_groups, d_S, d_E, d_total); launches += 2;
             seg.end(st);
             TCK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
+            n_words = (uint32_t)total;
             TCK(db.get(&d_starts, (size_t)total + 1));
-            size_t tmp_bytes = 0;
-            TCK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_starts, d_num, (int64_t)n, pred, st));
-            uint8_t* d_tmp; TCK(db.get(&d_tmp, tmp_bytes));
             seg.begin(st);
-            TCK(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_starts, d_num, (int64_t)n, pred, st)); launches += 2;
+            k_expand_starts<<<(n_groups + 255) / 256, 256, 0, st>>>(d_S, n_groups, d_starts, d_cursor); ++launches;
             seg.end(st);
-            TCK(cudaMemcpyAsync(&n_words, d_num, 4, cudaMemcpyDeviceToHost, st));
-            TCK(cudaStreamSynchronize(st));
-            tr.mark("breaks + word starts", st);
+            tr.mark("word bitmaps + starts", st);
         }
         if (n_words > 0) {
             // The table starts small (distinct words are a few per cent of the words of a text) and is rebuilt four times
@@ -650,9 +701,9 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
                 TCK(cudaMemsetAsync(tab.count, 0, (size_t)cap * 4, st));
                 TCK(cudaMemsetAsync(tab.rep, 0xFF, (size_t)cap * 4, st));
                 TCK(cudaMemsetAsync(d_fl, 0, sizeof(WordFlags), st));
-                k_word_insert<<<(n_words + WI_THREADS - 1) / WI_THREADS, WI_THREADS, 0, st>>>(d_text, d_brk, n, d_starts, n_words,
+                k_word_insert<<<(n_words + WI_THREADS - 1) / WI_THREADS, WI_THREADS, 0, st>>>(d_text, d_E, d_starts, n_words,
                                                                                            0x9E37ull + 0x51ED27ull * seed_no, tab, d_slot, d_fl);
-                k_word_verify<<<(n_words + 127) / 128, 128, 0, st>>>(d_text, d_brk, n, d_starts, n_words, tab, d_slot, d_fl); launches += 2;
+                k_word_verify<<<(n_words + 127) / 128, 128, 0, st>>>(d_text, d_E, d_starts, n_words, tab, d_slot, d_fl); launches += 2;
                 seg.end(st);
                 TCK(cudaMemcpyAsync(&fl, d_fl, sizeof fl, cudaMemcpyDeviceToHost, st));
                 TCK(cudaStreamSynchronize(st));
@@ -688,7 +739,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             TCK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, lens, d_uoff, (int64_t)n_unique + 1, st));
             uint8_t* d_tmp2; TCK(db.get(&d_tmp2, tb2));
             seg.begin(st);
-            k_unique_len<<<g, 128, 0, st>>>(d_text, d_brk, n, tab, d_uslot, n_unique, d_ulen, d_ucount, d_urep); ++launches;
+            k_unique_len<<<g, 128, 0, st>>>(d_E, tab, d_uslot, n_unique, d_ulen, d_ucount, d_urep); ++launches;
             TCK(cub::DeviceScan::ExclusiveSum(d_tmp2, tb2, lens, d_uoff, (int64_t)n_unique + 1, st)); launches += 2;
             seg.end(st);
             uoff_h.resize(n_unique + 1); ucount_h.resize(n_unique);
