@@ -6,8 +6,8 @@
 //   k_mark_breaks     one bit per text start (words do not span texts)
 //   k_word_bits       thread per 32 bytes: White_Space chars -> bitmaps S (a word starts) and E (a word continues)
 //   k_expand_starts   S -> list of word starts
-//   k_word_insert     one thread per word: walk it, 64-bit hash; equal hashes of a CTA's 512 words are merged in
-//                     shared memory, then inserted into an open-addressing table {hash, count, first position}
+//   k_word_insert     four words per thread (length from the E bits, 64-bit hash); equal hashes of a CTA's 1024 words are merged in
+//                     shared memory, then inserted into an open-addressing table {hash, count, one occurrence}
 //   k_word_verify     one thread per word: bytes == bytes of the slot's first occurrence (a 64-bit collision is
 //                     detected, never trusted; the call then repeats with another hash seed)
 //   k_unique_*        table -> packed unique words (bytes, offsets, counts) for the host
@@ -169,73 +169,133 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     return x;
 }
 
-struct WordTable { uint64_t* key; uint32_t* count; uint32_t* rep; uint32_t mask; };
+struct __align__(16) WordEntry { unsigned long long key; uint32_t count, rep; };   // one sector per distinct word: hash, occurrences, one occurrence's position
+struct WordTable { WordEntry* e; uint32_t mask; };
+
+__global__ void k_word_table_clear(WordTable tab) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= tab.mask) *reinterpret_cast<uint4*>(tab.e + i) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0xFFFFFFFFu);
+}
 
 // A CTA takes 256 consecutive words: each thread walks and hashes one, equal hashes are merged in a shared-memory
 // table first (the most frequent word of a text is ~5 % of all words: without this every one of its occurrences is an
 // atomic on the same global address), then one thread per distinct hash updates the global table.
-constexpr int WI_THREADS = 256, WI_SLOTS = 512;
+constexpr int WI_THREADS = 256, WI_PER = 4, WI_WORDS = WI_THREADS * WI_PER, WI_SLOTS = 2048;
 struct WordFlags { uint32_t collision, overflow, fill; };
 
+// hash of the word [s, s + len): four bytes per step, the tail masked
+__device__ __forceinline__ uint64_t word_hash_loop(const uint8_t* __restrict__ t, uint64_t s, uint32_t len, uint64_t seed) {
+    uint64_t h = seed;
+    Bytes4 rd(t, s);
+    for (uint32_t o = 0; o < len; o += 4) {
+        uint32_t v = rd.next();
+        if (len - o < 4) v &= (1u << (8 * (len - o))) - 1u;
+        h = (h ^ v) * P1; h ^= h >> 29;
+    }
+    return h;
+}
+
+// A CTA takes 1024 words, four per thread.  The kernel is a chain of dependent memory round trips (start -> E bits ->
+// text -> shared table -> global table), so every thread keeps the loads of its four words in flight together: for
+// words of at most 16 bytes (the rest take the loop) the addresses depend on the start position only.
 __global__ void __launch_bounds__(WI_THREADS) k_word_insert(const uint8_t* __restrict__ t, const uint32_t* __restrict__ E, const uint32_t* __restrict__ starts,
                                                             uint32_t n_words, uint64_t seed, WordTable tab, uint32_t* slot_of, WordFlags* fl) {
     __shared__ unsigned long long s_key[WI_SLOTS];
     __shared__ uint32_t s_count[WI_SLOTS], s_rep[WI_SLOTS], s_gslot[WI_SLOTS];
     for (int k = threadIdx.x; k < WI_SLOTS; k += WI_THREADS) { s_key[k] = EMPTY64; s_count[k] = 0; s_rep[k] = INVALID; }
+    const uint32_t w0 = blockIdx.x * WI_WORDS + threadIdx.x;
+    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(t);
+    uint32_t st[WI_PER], e0[WI_PER], e1[WI_PER], x[WI_PER][5];
+#pragma unroll
+    for (int k = 0; k < WI_PER; ++k) { const uint32_t w = w0 + k * WI_THREADS; st[k] = w < n_words ? starts[w] : 0u; }
+#pragma unroll
+    for (int k = 0; k < WI_PER; ++k) {
+        const uint32_t p = st[k] + 1;                                    // < 2^32: the call takes less than 4 GiB
+        e0[k] = E[p >> 5]; e1[k] = E[(p >> 5) + 1];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) x[k][j] = t32[(st[k] >> 2) + j];
+    }
     __syncthreads();
-    const uint32_t w = blockIdx.x * WI_THREADS + threadIdx.x;
-    uint32_t mine = INVALID;
-    if (w < n_words) {
-        const uint64_t s = starts[w];
-        const uint32_t len = word_len(E, s);
-        uint64_t h = seed;
-        Bytes4 rd(t, s);
-        for (uint32_t o = 0; o < len; o += 4) {                          // four bytes per step, the tail masked
-            uint32_t v = rd.next();
-            if (len - o < 4) v &= (1u << (8 * (len - o))) - 1u;
-            h = (h ^ v) * P1; h ^= h >> 29;
+    uint32_t mine[WI_PER];
+#pragma unroll
+    for (int k = 0; k < WI_PER; ++k) {
+        mine[k] = INVALID;
+        if (w0 + k * WI_THREADS >= n_words) continue;
+        const uint32_t p = st[k] + 1, sh = p & 31u;
+        const unsigned long long cont = (((unsigned long long)e1[k] << 32) | e0[k]) >> sh;    // E bits from p on, at least 33 of them
+        const uint32_t run = (uint32_t)__ffsll((long long)~cont) - 1u;
+        uint32_t len;
+        uint64_t h;
+        if (run < 16) {                                                  // the word is 1 + run <= 16 bytes: registers only
+            len = 1 + run;
+            h = seed;
+            const uint32_t bs = (st[k] & 3u) * 8u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if ((uint32_t)(4 * j) < len) {
+                    uint32_t v = __funnelshift_r(x[k][j], x[k][j + 1], bs);
+                    if (len - 4 * j < 4) v &= (1u << (8 * (len - 4 * j))) - 1u;
+                    h = (h ^ v) * P1; h ^= h >> 29;
+                }
+            }
+        } else {
+            len = word_len(E, st[k]);
+            h = word_hash_loop(t, st[k], len, seed);
         }
         h = mix64(h ^ (len * P2));
         if (h == EMPTY64) h = 0;
         uint32_t slot = (uint32_t)(h >> 40) & (WI_SLOTS - 1);
-        for (;;) {                                                       // 256 words, 512 slots: always ends
-            unsigned long long k = s_key[slot];
-            if (k == EMPTY64) k = atomicCAS(&s_key[slot], EMPTY64, h), k = (k == EMPTY64) ? h : k;
-            if (k == h) break;
+        for (;;) {                                                       // 1024 words, 2048 slots: always ends
+            unsigned long long q = s_key[slot];
+            if (q == EMPTY64) {
+                q = atomicCAS(&s_key[slot], EMPTY64, h);
+                if (q == EMPTY64) { s_rep[slot] = st[k]; q = h; }        // any occurrence can stand for the word: all are compared with it
+            }
+            if (q == h) break;
             slot = (slot + 1) & (WI_SLOTS - 1);
         }
         atomicAdd(&s_count[slot], 1u);
-        atomicMin(&s_rep[slot], (uint32_t)s);
-        mine = slot;
+        mine[k] = slot;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < WI_SLOTS; k += WI_THREADS) {
-        const uint64_t h = s_key[k];
+    // one thread per distinct hash of the CTA updates the global table; the first probes of a thread's slots go out together
+    constexpr int FL = WI_SLOTS / WI_THREADS;
+    unsigned long long hk[FL], g0[FL];
+#pragma unroll
+    for (int j = 0; j < FL; ++j) {
+        hk[j] = s_key[threadIdx.x + j * WI_THREADS];
+        g0[j] = hk[j] != EMPTY64 ? tab.e[(uint32_t)(hk[j] >> 20) & tab.mask].key : 0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < FL; ++j) {
+        const uint64_t h = hk[j];
         if (h == EMPTY64) continue;
+        const int k = threadIdx.x + j * WI_THREADS;
         uint32_t slot = (uint32_t)(h >> 20) & tab.mask, probes = 0;
+        uint64_t g = g0[j];
         for (;; ++probes) {
-            if (probes > tab.mask) { fl->overflow = 1; slot = 0; break; }
-            uint64_t g = tab.key[slot];
+            if (probes > 256u || probes > tab.mask) { fl->overflow = 1; slot = 0; break; }   // a probe this long means the table is too full: the host grows it
             if (g == EMPTY64) {
-                g = atomicCAS((unsigned long long*)&tab.key[slot], EMPTY64, h);
-                if (g == EMPTY64) { atomicAdd(&fl->fill, 1u); g = h; }
+                g = atomicCAS(&tab.e[slot].key, EMPTY64, h);
+                if (g == EMPTY64) { atomicAdd(&fl->fill, 1u); tab.e[slot].rep = s_rep[k]; g = h; }
             }
             if (g == h) break;
             slot = (slot + 1) & tab.mask;
+            g = tab.e[slot].key;
         }
-        atomicAdd(&tab.count[slot], s_count[k]);
-        atomicMin(&tab.rep[slot], s_rep[k]);
+        atomicAdd(&tab.e[slot].count, s_count[k]);
         s_gslot[k] = slot;
     }
     __syncthreads();
-    if (mine != INVALID) slot_of[w] = s_gslot[mine];
+#pragma unroll
+    for (int k = 0; k < WI_PER; ++k) if (mine[k] != INVALID) slot_of[w0 + k * WI_THREADS] = s_gslot[mine[k]];
 }
 
 __global__ void k_word_verify(const uint8_t* __restrict__ t, const uint32_t* __restrict__ E, const uint32_t* __restrict__ starts, uint32_t n_words,
                               WordTable tab, const uint32_t* __restrict__ slot_of, WordFlags* fl) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
-    const uint64_t s = starts[w], r = tab.rep[slot_of[w]];
+    const uint64_t s = starts[w], r = tab.e[slot_of[w]].rep;
     if (r == s) return;
     const uint32_t len = word_len(E, s);
     bool ok = word_len(E, r) == len;
@@ -253,17 +313,17 @@ __global__ void k_word_verify(const uint8_t* __restrict__ t, const uint32_t* __r
 struct U32ToU64 { __device__ uint64_t operator()(uint32_t v) const { return v; } };
 
 struct SlotUsed {
-    const uint64_t* key;
-    __device__ bool operator()(uint32_t i) const { return key[i] != EMPTY64; }
+    const WordEntry* e;
+    __device__ bool operator()(uint32_t i) const { return e[i].key != EMPTY64; }
 };
 
 __global__ void k_unique_len(const uint32_t* __restrict__ E, WordTable tab, const uint32_t* uslot,
                              uint32_t n_unique, uint32_t* ulen, uint32_t* ucount, uint32_t* urep) {
     uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_unique) return;
-    uint32_t slot = uslot[u], r = tab.rep[slot];
+    uint32_t slot = uslot[u], r = tab.e[slot].rep;
     ulen[u] = word_len(E, r);
-    ucount[u] = tab.count[slot];
+    ucount[u] = tab.e[slot].count;
     urep[u] = r;
 }
 
@@ -296,7 +356,7 @@ struct PairTable { TrainPair* e; uint32_t mask; };
 __device__ __forceinline__ void pair_add(const PairTable& pt, TrainState* st, uint32_t a, uint32_t b, uint32_t f) {
     uint64_t key = ((uint64_t)a << 32) | b;
     uint32_t slot = (uint32_t)(mix64(key) >> 24) & pt.mask;
-    for (uint32_t probes = 0; probes <= pt.mask; ++probes) {
+    for (uint32_t probes = 0; probes <= pt.mask && probes <= 512u; ++probes) {   // a longer probe = too full: overflow, the host rebuilds
         uint64_t k = pt.e[slot].key;
         if (k == EMPTY64) {
             k = atomicCAS(&pt.e[slot].key, EMPTY64, key);
@@ -686,7 +746,8 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             // larger when it fills beyond 5/8 -- at most up to 2 slots per word; a 64-bit collision repeats with a new seed.
             WordTable tab{}; uint32_t* d_slot; uint32_t* d_uslot; WordFlags* d_fl;
             const uint32_t cap_max = pow2_at_least(2ull * n_words);
-            uint32_t cap = std::min<uint32_t>(cap_max, std::max<uint32_t>(1u << 16, pow2_at_least(n_words / 8)));
+            const uint32_t div = getenv("CTK_TRAIN_WORD_TABLE_DIV") ? std::max(1, atoi(getenv("CTK_TRAIN_WORD_TABLE_DIV"))) : 16;
+            uint32_t cap = std::min<uint32_t>(cap_max, std::max<uint32_t>(1u << 16, pow2_at_least(n_words / div)));
             TCK(db.get(&d_slot, n_words)); TCK(db.get(&d_fl, 1));
             void* tab_mem = nullptr;
             struct MemGuard { void** p; ~MemGuard() { if (*p) cudaFree(*p); } } mg{&tab_mem};
@@ -694,14 +755,12 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             for (int attempt = 0, seed_no = 0; attempt < 24; ++attempt) {
                 if (!tab_mem) {
                     TCK(cudaMalloc(&tab_mem, (size_t)cap * 16));
-                    tab.key = (uint64_t*)tab_mem; tab.count = (uint32_t*)(tab.key + cap); tab.rep = tab.count + cap; tab.mask = cap - 1;
+                    tab.e = (WordEntry*)tab_mem; tab.mask = cap - 1;
                 }
                 seg.begin(st);
-                TCK(cudaMemsetAsync(tab.key, 0xFF, (size_t)cap * 8, st));
-                TCK(cudaMemsetAsync(tab.count, 0, (size_t)cap * 4, st));
-                TCK(cudaMemsetAsync(tab.rep, 0xFF, (size_t)cap * 4, st));
+                k_word_table_clear<<<(cap + 255) / 256, 256, 0, st>>>(tab); ++launches;
                 TCK(cudaMemsetAsync(d_fl, 0, sizeof(WordFlags), st));
-                k_word_insert<<<(n_words + WI_THREADS - 1) / WI_THREADS, WI_THREADS, 0, st>>>(d_text, d_E, d_starts, n_words,
+                k_word_insert<<<(n_words + WI_WORDS - 1) / WI_WORDS, WI_THREADS, 0, st>>>(d_text, d_E, d_starts, n_words,
                                                                                            0x9E37ull + 0x51ED27ull * seed_no, tab, d_slot, d_fl);
                 k_word_verify<<<(n_words + 127) / 128, 128, 0, st>>>(d_text, d_E, d_starts, n_words, tab, d_slot, d_fl); launches += 2;
                 seg.end(st);
@@ -720,7 +779,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             if (fl.collision) { set_last_error("ctk_train_bpe: word hash collisions under every seed"); return CTK_ERR_UNSUPPORTED; }
             TCK(db.get(&d_uslot, n_words));
             cub::CountingInputIterator<uint32_t> it(0);
-            SlotUsed used{tab.key};
+            SlotUsed used{tab.e};
             size_t tmp_bytes = 0;
             TCK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_uslot, d_num, (int64_t)cap, used, st));
             uint8_t* d_tmp; TCK(db.get(&d_tmp, tmp_bytes));

@@ -166,3 +166,16 @@ def test_properties_at_scale(built_lib):
     # the same input trained twice gives the same table (atomics only ever add: no order dependence)
     vocab2, merges2 = ct.BpeTrainer(vocab_size=3000, min_frequency=2, show_progress=False).train_packed(text, offs)
     assert merges2 == merges and vocab2 == vocab
+
+
+def test_word_table_growth(built_lib, monkeypatch):
+    """A word table that starts far too small (all words distinct) grows instead of probing a full table."""
+    monkeypatch.setenv('CTK_TRAIN_WORD_TABLE_DIV', '4096')
+    rng = random.Random(11)
+    words = sorted({"".join(rng.choice("abcdefghij") for _ in range(8)) for _ in range(200000)})
+    texts = [" ".join(words[i:i + 100]) for i in range(0, len(words), 100)]
+    import time
+    t0 = time.time()
+    _, stats = both(texts, vocab_size=4 + 10 + 12, min_frequency=1)
+    assert stats['n_unique_words'] == len(words)
+    assert time.time() - t0 < 60
