@@ -172,10 +172,7 @@ def test_word_table_growth(built_lib, monkeypatch):
     """A word table that starts far too small (all words distinct) grows instead of probing a full table."""
     monkeypatch.setenv('CTK_TRAIN_WORD_TABLE_DIV', '4096')
     rng = random.Random(11)
-    words = sorted({"".join(rng.choice("abcdefghij") for _ in range(8)) for _ in range(200000)})
+    words = sorted({"".join(rng.choice("abcdefghij") for _ in range(8)) for _ in range(120000)})
     texts = [" ".join(words[i:i + 100]) for i in range(0, len(words), 100)]
-    import time
-    t0 = time.time()
-    _, stats = both(texts, vocab_size=4 + 10 + 12, min_frequency=1)
-    assert stats['n_unique_words'] == len(words)
-    assert time.time() - t0 < 60
+    _, stats = both(texts, vocab_size=4 + 10 + 8, min_frequency=1)
+    assert stats['n_unique_words'] == len(words) > 65536           # more than the first table holds
