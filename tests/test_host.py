@@ -287,3 +287,18 @@ def test_trainer_has_no_cpu_fallback(built_lib):
         ct.BpeTrainer(vocab_size=100, min_frequency=1).train(['hello world'])
     assert ct.BpeTrainer(vocab_size=123, min_frequency=5).vocab_size == 123      # getters of src/bindings/trainers.rs:271-279
     assert ct.BpeTrainer(vocab_size=123, min_frequency=5).min_frequency == 5
+
+
+def test_trainer_argument_errors(built_lib):
+    """Argument checks of ctk_train_bpe come before any device work (include/ctk.h: CTK_ERR_ARG)."""
+    lib = built_lib
+    out = ctypes.c_void_p()
+    assert lib.ctk_train_bpe(None, 0, None, None, 0, ctypes.byref(out)) == 5
+    assert b'null' in (lib.ctk_last_error() or b'')
+    from complexity_tokenizer import _TrainerConfig
+    cfg = _TrainerConfig()
+    cfg.vocab_size, cfg.min_frequency, cfg.n_special, cfg.limit_alphabet = 100, 2, 3, -1      # three specials announced, none given
+    assert lib.ctk_train_bpe(ctypes.byref(cfg), 0, None, None, 0, ctypes.byref(out)) == 5
+    off = (ctypes.c_uint64 * 2)(0, 4)
+    cfg.n_special = 0
+    assert lib.ctk_train_bpe(ctypes.byref(cfg), 0, None, ctypes.addressof(off), 1, ctypes.byref(out)) == 5   # 4 bytes announced, no text
