@@ -122,7 +122,7 @@ def cpu_baseline(tok_path, text_np, offs, budget_s=12.0):
                       'the Rust reference cannot be built here)' % (k, nb / 2**20)}, orc
 
 
-def run_reference(args):
+def run_reference(args, json_out):
     """--impl reference: the reference's CPU algorithm (oracle port) with all host threads, same config/metric."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -161,7 +161,8 @@ def run_reference(args):
                          'sample': '%d docs (%.1f MiB) per step; oracle C core = restatement of the reference algorithm '
                                    '(Rust toolchain absent, reference not buildable)' % (k, nb / 2**20)},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
+        'gpu_launches': 0}), file=json_out)
+    json_out.flush()
 
 
 def main():
@@ -178,8 +179,12 @@ def main():
     ap.add_argument('--no-train', action='store_true')
     ap.add_argument('--train-bytes', type=int, default=3 << 20)
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: anything libraries print there (NCCL's version banner at N > 1) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
-        return run_reference(args)
+        return run_reference(args, json_out)
 
     import torch
     import torch.distributed as dist
@@ -428,7 +433,8 @@ def main():
                    'pretoken_cache': 'cleared inside every step', 'parallelism': 'documents sharded over %d GPU(s), no collective on the data path' % world},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
         'decode_batch': decode, 'encodings': encodings, 'train_bpe': train}
-    print(json.dumps(out))
+    print(json.dumps(out), file=json_out)
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
