@@ -79,6 +79,19 @@ def _lib():
         'ctk_from_file': (I, [ctypes.c_char_p, I, ctypes.POINTER(P)]),
         'ctk_from_json': (I, [P, S, I, ctypes.POINTER(P)]),
         'ctk_free': (None, [P]),
+        'ctk_from_file_devices': (I, [ctypes.c_char_p, I, P, ctypes.POINTER(P)]),
+        'ctk_from_json_devices': (I, [P, S, I, P, ctypes.POINTER(P)]),
+        'ctk_n_devices': (S, [P]),
+        'ctk_device_at': (I, [P, S]),
+        'ctk_numa_node': (I, [P, S]),
+        'ctk_device_numa_node': (I, [I]),
+        'ctk_id_width': (I, [P]),
+        'ctk_encode_batch_narrow': (I, [P, P, P, S, ctypes.POINTER(P)]),
+        'ctk_result_id_width': (I, [P]),
+        'ctk_result_ids_raw': (P, [P]),
+        'ctk_result_parts': (S, [P]),
+        'ctk_result_part': (I, [P, S, ctypes.POINTER(S), ctypes.POINTER(S), ctypes.POINTER(P), ctypes.POINTER(P)]),
+        'ctk_encode_batch_device_ex': (I, [P, P, P, S, U64, P, U64, I, P, ctypes.POINTER(U64), P]),
         'ctk_vocab_size': (S, [P]),
         'ctk_token_to_id': (I, [P, ctypes.c_char_p, S, ctypes.POINTER(ctypes.c_uint32)]),
         'ctk_id_to_token': (P, [P, ctypes.c_uint32, ctypes.POINTER(S)]),
@@ -217,23 +230,46 @@ class Tokenizer:
 
     # ---- constructors
     @staticmethod
-    def from_file(path, device=None):
+    def _device_list(devices):
+        """devices='all' or an iterable of device indices -> ctypes int array (None for all visible devices)"""
+        if isinstance(devices, str):
+            if devices != 'all':
+                raise ValueError("devices must be 'all' or a list of device indices")
+            return 0, None
+        ids = [int(d) for d in devices]
+        if not ids:
+            raise ValueError('devices is empty')
+        return len(ids), (ctypes.c_int * len(ids))(*ids)
+
+    @staticmethod
+    def from_file(path, device=None, devices=None):
+        """from_file(path): the reference's constructor (bindings/tokenizer.rs:19-23).  `device` picks the GPU;
+        `devices='all'` (or a list) makes ONE tokenizer that spreads every batch over several GPUs, the way the
+        reference's encode_batch uses every core of the machine (mod.rs:694-696)."""
         lib = _lib()
         h = ctypes.c_void_p()
-        dev = int(os.environ.get('CTK_DEVICE', '0')) if device is None else int(device)
-        rc = lib.ctk_from_file(os.fsencode(path), dev, ctypes.byref(h))
+        if devices is not None:
+            n, arr = Tokenizer._device_list(devices)
+            rc = lib.ctk_from_file_devices(os.fsencode(path), n, arr, ctypes.byref(h))
+        else:
+            dev = int(os.environ.get('CTK_DEVICE', '0')) if device is None else int(device)
+            rc = lib.ctk_from_file(os.fsencode(path), dev, ctypes.byref(h))
         if rc != CTK_OK:
             _raise(rc)
         return Tokenizer(h)
 
     @staticmethod
-    def from_str(json_text, device=None):
+    def from_str(json_text, device=None, devices=None):
         lib = _lib()
         data = json_text.encode('utf-8') if isinstance(json_text, str) else bytes(json_text)
         buf = ctypes.create_string_buffer(data, len(data))
         h = ctypes.c_void_p()
-        dev = int(os.environ.get('CTK_DEVICE', '0')) if device is None else int(device)
-        rc = lib.ctk_from_json(ctypes.addressof(buf), len(data), dev, ctypes.byref(h))
+        if devices is not None:
+            n, arr = Tokenizer._device_list(devices)
+            rc = lib.ctk_from_json_devices(ctypes.addressof(buf), len(data), n, arr, ctypes.byref(h))
+        else:
+            dev = int(os.environ.get('CTK_DEVICE', '0')) if device is None else int(device)
+            rc = lib.ctk_from_json(ctypes.addressof(buf), len(data), dev, ctypes.byref(h))
         if rc != CTK_OK:
             _raise(rc)
         return Tokenizer(h)
@@ -249,20 +285,50 @@ class Tokenizer:
                 pass
 
     # ---- packed (zero-object) API: numpy in, numpy out
-    def encode_packed(self, text, offsets):
-        """text: uint8 array (packed UTF-8), offsets: uint64[n+1] -> (ids uint32, ids_off uint64[n+1])"""
+    @staticmethod
+    def _result_parts(lib, res):
+        """[(first item, n items, data address, offsets address)] of a ctk_result (one per device that got items)"""
+        out = []
+        for i in range(int(lib.ctk_result_parts(res))):
+            first, cnt, data, off = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_void_p(), ctypes.c_void_p()
+            rc = lib.ctk_result_part(res, i, ctypes.byref(first), ctypes.byref(cnt), ctypes.byref(data), ctypes.byref(off))
+            if rc != CTK_OK:
+                _raise(rc)
+            out.append((int(first.value), int(cnt.value), data.value or 0, off.value or 0))
+        return out
+
+    def encode_packed(self, text, offsets, dtype=np.uint32):
+        """text: uint8 array (packed UTF-8), offsets: uint64[n+1] -> (ids, ids_off uint64[n+1]).
+        ids are `dtype` (uint32 like the reference's Vec<u32>); dtype=None keeps the element type the device
+        produced (uint16 when every id of the vocabulary fits: half the bytes over PCIe and in host memory)."""
         lib = _lib()
         text = np.ascontiguousarray(text, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
         res = ctypes.c_void_p()
-        rc = lib.ctk_encode_batch(self._h, text.ctypes.data if text.size else None, offsets.ctypes.data, n, ctypes.byref(res))
+        rc = lib.ctk_encode_batch_narrow(self._h, text.ctypes.data if text.size else None, offsets.ctypes.data, n, ctypes.byref(res))
         if rc != CTK_OK:
             _raise(rc)
         try:
-            off = np.ctypeslib.as_array(ctypes.cast(lib.ctk_result_offsets(res), ctypes.POINTER(ctypes.c_uint64)), (n + 1,)).copy()
-            tot = int(off[-1])
-            ids = np.ctypeslib.as_array(ctypes.cast(lib.ctk_result_ids(res), ctypes.POINTER(ctypes.c_uint32)), (max(tot, 1),))[:tot].copy()
+            width = int(lib.ctk_result_id_width(res))
+            src_t = np.uint16 if width == 2 else np.uint32
+            src_c = ctypes.c_uint16 if width == 2 else ctypes.c_uint32
+            parts = self._result_parts(lib, res)
+            off = np.empty(n + 1, dtype=np.uint64)
+            totals = []
+            base = 0
+            for first, cnt, data, poff in parts:
+                po = np.ctypeslib.as_array(ctypes.cast(poff, ctypes.POINTER(ctypes.c_uint64)), (cnt + 1,))
+                off[first:first + cnt] = po[:cnt] + np.uint64(base)
+                totals.append(int(po[cnt]))
+                base += totals[-1]
+            off[n] = base
+            ids = np.empty(base, dtype=src_t if dtype is None else dtype)
+            base = 0
+            for (first, cnt, data, poff), tot in zip(parts, totals):
+                if tot:
+                    ids[base:base + tot] = np.ctypeslib.as_array(ctypes.cast(data, ctypes.POINTER(src_c)), (tot,))
+                base += tot
         finally:
             lib.ctk_result_free(res)
         return ids, off
@@ -314,11 +380,15 @@ class Tokenizer:
             text, off = _marshal.pack_strs(texts if isinstance(texts, (list, tuple)) else list(texts))
             n = len(off) // 8 - 1
             res = ctypes.c_void_p()
-            rc = lib.ctk_encode_batch(self._h, text if text else None, off, n, ctypes.byref(res))
+            rc = lib.ctk_encode_batch_narrow(self._h, text if text else None, off, n, ctypes.byref(res))
             if rc != CTK_OK:
                 _raise(rc)
-            try:
-                return _marshal.unpack_ids(lib.ctk_result_ids(res) or 0, lib.ctk_result_offsets(res), n)
+            try:                        # one pass: device-width ids of every part -> Python ints (what PyO3 does with Vec<Vec<u32>>)
+                width = int(lib.ctk_result_id_width(res))
+                out = [None] * n
+                for first, cnt, data, poff in self._result_parts(lib, res):
+                    _marshal.unpack_ids(data, poff, cnt, width, out, first)
+                return out
             finally:
                 lib.ctk_result_free(res)
         buf, off = _pack_texts(list(texts))
@@ -551,6 +621,17 @@ class Tokenizer:
     def device(self):
         return int(_lib().ctk_device(self._h))
 
+    @property
+    def devices(self):
+        """devices this tokenizer spreads its batches over (one entry unless built with devices=...)"""
+        lib = _lib()
+        return [int(lib.ctk_device_at(self._h, i)) for i in range(int(lib.ctk_n_devices(self._h)))]
+
+    @property
+    def id_width(self):
+        """bytes per id the device produces: 2 when every id the tokenizer can emit is below 65 536, else 4"""
+        return int(_lib().ctk_id_width(self._h))
+
     def profile_enable(self, on=True):
         _lib().ctk_profile_enable(self._h, int(bool(on)))
 
@@ -565,11 +646,12 @@ class Tokenizer:
         return out
 
     # ---- device-resident API (pointers are device pointers on self.device; see include/ctk.h)
-    def encode_device(self, d_text, d_text_off, n_docs, total_bytes, d_ids, ids_cap, d_ids_off, stream=0, sync=True):
+    def encode_device(self, d_text, d_text_off, n_docs, total_bytes, d_ids, ids_cap, d_ids_off, stream=0, sync=True, id_width=4):
+        """device pointers in, device pointers out; id_width = element size of d_ids (2 only if self.id_width == 2)"""
         lib = _lib()
         tot = ctypes.c_uint64(0)
-        rc = lib.ctk_encode_batch_device(self._h, d_text, d_text_off, n_docs, total_bytes, d_ids, ids_cap, d_ids_off,
-                                         ctypes.byref(tot) if sync else None, stream or None)
+        rc = lib.ctk_encode_batch_device_ex(self._h, d_text, d_text_off, n_docs, total_bytes, d_ids, ids_cap, int(id_width), d_ids_off,
+                                            ctypes.byref(tot) if sync else None, stream or None)
         if rc != CTK_OK:
             _raise(rc)
         return int(tot.value) if sync else None

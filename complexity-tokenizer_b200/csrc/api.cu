@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -141,6 +142,12 @@ static int upload(Engine& eng) {
         }
         UP(23, eng.rich.byte_map2, map2, sizeof map2);
     }
+    {
+        uint64_t mx = m.id_present.empty() ? 0 : m.id_present.size() - 1;
+        for (const AddedTok& a : m.added) if (a.may_match) mx = std::max<uint64_t>(mx, a.id);
+        eng.max_emit_id = (uint32_t)std::min<uint64_t>(mx, 0xFFFFFFFFull);
+        eng.run_width = mx < 65536 && !getenv("CTK_WIDE_RUNS") ? 2 : 4;
+    }
     eng.tables.round_parallel = m.round_parallel ? 1u : 0u;
     UP(17, eng.tables.reach, m.reach.data(), m.reach.size() * 4);
 #undef UP
@@ -200,6 +207,7 @@ static int create(const uint8_t* json, size_t len, int device, ctk_tokenizer** o
     eng->device = device;
     e = cudaSetDevice(device);
     if (e != cudaSuccess) { rc = eng->cuda_fail(e, "cudaSetDevice"); delete eng; return rc; }
+    eng->numa_node = device_numa_node(device);
     rc = upload(*eng);
     if (rc != CTK_OK) { delete eng; return rc; }
     *out = reinterpret_cast<ctk_tokenizer*>(eng);
@@ -226,9 +234,73 @@ int ctk_from_file(const char* path, int device, ctk_tokenizer** out) {
     return create((const uint8_t*)data.data(), data.size(), device, out);
 }
 
+static void free_engine(Engine* eng);
+
 void ctk_free(ctk_tokenizer* tok) {
     if (!tok) return;
     Engine* eng = reinterpret_cast<Engine*>(tok);
+    std::vector<Engine*> peers = eng->peers;
+    for (Engine* p : peers) if (p != eng) free_engine(p);
+    free_engine(eng);
+}
+
+// Replaces HuggingFaceTokenizer::from_file for a tokenizer that drives several GPUs from one process: the reference's
+// encode_batch is one call that uses the whole machine (mod.rs:694-696).  Tables are replicated on every device.
+int ctk_from_json_devices(const uint8_t* json, size_t len, int n_devices, const int* device_ids, ctk_tokenizer** out) {
+    if (!json || !out) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
+    *out = nullptr;
+    std::vector<int> ids;
+    if (n_devices <= 0) {                                                  // all visible devices
+        int nd = 0;
+        cudaError_t e = cudaGetDeviceCount(&nd);
+        if (e != cudaSuccess || nd == 0) {
+            set_last_error(std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+            return CTK_ERR_CUDA;
+        }
+        for (int i = 0; i < nd; ++i) ids.push_back(i);
+    } else {
+        if (!device_ids) { set_last_error("device_ids is NULL"); return CTK_ERR_ARG; }
+        ids.assign(device_ids, device_ids + n_devices);
+        for (size_t i = 0; i < ids.size(); ++i)
+            for (size_t j = 0; j < i; ++j) if (ids[i] == ids[j]) { set_last_error("a device is listed twice"); return CTK_ERR_ARG; }
+    }
+    std::vector<Engine*> engines;
+    for (int d : ids) {
+        ctk_tokenizer* t = nullptr;
+        const int rc = create(json, len, d, &t);
+        if (rc != CTK_OK) { for (Engine* e : engines) free_engine(e); return rc; }
+        engines.push_back(reinterpret_cast<Engine*>(t));
+    }
+    if (engines.size() > 1) engines[0]->peers = engines;
+    *out = reinterpret_cast<ctk_tokenizer*>(engines[0]);
+    return CTK_OK;
+}
+
+int ctk_from_file_devices(const char* path, int n_devices, const int* device_ids, ctk_tokenizer** out) {
+    if (!path) { set_last_error("path is NULL"); return CTK_ERR_ARG; }
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { set_last_error(std::string("cannot open ") + path + ": No such file or directory (os error 2)"); return CTK_ERR_IO; }
+    std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (f.bad()) { set_last_error(std::string("read error on ") + path); return CTK_ERR_IO; }
+    return ctk_from_json_devices((const uint8_t*)data.data(), data.size(), n_devices, device_ids, out);
+}
+
+size_t ctk_n_devices(const ctk_tokenizer* tok) {
+    const Engine* eng = reinterpret_cast<const Engine*>(tok);
+    return eng->peers.empty() ? 1 : eng->peers.size();
+}
+int ctk_device_at(const ctk_tokenizer* tok, size_t i) {
+    const Engine* eng = reinterpret_cast<const Engine*>(tok);
+    if (eng->peers.empty()) return i == 0 ? eng->device : -1;
+    return i < eng->peers.size() ? eng->peers[i]->device : -1;
+}
+int ctk_numa_node(const ctk_tokenizer* tok, size_t i) {
+    const Engine* eng = reinterpret_cast<const Engine*>(tok);
+    if (eng->peers.empty()) return i == 0 ? eng->numa_node : -1;
+    return i < eng->peers.size() ? eng->peers[i]->numa_node : -1;
+}
+
+static void free_engine(Engine* eng) {
     cudaSetDevice(eng->device);
     cudaDeviceSynchronize();
     eng->ws.release();
@@ -267,6 +339,7 @@ const uint8_t* ctk_special_token(const ctk_tokenizer* tok, size_t i, size_t* len
     return (const uint8_t*)m.specials[i].first.data();
 }
 
+int ctk_device_numa_node(int device) { return device_numa_node(device); }
 int ctk_device(const ctk_tokenizer* tok) { return reinterpret_cast<const Engine*>(tok)->device; }
 size_t ctk_decode_max_bytes(const ctk_tokenizer* tok) { return reinterpret_cast<const Engine*>(tok)->model.dec_max_bytes; }
 const char* ctk_last_error(void) { return g_last_error.c_str(); }
@@ -289,7 +362,29 @@ size_t ctk_profile_report(ctk_tokenizer* tok, char* buf, size_t cap) {
     if (buf && cap) { size_t n = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(buf, s.data(), n); buf[n] = 0; }
     return s.size();
 }
-void ctk_set_cache_persistent(ctk_tokenizer* tok, int persistent) { reinterpret_cast<Engine*>(tok)->cache_persistent = persistent != 0; }
+void ctk_set_cache_persistent(ctk_tokenizer* tok, int persistent) {
+    Engine* eng = reinterpret_cast<Engine*>(tok);
+    eng->cache_persistent = persistent != 0;
+    for (Engine* p : eng->peers) p->cache_persistent = persistent != 0;
+}
+
+int ctk_encode_batch_device_ex(const ctk_tokenizer* tok, const uint8_t* d_text, const uint64_t* d_text_off, size_t n,
+                               uint64_t total_bytes, void* d_ids, uint64_t ids_cap, int id_width, uint64_t* d_ids_off,
+                               uint64_t* n_ids_host, void* stream) {
+    if (!tok || !d_text_off || !d_ids_off || (total_bytes && (!d_text || !d_ids))) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
+    Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
+    if (id_width != 4 && !(id_width == 2 && eng->run_width == 2)) {
+        set_last_error("id_width must be 4, or 2 when ctk_id_width(tok) == 2");
+        return CTK_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(eng->mu);
+    cudaError_t e = cudaSetDevice(eng->device);
+    if (e != cudaSuccess) return eng->cuda_fail(e, "cudaSetDevice");
+    eng->out_id_width = id_width;
+    const int rc = encode_device(*eng, d_text, d_text_off, n, total_bytes, static_cast<uint32_t*>(d_ids), ids_cap, d_ids_off, n_ids_host, (cudaStream_t)stream);
+    eng->out_id_width = 4;
+    return rc;
+}
 
 int ctk_encode_batch_device(const ctk_tokenizer* tok, const uint8_t* d_text, const uint64_t* d_text_off, size_t n,
                             uint64_t total_bytes, uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off,

@@ -64,12 +64,13 @@ struct FusedParams {
     const uint8_t* text; uint64_t n_bytes;
     const uint64_t* off; uint64_t n_docs;
     const uint32_t* first_doc; uint64_t n_slices; uint32_t n_tiles;
-    CacheSlot* cache; uint32_t cache_mask;
+    CacheSlot* cache; uint32_t cache_mask, cache_shift;                 // slot = hash >> cache_shift (top bits), probes wrap with cache_mask
     uint32_t id_bits, n_inline;                          // ids packed inline in a cache slot: n_inline x id_bits <= 96
     uint32_t* ovf_pool; uint32_t ovf_cap; uint32_t* ovf_cursor;
     uint32_t* long_pool; unsigned long long long_cap; unsigned long long* long_cursor;
     LongDesc* desc; uint32_t desc_cap; uint32_t* desc_cursor;
-    uint32_t* runs;                                      // n_slices x STAGE
+    void* runs;                                          // n_slices x STAGE ids of run_width bytes each
+    int run_width;                                       // 2: every id fits 16 bits (also 16 bits per id in a cache slot), else 4
     uint32_t* slice_cnt;                                 // ids of the slice (short + long)
     uint32_t* slice_info;                                // staged count | n_long << 16
     uint32_t* slice_desc;                                // first LongDesc of the slice (if n_long > 0)
@@ -84,15 +85,14 @@ struct FusedParams {
     XlEntry* xl_list;
     uint64_t* ids_off_rel;                               // slice-relative document offsets (k_doc_fixup makes them absolute)
     uint64_t* ids_off; uint32_t* err;
-    int ablate;                                          // debug: 1 = stop after boundaries, 2 = no slow path, 3 = no probe
+    int ablate;                                          // debug (CTK_ABLATE): 1 = stop after boundaries, 2 = no slow path, 3 = no probe, 4 = pre-token cache off
 };
 
+struct __align__(16) ChunkBuf { uint8_t pad0[16]; uint8_t chunk[CHUNK]; uint8_t pad1[16]; };
 struct __align__(16) WarpSmem {
-    uint8_t pad0[16];
-    uint8_t chunk[CHUNK];
-    uint8_t pad1[16];
+    ChunkBuf buf[2];                                     // this slice's chunk and the next one's (in flight)
     uint32_t ds[32];
-    uint16_t list[SLICE + 8];
+    uint16_t list[SLICE + 40];                           // owned starts + a round of sentinels
     uint16_t l_at[MAXLONG + 2], l_k[MAXLONG + 2], l_pos[MAXLONG + 2], l_len[MAXLONG + 2];
     uint32_t l_cnt[MAXLONG + 2];
 };
@@ -142,17 +142,20 @@ __device__ __forceinline__ void load_slot(const CacheSlot* p, uint32_t& k0, uint
                  : "=r"(k0), "=r"(k1), "=r"(k2), "=r"(k3), "=r"(meta), "=r"(t0), "=r"(t1), "=r"(t2) : "l"(p));
 }
 
+// the slot index is the TOP bits of this (h >> cache_shift): the last step is a multiply, whose high bits are the mixed ones
 __device__ __forceinline__ uint32_t key_hash(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t len) {
-    uint32_t h = x0 * 0x9E3779B1u ^ x1 * 0x85EBCA77u ^ x2 * 0xC2B2AE3Du ^ x3 * 0x27D4EB2Fu ^ len * 0x165667B1u;
-    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
-    return h;
+    uint32_t h = (x0 * 0x9E3779B1u + x1 * 0x85EBCA77u) ^ (x2 * 0xC2B2AE3Du + x3 * 0x27D4EB2Fu + len * 0x165667B1u);
+    h ^= h >> 15;
+    return h * 0x2C1B3C6Du;
 }
 
+// SHFL.UP sets a predicate where the source lane exists: two instructions per step (shuffle, predicated add)
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t& total, int lane) {
     const unsigned full = 0xFFFFFFFFu;
     uint32_t incl = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(full, incl, o); if (lane >= o) incl += u; }
+    for (int o = 1; o < 32; o <<= 1)
+        asm volatile("{ .reg .u32 t; .reg .pred q; shfl.sync.up.b32 t|q, %0, %1, 0, 0xffffffff; @q add.u32 %0, %0, t; }" : "+r"(incl) : "r"(o));
     total = __shfl_sync(full, incl, 31);
     return incl - v;
 }
@@ -184,16 +187,30 @@ namespace ctk {
 #ifndef CTK_LB
 #define CTK_LB 4
 #endif
-#ifndef CTK_EMIT_PTR
-#define CTK_EMIT_PTR 1       // measured -1.3 % kernel time
+#ifndef CTK_ASYNC_CHUNK
+#define CTK_ASYNC_CHUNK 1    // the next slice's chunk travels global -> shared with cp.async while this one is processed (no registers)
 #endif
-#ifndef CTK_COMPACT_PRED
-#define CTK_COMPACT_PRED 1   // measured -0.8 % kernel time
-#endif
-#ifndef CTK_PREFETCH
-#define CTK_PREFETCH 0   // measured: loading the next slice one iteration ahead costs more (registers) than it hides
-#endif
+
+template <int RW> struct RunId;
+template <> struct RunId<2> { typedef uint16_t type; };
+template <> struct RunId<4> { typedef uint32_t type; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// st.shared.u16 only where `bits` != 0: one ISETP + one predicated STS, no branch
+__device__ __forceinline__ void sts16_if(uint32_t saddr, uint32_t v, uint32_t bits) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u16 [%0], %1; }" :: "r"(saddr), "h"((unsigned short)v), "r"(bits) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t saddr, const void* g, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(saddr), "l"(g), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// RW = bytes per id in the slice runs: 2 when every id the tokenizer can emit is below 65 536 (half the scratch
+// traffic of this kernel and of k_compact), else 4.  In a cache slot ids then take 16 bits each (p.id_bits == 16).
+template <int RW>
 __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedParams p) {
+    typedef typename RunId<RW>::type run_t;
     const unsigned full = 0xFFFFFFFFu;
     __shared__ WarpSmem sm[FW];
     __shared__ uint32_t s_byte_init[256];
@@ -206,122 +223,125 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
         s_kmask[tid] = make_uint4(m[0], m[1], m[2], m[3]);
     }
     WarpSmem& S = sm[w];
-    if (lane == 0) {
-        *reinterpret_cast<uint4*>(S.pad0) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(S.pad1) = make_uint4(0, 0, 0, 0);
+    if (lane < 4) {
+        uint4* z = reinterpret_cast<uint4*>(lane & 1 ? S.buf[lane >> 1].pad1 : S.buf[lane >> 1].pad0);
+        *z = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     const CacheSlot* const cache = p.cache;
-    const uint32_t cmask = p.cache_mask, idb = p.id_bits, idmask = (1u << p.id_bits) - 1u, ninl = p.n_inline;
+    const uint32_t cshift = p.cache_shift, idb = p.id_bits, idmask = p.id_bits >= 32 ? 0xFFFFFFFFu : (1u << p.id_bits) - 1u, ninl = p.n_inline;
     const uint8_t* const text = p.text;
-    const uint64_t n_bytes = p.n_bytes;
+    const uint32_t nb32 = (uint32_t)p.n_bytes;                           // a device call takes < 4 GiB: positions are 32-bit here
+    const uint32_t n_slices = (uint32_t)p.n_slices;
+    const uint32_t stride = gridDim.x * FW;
+    uint32_t slice = blockIdx.x * FW + w;
+    if (slice >= n_slices) return;
 
-    // one 16-byte vector per lane, zero beyond the text (the tail is masked when it is used)
-    auto load_vec = [&](uint64_t sl) -> uint4 {
-        const long long qq = (long long)sl * SLICE - LCTX + 16 * lane;
-        uint4 r = make_uint4(0, 0, 0, 0);
-        if (qq >= 0 && qq < (long long)n_bytes) r = __ldg(reinterpret_cast<const uint4*>(text + qq));
-        return r;
-    };
-    const uint64_t stride = (uint64_t)gridDim.x * FW;
-    uint64_t slice = (uint64_t)blockIdx.x * FW + w;
-#if CTK_PREFETCH
-    uint4 vn = make_uint4(0, 0, 0, 0);
-    uint32_t fdn = 0;
-    if (slice < p.n_slices) { vn = load_vec(slice); fdn = __ldg(p.first_doc + slice); }
-#endif
-    for (; slice < p.n_slices; slice += stride) {
-        const long long lo = (long long)slice * SLICE, cb = lo - LCTX;     // chunk base (may be -16 for slice 0)
-        uint32_t* const run = p.runs + slice * STAGE;
-        uint32_t n_owned = 0, stage_cnt = 0, n_long = 0, first_k = 0, ownm = 0;
-
-        // ---- 1. the chunk (loaded one slice ahead: its latency hides behind the previous slice's work)
-        const long long q = cb + 16 * lane;
-        const long long room = (long long)n_bytes - q;                     // valid bytes from this lane's first byte on
-#if CTK_PREFETCH
-        uint4 v = vn;
-        const uint32_t fd = fdn;
-        if (slice + stride < p.n_slices) { vn = load_vec(slice + stride); fdn = __ldg(p.first_doc + slice + stride); }
-#else
-        uint4 v = load_vec(slice);
-        const uint32_t fd = __ldg(p.first_doc + slice);
-#endif
-        const uint32_t d0 = fd & 0x7FFFFFFFu;
-        if (room > 0 && room < 16) {                                       // last bytes of the text: zero the rest
-            uint4 km = s_kmask[room];
-            v.x &= km.x; v.y &= km.y; v.z &= km.z; v.w &= km.w;
+    // this lane's 16 bytes of a slice's chunk -> shared memory, zero beyond either end of the text
+    auto fetch = [&](uint32_t sl, int b) {
+        const uint32_t q = sl * SLICE - LCTX + 16 * lane;                 // (wraps for lane 0 of slice 0, which reads nothing)
+        uint32_t sz = 16;
+        if (sl == 0 || sl * SLICE + (CHUNK - LCTX) > nb32) {              // warp-uniform: the chunk sticks out of the text
+            const uint32_t left = nb32 - sl * SLICE + LCTX;               // bytes from the chunk's first byte to the end of the text
+            const uint32_t mine = left > 16u * lane ? left - 16u * lane : 0u;
+            sz = (sl == 0 && lane == 0) ? 0u : (mine < 16u ? mine : 16u);
         }
-        __syncwarp();                                                      // previous slice's readers are done
-        *reinterpret_cast<uint4*>(S.chunk + 16 * lane) = v;
+#if CTK_ASYNC_CHUNK
+        cp_async16_zfill(smem_u32(S.buf[b].chunk + 16 * lane), text + (sz ? q : 0), sz);
+#else
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (sz) r = __ldg(reinterpret_cast<const uint4*>(text + q));
+        if (sz && sz < 16) { const uint4 km = s_kmask[sz]; r.x &= km.x; r.y &= km.y; r.z &= km.z; r.w &= km.w; }
+        *reinterpret_cast<uint4*>(S.buf[b].chunk + 16 * lane) = r;
+#endif
+    };
+    int buf = 0;
+#if CTK_ASYNC_CHUNK
+    fetch(slice, 0);
+#endif
+    uint32_t fd_next = __ldg(p.first_doc + slice);
+    for (; slice < n_slices; slice += stride, buf ^= 1) {
+        const uint32_t lo = slice * SLICE;                                 // first owned byte; the chunk starts LCTX bytes before it
+        run_t* const run = reinterpret_cast<run_t*>(p.runs) + (uint64_t)slice * STAGE;
+        uint8_t* const chunk = S.buf[buf].chunk;
+        uint32_t n_owned = 0, stage_cnt = 0, n_long = 0, first_k = 0, ownm = 0;
+        // interior slice (warp-uniform): the whole chunk lies inside the text
+        const bool edge = slice == 0 || lo + (CHUNK - LCTX) > nb32;
+        // valid bytes from this lane's first byte on (only its sign and values below 16 matter)
+        const int room = edge ? (int)min(nb32 - lo, 1024u) + LCTX - 16 * lane : 16;
+
+        // ---- 1. the chunk: fetched one slice ahead, so its latency hides behind the previous slice's work
+        const uint32_t fd = fd_next;
+#if CTK_ASYNC_CHUNK
+        cp_async_wait_all();
+        __syncwarp();                                                      // every lane's 16 bytes have landed; the previous slice's readers are done
+        if (slice + stride < n_slices) { fetch(slice + stride, buf ^ 1); fd_next = __ldg(p.first_doc + slice + stride); }
+#else
+        __syncwarp();
+        fetch(slice, buf);
+        if (slice + stride < n_slices) fd_next = __ldg(p.first_doc + slice + stride);
+        __syncwarp();
+#endif
+        const uint4 v = *reinterpret_cast<const uint4*>(chunk + 16 * lane);
+        const uint32_t d0 = fd & 0x7FFFFFFFu;
         // ---- document starts inside the chunk (position n_bytes = off[n_docs] counts as one)
         uint32_t ds16 = 0;
         const bool docs_here = (fd >> 31) != 0;                            // warp-uniform
         if (docs_here) {
             S.ds[lane] = 0;
             __syncwarp();
-            for (uint64_t d = (uint64_t)d0 + lane;; d += 32) {
-                uint64_t pos = d <= p.n_docs ? __ldg(p.off + d) : ~0ull;
-                bool in = (long long)pos < cb + CHUNK && pos != ~0ull;
-                if (in) { uint32_t rel = (uint32_t)((long long)pos - cb); atomicOr(&S.ds[rel >> 4], 1u << (rel & 15)); }
+            for (uint64_t d = (uint64_t)d0 + lane;; d += 32) {            // off[d0] is the first offset at or after the chunk's first byte
+                const uint32_t rel = d <= p.n_docs ? (uint32_t)__ldg(p.off + d) - lo + LCTX : 0xFFFFFFFFu;   // chunk-relative
+                const bool in = rel < (uint32_t)CHUNK;
+                if (in) atomicOr(&S.ds[rel >> 4], 1u << (rel & 15));
                 if (!__all_sync(full, in)) break;
             }
             __syncwarp();
             ds16 = S.ds[lane];
         }
-        __syncwarp();
         // ---- 2. classes and boundaries
+        uint32_t own16;
         {
-            Masks16 m = classify16(S.chunk, 16 * lane, v.x, v.y, v.z, v.w, p.t.trie_index, p.t.trie_blocks);
+            Masks16 m = classify16(chunk, 16 * lane, v.x, v.y, v.z, v.w, p.t.trie_index, p.t.trie_blocks);
             if (m.SUSP && p.check_nfc) atomicOr(p.err, ERRF_NFC_SUSPECT);
-            uint32_t pa = m.L | (m.N << 16), pb = m.W | (m.SP << 16), pc = m.AP | (m.CONT << 16);
-            uint32_t ua = __shfl_up_sync(full, pa, 1), ub = __shfl_up_sync(full, pb, 1), uc = __shfl_up_sync(full, pc, 1),
-                     ud = __shfl_up_sync(full, ds16, 1);
-            uint32_t na = __shfl_down_sync(full, pa, 1), nb = __shfl_down_sync(full, pb, 1), nc = __shfl_down_sync(full, pc, 1),
-                     nd = __shfl_down_sync(full, ds16, 1);
-            if (lane == 0) { ua = ub = uc = ud = 0; }
-            if (lane == 31) { na = nb = nc = nd = 0; }
-            // windows = [previous lane's byte 1 | own bytes 0,1 | next lane's byte 0] of each 16-bit mask: two PRMT each
-            #define WLO(u, o, nx) __byte_perm(__byte_perm(u, o, 0x0541), nx, 0x4210)
-            #define WHI(u, o, nx) __byte_perm(__byte_perm(u, o, 0x0763), nx, 0x6210)
-            uint32_t S32 = start_window(WLO(ua, pa, na), WHI(ua, pa, na), WLO(ub, pb, nb), WHI(ub, pb, nb),
-                                        WLO(uc, pc, nc), WHI(uc, pc, nc), WLO(ud, ds16, nd), S.chunk + 16 * lane - 8);
-            #undef WLO
-            #undef WHI
-            uint32_t own16 = (S32 >> 8) & 0xFFFFu;
-            uint32_t valid = room >= 16 ? 0xFFFFu : (room <= 0 ? 0u : ((1u << room) - 1u));
+            const uint32_t pa = m.L | (m.N << 16), pb = m.W | (m.SP << 16), pc = m.AP | (m.CONT << 16);
+            // neighbours need only the adjoining byte of each mask: four shuffles move all seven masks
+            // (lane 0's "previous" and lane 31's "next" are its own values: those lanes own nothing, their result is not used)
+            const uint32_t ua = __shfl_up_sync(full, __byte_perm(pa, pb, 0x7531), 1), ub = __shfl_up_sync(full, __byte_perm(pc, ds16, 0x7531), 1);
+            const uint32_t na = __shfl_down_sync(full, __byte_perm(pa, pb, 0x6420), 1), nb = __shfl_down_sync(full, __byte_perm(pc, ds16, 0x6420), 1);
+            // windows = [previous lane's high byte | own two bytes | next lane's low byte] of each 16-bit mask: two PRMT each
+            #define WIN(u, o, nx, s1, s2) __byte_perm(__byte_perm(u, o, s1), nx, s2)
+            const uint32_t S32 = start_window(WIN(ua, pa, na, 0x0540, 0x4210), WIN(ua, pa, na, 0x0761, 0x5210), WIN(ua, pb, na, 0x0542, 0x6210),
+                                              WIN(ua, pb, na, 0x0763, 0x7210), WIN(ub, pc, nb, 0x0540, 0x4210), WIN(ub, pc, nb, 0x0761, 0x5210),
+                                              WIN(ub, ds16, nb, 0x0542, 0x6210), chunk + 16 * lane - 8);
+            #undef WIN
+            own16 = (S32 >> 8) & 0xFFFFu;
+        }
+        {
+            const uint32_t valid = room >= 16 ? 0xFFFFu : (room <= 0 ? 0u : ((1u << room) - 1u));
             ownm = (lane >= 1 && lane <= 28) ? (own16 & valid) : 0u;
             // ---- 3. compaction: list of owned pre-token starts, then the sentinel (first start after them)
-            uint32_t c = __popc(ownm);
-            first_k = warp_excl_scan(c, n_owned, lane);
+            first_k = warp_excl_scan(__popc(ownm), n_owned, lane);
             uint32_t bits = ownm;
-            uint16_t* lp = S.list + first_k;
-            const uint32_t lb = 16 * lane;
-#if CTK_COMPACT_PRED
-            // predicated, no branches: the first four starts of the lane (a lane rarely has more)
+            const uint32_t lb = 16 * lane - 1;
+            uint32_t la = smem_u32(S.list + first_k);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool any = bits != 0;
-                const uint16_t v = (uint16_t)(lb + __ffs(bits) - 1);
-                if (any) lp[j] = v;
+            for (int j = 0; j < 4; ++j) {                                  // predicated, no branches: a lane rarely has more than four starts
+                sts16_if(la + 2 * j, lb + __ffs(bits), bits);
                 bits &= bits - 1;                                          // 0 stays 0
             }
-            if (bits) { lp += 4; do { *lp++ = (uint16_t)(lb + __ffs(bits) - 1); bits &= bits - 1; } while (bits); }
-#else
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (bits) { *lp++ = (uint16_t)(lb + __ffs(bits) - 1); bits &= bits - 1; }
-            }
-            while (bits) { *lp++ = (uint16_t)(lb + __ffs(bits) - 1); bits &= bits - 1; }
-#endif
+            if (bits) { uint16_t* lp = S.list + first_k + 4; do { *lp++ = (uint16_t)(lb + __ffs(bits)); bits &= bits - 1; } while (bits); }
             // sentinel candidates: starts in the right context (lanes 29, 30) and the end of the text
             // (position n_bytes is a start thanks to its DS bit) wherever it falls
             uint32_t rc = 0;
             if (lane == 29 || lane == 30) rc = own16 & (room >= 16 ? 0xFFFFu : (room < 0 ? 0u : ((2u << room) - 1u)));
-            else if (lane >= 1 && lane <= 28 && room >= 0 && room < 16) rc = own16 & (1u << room);
-            unsigned bal = __ballot_sync(full, rc != 0);
+            else if (edge && lane >= 1 && lane <= 28 && room >= 0 && room < 16) rc = own16 & (1u << room);
+            const unsigned bal = __ballot_sync(full, rc != 0);
             uint32_t sent = END_UNKNOWN;
-            if (bal) { int sl = __ffs(bal) - 1; uint32_t r2 = __shfl_sync(full, rc, sl); sent = 16 * sl + (__ffs(r2) - 1); }
-            if (lane == 0) { S.list[n_owned] = (uint16_t)sent; S.list[n_owned + 1] = (uint16_t)sent; }
+            if (bal) { const int sl = __ffs(bal) - 1; const uint32_t r2 = __shfl_sync(full, rc, sl); sent = 16 * sl + (__ffs(r2) - 1); }
+            // list[n_owned ..] = sentinel for a whole round and one more: the lanes beyond the last pre-token see length 0
+            S.list[n_owned + lane] = (uint16_t)sent;
+            if (lane < 2) S.list[n_owned + 32 + lane] = (uint16_t)sent;
         }
         __syncwarp();
         if (lane == 0) p.slice_first[slice] = n_owned ? S.list[0] : (uint16_t)0xFFFFu;
@@ -330,46 +350,50 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
         // ---- 4. pre-tokens, 32 per round
         for (uint32_t base_k = 0; base_k < n_owned; base_k += 32) {
             const uint32_t k = base_k + lane;
-            const bool have = k < n_owned;
-            const uint32_t kk = have ? k : n_owned;                        // clamp: list[n_owned], list[n_owned+1] exist
-            const uint32_t pos = S.list[kk], end = S.list[kk + 1];
-            const uint32_t len = end - pos;                                // huge when the end is unknown
-            __syncwarp();
+            const uint32_t pos = S.list[k], end = S.list[k + 1];
+            const uint32_t len = end - pos;                                // 0 beyond the last pre-token; huge when the end is unknown
+            const bool have = len != 0;
             // straight line: key bytes, hash, one slot load, compare
-            const uint32_t pc = pos < CHUNK ? pos : 0u;
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(S.chunk + (pc & ~3u));
+            const uint32_t pc = pos & (CHUNK - 1);                         // (only a lane without a pre-token can hold END_UNKNOWN here)
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(chunk + (pc & ~3u));
             const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
             const uint32_t sh = (pc & 3u) * 8;
             const uint4 km = s_kmask[len < 16 ? len : 16];
             const uint32_t x0 = __funnelshift_r(a0, a1, sh) & km.x, x1 = __funnelshift_r(a1, a2, sh) & km.y,
                            x2 = __funnelshift_r(a2, a3, sh) & km.z, x3 = __funnelshift_r(a3, a4, sh) & km.w;
-            const uint32_t h = key_hash(x0, x1, x2, x3, len);
+            const uint32_t idx0 = key_hash(x0, x1, x2, x3, len) >> cshift;
             uint32_t s0, s1, s2, s3, meta, t0, t1, t2;
-            load_slot(cache + (h & cmask), s0, s1, s2, s3, meta, t0, t1, t2);
-            bool match = have && len <= 16 && (meta & 0xFFu) == len && (((s0 ^ x0) | (s1 ^ x1)) | ((s2 ^ x2) | (s3 ^ x3))) == 0;
-            // displaced keys (0.8% of occurrences): the lane itself walks on; the others idle for a few instructions
-            uint32_t ins_slot = kNone;
-            {
-                bool open = have && len <= 16 && !match;
-                if (open && meta == META_EMPTY) { ins_slot = h & cmask; open = false; }
-                for (int pr = 1; pr < PROBES && __any_sync(full, open); ++pr) {
-                    if (open) {
-                        uint32_t r0, r1, r2, r3, rm, v0, v1, v2;
-                        const uint32_t idx = (h + pr) & cmask;
-                        load_slot(cache + idx, r0, r1, r2, r3, rm, v0, v1, v2);
-                        if ((rm & 0xFFu) == len && (((r0 ^ x0) | (r1 ^ x1)) | ((r2 ^ x2) | (r3 ^ x3))) == 0) {
-                            match = true; open = false; meta = rm; t0 = v0; t1 = v1; t2 = v2;
-                        } else if (rm == META_EMPTY) { ins_slot = idx; open = false; }
-                    }
-                }
-            }
-            uint32_t ntok = (meta >> 8) & 0xFFu;
-            const bool fast = match && ntok <= ninl;
-            if (!fast) ntok = 0;
-            // everything else: warp-cooperative, one pre-token after the other, in lane order
+            load_slot(cache + idx0, s0, s1, s2, s3, meta, t0, t1, t2);
+            // the table only holds pre-tokens of 1..16 bytes and an EMPTY / BUSY slot has 0xFF / 0xFE in its length byte: lanes
+            // without a pre-token (len 0) or with a longer one can never compare equal
+            if (p.ablate == 4) meta = META_BUSY;                           // measurement: cache off, every pre-token is merged where it stands
+            bool match = (meta & 0xFFu) == len && (((s0 ^ x0) | (s1 ^ x1)) | ((s2 ^ x2) | (s3 ^ x3))) == 0;
+            uint32_t ntok = __byte_perm(meta, 0, 0x4441);                  // (meta >> 8) & 0xFF
+            bool fast = match && ntok <= ninl;
+            // everything else: displaced keys walk on; then warp-cooperative, one pre-token after the other, in lane order
             unsigned slow = __ballot_sync(full, have && !fast);
             if (p.ablate == 2) slow = 0;
             if (slow) {
+                uint32_t ins_slot = kNone;
+                {
+                    bool open = have && len <= 16 && !match;
+                    if (open && meta == META_EMPTY) { ins_slot = idx0; open = false; }
+                    if (p.ablate == 3 || p.ablate == 4) open = false;
+                    for (int pr = 1; pr < PROBES && __any_sync(full, open); ++pr) {
+                        if (open) {
+                            uint32_t r0, r1, r2, r3, rm, v0, v1, v2;
+                            const uint32_t idx = (idx0 + pr) & p.cache_mask;
+                            load_slot(cache + idx, r0, r1, r2, r3, rm, v0, v1, v2);
+                            if ((rm & 0xFFu) == len && (((r0 ^ x0) | (r1 ^ x1)) | ((r2 ^ x2) | (r3 ^ x3))) == 0) {
+                                match = true; open = false; meta = rm; t0 = v0; t1 = v1; t2 = v2;
+                            } else if (rm == META_EMPTY) { ins_slot = idx; open = false; }
+                        }
+                    }
+                    ntok = (meta >> 8) & 0xFFu;
+                    fast = match && ntok <= ninl;
+                    slow = __ballot_sync(full, have && !fast);
+                }
+                if (!fast) ntok = 0;
                 uint32_t hit_total;
                 const uint32_t E = warp_excl_scan(ntok, hit_total, lane);  // ids of fast lanes before each lane
                 uint32_t extra = 0;                                        // ids of slow lanes handled so far
@@ -387,34 +411,34 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
                     if (__shfl_sync(full, (uint32_t)match, src)) {         // cached, but its ids live in the overflow pool
                         cnt = (int)((__shfl_sync(full, meta, src) >> 8) & 0xFFu);
                         const uint32_t rec = __shfl_sync(full, t0, src);
-                        if (lane < cnt) run[o + lane] = p.ovf_pool[(uint64_t)rec * 16 + lane];
+                        if (lane < cnt) run[o + lane] = (run_t)p.ovf_pool[(uint64_t)rec * 16 + lane];
                         if (p.ablate == 9 && lane == 0) atomicAdd(p.err + 17, 1u);
                     }
                     if (cnt < 0) {                                         // merge now
                         uint32_t sym;
                         if (p.ablate == 9 && lane == 0) atomicAdd(p.err + 19 + (slen > 16 ? 1 : 0) + (slen <= 16 && ins == kNone ? 2 : 0), 1u);
                         if (p.t.n_added == 0) {
-                            int n = init_symbols32(s_byte_init, S.chunk + spos, (int)slen, sym, lane);
+                            int n = init_symbols32(s_byte_init, chunk + spos, (int)slen, sym, lane);
                             cnt = n ? bpe_warp32(p.t, sym, n) : 0;
-                            if (lane < cnt) run[o + lane] = sym;
+                            if (lane < cnt) run[o + lane] = (run_t)sym;
                         } else {                                           // mod.rs:566-610: added tokens inside the word
                             int r = 0;
                             cnt = 0;
                             while (r < (int)slen) {
                                 uint32_t aid;
-                                const int pl = added_next_piece(p.t, S.chunk + spos + r, (int)slen - r, lane, &aid);
-                                if (aid != kNone) { if (lane == 0) run[o + cnt] = aid; cnt += 1; }
+                                const int pl = added_next_piece(p.t, chunk + spos + r, (int)slen - r, lane, &aid);
+                                if (aid != kNone) { if (lane == 0) run[o + cnt] = (run_t)aid; cnt += 1; }
                                 else {
                                     uint32_t ps;
-                                    int n = init_symbols32(s_byte_init, S.chunk + spos + r, pl, ps, lane);
+                                    int n = init_symbols32(s_byte_init, chunk + spos + r, pl, ps, lane);
                                     int c = n ? bpe_warp32(p.t, ps, n) : 0;
-                                    if (lane < c) run[o + cnt + lane] = ps;
+                                    if (lane < c) run[o + cnt + lane] = (run_t)ps;
                                     cnt += c;
                                 }
                                 r += pl;
                             }
                             __syncwarp();
-                            sym = lane < cnt ? __ldcg(run + o + lane) : kNone;  // back into lanes for the cache entry
+                            sym = lane < cnt ? (uint32_t)__ldcg(run + o + lane) : kNone;  // back into lanes for the cache entry
                         }
                         if (ins != kNone) {                                // publish in the batch cache
                             uint32_t w0 = 0, w1 = 0, w2 = 0;
@@ -463,27 +487,36 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
             // ids of all lower lanes (fast and slow): the slow lanes wrote theirs at exactly these offsets
             uint32_t round_total;
             const uint32_t o = stage_cnt + warp_excl_scan(ntok, round_total, lane);
-            if (fast) {
-#if CTK_EMIT_PTR
-                uint32_t* const dst = run + o;                             // one address, immediate offsets
-#pragma unroll
-                for (int i = 0; i < MAXINLINE; ++i) {
-                    if (i < (int)ntok) dst[i] = t0 & idmask;
-                    t0 = __funnelshift_r(t0, t1, idb); t1 = __funnelshift_r(t1, t2, idb); t2 >>= idb;
+            {
+                const uint32_t en = fast ? ntok : 0u;                      // ids this lane unpacks from its slot (a slot may hold none: every byte dropped)
+                const uint32_t mx = __reduce_max_sync(full, en);           // most pre-tokens are one or two ids: stop at the round's longest
+                run_t* const dst = run + o;
+                if (RW == 2) {                                             // 16 bits per id in the slot, 16-bit stores
+                    if (en >= 1) dst[0] = (run_t)t0;
+                    if (mx >= 2) {
+                        if (en >= 2) dst[1] = (run_t)(t0 >> 16);
+                        if (mx >= 3) {
+                            if (en >= 3) dst[2] = (run_t)t1;
+                            if (mx >= 4) {
+                                if (en >= 4) dst[3] = (run_t)(t1 >> 16);
+                                if (en >= 5) dst[4] = (run_t)t2;
+                                if (en >= 6) dst[5] = (run_t)(t2 >> 16);
+                            }
+                        }
+                    }
+                } else {
+                    if (en >= 1) dst[0] = (run_t)(t0 & idmask);
+                    for (uint32_t i = 1; i < mx; ++i) {
+                        t0 = __funnelshift_r(t0, t1, idb); t1 = __funnelshift_r(t1, t2, idb); t2 >>= idb;
+                        if (i < en) dst[i] = (run_t)(t0 & idmask);
+                    }
                 }
-#else
-#pragma unroll
-                for (int i = 0; i < MAXINLINE; ++i) {
-                    if (i < (int)ntok) run[o + i] = t0 & idmask;
-                    t0 = __funnelshift_r(t0, t1, idb); t1 = __funnelshift_r(t1, t2, idb); t2 >>= idb;
-                }
-#endif
             }
             // the list entry now becomes the pre-token's id offset inside the slice's run (ids_off, long ones)
-            if (have && (docs_here || n_long)) S.list[k] = (uint16_t)o;
+            if (docs_here || n_long) { __syncwarp(); if (have) S.list[k] = (uint16_t)o; }
             stage_cnt += round_total;
-            __syncwarp();
         }
+        __syncwarp();
         if (lane == 0) S.list[n_owned] = (uint16_t)stage_cnt;
 
         // ---- long pre-tokens (> 32 bytes): described here, merged by k_encode_long
@@ -496,9 +529,9 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
             __syncwarp();
             if (lane < (int)n_long) {
                 LongDesc dd;
-                dd.gstart = (uint64_t)(cb + S.l_pos[lane]);
+                dd.gstart = (uint64_t)(lo + S.l_pos[lane] - LCTX);
                 dd.len = S.l_len[lane] == END_UNKNOWN ? 0xFFFFFFFFu : (uint32_t)S.l_len[lane];
-                dd.slice = (uint32_t)slice;
+                dd.slice = slice;
                 dd.k_at = ((uint32_t)S.l_k[lane] << 16) | (uint32_t)S.list[S.l_k[lane]];
                 dd.pool = 0; dd.cnt = 0; dd.chunk_end = (uint32_t)(CHUNK - 16) - (uint32_t)S.l_pos[lane];
                 p.desc[desc0 + lane] = dd;
@@ -509,13 +542,12 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
         // ---- ids_off (relative to this slice) for the documents that start in the owned bytes, or at
         //      the very end of the text (owned by the last slice)
         if (docs_here) {
-            const bool last_slice = slice + 1 == p.n_slices;
+            const bool last_slice = slice + 1 == n_slices;
             for (uint64_t d = (uint64_t)d0 + lane;; d += 32) {
-                uint64_t pos = d <= p.n_docs ? __ldg(p.off + d) : ~0ull;
-                bool in = (long long)pos < cb + CHUNK && pos != ~0ull;
-                bool own = in && (((long long)pos >= lo && (long long)pos < lo + SLICE) ||
-                                  (last_slice && pos == n_bytes && (long long)pos >= lo));
-                uint32_t rel = own ? (uint32_t)((long long)pos - cb) : 0u;
+                const uint32_t crel = d <= p.n_docs ? (uint32_t)__ldg(p.off + d) - lo + LCTX : 0xFFFFFFFFu;
+                const bool in = crel < (uint32_t)CHUNK;
+                const bool own = in && crel >= (uint32_t)LCTX && (crel < (uint32_t)(LCTX + SLICE) || (last_slice && crel - LCTX == nb32 - lo));
+                const uint32_t rel = own ? crel : 0u;
                 uint32_t fk = __shfl_sync(full, first_k, rel >> 4), sb = __shfl_sync(full, ownm, rel >> 4);
                 if (own) {
                     uint32_t k = fk + __popc(sb & ((1u << (rel & 15)) - 1u));
@@ -534,46 +566,50 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
     }
 }
 
-// one warp per slice: the slice's run -> its final place (four loads in flight per lane)
-__global__ void __launch_bounds__(256) k_compact(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ slice_base,
+// one warp per slice: the slice's run -> its final place (four loads in flight per lane).
+// RW / OW = bytes per id in the runs / in the packed output (2 or 4 each)
+template <int RW, int OW>
+__global__ void __launch_bounds__(256) k_compact(const void* __restrict__ runs_v, const uint32_t* __restrict__ slice_base,
                                                  const uint32_t* __restrict__ slice_info, const uint32_t* __restrict__ slice_desc,
                                                  const LongDesc* __restrict__ desc, const uint32_t* __restrict__ long_pool,
-                                                 uint64_t n_slices, uint32_t* __restrict__ out, uint64_t out_cap,
+                                                 uint64_t n_slices, void* __restrict__ out_v, uint64_t out_cap,
                                                  uint32_t* __restrict__ err) {
+    typedef typename RunId<RW>::type run_t;
+    typedef typename RunId<OW>::type out_t;
     const int lane = threadIdx.x & 31;
     const uint64_t s = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     if (s >= n_slices) return;
     const uint32_t b = __ldg(slice_base + s), nxt = __ldg(slice_base + s + 1), inf = __ldg(slice_info + s);
     if ((uint64_t)nxt > out_cap) { if (lane == 0) atomicOr(err, ERRF_CAPACITY); return; }
     const uint32_t n_stage = inf & 0xFFFFu, n_long = inf >> 16;
-    const uint32_t* src = runs + s * STAGE;
-    uint32_t* dst = out + b;
+    const run_t* src = static_cast<const run_t*>(runs_v) + s * STAGE;
+    out_t* dst = static_cast<out_t*>(out_v) + b;
     if (n_long == 0) {
         for (uint32_t i0 = 0; i0 < n_stage; i0 += 128) {
             const uint32_t i = i0 + lane;
-            uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            run_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
             if (i < n_stage) v0 = __ldcs(src + i);
             if (i + 32 < n_stage) v1 = __ldcs(src + i + 32);
             if (i + 64 < n_stage) v2 = __ldcs(src + i + 64);
             if (i + 96 < n_stage) v3 = __ldcs(src + i + 96);
-            if (i < n_stage) dst[i] = v0;
-            if (i + 32 < n_stage) dst[i + 32] = v1;
-            if (i + 64 < n_stage) dst[i + 64] = v2;
-            if (i + 96 < n_stage) dst[i + 96] = v3;
+            if (i < n_stage) dst[i] = (out_t)v0;
+            if (i + 32 < n_stage) dst[i + 32] = (out_t)v1;
+            if (i + 64 < n_stage) dst[i + 64] = (out_t)v2;
+            if (i + 96 < n_stage) dst[i + 96] = (out_t)v3;
         }
     } else {                                            // run ids interleaved with long pre-tokens' ids (rare)
         const LongDesc* dd = desc + slice_desc[s];
         for (uint32_t i = lane; i < n_stage; i += 32) {
             uint32_t add = 0;
             for (uint32_t q = 0; q < n_long; ++q) if ((dd[q].k_at & 0xFFFFu) <= i) add += dd[q].cnt;
-            dst[i + add] = src[i];
+            dst[i + add] = (out_t)src[i];
         }
         uint32_t before = 0;
         for (uint32_t q = 0; q < n_long; ++q) {
             const uint32_t* ls = long_pool + dd[q].pool;
-            uint32_t* ld = dst + (dd[q].k_at & 0xFFFFu) + before;
+            out_t* ld = dst + (dd[q].k_at & 0xFFFFu) + before;
             if (dd[q].pool != kNone)                       // kNone: a very long one, placed by k_xl_place
-                for (uint32_t i = lane; i < dd[q].cnt; i += 32) ld[i] = ls[i];
+                for (uint32_t i = lane; i < dd[q].cnt; i += 32) ld[i] = (out_t)ls[i];
             before += dd[q].cnt;
         }
     }
@@ -657,8 +693,11 @@ static int xlong_rounds(Engine& eng, const FusedParams& p, uint64_t cursor, uint
 }
 
 int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
-                 uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st, bool check_nfc) {
-    if (n_bytes >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_ARG, "one device call handles less than 4 GiB of text");
+                 uint32_t* d_ids_u32, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st, bool check_nfc) {
+    // eng.out_id_width == 2: the caller's buffer takes uint16 ids (ctk_encode_batch_device_ex; only offered when every id fits)
+    void* const d_ids = d_ids_u32;
+    const int out_width = eng.out_id_width == 2 && eng.run_width == 2 ? 2 : 4;
+    if (n_bytes >= 0xFFFFF000ull) return eng.fail(CTK_ERR_ARG, "one device call handles less than 4 GiB of text");
     if (n_bytes == 0) {
         CK(cudaMemsetAsync(d_ids_off, 0, (n_docs + 1) * 8, st));
         if (n_ids_host) { CK(cudaStreamSynchronize(st)); *n_ids_host = 0; }
@@ -666,7 +705,8 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     }
     if (eng.fused_grid == 0) {
         int per_sm = 0, sms = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_slices, FW * 32, 0));
+        if (eng.run_width == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_slices<2>, FW * 32, 0));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_slices<4>, FW * 32, 0));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, eng.device));
         if (per_sm < 1) return eng.fail(CTK_ERR_CUDA, "encode kernel does not fit on an SM");
         eng.fused_grid = per_sm * sms;
@@ -696,7 +736,8 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     CK(ws.get(2, (p.n_slices + 2) * 4, (void**)&slice_base));
     CK(ws.get(3, (p.n_slices + 2) * 4, (void**)&p.slice_info));
     CK(ws.get(6, (p.n_slices + 2) * 4, (void**)&p.slice_desc));
-    CK(ws.get(8, p.n_slices * (uint64_t)STAGE * 4, (void**)&p.runs));
+    p.run_width = eng.run_width;
+    CK(ws.get(8, p.n_slices * (uint64_t)STAGE * p.run_width, (void**)&p.runs));
     p.long_cap = n_bytes + 64;
     CK(ws.get(7, p.long_cap * 4, (void**)&p.long_pool));
     p.desc_cap = (uint32_t)(n_bytes / 33 + 16);
@@ -711,9 +752,12 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.mid_enabled = n_bytes > (256u << 10) && eng.tables.n_added == 0 && (eng.model.pairs.empty() || eng.model.pairs.back().rank < (1u << 24)) && !getenv("CTK_NO_MID");   // rank << 8 | slot keys
     p.check_nfc = check_nfc ? 1 : 0;
     p.first_doc = first_doc; p.cache_mask = cache_slots - 1; p.ovf_cap = ovf_cap;
-    uint32_t max_id = eng.model.id_present.empty() ? 1u : (uint32_t)eng.model.id_present.size() - 1;
+    p.cache_shift = 32;
+    while ((1ull << (32 - p.cache_shift)) < cache_slots) --p.cache_shift;
+    uint32_t max_id = eng.max_emit_id ? eng.max_emit_id : 1u;
     p.id_bits = 1;
     while ((1ull << p.id_bits) <= max_id) ++p.id_bits;
+    if (p.run_width == 2) p.id_bits = 16;                                 // k_encode_slices<2> unpacks fixed 16-bit fields
     p.n_inline = 96 / p.id_bits;
     if (p.n_inline > MAXINLINE) p.n_inline = MAXINLINE;
     // ctrl words: [0] err flags, [2] desc cursor, [3] ovf cursor, [4..5] long cursor, [6..7] xlong cursor, [8] holes, [9] round size,
@@ -742,7 +786,8 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     k_first_doc<<<doc_grid, 256, 0, st>>>(d_off, n_docs, n_bytes, p.n_slices, first_doc, p.err);
     eng.launched(1); eng.mark("k_first_doc", st);
     unsigned grid = p.n_tiles < (uint32_t)eng.fused_grid ? p.n_tiles : (unsigned)eng.fused_grid;
-    k_encode_slices<<<grid, FW * 32, 0, st>>>(p);
+    if (p.run_width == 2) k_encode_slices<2><<<grid, FW * 32, 0, st>>>(p);
+    else k_encode_slices<4><<<grid, FW * 32, 0, st>>>(p);
     eng.launched(1); eng.mark("k_encode_slices", st);
     k_long_prep<<<eng.long_grid, 256, 0, st>>>(p);
     if (p.mid_enabled) {
@@ -763,12 +808,19 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     for (int pass = 0;; ++pass) {
         CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, p.slice_cnt, slice_base, p.n_slices + 1, st));
         eng.launched(1); eng.mark("scan(slice counts)", st);
-        k_compact<<<(unsigned)((p.n_slices + 7) / 8), 256, 0, st>>>(p.runs, slice_base, p.slice_info, p.slice_desc, p.desc, p.long_pool,
-                                                                        p.n_slices, d_ids, ids_cap, p.err);
+        {
+            const unsigned cg = (unsigned)((p.n_slices + 7) / 8);
+#define CTK_COMPACT(RW_, OW_) k_compact<RW_, OW_><<<cg, 256, 0, st>>>(p.runs, slice_base, p.slice_info, p.slice_desc, p.desc, p.long_pool, \
+                                                                     p.n_slices, d_ids, ids_cap, p.err)
+            if (p.run_width == 2) { if (out_width == 2) CTK_COMPACT(2, 2); else CTK_COMPACT(2, 4); }
+            else { if (out_width == 2) CTK_COMPACT(4, 2); else CTK_COMPACT(4, 4); }
+#undef CTK_COMPACT
+        }
         eng.launched(1); eng.mark("k_compact", st);
         if (pass == 1) {
             k_xl_dst<<<(xl.n_list + 255) / 256, 256, 0, st>>>(p, p.xl_list, xl.n_list, slice_base, xl.region_dst);
-            k_xl_place<<<(xl.n + 255) / 256, 256, 0, st>>>(xl.xs, xl.n, xl.n_list, xl.sep_pos, xl.region_dst, d_ids, ids_cap);
+            if (out_width == 2) k_xl_place<uint16_t><<<(xl.n + 255) / 256, 256, 0, st>>>(xl.xs, xl.n, xl.n_list, xl.sep_pos, xl.region_dst, (uint16_t*)d_ids, ids_cap);
+            else k_xl_place<uint32_t><<<(xl.n + 255) / 256, 256, 0, st>>>(xl.xs, xl.n, xl.n_list, xl.sep_pos, xl.region_dst, (uint32_t*)d_ids, ids_cap);
             eng.launched(2); eng.mark("k_xl_place", st);
         }
         k_doc_fixup<<<doc_grid, 256, 0, st>>>(d_off, n_docs, p.n_slices, slice_base, p.slice_info, p.slice_desc, p.desc, p.ids_off_rel, d_ids_off);

@@ -209,9 +209,10 @@ __global__ void __launch_bounds__(256) k_xl_dst(const FusedParams p, const XlEnt
 }
 
 // every id of the final X straight to its place in the packed output (k_compact leaves these ranges alone)
+template <typename out_t>
 __global__ void __launch_bounds__(256) k_xl_place(const uint32_t* __restrict__ xs, uint32_t n, uint32_t n_list,
                                                   const uint32_t* __restrict__ sep_pos, const uint32_t* __restrict__ region_dst,
-                                                  uint32_t* __restrict__ out, uint64_t out_cap) {
+                                                  out_t* __restrict__ out, uint64_t out_cap) {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i >= n) return;
     uint32_t lo = 0, hi = n_list - 1;                          // region of i: first separator at or after i
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) k_xl_place(const uint32_t* __restrict__ x
     if (sep_pos[lo] == i) return;
     const uint32_t start = lo ? sep_pos[lo - 1] + 1 : 0;
     const uint64_t dst = (uint64_t)region_dst[lo] + (i - start);
-    if (dst < out_cap) out[dst] = xs[i];                       // a too small output was flagged by k_compact
+    if (dst < out_cap) out[dst] = (out_t)xs[i];                // a too small output was flagged by k_compact
 }
 
 }  // namespace ctk

@@ -73,6 +73,10 @@ struct RichTables {
 struct Engine {
     HostModel model;
     int device = 0;
+    int numa_node = -1;                 // host memory node next to the device (sysfs), -1 unknown: page-locked buffers are placed there
+    // ctk_from_file_devices: one engine per device, peers[0] == this (the handle); empty for a single-device tokenizer.
+    // The host-buffer entry points split a batch over the peers by contiguous document ranges (host_api.cu).
+    std::vector<Engine*> peers;
     DevTables tables{};
     DecodeTables dec{};
     NfcTables nfc{};
@@ -84,6 +88,9 @@ struct Engine {
     bool cache_valid = false;           // the pre-token cache holds entries of earlier calls
     uint32_t cache_init_slots = 0;      // slots [0, this) hold entries or EMPTY; the rest of the table was never cleared since the last full clear
     bool use_general = false;           // debug: run the multi-kernel pipeline instead of the fused kernel
+    uint32_t max_emit_id = 0;           // largest id encode can emit (vocabulary and in-word added tokens)
+    int run_width = 4;                  // bytes per id in the encode kernels' scratch runs: 2 when max_emit_id < 65 536
+    int out_id_width = 4;               // bytes per id of the CURRENT device call's output buffer (4, or 2 via the _ex / narrow entry points)
     int long_grid = 0;
     int mid_grid[4] = {};               // co-resident single-warp CTAs of the four k_encode_mid instantiations
     uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // bytes the last host-buffer encode call moved over PCIe
@@ -159,6 +166,7 @@ int starts_bitmap(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, siz
                   uint32_t* start_bits, uint32_t* block_counts, uint32_t* err, cudaStream_t st);
 cudaError_t pinned_get(size_t bytes, void** out, size_t* cap);      // process-wide pool of page-locked buffers (host_api.cu)
 void pinned_put(void* p, size_t cap);
+int device_numa_node(int device);
 
 // ---- rich `Encoding` outputs (encoding.cu) ------------------------------------------------------
 struct RichOut {                            // device pointers into the engine's workspace, valid until its next call

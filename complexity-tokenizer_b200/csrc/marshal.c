@@ -76,7 +76,14 @@ static PyObject* pack_id_lists(PyObject* self, PyObject* arg) {
             const Py_ssize_t m = PySequence_Fast_GET_SIZE(inner[i]);
             PyObject** v = PySequence_Fast_ITEMS(inner[i]);
             for (Py_ssize_t k = 0; k < m; ++k) {
-                const unsigned long x = PyLong_AsUnsignedLong(v[k]);           /* negative / non-int: error set */
+                unsigned long x;
+                if (PyLong_CheckExact(v[k])) x = PyLong_AsUnsignedLong(v[k]);   /* negative: error set */
+                else {                                                         /* numpy integers, anything with __index__ (PyO3's u32 extraction takes them too) */
+                    PyObject* ix = PyNumber_Index(v[k]);
+                    if (!ix) goto fail;
+                    x = PyLong_AsUnsignedLong(ix);
+                    Py_DECREF(ix);
+                }
                 if ((x == (unsigned long)-1 && PyErr_Occurred()) || x > 0xFFFFFFFFul) {
                     if (!PyErr_Occurred()) PyErr_SetString(PyExc_OverflowError, "out of range integral type conversion attempted");
                     goto fail;
@@ -100,26 +107,41 @@ fail:
     return NULL;
 }
 
-/* unpack_ids(ids_addr, off_addr, n) -> list[list[int]] from the packed result of ctk_encode_batch */
+/* unpack_ids(ids_addr, off_addr, n[, width = 4[, out, first]]) -> list[list[int]] from one part of a packed encode result
+ * (include/ctk.h: ctk_result_part).  width = bytes per id (2 or 4: ctk_result_id_width); with `out` (a list of the whole
+ * batch's length) the rows are stored at out[first ..] and out is returned. */
 static PyObject* unpack_ids(PyObject* self, PyObject* args) {
     (void)self;
     unsigned long long a_ids, a_off;
-    Py_ssize_t n;
-    if (!PyArg_ParseTuple(args, "KKn", &a_ids, &a_off, &n)) return NULL;
-    const uint32_t* ids = (const uint32_t*)(uintptr_t)a_ids;
+    Py_ssize_t n, first = 0;
+    int width = 4;
+    PyObject* into = NULL;
+    if (!PyArg_ParseTuple(args, "KKn|iOn", &a_ids, &a_off, &n, &width, &into, &first)) return NULL;
+    if (width != 2 && width != 4) { PyErr_SetString(PyExc_ValueError, "width must be 2 or 4"); return NULL; }
+    const uint32_t* ids32 = (const uint32_t*)(uintptr_t)a_ids;
+    const uint16_t* ids16 = (const uint16_t*)(uintptr_t)a_ids;
     const uint64_t* off = (const uint64_t*)(uintptr_t)a_off;
-    PyObject* out = PyList_New(n);
-    if (!out) return NULL;
+    PyObject* out;
+    if (into && into != Py_None) {
+        if (!PyList_CheckExact(into) || first < 0 || PyList_GET_SIZE(into) < first + n) { PyErr_SetString(PyExc_ValueError, "bad output list"); return NULL; }
+        out = into;
+        Py_INCREF(out);
+    } else {
+        out = PyList_New(n);
+        first = 0;
+        if (!out) return NULL;
+    }
     for (Py_ssize_t i = 0; i < n; ++i) {
         const uint64_t lo = off[i], hi = off[i + 1];
         PyObject* row = PyList_New((Py_ssize_t)(hi - lo));
         if (!row) { Py_DECREF(out); return NULL; }
         for (uint64_t k = lo; k < hi; ++k) {
-            PyObject* v = PyLong_FromUnsignedLong(ids[k]);
+            PyObject* v = PyLong_FromUnsignedLong(width == 2 ? (unsigned long)ids16[k] : (unsigned long)ids32[k]);
             if (!v) { Py_DECREF(row); Py_DECREF(out); return NULL; }
             PyList_SET_ITEM(row, (Py_ssize_t)(k - lo), v);
         }
-        PyList_SET_ITEM(out, i, row);
+        if (into && into != Py_None) { if (PyList_SetItem(out, first + i, row) < 0) { Py_DECREF(out); return NULL; } }
+        else PyList_SET_ITEM(out, i, row);
     }
     return out;
 }
@@ -145,7 +167,7 @@ static PyObject* unpack_strs(PyObject* self, PyObject* args) {
 static PyMethodDef methods[] = {
     {"pack_strs", pack_strs, METH_O, "list[str] -> (utf-8 bytes, uint64 offsets)"},
     {"pack_id_lists", pack_id_lists, METH_O, "list[list[int]] -> (uint32 ids, uint64 offsets)"},
-    {"unpack_ids", unpack_ids, METH_VARARGS, "(ids address, offsets address, n) -> list[list[int]]"},
+    {"unpack_ids", unpack_ids, METH_VARARGS, "(ids address, offsets address, n[, width, out, first]) -> list[list[int]]"},
     {"unpack_strs", unpack_strs, METH_VARARGS, "(bytes address, offsets address, n) -> list[str]"},
     {NULL, NULL, 0, NULL}};
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_ctk_marshal", "list <-> packed buffer conversions for complexity_tokenizer", -1, methods,

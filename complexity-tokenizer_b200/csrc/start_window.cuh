@@ -17,58 +17,76 @@ struct Masks16 {            // one bit per byte of a 16-byte group
     uint32_t SUSP;          // != 0: the group touches an NFC-suspect code point (NFC_QC != Yes or ccc != 0; trie bit 2)
 };
 
-CTK_HD uint32_t movemask4(uint32_t hi) {             // bit 7 of each byte -> 4 bits
-    return (((hi >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+// byte select (PRMT): result byte i = byte (sel >> 4i) & 7 of {b:a}
+CTK_HD uint32_t ctk_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
 }
 
-// SWAR classification of 4 ASCII bytes (every byte < 0x80): per-byte flags in bit 7
-CTK_HD void classify_word_ascii(uint32_t x, uint32_t& l, uint32_t& n, uint32_t& w, uint32_t& sp, uint32_t& ap) {
-    const uint32_t H = 0x80808080u;
-    uint32_t y = x | 0x20202020u;
-    l = (y + 0x1F1F1F1Fu) & ~(y + 0x05050505u) & H;                   // 'a' <= y <= 'z'
-    n = (x + 0x50505050u) & ~(x + 0x46464646u) & H;                   // '0' <= x <= '9'
-    sp = ~((x ^ 0x20202020u) + 0x7F7F7F7Fu) & H;                      // x == ' '
-    ap = ~((x ^ 0x27272727u) + 0x7F7F7F7Fu) & H;                      // x == '\''
-    w = sp | ((x + 0x77777777u) & ~(x + 0x72727272u) & H);            // 9 <= x <= 13
+// Per-byte flags (bit 7 of every byte) of the four TRANSPOSED words -> one word whose byte j holds, in bits 0..3,
+// the flags of positions 4j .. 4j+3; nib_compress packs those four nibbles into 16 bits (bit k = position k).
+CTK_HD uint32_t flag_combine(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    return (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
+}
+CTK_HD uint32_t nib_compress(uint32_t F) {
+    const uint32_t G = (F | (F >> 4)) & 0x00FF00FFu;
+    return (G | (G >> 8)) & 0xFFFFu;
 }
 
 // Classify the 16-byte group that starts at chunk[pos]; `chunk` must be readable from pos-3 to pos+18
 // (continuation bytes look back for their lead, lead bytes look ahead for their tail).
+//
+// ASCII bytes are classified with SWAR range tests on words that are first TRANSPOSED (word k = bytes k, 4+k, 8+k,
+// 12+k): the per-byte flags of the four words then combine with four shifts into nibbles that are already in
+// position order, and one 16-bit mask costs ten instructions instead of a multiply-and-funnel per word and mask.
 CTK_HD Masks16 classify16(const uint8_t* chunk, int pos, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
                           const uint8_t* trie_index, const uint8_t* trie_blocks) {
     Masks16 m;
-    uint32_t l, n, w, sp, ap;
     m.CONT = 0;
     m.SUSP = 0;
-    uint32_t words[4] = {w0, w1, w2, w3};
-    // bit 7 of byte k times 0x00204081 lands on bit 28 + k (no carries: all partial products are distinct bits);
-    // four words are funnelled into the top 16 bits of an accumulator, 3 instructions per word and mask
-    uint32_t aL = 0, aN = 0, aW = 0, aS = 0, aA = 0;
+    const uint32_t H = 0x80808080u;
+    uint32_t T[4];
+    {
+        const uint32_t a = ctk_prmt(w0, w1, 0x5140u), b = ctk_prmt(w2, w3, 0x5140u);
+        const uint32_t c = ctk_prmt(w0, w1, 0x7362u), d = ctk_prmt(w2, w3, 0x7362u);
+        T[0] = ctk_prmt(a, b, 0x5410u); T[1] = ctk_prmt(a, b, 0x7632u);
+        T[2] = ctk_prmt(c, d, 0x5410u); T[3] = ctk_prmt(c, d, 0x7632u);
+    }
+    uint32_t l[4], n[4], sp[4], ap[4], ct[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int k = 0; k < 4; ++k) {
-        uint32_t x = words[k] & 0x7F7F7F7Fu;                           // non-ASCII bytes are fixed up below
-        classify_word_ascii(x, l, n, w, sp, ap);
-        uint32_t ascii = ~words[k] & 0x80808080u;
-        aL = (aL >> 4) | (((l & ascii) * 0x00204081u) & 0xF0000000u);
-        aN = (aN >> 4) | (((n & ascii) * 0x00204081u) & 0xF0000000u);
-        aW = (aW >> 4) | (((w & ascii) * 0x00204081u) & 0xF0000000u);
-        aS = (aS >> 4) | (((sp & ascii) * 0x00204081u) & 0xF0000000u);
-        aA = (aA >> 4) | (((ap & ascii) * 0x00204081u) & 0xF0000000u);
+        const uint32_t x = T[k] & 0x7F7F7F7Fu;                         // non-ASCII bytes are masked out below
+        const uint32_t y = x | 0x20202020u;
+        l[k] = (y + 0x1F1F1F1Fu) & ~(y + 0x05050505u) & H;             // 'a' <= y <= 'z'
+        n[k] = (x + 0x50505050u) & ~(x + 0x46464646u) & H;             // '0' <= x <= '9'
+        sp[k] = ~((x ^ 0x20202020u) + 0x7F7F7F7Fu) & H;                // x == ' '
+        ap[k] = ~((x ^ 0x27272727u) + 0x7F7F7F7Fu) & H;                // x == '\''
+        ct[k] = (x + 0x77777777u) & ~(x + 0x72727272u) & H;            // 9 <= x <= 13
     }
-    m.L = aL >> 16; m.N = aN >> 16; m.W = aW >> 16; m.SP = aS >> 16; m.AP = aA >> 16;
-    uint32_t non_ascii = movemask4(w0 & 0x80808080u) | (movemask4(w1 & 0x80808080u) << 4) |
-                         (movemask4(w2 & 0x80808080u) << 8) | (movemask4(w3 & 0x80808080u) << 12);
+    const uint32_t NA = flag_combine(T[0] & H, T[1] & H, T[2] & H, T[3] & H);   // non-ASCII bytes, nibble form
+    m.L = nib_compress(flag_combine(l[0], l[1], l[2], l[3]) & ~NA);
+    m.SP = nib_compress(flag_combine(sp[0], sp[1], sp[2], sp[3]) & ~NA);
+    m.N = 0; m.AP = 0; m.W = m.SP;
+    if ((n[0] | n[1] | n[2] | n[3]) | (ap[0] | ap[1] | ap[2] | ap[3]) | (ct[0] | ct[1] | ct[2] | ct[3])) {   // digits, apostrophes, tabs / newlines: rare
+        m.N = nib_compress(flag_combine(n[0], n[1], n[2], n[3]) & ~NA);
+        m.AP = nib_compress(flag_combine(ap[0], ap[1], ap[2], ap[3]) & ~NA);
+        m.W |= nib_compress(flag_combine(ct[0], ct[1], ct[2], ct[3]) & ~NA);
+    }
+    const uint32_t non_ascii = NA;
     if (non_ascii) {                                                   // rare path: multi-byte code points, ONE lookup per character
         // continuation bytes 10xxxxxx: bit 7 set, bit 6 clear
-        uint32_t cont = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int k = 0; k < 4; ++k) cont |= movemask4(words[k] & 0x80808080u & ~(words[k] << 1)) << (4 * k);
+        const uint32_t cont = nib_compress(flag_combine(T[0] & H & ~(T[0] << 1), T[1] & H & ~(T[1] << 1), T[2] & H & ~(T[2] << 1),
+                                                        T[3] & H & ~(T[3] << 1)));
         m.CONT = cont;
-        uint32_t leads = non_ascii & ~cont;
+        uint32_t leads = nib_compress(NA) & ~cont;
         // continuation bytes at the start of the group belong to a character that began in the previous group
         const uint32_t run0 = cont & ~(cont + 1u);
         if (run0) {

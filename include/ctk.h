@@ -42,6 +42,17 @@ typedef struct ctk_result ctk_result;         /* opaque, owns host (pinned) resu
  * :247-334; bpe.rs:52-79; parsing.rs defaults) and uploads the tables to `device`. */
 int ctk_from_file(const char* path, int device, ctk_tokenizer** out);
 int ctk_from_json(const uint8_t* json, size_t len, int device, ctk_tokenizer** out);
+/* One tokenizer that drives SEVERAL devices from one process: the reference's encode_batch / decode_batch are single calls
+ * that use the whole machine (rayon over documents, src/huggingface/mod.rs:694-696, :771-785).  Tables are replicated on
+ * every listed device (n_devices <= 0: every visible device); the host-buffer entry points below cut a batch into
+ * contiguous document ranges balanced by bytes, one per device, each served by a host thread bound to the device's NUMA
+ * node.  No data crosses between devices.  The device-resident entry points use the first device. */
+int ctk_from_file_devices(const char* path, int n_devices, const int* device_ids, ctk_tokenizer** out);
+int ctk_from_json_devices(const uint8_t* json, size_t len, int n_devices, const int* device_ids, ctk_tokenizer** out);
+size_t ctk_n_devices(const ctk_tokenizer* tok);
+int ctk_device_at(const ctk_tokenizer* tok, size_t i);      /* i-th device, -1 if out of range */
+int ctk_numa_node(const ctk_tokenizer* tok, size_t i);      /* host NUMA node next to the i-th device, -1 if unknown */
+int ctk_device_numa_node(int device);                       /* the same for any visible device (sysfs: PCI bus id -> numa_node) */
 void ctk_free(ctk_tokenizer* tok);
 
 /* ---- cheap getters (src/bindings/tokenizer.rs:271-289) ------------------------------------- */
@@ -65,6 +76,26 @@ int ctk_encode_batch(const ctk_tokenizer* tok, const uint8_t* text, const uint64
 const uint32_t* ctk_result_ids(const ctk_result* res);
 const uint64_t* ctk_result_offsets(const ctk_result* res);   /* n+1 entries */
 size_t ctk_result_count(const ctk_result* res);              /* n */
+
+/* ---- narrow ids and per-device parts (what a binding should use for large batches) ----------------
+ * The copy of the ids back to the host is as large as the copy of the text to the device.  When every id the tokenizer
+ * can emit is below 65 536 (ctk_id_width(tok) == 2) ctk_encode_batch_narrow writes and returns uint16 ids: half the
+ * device-to-host bytes, and nothing is widened on the host -- the binding's per-document copy into its own Vec<u32>
+ * (src/bindings: Vec<Vec<u32>> -> list[list[int]]) reads the 16-bit ids directly.  Otherwise it equals ctk_encode_batch.
+ *   ctk_result_id_width  2 or 4: element size of the ids of this result
+ *   ctk_result_parts     1, or the number of devices that received documents (ctk_from_file_devices)
+ *   ctk_result_part      part i: its first item, item count, ids (id_width each; bytes for a decode result) and
+ *                        offsets[n_items + 1] RELATIVE to the part.  Parts are in item order.  Zero-copy.
+ * ctk_result_ids / ctk_result_offsets / ctk_result_bytes still work on any result: they gather the parts (and widen
+ * narrow ids) into one buffer on first use. */
+int ctk_id_width(const ctk_tokenizer* tok);
+int ctk_encode_batch_narrow(const ctk_tokenizer* tok, const uint8_t* text, const uint64_t* text_off, size_t n,
+                            ctk_result** res);
+int ctk_result_id_width(const ctk_result* res);
+const void* ctk_result_ids_raw(const ctk_result* res);       /* single-part results; NULL when there are several parts */
+size_t ctk_result_parts(const ctk_result* res);
+int ctk_result_part(const ctk_result* res, size_t i, size_t* first_item, size_t* n_items, const void** data,
+                    const uint64_t** offsets);
 
 /* ---- decode_batch, host buffers ------------------------------------------------------------
  * Replaces HuggingFaceTokenizer::decode_batch_with_options (src/huggingface/mod.rs:775-785);
@@ -97,6 +128,10 @@ int ctk_decode_batch_device(const ctk_tokenizer* tok, const uint32_t* d_ids, con
                             int clean_up_tokenization_spaces, uint8_t* d_text_out, uint64_t text_cap,
                             uint64_t* d_text_off_out, uint64_t* n_bytes_host, void* stream);
 size_t ctk_decode_max_bytes(const ctk_tokenizer* tok);   /* longest decoded token, in bytes */
+/* ctk_encode_batch_device with the element size of d_ids chosen by the caller: id_width 4, or 2 when ctk_id_width(tok) == 2 */
+int ctk_encode_batch_device_ex(const ctk_tokenizer* tok, const uint8_t* d_text, const uint64_t* d_text_off,
+                               size_t n, uint64_t total_bytes, void* d_ids, uint64_t ids_cap, int id_width,
+                               uint64_t* d_ids_off, uint64_t* n_ids_host, void* stream);
 
 /* ---- rich `Encoding` outputs ----------------------------------------
  * Replaces, for a whole batch and on the GPU,
@@ -192,8 +227,7 @@ uint64_t ctk_kernel_launches(void);
  * one line per kernel: name <TAB> total milliseconds <TAB> launches; returns the full length. */
 void ctk_profile_enable(ctk_tokenizer* tok, int on);
 size_t ctk_profile_report(ctk_tokenizer* tok, char* buf, size_t cap);
-/* Bytes the last ctk_encode_batch call moved host->device and device->host.  (Opt-in, CTK_WIDEN_THREADS=n: ids cross
- * the link packed to 2 or 3 bytes when every id fits and n host threads widen them to uint32.) */
+/* Bytes the last ctk_encode_batch / ctk_encode_batch_narrow call moved host->device and device->host (all devices). */
 void ctk_last_transfer_bytes(const ctk_tokenizer* tok, uint64_t* h2d, uint64_t* d2h);
 /* Reset the per-batch pre-token cache policy: 0 = clear at the start of every encode call
  * (default; every call does all of its own work), 1 = keep entries across calls. */

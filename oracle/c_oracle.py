@@ -23,7 +23,7 @@ def build_lib(force=False):
     srcs = [os.path.join(HERE, 'oracle_core.c'), os.path.join(HERE, 'unicode_ranges_gen.h')]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(['gcc', '-O2', '-std=c11', '-shared', '-fPIC', '-pthread', srcs[0], '-o', so])
+        subprocess.check_call(['gcc', '-O3', '-std=c11', '-shared', '-fPIC', '-pthread', srcs[0], '-o', so])   # the reference ships opt-level 3
         _LIB = None
     if _LIB is None:
         lib = ctypes.CDLL(so)

@@ -302,3 +302,39 @@ def test_trainer_argument_errors(built_lib):
     off = (ctypes.c_uint64 * 2)(0, 4)
     cfg.n_special = 0
     assert lib.ctk_train_bpe(ctypes.byref(cfg), 0, None, ctypes.addressof(off), 1, ctypes.byref(out)) == 5   # 4 bytes announced, no text
+
+
+def test_marshal_takes_numpy_ids_like_the_fallback():
+    """decode's list marshalling accepts anything with __index__ (PyO3's Vec<u32> extraction does): ADVICE r1, marshal.c"""
+    import numpy as np
+    from complexity_tokenizer import _marshal
+    assert _marshal is not None, '_ctk_marshal is not built'
+    want_ids = np.array([1, 2, 3, 70000, 5], dtype=np.uint32).tobytes()
+    want_off = np.array([0, 3, 5], dtype=np.uint64).tobytes()
+    for batch in ([[1, 2, 3], [70000, 5]], [np.array([1, 2, 3]), np.array([70000, 5], dtype=np.int64)],
+                  [[np.int64(1), np.uint8(2), 3], (np.uint32(70000), 5)]):
+        ids, off = _marshal.pack_id_lists(batch)
+        assert ids == want_ids and off == want_off
+    import pytest
+    with pytest.raises(OverflowError):
+        _marshal.pack_id_lists([[-1]])
+    with pytest.raises(OverflowError):
+        _marshal.pack_id_lists([[np.int64(1 << 33)]])
+    with pytest.raises(TypeError):
+        _marshal.pack_id_lists([[1.5]])
+
+
+def test_marshal_unpacks_narrow_ids_and_parts():
+    """unpack_ids reads 16-bit and 32-bit ids and fills one output list part by part (ctk_result_part)"""
+    import numpy as np
+    from complexity_tokenizer import _marshal
+    ids16 = np.array([7, 65535, 9, 10], dtype=np.uint16)
+    ids32 = np.array([7, 65536, 9, 10], dtype=np.uint32)
+    off = np.array([0, 1, 1, 4], dtype=np.uint64)
+    assert _marshal.unpack_ids(ids16.ctypes.data, off.ctypes.data, 3, 2) == [[7], [], [65535, 9, 10]]
+    assert _marshal.unpack_ids(ids32.ctypes.data, off.ctypes.data, 3) == [[7], [], [65536, 9, 10]]
+    out = [None] * 5
+    _marshal.unpack_ids(ids16.ctypes.data, off.ctypes.data, 3, 2, out, 2)
+    off2 = np.array([0, 2, 4], dtype=np.uint64)
+    _marshal.unpack_ids(ids32.ctypes.data, off2.ctypes.data, 2, 4, out, 0)
+    assert out == [[7, 65536], [9, 10], [7], [], [65535, 9, 10]]

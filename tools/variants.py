@@ -38,7 +38,7 @@ def run(nbytes):
     for f in [None] + libs:
         env = dict(os.environ)
         if f: env['CTK_LIB_VARIANT'] = os.path.join(VAR, f)
-        out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '5', '--warmup', '3', '--no-cpu', '--e2e-steps', '1', '--bytes', str(nbytes)],
+        out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '5', '--warmup', '3', '--no-cpu', '--no-extras', '--e2e-steps', '1', '--bytes', str(nbytes)],
                              env=env, capture_output=True, text=True)
         for l in out.stdout.splitlines():
             if l.startswith('{'):
