@@ -119,6 +119,7 @@ def _lib():
         'ctk_debug_load_only': (I, [P, S, ctypes.POINTER(U64), ctypes.POINTER(U64), ctypes.POINTER(I), ctypes.POINTER(I)]),
         'ctk_debug_merge_props': (I, [P, S, ctypes.POINTER(I), ctypes.POINTER(ctypes.c_uint32)]),
         'ctk_debug_xlong_rounds': (I, [P]),
+        'ctk_debug_cp_classes': (I, [ctypes.c_uint32, ctypes.c_uint32, P]),
         'ctk_last_transfer_bytes': (None, [P, ctypes.POINTER(U64), ctypes.POINTER(U64)]),
         'ctk_debug_parallel_copy': (I, [P, P, S, I, I]),
         'ctk_encode_batch_to_encoding': (I, [P, P, P, S, ctypes.POINTER(_EncodingOptions), ctypes.POINTER(P)]),

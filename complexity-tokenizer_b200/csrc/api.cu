@@ -85,6 +85,7 @@ static int upload(Engine& eng) {
         const size_t nid = m.dec_special.size();
         std::vector<uint8_t> l8(nid + 1, 0), l8s(nid + 1, 0);
         std::vector<uint4> rec(nid + 1, make_uint4(0, 0, 0, 0));
+
         for (size_t id = 0; id < nid; ++id) {
             const uint32_t b = m.dec_off[id], L = m.dec_off[id + 1] - b;
             l8[id] = (uint8_t)(L < 255 ? L : 255);
@@ -373,7 +374,7 @@ int ctk_encode_batch_device_ex(const ctk_tokenizer* tok, const uint8_t* d_text, 
                                uint64_t* n_ids_host, void* stream) {
     if (!tok || !d_text_off || !d_ids_off || (total_bytes && (!d_text || !d_ids))) { set_last_error("NULL argument"); return CTK_ERR_ARG; }
     Engine* eng = const_cast<Engine*>(reinterpret_cast<const Engine*>(tok));
-    if (id_width != 4 && !(id_width == 2 && eng->run_width == 2)) {
+    if (id_width != 4 && !(id_width == 2 && eng->run_width == 2 && !eng->use_general)) {
         set_last_error("id_width must be 4, or 2 when ctk_id_width(tok) == 2");
         return CTK_ERR_ARG;
     }
@@ -454,6 +455,13 @@ int ctk_debug_starts_window_host(const uint8_t* text, uint64_t n, const uint64_t
             if (pos < n && ((S >> (8 + k)) & 1u)) out_bits[pos >> 5] |= 1u << (pos & 31);
         }
     }
+    return CTK_OK;
+}
+
+// the product's code point table (class in bits 0-1: 0 Other, 1 L, 2 N, 3 White_Space; bit 2: NFC-suspect), for the CPU
+// test that checks every code point against Python's `regex` / `unicodedata`
+int ctk_debug_cp_classes(uint32_t first, uint32_t count, uint8_t* out) {
+    for (uint32_t i = 0; i < count; ++i) out[i] = (uint8_t)trie_nibble(CTK_TRIE_INDEX, CTK_TRIE_BLOCKS, first + i);
     return CTK_OK;
 }
 

@@ -26,7 +26,8 @@ struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { re
 // byte offsets on the way.  (The first version wrote a uint64 offset per token -- 2 bytes of scratch traffic per
 // output byte -- and one thread copied each token's bytes to global memory.)
 constexpr int DT = 2048, DTH = 256, DPT = DT / DTH;
-constexpr int DSTAGE = 24 * 1024;                        // bytes of a tile staged in shared memory (a tile averages ~9 KB)
+constexpr int DSTAGE = 16 * 1024;                        // bytes of a tile staged in shared memory (a tile averages ~9 KB); the less shared memory, the more L1 for the token table
+static_assert(DPT == 8, "a thread takes its eight ids with two 16-byte loads");
 
 __device__ __forceinline__ uint32_t dec_tok_len(const DecodeTables& t, uint32_t id, int skip_special) {
     if (id >= t.n_ids) return 0;                                       // unknown ids are dropped (mod.rs:717-735)
@@ -34,16 +35,27 @@ __device__ __forceinline__ uint32_t dec_tok_len(const DecodeTables& t, uint32_t 
     return L < 255 ? L : __ldg(t.off + id + 1) - __ldg(t.off + id);    // (a special token is never that long)
 }
 
+// ids of the thread's DPT consecutive tokens: two aligned 16-byte loads (ids is 16-byte aligned when it comes from this
+// library or from cudaMalloc; otherwise, and in the tile that holds the end, one by one); 0xFFFFFFFF beyond the end
+__device__ __forceinline__ void dec_load_ids(const uint32_t* __restrict__ ids, uint64_t n, uint64_t j0, bool vec_ok, uint32_t (&id)[DPT]) {
+    if (vec_ok && j0 + DPT <= n) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(ids + j0)), b = __ldg(reinterpret_cast<const uint4*>(ids + j0) + 1);
+        id[0] = a.x; id[1] = a.y; id[2] = a.z; id[3] = a.w; id[4] = b.x; id[5] = b.y; id[6] = b.z; id[7] = b.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) id[q] = j0 + q < n ? __ldg(ids + j0 + q) : 0xFFFFFFFFu;
+    }
+}
+
 __global__ void __launch_bounds__(DTH) k_dec_tile_sums(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
                                                        uint32_t* __restrict__ tile_sum) {
     __shared__ uint32_t s_part[DTH / 32];
     const uint64_t t0 = (uint64_t)blockIdx.x * DT;
-    uint32_t sum = 0;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(ids) & 15) == 0;
+    uint32_t id[DPT], sum = 0;
+    dec_load_ids(ids, n, t0 + (uint64_t)threadIdx.x * DPT, vec_ok, id);
 #pragma unroll
-    for (int q = 0; q < DPT; ++q) {
-        const uint64_t j = t0 + (uint64_t)q * DTH + threadIdx.x;
-        if (j < n) sum += dec_tok_len(t, __ldg(ids + j), skip_special);
-    }
+    for (int q = 0; q < DPT; ++q) sum += dec_tok_len(t, id[q], skip_special);     // (0xFFFFFFFF is no id: length 0)
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
     __syncthreads();
@@ -54,80 +66,137 @@ __global__ void __launch_bounds__(DTH) k_dec_tile_sums(DecodeTables t, const uin
     }
 }
 
+// first_doc[tile] = first document d with ids_off[d] >= tile * DT (one thread per document: k_dec_write then finds the
+// documents that start inside its tile with one load instead of a binary search of 20 dependent loads per tile)
+__global__ void k_dec_first_doc(const uint64_t* __restrict__ ids_off, uint64_t n_docs, uint64_t n_tiles, uint32_t* __restrict__ first_doc) {
+    const uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d > n_docs) return;
+    const uint64_t hi = ids_off[d] / DT;                                           // tiles [lo, hi] start at or before ids_off[d] ...
+    const uint64_t lo = d ? ids_off[d - 1] / DT + 1 : 0;                           // ... and after ids_off[d - 1]
+    for (uint64_t tl = lo; tl <= hi && tl <= n_tiles; ++tl) first_doc[tl] = (uint32_t)d;
+}
+
 __global__ void __launch_bounds__(DTH) k_dec_write(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
                                                    const uint64_t* __restrict__ tile_base, const uint64_t* __restrict__ ids_off,
+                                                   const uint32_t* __restrict__ first_doc,
                                                    uint64_t n_docs, uint8_t* __restrict__ out, uint64_t out_cap,
-                                                   uint64_t* __restrict__ raw_off, uint32_t* __restrict__ err) {
+                                                   uint64_t* __restrict__ raw_off, uint32_t* __restrict__ err, uint32_t* __restrict__ non_ascii) {
     __shared__ uint32_t s_off[DT + 1];                    // byte offset of every token inside the tile
     __shared__ uint32_t s_warp[DTH / 32];
-    __shared__ __align__(16) uint8_t s_stage[DSTAGE + 16];
+    __shared__ __align__(16) uint8_t s_stage[DSTAGE + 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t t0 = (uint64_t)blockIdx.x * DT, base = tile_base[blockIdx.x];
     const uint32_t total = (uint32_t)(tile_base[blockIdx.x + 1] - base);
     if (base + total > out_cap) { if (tid == 0) atomicOr(err, ERRF_CAPACITY); return; }
-    // lengths of this thread's DPT consecutive tokens, exclusive scan over the CTA
+    const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15u);
+    const bool staged = total + shift <= (uint32_t)DSTAGE;
+    // the stage is filled with whole words and, where two threads share a word, with atomicOr: it starts at zero
+    if (staged) for (uint32_t v = tid; 16 * v < total + shift + 4; v += DTH) *reinterpret_cast<uint4*>(s_stage + 16 * v) = make_uint4(0, 0, 0, 0);
+    // One 16-byte record per token {first 12 bytes, length}: ONE gather gives this pass both the length and the bytes.
+    // The thread's DPT consecutive tokens, then an exclusive scan of their lengths over the CTA.
     uint32_t id[DPT], len[DPT], mine = 0;
+    uint4 rec[DPT];
+    dec_load_ids(ids, n, t0 + (uint64_t)tid * DPT, (reinterpret_cast<uintptr_t>(ids) & 15) == 0, id);
 #pragma unroll
-    for (int q = 0; q < DPT; ++q) {
-        const uint64_t j = t0 + (uint64_t)tid * DPT + q;
-        id[q] = j < n ? __ldg(ids + j) : 0xFFFFFFFFu;
-        len[q] = j < n ? dec_tok_len(t, id[q], skip_special) : 0u;
-        mine += len[q];
+    for (int q = 0; q < DPT; ++q) rec[q] = id[q] < t.n_ids ? __ldg(t.rec + id[q]) : make_uint4(0, 0, 0, 0);   // unknown ids are dropped (mod.rs:717-735)
+    if (skip_special) {
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) if (id[q] < t.n_ids && __ldg(t.special + id[q])) rec[q] = make_uint4(0, 0, 0, 0);
     }
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) { len[q] = rec[q].w; mine += len[q]; }
     uint32_t incl = mine;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
     uint32_t off = incl - mine;
     for (int w = 0; w < wid; ++w) off += s_warp[w];
+    const uint32_t my_off = off;
 #pragma unroll
     for (int q = 0; q < DPT; ++q) { s_off[tid * DPT + q] = off; off += len[q]; }
     if (tid == DTH - 1) s_off[DT] = off;
-    // bytes: staged in shared memory at the same alignment (mod 16) as their place in the output.  Tokens are taken in
-    // stripes (thread t: tokens t, t + 256, ...): neighbouring threads write neighbouring bytes, and a token of up to 12
-    // bytes comes out of ONE 16-byte record.
-    const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15u);
-    const bool staged = total + shift <= (uint32_t)DSTAGE;
-    uint8_t* const dst0 = staged ? s_stage + shift : out + base;
-    __syncthreads();                                                   // s_off complete
+    if (staged) {
+        // The thread's tokens are one contiguous byte range of the tile.  Their bytes go through a 64-bit accumulator, up to
+        // four at a time, and leave as whole words OR-ed into the zeroed stage (a word at either end of the range also holds
+        // a neighbour's bytes).  Straight-line code: three pushes per token, every store predicated, no branch on the data.
+        const uint32_t stage_a = (uint32_t)__cvta_generic_to_shared(s_stage);
+        uint32_t bpos = shift + my_off;                                // byte position in the stage of the next byte
+        uint32_t fill = bpos & 3u, acc_lo = 0, acc_hi = 0;
+        auto push = [&](uint32_t w, uint32_t nb) {                      // appends the low nb (0..4) bytes of w; bytes above nb are zero
+            const uint32_t sh = 8u * fill;
+            acc_lo |= w << sh;
+            acc_hi |= __funnelshift_l(w, 0u, sh);                      // (w >> (32 - sh)), 0 for sh == 0
+            fill += nb;
+            bpos += nb;
+            const uint32_t full = fill >> 2;                           // 0 or 1
+            asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.shared.or.b32 [%0], %1; }"
+                         :: "r"(stage_a + ((bpos - fill) & ~3u)), "r"(acc_lo), "r"(full) : "memory");
+            acc_lo = full ? acc_hi : acc_lo;
+            acc_hi = full ? 0u : acc_hi;
+            fill &= 3u;
+        };
+        bool any_long = false;
 #pragma unroll
-    for (int q = 0; q < DPT; ++q) {
-        const int j = q * DTH + tid;
-        const uint32_t o = s_off[j], L = s_off[j + 1] - o;
-        if (L == 0) continue;
-        const uint32_t tid_id = __ldg(ids + t0 + j);
-        uint8_t* d = dst0 + o;
-        if (L <= 12) {
-            const uint4 r = __ldg(t.rec + tid_id);
-            uint32_t w = r.x;
-#pragma unroll
-            for (uint32_t k = 0; k < 12; ++k) {
-                if (k == 4) w = r.y;
-                if (k == 8) w = r.z;
-                if (k < L) d[k] = (uint8_t)(w >> (8 * (k & 3)));
+        for (int q = 0; q < DPT; ++q) {
+            const uint32_t L = len[q];
+            if (L <= 12) {                                             // (predicated: a longer token leaves a hole that is filled below)
+                push(rec[q].x, L < 4 ? L : 4u);
+                push(rec[q].y, L < 4 ? 0u : (L < 8 ? L - 4 : 4u));
+                push(rec[q].z, L < 8 ? 0u : L - 8);
+            } else {
+                any_long = true;
+                if (fill) atomicOr(reinterpret_cast<uint32_t*>(s_stage) + ((bpos - fill) >> 2), acc_lo);   // flush, jump over the token
+                bpos += L; fill = bpos & 3u; acc_lo = 0; acc_hi = 0;
             }
-        } else {
-            const uint8_t* src = t.blob + __ldg(t.off + tid_id);
-            for (uint32_t k = 0; k < L; ++k) d[k] = __ldg(src + k);
+        }
+        if (fill) atomicOr(reinterpret_cast<uint32_t*>(s_stage) + ((bpos - fill) >> 2), acc_lo);         // the range's last, partial word
+        if (any_long) {                                                // tokens longer than 12 bytes (rare): byte by byte from the blob
+            uint32_t o = shift + my_off;
+            for (int q = 0; q < DPT; ++q) {
+                const uint32_t L = len[q];
+                if (L > 12) {
+                    const uint8_t* src = t.blob + __ldg(t.off + id[q]);
+                    for (uint32_t k = 0; k < L; ++k)
+                        atomicOr(reinterpret_cast<uint32_t*>(s_stage) + ((o + k) >> 2), (uint32_t)__ldg(src + k) << (8u * ((o + k) & 3u)));
+                }
+                o += L;
+            }
         }
     }
-    __syncthreads();
-    if (staged && total) {
+    __syncthreads();                                                   // s_off complete (and the stage, if used)
+    if (!staged) {
+        // a tile of unusually long tokens: byte by byte, straight to global memory, tokens in stripes
+        uint8_t* const dst0 = out + base;
+#pragma unroll 1
+        for (int q = 0; q < DPT; ++q) {
+            const int j = q * DTH + tid;
+            const uint32_t o = s_off[j], L = s_off[j + 1] - o;
+            if (L == 0) continue;
+            const uint32_t tid_id = __ldg(ids + t0 + j);
+            const uint8_t* src = t.blob + __ldg(t.off + tid_id);
+            for (uint32_t k = 0; k < L; ++k) dst0[o + k] = __ldg(src + k);
+        }
+        if (tid == 0 && total) atomicOr(non_ascii, 1u);                 // not looked at here: let the validation kernel decide
+    } else if (total) {
         uint8_t* const g = out + base;
         const uint32_t head = min(total, (16u - shift) & 15u);            // bytes before the first aligned 16-byte group
-        if ((uint32_t)tid < head) g[tid] = s_stage[shift + tid];
+        uint32_t hib = 0;
+        if ((uint32_t)tid < head) { const uint8_t c = s_stage[shift + tid]; g[tid] = c; hib |= c; }
         const uint32_t body = (total - head) >> 4;
-        for (uint32_t v = tid; v < body; v += DTH)
-            *reinterpret_cast<uint4*>(g + head + 16 * v) = *reinterpret_cast<const uint4*>(s_stage + shift + head + 16 * v);
+        for (uint32_t v = tid; v < body; v += DTH) {
+            const uint4 x = *reinterpret_cast<const uint4*>(s_stage + shift + head + 16 * v);
+            *reinterpret_cast<uint4*>(g + head + 16 * v) = x;
+            hib |= (x.x | x.y) | (x.z | x.w);
+        }
         const uint32_t done = head + 16 * body;
-        if ((uint32_t)tid < total - done) g[done + tid] = s_stage[shift + done + tid];
+        if ((uint32_t)tid < total - done) { const uint8_t c = s_stage[shift + done + tid]; g[done + tid] = c; hib |= c; }
+        // pure ASCII output is valid UTF-8 whatever the document cuts: only a tile with a byte >= 0x80 asks for the validation pass
+        if (__any_sync(0xFFFFFFFFu, (hib & 0x80808080u) != 0) && lane == 0) atomicOr(non_ascii, 1u);
     }
     // byte offsets of the documents whose first token lies in this tile (and, in the last tile, of those at the very end)
     const uint64_t t1 = t0 + DT < n ? t0 + DT : n;
     const bool last = t0 + DT >= n;
-    uint64_t lo = 0, hi = n_docs + 1;                                     // first d with ids_off[d] >= t0
-    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (ids_off[mid] >= t0) hi = mid; else lo = mid + 1; }
-    for (uint64_t d = lo + tid; d <= n_docs; d += DTH) {
+    for (uint64_t d = (uint64_t)first_doc[blockIdx.x] + tid; d <= n_docs; d += DTH) {
         const uint64_t j = ids_off[d];
         if (j < t1 || (last && j == n)) raw_off[d] = base + s_off[j - t0];
         else break;
@@ -298,16 +367,22 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
                   int skip_special, int cleanup, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off,
                   uint64_t* n_bytes_host, cudaStream_t st) {
     Workspace& ws = eng.ws;
-    uint32_t *tile_sum, *err;
+    uint32_t *tile_sum, *err, *first_doc;
     uint64_t *tile_base, *raw_off;
     const uint64_t n_tiles = (T + DT - 1) / DT;
+    if (n_docs >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_ARG, "too many documents in one decode call");
     CK(ws.get(4, 256, (void**)&err));
     CK(cudaMemsetAsync(err, 0, 256, st));
     CK(ws.get(10, (n_tiles + 2) * 4, (void**)&tile_sum));
     CK(ws.get(11, (n_tiles + 2) * 8, (void**)&tile_base));
     CK(ws.get(12, (n_docs + 2) * 8, (void**)&raw_off));
+    CK(ws.get(37, (n_tiles + 2) * 4, (void**)&first_doc));
     eng.mark(nullptr, st);
-    if (n_tiles) { k_dec_tile_sums<<<(unsigned)n_tiles, DTH, 0, st>>>(eng.dec, d_ids, T, skip_special, tile_sum); eng.launched(1); }
+    if (n_tiles) {
+        k_dec_tile_sums<<<(unsigned)n_tiles, DTH, 0, st>>>(eng.dec, d_ids, T, skip_special, tile_sum);
+        k_dec_first_doc<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_ids_off, n_docs, n_tiles, first_doc);
+        eng.launched(2);
+    }
     CK(cudaMemsetAsync(tile_sum + n_tiles, 0, 4, st));
     eng.mark("k_dec_tile_sums", st);
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(tile_sum, U32ToU64());
@@ -328,14 +403,21 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
     else CK(ws.get(13, raw_total + 16, (void**)&raw));
     eng.mark(nullptr, st);
     if (n_tiles) {
-        k_dec_write<<<(unsigned)n_tiles, DTH, 0, st>>>(eng.dec, d_ids, T, skip_special, tile_base, d_ids_off, n_docs, raw,
-                                                       direct ? out_cap : raw_total + 16, raw_off, err);
+        k_dec_write<<<(unsigned)n_tiles, DTH, 0, st>>>(eng.dec, d_ids, T, skip_special, tile_base, d_ids_off, first_doc, n_docs, raw,
+                                                       direct ? out_cap : raw_total + 16, raw_off, err, err + 2);
         eng.launched(1);
     } else CK(cudaMemsetAsync(raw_off, 0, (n_docs + 1) * 8, st));
     eng.mark("k_dec_write", st);
-    // Is the gathered byte string already valid UTF-8?  Then String::from_utf8_lossy is the identity.
-    bool invalid = false;
+    // Is the gathered byte string already valid UTF-8?  Then String::from_utf8_lossy is the identity.  Pure ASCII is
+    // (k_dec_write looked at every byte on its way out); anything else is checked sequence by sequence.
+    bool invalid = false, has_high = false;
     if (n_docs && raw_total) {
+        CK(eng.publish({{err + 2, 1, 15}}, st));
+        CK(cudaStreamSynchronize(st));
+        has_high = eng.h_flags[15] != 0;
+    }
+    if (has_high) {
+        eng.mark(nullptr, st);
         k_dec_valid_bytes<<<(unsigned)(((raw_total + 15) / 16 + 255) / 256), 256, 0, st>>>(raw, raw_total, err + 1);
         k_dec_valid_docs<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(raw, raw_off, n_docs, err + 1);
         eng.launched(2); eng.mark("k_dec_valid", st);

@@ -50,6 +50,7 @@ constexpr int MAXLONG = 14;      // pre-tokens longer than 32 bytes that can sta
 constexpr int MAXINLINE = 6;     // ids the straight-line path unpacks
 constexpr uint32_t META_EMPTY = 0xFFFFFFFFu, META_BUSY = 0xFFFFFFFEu;
 constexpr int PROBES = 4;
+constexpr int CACHE_LOG2 = 22;        // slots of the per-batch pre-token cache (32 B each)
 constexpr uint32_t END_UNKNOWN = 0xFFFFu;
 
 // A pre-token longer than 32 bytes: found by k_encode_slices, merged by k_encode_long.
@@ -187,6 +188,15 @@ namespace ctk {
 #ifndef CTK_LB
 #define CTK_LB 4
 #endif
+#ifndef CTK_OPAQUE_WARP
+#define CTK_OPAQUE_WARP 0     // measured: 3.50 -> 3.44 ms without
+#endif
+#ifndef CTK_PIPELINE_ROUNDS
+#define CTK_PIPELINE_ROUNDS 1
+#endif
+#ifndef CTK_COMPACT_UNROLL
+#define CTK_COMPACT_UNROLL 6   // measured: 4 -> 6: 3.50 -> 3.47 ms
+#endif
 #ifndef CTK_ASYNC_CHUNK
 #define CTK_ASYNC_CHUNK 1    // the next slice's chunk travels global -> shared with cp.async while this one is processed (no registers)
 #endif
@@ -215,13 +225,18 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
     __shared__ WarpSmem sm[FW];
     __shared__ uint32_t s_byte_init[256];
     __shared__ uint4 s_kmask[17];                       // byte masks: keep the first n bytes of 16
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    int w = tid >> 5;
     s_byte_init[tid] = __ldg(p.t.byte_init + tid);
     if (tid < 17) {
         uint32_t m[4];
         for (int j = 0; j < 4; ++j) { int b = tid - 4 * j; m[j] = b >= 4 ? 0xFFFFFFFFu : (b <= 0 ? 0u : ((1u << (8 * b)) - 1u)); }
         s_kmask[tid] = make_uint4(m[0], m[1], m[2], m[3]);
     }
+#if CTK_OPAQUE_WARP
+    asm volatile("" : "+r"(w));                          // keep the warp index in a register: ptxas otherwise rebuilds the warp's shared-memory base
+                                                         // from the thread id (two S2R + four ALU) at half a dozen places of the slice loop
+#endif
     WarpSmem& S = sm[w];
     if (lane < 4) {
         uint4* z = reinterpret_cast<uint4*>(lane & 1 ? S.buf[lane >> 1].pad1 : S.buf[lane >> 1].pad0);
@@ -326,11 +341,11 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
             const uint32_t lb = 16 * lane - 1;
             uint32_t la = smem_u32(S.list + first_k);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {                                  // predicated, no branches: a lane rarely has more than four starts
+            for (int j = 0; j < CTK_COMPACT_UNROLL; ++j) {                 // predicated, no branches: a lane rarely has more starts
                 sts16_if(la + 2 * j, lb + __ffs(bits), bits);
                 bits &= bits - 1;                                          // 0 stays 0
             }
-            if (bits) { uint16_t* lp = S.list + first_k + 4; do { *lp++ = (uint16_t)(lb + __ffs(bits)); bits &= bits - 1; } while (bits); }
+            if (bits) { uint16_t* lp = S.list + first_k + CTK_COMPACT_UNROLL; do { *lp++ = (uint16_t)(lb + __ffs(bits)); bits &= bits - 1; } while (bits); }
             // sentinel candidates: starts in the right context (lanes 29, 30) and the end of the text
             // (position n_bytes is a start thanks to its DS bit) wherever it falls
             uint32_t rc = 0;
@@ -347,29 +362,35 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
         if (lane == 0) p.slice_first[slice] = n_owned ? S.list[0] : (uint16_t)0xFFFFu;
 
         if (p.ablate == 1) { if (lane == 0) { p.slice_cnt[slice] = n_owned; p.slice_info[slice] = 0; } continue; }
-        // ---- 4. pre-tokens, 32 per round
+        // ---- 4. pre-tokens, 32 per round.  The round's key, hash and cache-slot load are ISSUED one round ahead (right after
+        //      the previous round's compare, before its scan and stores), so the slot's L2 round trip runs behind that work.
+        uint32_t pos, end, len, x0, x1, x2, x3, idx0, s0, s1, s2, s3, meta, t0, t1, t2;
+#define CTK_ISSUE_ROUND(BK)                                                                                             \
+        {                                                                                                               \
+            const uint32_t k_ = (BK) + lane;                                                                            \
+            pos = S.list[k_]; end = S.list[k_ + 1];                                                                     \
+            len = end - pos;                       /* 0 beyond the last pre-token; huge when the end is unknown */      \
+            const uint32_t pc = pos & (CHUNK - 1); /* (only a lane without a pre-token can hold END_UNKNOWN here) */     \
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(chunk + (pc & ~3u));                                 \
+            const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];                                  \
+            const uint32_t sh = (pc & 3u) * 8;                                                                          \
+            const uint4 km = s_kmask[len < 16 ? len : 16];                                                              \
+            x0 = __funnelshift_r(a0, a1, sh) & km.x; x1 = __funnelshift_r(a1, a2, sh) & km.y;                           \
+            x2 = __funnelshift_r(a2, a3, sh) & km.z; x3 = __funnelshift_r(a3, a4, sh) & km.w;                           \
+            idx0 = key_hash(x0, x1, x2, x3, len) >> cshift;                                                             \
+            load_slot(cache + idx0, s0, s1, s2, s3, meta, t0, t1, t2);                                                  \
+        }
+        if (n_owned) CTK_ISSUE_ROUND(0u)
         for (uint32_t base_k = 0; base_k < n_owned; base_k += 32) {
             const uint32_t k = base_k + lane;
-            const uint32_t pos = S.list[k], end = S.list[k + 1];
-            const uint32_t len = end - pos;                                // 0 beyond the last pre-token; huge when the end is unknown
             const bool have = len != 0;
-            // straight line: key bytes, hash, one slot load, compare
-            const uint32_t pc = pos & (CHUNK - 1);                         // (only a lane without a pre-token can hold END_UNKNOWN here)
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(chunk + (pc & ~3u));
-            const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
-            const uint32_t sh = (pc & 3u) * 8;
-            const uint4 km = s_kmask[len < 16 ? len : 16];
-            const uint32_t x0 = __funnelshift_r(a0, a1, sh) & km.x, x1 = __funnelshift_r(a1, a2, sh) & km.y,
-                           x2 = __funnelshift_r(a2, a3, sh) & km.z, x3 = __funnelshift_r(a3, a4, sh) & km.w;
-            const uint32_t idx0 = key_hash(x0, x1, x2, x3, len) >> cshift;
-            uint32_t s0, s1, s2, s3, meta, t0, t1, t2;
-            load_slot(cache + idx0, s0, s1, s2, s3, meta, t0, t1, t2);
             // the table only holds pre-tokens of 1..16 bytes and an EMPTY / BUSY slot has 0xFF / 0xFE in its length byte: lanes
             // without a pre-token (len 0) or with a longer one can never compare equal
             if (p.ablate == 4) meta = META_BUSY;                           // measurement: cache off, every pre-token is merged where it stands
             bool match = (meta & 0xFFu) == len && (((s0 ^ x0) | (s1 ^ x1)) | ((s2 ^ x2) | (s3 ^ x3))) == 0;
             uint32_t ntok = __byte_perm(meta, 0, 0x4441);                  // (meta >> 8) & 0xFF
             bool fast = match && ntok <= ninl;
+            if (!fast) ntok = 0;                                           // (also the lanes beyond the last pre-token, whose slot is whatever their zero key hashed to)
             // everything else: displaced keys walk on; then warp-cooperative, one pre-token after the other, in lane order
             unsigned slow = __ballot_sync(full, have && !fast);
             if (p.ablate == 2) slow = 0;
@@ -391,9 +412,9 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
                     }
                     ntok = (meta >> 8) & 0xFFu;
                     fast = match && ntok <= ninl;
+                    if (!fast) ntok = 0;
                     slow = __ballot_sync(full, have && !fast);
                 }
-                if (!fast) ntok = 0;
                 uint32_t hit_total;
                 const uint32_t E = warp_excl_scan(ntok, hit_total, lane);  // ids of fast lanes before each lane
                 uint32_t extra = 0;                                        // ids of slow lanes handled so far
@@ -485,6 +506,10 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
                 }
             }
             // ids of all lower lanes (fast and slow): the slow lanes wrote theirs at exactly these offsets
+            uint32_t e0 = t0, e1 = t1, e2 = t2;                            // this round's packed ids (the next round's load reuses t0..t2)
+#if CTK_PIPELINE_ROUNDS
+            if (base_k + 32 < n_owned) CTK_ISSUE_ROUND(base_k + 32)
+#endif
             uint32_t round_total;
             const uint32_t o = stage_cnt + warp_excl_scan(ntok, round_total, lane);
             {
@@ -492,30 +517,34 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
                 const uint32_t mx = __reduce_max_sync(full, en);           // most pre-tokens are one or two ids: stop at the round's longest
                 run_t* const dst = run + o;
                 if (RW == 2) {                                             // 16 bits per id in the slot, 16-bit stores
-                    if (en >= 1) dst[0] = (run_t)t0;
+                    if (en >= 1) dst[0] = (run_t)e0;
                     if (mx >= 2) {
-                        if (en >= 2) dst[1] = (run_t)(t0 >> 16);
+                        if (en >= 2) dst[1] = (run_t)(e0 >> 16);
                         if (mx >= 3) {
-                            if (en >= 3) dst[2] = (run_t)t1;
+                            if (en >= 3) dst[2] = (run_t)e1;
                             if (mx >= 4) {
-                                if (en >= 4) dst[3] = (run_t)(t1 >> 16);
-                                if (en >= 5) dst[4] = (run_t)t2;
-                                if (en >= 6) dst[5] = (run_t)(t2 >> 16);
+                                if (en >= 4) dst[3] = (run_t)(e1 >> 16);
+                                if (en >= 5) dst[4] = (run_t)e2;
+                                if (en >= 6) dst[5] = (run_t)(e2 >> 16);
                             }
                         }
                     }
                 } else {
-                    if (en >= 1) dst[0] = (run_t)(t0 & idmask);
+                    if (en >= 1) dst[0] = (run_t)(e0 & idmask);
                     for (uint32_t i = 1; i < mx; ++i) {
-                        t0 = __funnelshift_r(t0, t1, idb); t1 = __funnelshift_r(t1, t2, idb); t2 >>= idb;
-                        if (i < en) dst[i] = (run_t)(t0 & idmask);
+                        e0 = __funnelshift_r(e0, e1, idb); e1 = __funnelshift_r(e1, e2, idb); e2 >>= idb;
+                        if (i < en) dst[i] = (run_t)(e0 & idmask);
                     }
                 }
             }
             // the list entry now becomes the pre-token's id offset inside the slice's run (ids_off, long ones)
             if (docs_here || n_long) { __syncwarp(); if (have) S.list[k] = (uint16_t)o; }
             stage_cnt += round_total;
+#if !CTK_PIPELINE_ROUNDS
+            if (base_k + 32 < n_owned) CTK_ISSUE_ROUND(base_k + 32)
+#endif
         }
+#undef CTK_ISSUE_ROUND
         __syncwarp();
         if (lane == 0) S.list[n_owned] = (uint16_t)stage_cnt;
 
@@ -579,19 +608,23 @@ __global__ void __launch_bounds__(256) k_compact(const void* __restrict__ runs_v
     const int lane = threadIdx.x & 31;
     const uint64_t s = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     if (s >= n_slices) return;
+    const run_t* src = static_cast<const run_t*>(runs_v) + s * STAGE;
+    // the first 128 ids of the run are fetched together with the slice's base and count, not after them: one dependent
+    // round trip less per slice (a run has STAGE entries whatever its count: reading past the count is harmless)
+    run_t v0 = __ldcs(src + lane), v1 = __ldcs(src + lane + 32), v2 = __ldcs(src + lane + 64), v3 = __ldcs(src + lane + 96);
     const uint32_t b = __ldg(slice_base + s), nxt = __ldg(slice_base + s + 1), inf = __ldg(slice_info + s);
     if ((uint64_t)nxt > out_cap) { if (lane == 0) atomicOr(err, ERRF_CAPACITY); return; }
     const uint32_t n_stage = inf & 0xFFFFu, n_long = inf >> 16;
-    const run_t* src = static_cast<const run_t*>(runs_v) + s * STAGE;
     out_t* dst = static_cast<out_t*>(out_v) + b;
     if (n_long == 0) {
         for (uint32_t i0 = 0; i0 < n_stage; i0 += 128) {
             const uint32_t i = i0 + lane;
-            run_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-            if (i < n_stage) v0 = __ldcs(src + i);
-            if (i + 32 < n_stage) v1 = __ldcs(src + i + 32);
-            if (i + 64 < n_stage) v2 = __ldcs(src + i + 64);
-            if (i + 96 < n_stage) v3 = __ldcs(src + i + 96);
+            if (i0) {
+                if (i < n_stage) v0 = __ldcs(src + i);
+                if (i + 32 < n_stage) v1 = __ldcs(src + i + 32);
+                if (i + 64 < n_stage) v2 = __ldcs(src + i + 64);
+                if (i + 96 < n_stage) v3 = __ldcs(src + i + 96);
+            }
             if (i < n_stage) dst[i] = (out_t)v0;
             if (i + 32 < n_stage) dst[i + 32] = (out_t)v1;
             if (i + 64 < n_stage) dst[i + 64] = (out_t)v2;
@@ -724,12 +757,16 @@ int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size
     p.n_slices = (n_bytes + SLICE - 1) / SLICE;
     p.n_tiles = (uint32_t)((p.n_slices + FW - 1) / FW);
     // small inputs: a small cache (the clear is part of every call) and the plain long path (fewer launches)
-    uint32_t cache_slots = 1u << 20;
+    // Slots never touched cost nothing but their share of the clear: a large table keeps hot keys in their first slot (a
+    // displaced key sends its whole round through the probe loop) and leaves room for corpora with millions of distinct
+    // pre-tokens.  2^22 slots = 128 MB, cleared in ~0.04 ms; small inputs use a prefix sized to them (the clear is part of every call).
+    uint32_t cache_slots = 1u << CACHE_LOG2;
+    if (const char* e = getenv("CTK_CACHE_LOG2")) { int v = atoi(e); if (v >= 10 && v <= CACHE_LOG2) cache_slots = 1u << v; }
     while (cache_slots > 1024 && (uint64_t)cache_slots * 4 > n_bytes) cache_slots >>= 1;   // ~one slot per 4-8 input bytes
     const uint32_t ovf_cap = 1u << 18;
     uint32_t *first_doc, *ctrl, *slice_base;
     CK(ws.get(0, (p.n_slices + 1) * 4, (void**)&first_doc));
-    CK(ws.get(18, (uint64_t)(1u << 20) * sizeof(CacheSlot), (void**)&p.cache));       // always the full table; a call uses a prefix
+    CK(ws.get(18, (uint64_t)(1u << CACHE_LOG2) * sizeof(CacheSlot), (void**)&p.cache));       // always the full table; a call uses a prefix
     CK(ws.get(19, (uint64_t)ovf_cap * 64, (void**)&p.ovf_pool));
     CK(ws.get(4, 256, (void**)&ctrl));
     CK(ws.get(1, (p.n_slices + 2) * 4, (void**)&p.slice_cnt));

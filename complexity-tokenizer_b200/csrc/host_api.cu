@@ -316,7 +316,7 @@ static int encode_single_try(Engine* eng, const uint8_t* text, const uint64_t* t
     int rc = CTK_OK;
     Result* r = new Result();
     r->n = n;
-    const int width = narrow && eng->run_width == 2 ? 2 : 4;
+    const int width = narrow && eng->run_width == 2 && !eng->use_general ? 2 : 4;   // (the debug multi-kernel pipeline only writes uint32)
     r->id_width = width;
     PinnedPool* const pool = pool_for_node(eng->numa_node);
     uint8_t* d_text = nullptr; uint64_t *d_roff = nullptr, *d_ids_off = nullptr; uint8_t* d_ids = nullptr;
@@ -555,7 +555,7 @@ static int encode_host(const ctk_tokenizer* tok, const uint8_t* text, const uint
         for (size_t i = 0; i < n; ++i) if (text_off[i + 1] < text_off[i]) { set_last_error("text_off must be non-decreasing"); return CTK_ERR_ARG; }
         r = new Result();
         r->n = n;
-        r->id_width = narrow && eng->run_width == 2 ? 2 : 4;
+        r->id_width = narrow && eng->run_width == 2 && !eng->use_general ? 2 : 4;
         const std::vector<size_t> cut = balanced_cuts(text_off, n, eng->peers.size());
         rc = run_on_peers(eng, cut, r, [&](Engine* pe, size_t d0, size_t nd, Result** out) { return encode_single(pe, text, text_off + d0, nd, narrow, out); });
         if (rc != CTK_OK) { free_result(r); r = nullptr; }
