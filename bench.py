@@ -278,8 +278,10 @@ def main():
     torch.cuda.set_device(local)
     # one rank per GPU: run next to it -- this process's pages (the pinned corpus, the result buffers) then live on the GPU's NUMA node
     placement = numa.bind_process_to_device(local) if world > 1 else numa.describe(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        cpu_group = dist.new_group(backend='gloo')          # for waits that must not keep a GPU busy (an NCCL barrier spins in a kernel)
     dev = torch.device('cuda', local)
 
     tok_path = synth.tokenizer_config2()
@@ -433,6 +435,8 @@ def main():
     if world > 1:
         del d_back, d_back_off
         barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)                       # from here the other ranks wait on the CPU: their GPUs are free for rank 0's process
         if rank == 0:
             try:
                 # this rank was bound to GPU 0's node: let the library's per-device threads place themselves
@@ -478,7 +482,7 @@ def main():
                 del mt, big, big_np
             except Exception as ex:                       # never lose the headline line over the extra
                 single = {'error': repr(ex)}
-        barrier()
+        dist.barrier(group=cpu_group)
 
     if rank != 0:
         if world > 1:

@@ -83,7 +83,7 @@ static int upload(Engine& eng) {
     UP(6, eng.dec.special, m.dec_special.data(), m.dec_special.size());
     {
         const size_t nid = m.dec_special.size();
-        std::vector<uint8_t> l8(nid + 1, 0), l8s(nid + 1, 0);
+        std::vector<uint8_t> l8((nid + 1 + 31) / 16 * 16, 0), l8s((nid + 1 + 31) / 16 * 16, 0);   // padded: k_dec_tile_sums_smem copies them 16 bytes at a time
         std::vector<uint4> rec(nid + 1, make_uint4(0, 0, 0, 0));
 
         for (size_t id = 0; id < nid; ++id) {

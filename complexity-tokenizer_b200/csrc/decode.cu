@@ -11,6 +11,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.hpp"
@@ -47,22 +49,62 @@ __device__ __forceinline__ void dec_load_ids(const uint32_t* __restrict__ ids, u
     }
 }
 
-__global__ void __launch_bounds__(DTH) k_dec_tile_sums(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
-                                                       uint32_t* __restrict__ tile_sum) {
-    __shared__ uint32_t s_part[DTH / 32];
+// pass 1: 128 threads per tile, 16 ids each (four 16-byte loads and sixteen 1-byte gathers in flight per thread)
+constexpr int DTH1 = DT / (2 * DPT);
+__global__ void __launch_bounds__(DTH1) k_dec_tile_sums(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
+                                                        uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t s_part[DTH1 / 32];
     const uint64_t t0 = (uint64_t)blockIdx.x * DT;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(ids) & 15) == 0;
-    uint32_t id[DPT], sum = 0;
-    dec_load_ids(ids, n, t0 + (uint64_t)threadIdx.x * DPT, vec_ok, id);
+    uint32_t ida[DPT], idb[DPT], sum = 0;
+    dec_load_ids(ids, n, t0 + (uint64_t)threadIdx.x * 2 * DPT, vec_ok, ida);
+    dec_load_ids(ids, n, t0 + (uint64_t)threadIdx.x * 2 * DPT + DPT, vec_ok, idb);
+    uint32_t la[DPT], lb[DPT];
 #pragma unroll
-    for (int q = 0; q < DPT; ++q) sum += dec_tok_len(t, id[q], skip_special);     // (0xFFFFFFFF is no id: length 0)
+    for (int q = 0; q < DPT; ++q) { la[q] = dec_tok_len(t, ida[q], skip_special); lb[q] = dec_tok_len(t, idb[q], skip_special); }   // (0xFFFFFFFF is no id: length 0)
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) sum += la[q] + lb[q];
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t tot = 0;
-        for (int w = 0; w < DTH / 32; ++w) tot += s_part[w];
+        for (int w = 0; w < DTH1 / 32; ++w) tot += s_part[w];
         tile_sum[blockIdx.x] = tot;
+    }
+}
+
+// pass 1 with the 1-byte length table in SHARED memory: a gather from global memory costs the load/store unit one wavefront
+// per distinct cache line (about twenty per warp for these ids), a gather from shared memory three or four.  Persistent CTAs
+// (the table is loaded once per CTA), one tile of DT ids per iteration.
+__global__ void __launch_bounds__(DTH) k_dec_tile_sums_smem(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
+                                                            uint32_t* __restrict__ tile_sum, uint32_t n_tiles) {
+    extern __shared__ __align__(16) uint8_t s_len[];                   // t.n_ids bytes, rounded up to 16
+    __shared__ uint32_t s_part[2][DTH / 32];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(skip_special ? t.len8_skip : t.len8);   // (padded to a multiple of 16 at upload)
+        for (uint32_t v = threadIdx.x; 16 * v < t.n_ids; v += DTH) reinterpret_cast<uint4*>(s_len)[v] = __ldg(src + v);
+    }
+    __syncthreads();
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(ids) & 15) == 0;
+    int par = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
+        uint32_t id[DPT], sum = 0;
+        dec_load_ids(ids, n, (uint64_t)tile * DT + (uint64_t)threadIdx.x * DPT, vec_ok, id);
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            uint32_t L = id[q] < t.n_ids ? s_len[id[q]] : 0u;
+            if (L == 255u) L = __ldg(t.off + id[q] + 1) - __ldg(t.off + id[q]);
+            sum += L;
+        }
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        if ((threadIdx.x & 31) == 0) s_part[par][threadIdx.x >> 5] = sum;
+        __syncthreads();                                               // (two buffers: the next tile's partial sums do not wait for this read)
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < DTH / 32; ++w) tot += s_part[par][w];
+            tile_sum[tile] = tot;
+        }
     }
 }
 
@@ -81,17 +123,17 @@ __global__ void __launch_bounds__(DTH) k_dec_write(DecodeTables t, const uint32_
                                                    const uint32_t* __restrict__ first_doc,
                                                    uint64_t n_docs, uint8_t* __restrict__ out, uint64_t out_cap,
                                                    uint64_t* __restrict__ raw_off, uint32_t* __restrict__ err, uint32_t* __restrict__ non_ascii) {
-    __shared__ uint32_t s_off[DT + 1];                    // byte offset of every token inside the tile
+    __shared__ uint32_t s_toff[DTH + 1];                  // byte offset inside the tile of every thread's first token
     __shared__ uint32_t s_warp[DTH / 32];
-    __shared__ __align__(16) uint8_t s_stage[DSTAGE + 32];
+    __shared__ __align__(16) uint8_t s_stage[DSTAGE + 48];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t t0 = (uint64_t)blockIdx.x * DT, base = tile_base[blockIdx.x];
     const uint32_t total = (uint32_t)(tile_base[blockIdx.x + 1] - base);
     if (base + total > out_cap) { if (tid == 0) atomicOr(err, ERRF_CAPACITY); return; }
     const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15u);
     const bool staged = total + shift <= (uint32_t)DSTAGE;
-    // the stage is filled with whole words and, where two threads share a word, with atomicOr: it starts at zero
-    if (staged) for (uint32_t v = tid; 16 * v < total + shift + 4; v += DTH) *reinterpret_cast<uint4*>(s_stage + 16 * v) = make_uint4(0, 0, 0, 0);
+    // the stage is filled by OR-ing whole words into it: it starts at zero (a token's last word may reach 15 bytes past the tile)
+    if (staged) for (uint32_t v = tid; 16 * v < total + shift + 20; v += DTH) *reinterpret_cast<uint4*>(s_stage + 16 * v) = make_uint4(0, 0, 0, 0);
     // One 16-byte record per token {first 12 bytes, length}: ONE gather gives this pass both the length and the bytes.
     // The thread's DPT consecutive tokens, then an exclusive scan of their lengths over the CTA.
     uint32_t id[DPT], len[DPT], mine = 0;
@@ -109,75 +151,56 @@ __global__ void __launch_bounds__(DTH) k_dec_write(DecodeTables t, const uint32_
     for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
-    uint32_t off = incl - mine;
-    for (int w = 0; w < wid; ++w) off += s_warp[w];
-    const uint32_t my_off = off;
-#pragma unroll
-    for (int q = 0; q < DPT; ++q) { s_off[tid * DPT + q] = off; off += len[q]; }
-    if (tid == DTH - 1) s_off[DT] = off;
+    uint32_t my_off = incl - mine;
+    for (int w = 0; w < wid; ++w) my_off += s_warp[w];
+    s_toff[tid] = my_off;
+    if (tid == DTH - 1) s_toff[DTH] = my_off + mine;
     if (staged) {
-        // The thread's tokens are one contiguous byte range of the tile.  Their bytes go through a 64-bit accumulator, up to
-        // four at a time, and leave as whole words OR-ed into the zeroed stage (a word at either end of the range also holds
-        // a neighbour's bytes).  Straight-line code: three pushes per token, every store predicated, no branch on the data.
+        // A record is zero beyond its token's length, so it can be laid over the zeroed stage as it is: shifted to the token's
+        // byte position it spans four aligned words, each OR-ed in with one shared-memory reduction (only where it is not
+        // zero: most tokens touch two words).  Neighbouring tokens only overlap in bytes that are zero in one of them.
+        // A dozen instructions per token, none of them a branch on the data.
         const uint32_t stage_a = (uint32_t)__cvta_generic_to_shared(s_stage);
-        uint32_t bpos = shift + my_off;                                // byte position in the stage of the next byte
-        uint32_t fill = bpos & 3u, acc_lo = 0, acc_hi = 0;
-        auto push = [&](uint32_t w, uint32_t nb) {                      // appends the low nb (0..4) bytes of w; bytes above nb are zero
-            const uint32_t sh = 8u * fill;
-            acc_lo |= w << sh;
-            acc_hi |= __funnelshift_l(w, 0u, sh);                      // (w >> (32 - sh)), 0 for sh == 0
-            fill += nb;
-            bpos += nb;
-            const uint32_t full = fill >> 2;                           // 0 or 1
-            asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.shared.or.b32 [%0], %1; }"
-                         :: "r"(stage_a + ((bpos - fill) & ~3u)), "r"(acc_lo), "r"(full) : "memory");
-            acc_lo = full ? acc_hi : acc_lo;
-            acc_hi = full ? 0u : acc_hi;
-            fill &= 3u;
-        };
+        uint32_t o = shift + my_off;                                   // byte position of the token in the stage
         bool any_long = false;
 #pragma unroll
         for (int q = 0; q < DPT; ++q) {
-            const uint32_t L = len[q];
-            if (L <= 12) {                                             // (predicated: a longer token leaves a hole that is filled below)
-                push(rec[q].x, L < 4 ? L : 4u);
-                push(rec[q].y, L < 4 ? 0u : (L < 8 ? L - 4 : 4u));
-                push(rec[q].z, L < 8 ? 0u : L - 8);
-            } else {
-                any_long = true;
-                if (fill) atomicOr(reinterpret_cast<uint32_t*>(s_stage) + ((bpos - fill) >> 2), acc_lo);   // flush, jump over the token
-                bpos += L; fill = bpos & 3u; acc_lo = 0; acc_hi = 0;
-            }
+            const uint32_t sh = 8u * (o & 3u), wa = stage_a + (o & ~3u);
+            const uint32_t w0 = rec[q].x << sh, w1 = __funnelshift_l(rec[q].x, rec[q].y, sh), w2 = __funnelshift_l(rec[q].y, rec[q].z, sh),
+                           w3 = __funnelshift_l(rec[q].z, 0u, sh);
+            asm volatile("{ .reg .pred p0, p1, p2, p3;\n\t"
+                         "setp.ne.u32 p0, %1, 0; setp.ne.u32 p1, %2, 0; setp.ne.u32 p2, %3, 0; setp.ne.u32 p3, %4, 0;\n\t"
+                         "@p0 red.shared.or.b32 [%0], %1; @p1 red.shared.or.b32 [%0+4], %2; @p2 red.shared.or.b32 [%0+8], %3; @p3 red.shared.or.b32 [%0+12], %4; }"
+                         :: "r"(wa), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            any_long = any_long || len[q] > 12;
+            o += len[q];
         }
-        if (fill) atomicOr(reinterpret_cast<uint32_t*>(s_stage) + ((bpos - fill) >> 2), acc_lo);         // the range's last, partial word
-        if (any_long) {                                                // tokens longer than 12 bytes (rare): byte by byte from the blob
-            uint32_t o = shift + my_off;
+        if (any_long) {                                                // bytes 12.. of longer tokens (rare): one by one from the blob
+            o = shift + my_off;
             for (int q = 0; q < DPT; ++q) {
                 const uint32_t L = len[q];
                 if (L > 12) {
                     const uint8_t* src = t.blob + __ldg(t.off + id[q]);
-                    for (uint32_t k = 0; k < L; ++k)
+                    for (uint32_t k = 12; k < L; ++k)
                         atomicOr(reinterpret_cast<uint32_t*>(s_stage) + ((o + k) >> 2), (uint32_t)__ldg(src + k) << (8u * ((o + k) & 3u)));
                 }
                 o += L;
             }
         }
-    }
-    __syncthreads();                                                   // s_off complete (and the stage, if used)
-    if (!staged) {
-        // a tile of unusually long tokens: byte by byte, straight to global memory, tokens in stripes
-        uint8_t* const dst0 = out + base;
-#pragma unroll 1
+    } else {
+        // a tile of unusually long tokens: every thread writes its own tokens byte by byte, straight to global memory
+        uint8_t* d = out + base + my_off;
         for (int q = 0; q < DPT; ++q) {
-            const int j = q * DTH + tid;
-            const uint32_t o = s_off[j], L = s_off[j + 1] - o;
+            const uint32_t L = len[q];
             if (L == 0) continue;
-            const uint32_t tid_id = __ldg(ids + t0 + j);
-            const uint8_t* src = t.blob + __ldg(t.off + tid_id);
-            for (uint32_t k = 0; k < L; ++k) dst0[o + k] = __ldg(src + k);
+            const uint8_t* src = t.blob + __ldg(t.off + id[q]);
+            for (uint32_t k = 0; k < L; ++k) d[k] = __ldg(src + k);
+            d += L;
         }
         if (tid == 0 && total) atomicOr(non_ascii, 1u);                 // not looked at here: let the validation kernel decide
-    } else if (total) {
+    }
+    __syncthreads();                                                   // s_toff and the stage are complete
+    if (staged && total) {
         uint8_t* const g = out + base;
         const uint32_t head = min(total, (16u - shift) & 15u);            // bytes before the first aligned 16-byte group
         uint32_t hib = 0;
@@ -193,13 +216,19 @@ __global__ void __launch_bounds__(DTH) k_dec_write(DecodeTables t, const uint32_
         // pure ASCII output is valid UTF-8 whatever the document cuts: only a tile with a byte >= 0x80 asks for the validation pass
         if (__any_sync(0xFFFFFFFFu, (hib & 0x80808080u) != 0) && lane == 0) atomicOr(non_ascii, 1u);
     }
-    // byte offsets of the documents whose first token lies in this tile (and, in the last tile, of those at the very end)
+    // byte offsets of the documents whose first token lies in this tile (and, in the last tile, of those at the very end):
+    // the offset of the thread that holds the token, plus the lengths of that thread's tokens before it (looked up again:
+    // there are one or two documents per tile)
     const uint64_t t1 = t0 + DT < n ? t0 + DT : n;
     const bool last = t0 + DT >= n;
     for (uint64_t d = (uint64_t)first_doc[blockIdx.x] + tid; d <= n_docs; d += DTH) {
         const uint64_t j = ids_off[d];
-        if (j < t1 || (last && j == n)) raw_off[d] = base + s_off[j - t0];
-        else break;
+        if (j < t1 || (last && j == n)) {
+            const uint32_t r = (uint32_t)(j - t0);
+            uint32_t o = s_toff[r / DPT];
+            for (uint32_t q = 0; q < r % DPT; ++q) o += dec_tok_len(t, __ldg(ids + t0 + (r / DPT) * DPT + q), skip_special);
+            raw_off[d] = base + o;
+        } else break;
     }
 }
 
@@ -379,7 +408,23 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
     CK(ws.get(37, (n_tiles + 2) * 4, (void**)&first_doc));
     eng.mark(nullptr, st);
     if (n_tiles) {
-        k_dec_tile_sums<<<(unsigned)n_tiles, DTH, 0, st>>>(eng.dec, d_ids, T, skip_special, tile_sum);
+        const size_t table = ((size_t)eng.dec.n_ids + 15) / 16 * 16;
+        if (eng.dec_sums_grid == 0) {                                   // once: does the length table fit in shared memory, and how many CTAs per SM
+            eng.dec_sums_grid = -1;
+            int dev_smem = 0, sms = 0, occ = 0;
+            cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng.device);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, eng.device);
+            if (table + 1024 <= (size_t)dev_smem && !getenv("CTK_DEC_SUMS_GLOBAL") &&
+                cudaFuncSetAttribute(k_dec_tile_sums_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dec_tile_sums_smem, DTH, table) == cudaSuccess && occ > 0)
+                eng.dec_sums_grid = sms * occ;
+            cudaGetLastError();
+        }
+        if (eng.dec_sums_grid > 0 && n_tiles >= 64 && n_tiles < 0xFFFFFFFFull)
+            k_dec_tile_sums_smem<<<(unsigned)std::min<uint64_t>(n_tiles, (uint64_t)eng.dec_sums_grid), DTH, table, st>>>(eng.dec, d_ids, T, skip_special,
+                                                                                                                          tile_sum, (uint32_t)n_tiles);
+        else
+            k_dec_tile_sums<<<(unsigned)n_tiles, DTH1, 0, st>>>(eng.dec, d_ids, T, skip_special, tile_sum);
         k_dec_first_doc<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(d_ids_off, n_docs, n_tiles, first_doc);
         eng.launched(2);
     }

@@ -83,4 +83,4 @@ def test_nfc_of_the_c_oracle_against_unicodedata():
     for i in range(0, len(texts), 5000):
         chunk = texts[i:i + 5000]
         joined = '\x00'.join(chunk)
-        assert c_oracle.nfc(joined) == ud.normalize('NFC', joined)
+        assert c_oracle.nfc(joined.encode('utf-8')).decode('utf-8') == ud.normalize('NFC', joined)
