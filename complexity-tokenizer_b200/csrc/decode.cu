@@ -88,9 +88,13 @@ __global__ void __launch_bounds__(DTH) k_dec_tile_sums_smem(DecodeTables t, cons
     __syncthreads();
     const bool vec_ok = (reinterpret_cast<uintptr_t>(ids) & 15) == 0;
     int par = 0;
+    uint32_t nxt[DPT];                                                 // the next tile's ids are in flight while this tile's lengths are summed
+    if (blockIdx.x < n_tiles) dec_load_ids(ids, n, (uint64_t)blockIdx.x * DT + (uint64_t)threadIdx.x * DPT, vec_ok, nxt);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
         uint32_t id[DPT], sum = 0;
-        dec_load_ids(ids, n, (uint64_t)tile * DT + (uint64_t)threadIdx.x * DPT, vec_ok, id);
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) id[q] = nxt[q];
+        if (tile + gridDim.x < n_tiles) dec_load_ids(ids, n, (uint64_t)(tile + gridDim.x) * DT + (uint64_t)threadIdx.x * DPT, vec_ok, nxt);
 #pragma unroll
         for (int q = 0; q < DPT; ++q) {
             uint32_t L = id[q] < t.n_ids ? s_len[id[q]] : 0u;
@@ -118,18 +122,26 @@ __global__ void k_dec_first_doc(const uint64_t* __restrict__ ids_off, uint64_t n
     for (uint64_t tl = lo; tl <= hi && tl <= n_tiles; ++tl) first_doc[tl] = (uint32_t)d;
 }
 
+// Persistent CTAs, one tile of DT tokens per iteration.  The records of the first `n_hot` ids live in shared memory (a
+// byte-level BPE vocabulary is ordered by frequency: single bytes, then merges in the order they were learnt, so the low ids
+// are most of the occurrences): a gather from shared memory costs the load/store unit a third of what a gather from global
+// memory does (one wavefront per distinct cache line), and that unit is what bounds this kernel.
 __global__ void __launch_bounds__(DTH) k_dec_write(DecodeTables t, const uint32_t* __restrict__ ids, uint64_t n, int skip_special,
                                                    const uint64_t* __restrict__ tile_base, const uint64_t* __restrict__ ids_off,
-                                                   const uint32_t* __restrict__ first_doc,
+                                                   const uint32_t* __restrict__ first_doc, uint32_t n_tiles, uint32_t n_hot,
                                                    uint64_t n_docs, uint8_t* __restrict__ out, uint64_t out_cap,
                                                    uint64_t* __restrict__ raw_off, uint32_t* __restrict__ err, uint32_t* __restrict__ non_ascii) {
+    extern __shared__ __align__(16) uint4 s_hot[];        // records of ids 0 .. n_hot - 1
     __shared__ uint32_t s_toff[DTH + 1];                  // byte offset inside the tile of every thread's first token
     __shared__ uint32_t s_warp[DTH / 32];
     __shared__ __align__(16) uint8_t s_stage[DSTAGE + 48];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t t0 = (uint64_t)blockIdx.x * DT, base = tile_base[blockIdx.x];
-    const uint32_t total = (uint32_t)(tile_base[blockIdx.x + 1] - base);
-    if (base + total > out_cap) { if (tid == 0) atomicOr(err, ERRF_CAPACITY); return; }
+    for (uint32_t v = tid; v < n_hot; v += DTH) s_hot[v] = __ldg(t.rec + v);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();                                                   // the hot records are loaded / the previous tile is done with the shared arrays
+    const uint64_t t0 = (uint64_t)tile * DT, base = tile_base[tile];
+    const uint32_t total = (uint32_t)(tile_base[tile + 1] - base);
+    if (base + total > out_cap) { if (tid == 0) atomicOr(err, ERRF_CAPACITY); continue; }
     const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15u);
     const bool staged = total + shift <= (uint32_t)DSTAGE;
     // the stage is filled by OR-ing whole words into it: it starts at zero (a token's last word may reach 15 bytes past the tile)
@@ -140,7 +152,8 @@ __global__ void __launch_bounds__(DTH) k_dec_write(DecodeTables t, const uint32_
     uint4 rec[DPT];
     dec_load_ids(ids, n, t0 + (uint64_t)tid * DPT, (reinterpret_cast<uintptr_t>(ids) & 15) == 0, id);
 #pragma unroll
-    for (int q = 0; q < DPT; ++q) rec[q] = id[q] < t.n_ids ? __ldg(t.rec + id[q]) : make_uint4(0, 0, 0, 0);   // unknown ids are dropped (mod.rs:717-735)
+    for (int q = 0; q < DPT; ++q)                                     // unknown ids are dropped (mod.rs:717-735)
+        rec[q] = id[q] < n_hot ? s_hot[id[q]] : (id[q] < t.n_ids ? __ldg(t.rec + id[q]) : make_uint4(0, 0, 0, 0));
     if (skip_special) {
 #pragma unroll
         for (int q = 0; q < DPT; ++q) if (id[q] < t.n_ids && __ldg(t.special + id[q])) rec[q] = make_uint4(0, 0, 0, 0);
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(DTH) k_dec_write(DecodeTables t, const uint32_
     // there are one or two documents per tile)
     const uint64_t t1 = t0 + DT < n ? t0 + DT : n;
     const bool last = t0 + DT >= n;
-    for (uint64_t d = (uint64_t)first_doc[blockIdx.x] + tid; d <= n_docs; d += DTH) {
+    for (uint64_t d = (uint64_t)first_doc[tile] + tid; d <= n_docs; d += DTH) {
         const uint64_t j = ids_off[d];
         if (j < t1 || (last && j == n)) {
             const uint32_t r = (uint32_t)(j - t0);
@@ -229,6 +242,7 @@ __global__ void __launch_bounds__(DTH) k_dec_write(DecodeTables t, const uint32_
             for (uint32_t q = 0; q < r % DPT; ++q) o += dec_tok_len(t, __ldg(ids + t0 + (r / DPT) * DPT + q), skip_special);
             raw_off[d] = base + o;
         } else break;
+    }
     }
 }
 
@@ -448,8 +462,23 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
     else CK(ws.get(13, raw_total + 16, (void**)&raw));
     eng.mark(nullptr, st);
     if (n_tiles) {
-        k_dec_write<<<(unsigned)n_tiles, DTH, 0, st>>>(eng.dec, d_ids, T, skip_special, tile_base, d_ids_off, first_doc, n_docs, raw,
-                                                       direct ? out_cap : raw_total + 16, raw_off, err, err + 2);
+        if (eng.dec_write_grid == 0) {                                  // once: how many hot records fit beside two CTAs per SM
+            int dev_smem = 0, sms = 0, occ = 0;
+            cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, eng.device);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, eng.device);
+            uint32_t hot = 1024;                                        // measured on 1 GiB: 0 -> 1.42, 1024 -> 1.39, 2048 -> 1.46, 4096 -> 2.25 ms (occupancy)
+            if (const char* e = getenv("CTK_DEC_HOT")) hot = (uint32_t)atoi(e);
+            if (hot > eng.dec.n_ids) hot = eng.dec.n_ids;
+            while (hot && (size_t)hot * 16 + 24 * 1024 > (size_t)dev_smem) hot /= 2;
+            if (cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(hot * 16)) != cudaSuccess) { cudaGetLastError(); hot = 0; }
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dec_write, DTH, (size_t)hot * 16) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+            eng.dec_hot = hot;
+            eng.dec_write_grid = sms * occ;
+        }
+        if (n_tiles >= 0xFFFFFFFFull) return eng.fail(CTK_ERR_ARG, "too many ids in one decode call");
+        k_dec_write<<<(unsigned)std::min<uint64_t>(n_tiles, (uint64_t)eng.dec_write_grid), DTH, (size_t)eng.dec_hot * 16, st>>>(
+            eng.dec, d_ids, T, skip_special, tile_base, d_ids_off, first_doc, (uint32_t)n_tiles, eng.dec_hot, n_docs, raw,
+            direct ? out_cap : raw_total + 16, raw_off, err, err + 2);
         eng.launched(1);
     } else CK(cudaMemsetAsync(raw_off, 0, (n_docs + 1) * 8, st));
     eng.mark("k_dec_write", st);

@@ -92,6 +92,8 @@ struct Engine {
     int run_width = 4;                  // bytes per id in the encode kernels' scratch runs: 2 when max_emit_id < 65 536
     int out_id_width = 4;               // bytes per id of the CURRENT device call's output buffer (4, or 2 via the _ex / narrow entry points)
     int long_grid = 0;
+    int dec_write_grid = 0;             // persistent CTAs of k_dec_write
+    uint32_t dec_hot = 0;               // records k_dec_write keeps in shared memory (ids 0 .. dec_hot - 1)
     int dec_sums_grid = 0;              // persistent CTAs of k_dec_tile_sums_smem (0: not computed yet, -1: the length table does not fit in shared memory)
     int mid_grid[4] = {};               // co-resident single-warp CTAs of the four k_encode_mid instantiations
     uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // bytes the last host-buffer encode call moved over PCIe

@@ -44,14 +44,39 @@ uint32_t next_cp(const std::string& s, size_t& i) {
     return r;
 }
 
-bool rust_regex_would_compile(const std::string& p) {
-    // Rust `regex` has no look-around and no back-references: Regex::new fails and
-    // regex_split_with_behavior returns the text unchanged (pretokenizers.rs:299-302).
-    static const char* bad[] = {"(?=", "(?!", "(?<=", "(?<!"};
-    for (const char* b : bad) if (p.find(b) != std::string::npos) return false;
-    for (char d = '1'; d <= '9'; ++d) { char pat[3] = {'\\', d, 0}; if (p.find(pat) != std::string::npos) return false; }
-    return true;
+// Does Rust `regex` certainly REJECT this pattern?  It has no look-around and no back-references: Regex::new then fails
+// and regex_split_with_behavior returns the text unchanged (pretokenizers.rs:299-302).  The scan knows escapes and
+// character classes: an escaped `\(\?=` or a `(?=` inside `[...]` is no look-around, and `\1` inside a class is no
+// back-reference the decision may rest on.  Anything not certainly rejected is treated as compiling, i.e. as a Split
+// this library would have to apply -- and reports UNSUPPORTED rather than guessing (never a silent pass-through).
+bool rust_regex_certainly_rejected(const std::string& p) {
+    int cls = 0;                                                // depth of [...] nesting (Rust allows nested classes)
+    for (size_t i = 0; i < p.size(); ++i) {
+        const char c = p[i];
+        if (c == '\\') {
+            if (i + 1 < p.size() && !cls && p[i + 1] >= '1' && p[i + 1] <= '9') return true;      // back-reference
+            ++i;                                                // whatever is escaped is not syntax
+            continue;
+        }
+        if (cls) {
+            if (c == '[') ++cls;
+            else if (c == ']') --cls;
+            continue;
+        }
+        if (c == '[') {
+            cls = 1;
+            if (i + 1 < p.size() && p[i + 1] == '^') ++i;
+            if (i + 1 < p.size() && p[i + 1] == ']') ++i;       // a leading ] is a literal
+            continue;
+        }
+        if (c == '(' && i + 2 < p.size() && p[i + 1] == '?') {
+            if (p[i + 2] == '=' || p[i + 2] == '!') return true;
+            if (p[i + 2] == '<' && i + 3 < p.size() && (p[i + 3] == '=' || p[i + 3] == '!')) return true;
+        }
+    }
+    return false;
 }
+bool rust_regex_would_compile(const std::string& p) { return !rust_regex_certainly_rejected(p); }
 
 const char* type_of(const JValue* v) {
     if (!v || !v->is_obj()) return nullptr;
