@@ -11,7 +11,9 @@ def val(k):
 tot = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'traffic.json')
 d = json.load(open(path)) if os.path.exists(path) else {}
-d[kernel] = {'dram_bytes_per_launch': int(tot), 'input_bytes': nbytes, 'source': note}
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+d[kernel] = {'dram_bytes_per_launch': int(tot), 'input_bytes': nbytes, 'source': note, 'kernel_source_sha': bench.kernel_source_sha()}
 json.dump(d, open(path, 'w'), indent=1)
 json.dump(d, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bench_traffic.json'), 'w'), indent=1)   # copy that travels with the repo snapshot
 print(kernel, int(tot), 'bytes per launch')
