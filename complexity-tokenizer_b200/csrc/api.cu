@@ -164,17 +164,47 @@ static int upload(Engine& eng) {
     return CTK_OK;
 }
 
+// [Split stages ->] ByteLevel prefix space -> fused encode, on text that is already normalised.  With Split stages the pieces
+// travel as documents and the per-piece id offsets are folded back to per-document offsets (split.cu).
+static int encode_normalised(Engine& eng, const uint8_t* t, const uint64_t* o, size_t n, uint64_t b, uint32_t* d_ids, uint64_t ids_cap,
+                             uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st, bool check_nfc) {
+    const uint64_t* first_piece = nullptr;
+    size_t n_pieces = n;
+    int rc = split_stages(eng, t, o, n, b, &t, &o, &n_pieces, &b, &first_piece, st);
+    if (rc != CTK_OK) return rc;
+    rc = prefix_space_stage(eng, t, o, n_pieces, b, &t, &o, &b, st);
+    if (rc != CTK_OK) return rc;
+    if (!first_piece) {
+        if (eng.use_general && !check_nfc) return encode_general(eng, t, o, n, b, d_ids, ids_cap, d_ids_off, n_ids_host, st);
+        return encode_fused(eng, t, o, n, b, d_ids, ids_cap, d_ids_off, n_ids_host, st, check_nfc);
+    }
+    uint64_t* piece_ids_off;
+    cudaError_t e = eng.ws.get(59, (n_pieces + 2) * 8, (void**)&piece_ids_off);
+    if (e != cudaSuccess) return eng.cuda_fail(e, "workspace");
+    uint64_t total = 0;
+    rc = encode_fused(eng, t, o, n_pieces, b, d_ids, ids_cap, piece_ids_off, &total, st, check_nfc);
+    if (rc != CTK_OK) return rc;
+    rc = split_fold_ids(eng, first_piece, piece_ids_off, n, d_ids_off, st);
+    if (rc != CTK_OK) return rc;
+    if (n_ids_host) {
+        *n_ids_host = total;
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return eng.cuda_fail(e, "split fold");
+    }
+    return CTK_OK;
+}
+
 // normaliser -> pre-tokenise -> BPE -> emit, all on the device (mod.rs:551-613 for every document)
 int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n, uint64_t n_bytes, uint32_t* d_ids,
                          uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st) {
     if (n_bytes && (reinterpret_cast<uintptr_t>(d_text) & 15)) return eng.fail(CTK_ERR_ARG, "device text buffer must be 16-byte aligned");
     const uint8_t* t2; const uint64_t* o2; uint64_t b2;
     int rc;
-    if (eng.model.nfc && eng.nfc_optimistic && n_ids_host && !eng.use_general && !getenv("CTK_NO_NFC_OPTIMISM")) {
-        rc = prefix_space_stage(eng, d_text, d_off, n, n_bytes, &t2, &o2, &b2, st);
-        if (rc != CTK_OK) return rc;
+    const bool sync_call = n_ids_host != nullptr || !eng.split_dev.empty();     // (Split stages synchronise anyway)
+    if (eng.model.nfc && eng.nfc_optimistic && sync_call && !eng.use_general && !getenv("CTK_NO_NFC_OPTIMISM")) {
         const bool keep = eng.keep_cache_once;
-        rc = encode_fused(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st, true);
+        uint64_t dummy;
+        rc = encode_normalised(eng, d_text, d_off, n, n_bytes, d_ids, ids_cap, d_ids_off, n_ids_host ? n_ids_host : &dummy, st, true);
         if (rc != CTK_RETRY_NFC) return rc;
         eng.nfc_optimistic = false;                          // this text needs the normaliser: scan first from now on
         eng.keep_cache_once = keep;
@@ -182,10 +212,7 @@ int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, siz
     rc = nfc_stage(eng, d_text, d_off, n, n_bytes, &t2, &o2, &b2, st);
     if (rc != CTK_OK) return rc;
     if (n_bytes) eng.nfc_optimistic = !eng.last_nfc_needed;  // a clean call switches the optimistic path back on
-    rc = prefix_space_stage(eng, t2, o2, n, b2, &t2, &o2, &b2, st);
-    if (rc != CTK_OK) return rc;
-    if (eng.use_general) return encode_general(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st);
-    return encode_fused(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st);
+    return encode_normalised(eng, t2, o2, n, b2, d_ids, ids_cap, d_ids_off, n_ids_host, st, false);
 }
 
 static int create(const uint8_t* json, size_t len, int device, ctk_tokenizer** out) {
@@ -210,6 +237,7 @@ static int create(const uint8_t* json, size_t len, int device, ctk_tokenizer** o
     if (e != cudaSuccess) { rc = eng->cuda_fail(e, "cudaSetDevice"); delete eng; return rc; }
     eng->numa_node = device_numa_node(device);
     rc = upload(*eng);
+    if (rc == CTK_OK) rc = split_upload(*eng);
     if (rc != CTK_OK) { delete eng; return rc; }
     *out = reinterpret_cast<ctk_tokenizer*>(eng);
     return CTK_OK;
@@ -306,6 +334,7 @@ static void free_engine(Engine* eng) {
     cudaDeviceSynchronize();
     eng->ws.release();
     for (void* p : eng->d_table_mem) if (p) cudaFree(p);
+    for (void* p : eng->split_mem) if (p) cudaFree(p);
     if (eng->h_flags) cudaFreeHost(eng->h_flags);
     for (cudaStream_t sp : {eng->st_h2d, eng->st_comp, eng->st_d2h}) if (sp) cudaStreamDestroy(sp);
     for (cudaEvent_t ev : eng->ev_pool) cudaEventDestroy(ev);
@@ -460,6 +489,50 @@ int ctk_debug_starts_window_host(const uint8_t* text, uint64_t n, const uint64_t
 
 // the product's code point table (class in bits 0-1: 0 Other, 1 L, 2 N, 3 White_Space; bit 2: NFC-suspect), for the CPU
 // test that checks every code point against Python's `regex` / `unicodedata`
+// TEST HOOK (no device involved, never on a product path): compiles `pattern` like the loader does and walks ONE text through the
+// automaton on the host with the same split_walk() the device kernels run.  pieces = (start, end) pairs.
+// Returns 0, CTK_ERR_UNSUPPORTED (pattern outside the subset), or -1 when the `regex` crate would reject the pattern.
+namespace { struct HostPieces {
+    uint64_t *cuts, *spans; size_t nc = 0, ns = 0;
+    CTK_HD void boundary(uint64_t p) { if (nc == 0 || cuts[nc - 1] != p) cuts[nc++] = p; }
+    CTK_HD void span(uint64_t a, uint64_t b) { spans[ns++] = a; spans[ns++] = b; }
+}; }
+int ctk_debug_split_pieces(const char* pattern, int behavior, int invert, const uint8_t* text, uint64_t n, uint64_t* pieces, size_t cap_pairs, size_t* n_pairs,
+                           uint32_t* n_states, uint32_t* n_classes) {
+    std::string json = std::string("{\"model\":{\"vocab\":{},\"merges\":[]},\"pre_tokenizer\":{\"type\":\"Sequence\",\"pretokenizers\":[{\"type\":\"Split\",\"pattern\":{\"Regex\":");
+    json += '"';
+    for (const char* c = pattern; *c; ++c) {
+        if (*c == '"' || *c == '\\') { json += '\\'; json += *c; }
+        else if ((unsigned char)*c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", (unsigned)(unsigned char)*c); json += b; }
+        else json += *c;
+    }
+    json += "\"},\"behavior\":\"Isolated\"},{\"type\":\"ByteLevel\"}]}}";
+    HostModel m;
+    std::string err;
+    int rc = load_model(reinterpret_cast<const uint8_t*>(json.data()), json.size(), m, err);
+    if (rc != CTK_OK) { set_last_error(err); return rc; }
+    if (m.split_stages.empty()) return -1;
+    const SplitDfa& d = m.split_stages[0].dfa;
+    if (n_states) *n_states = d.n_states;
+    if (n_classes) *n_classes = d.n_classes;
+    SplitTables t{d.trans.data(), d.ascii_class.data(), d.stage1.data(), d.blocks.data(), d.n_classes, d.start, behavior, invert};
+    std::vector<uint64_t> cuts(n + 2), spans(2 * n + 4);
+    HostPieces hp;
+    hp.cuts = cuts.data(); hp.spans = spans.data();
+    split_walk(t, text, 0, n, hp);
+    std::vector<uint64_t> out;
+    if (behavior == 0) out.assign(spans.begin(), spans.begin() + hp.ns);
+    else if (n) {
+        uint64_t prev = 0;
+        for (size_t k = 0; k < hp.nc; ++k) { out.push_back(prev); out.push_back(cuts[k]); prev = cuts[k]; }
+        out.push_back(prev); out.push_back(n);
+    }
+    *n_pairs = out.size() / 2;
+    if (out.size() / 2 > cap_pairs) { set_last_error("capacity"); return CTK_ERR_ARG; }
+    for (size_t i = 0; i < out.size(); ++i) pieces[i] = out[i];
+    return 0;
+}
+
 int ctk_debug_cp_classes(uint32_t first, uint32_t count, uint8_t* out) {
     for (uint32_t i = 0; i < count; ++i) out[i] = (uint8_t)trie_nibble(CTK_TRIE_INDEX, CTK_TRIE_BLOCKS, first + i);
     return CTK_OK;

@@ -12,6 +12,7 @@
 #include "../../include/ctk.h"
 #include "device_common.cuh"
 #include "model.hpp"
+#include "split_walk.cuh"
 
 namespace ctk {
 
@@ -82,6 +83,8 @@ struct Engine {
     NfcTables nfc{};
     RichTables rich{};
     void* d_table_mem[32] = {};
+    std::vector<SplitTables> split_dev;  // device tables of model.split_stages (split.cu)
+    std::vector<void*> split_mem;
     Workspace ws;
     std::mutex mu;                      // serialises device work issued through this tokenizer
     bool cache_persistent = false;
@@ -159,6 +162,10 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
               const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st);
 int prefix_space_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                        const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st);
+int split_upload(Engine& eng);
+int split_stages(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
+                 const uint8_t** o_text, const uint64_t** o_off, size_t* o_n, uint64_t* o_bytes, const uint64_t** first_piece, cudaStream_t st);
+int split_fold_ids(Engine& eng, const uint64_t* first_piece, const uint64_t* piece_ids_off, size_t n_docs, uint64_t* d_ids_off, cudaStream_t st);
 int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n, uint64_t n_bytes, uint32_t* d_ids,
                   uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int encode_fused(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,

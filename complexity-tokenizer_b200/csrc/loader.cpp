@@ -76,7 +76,6 @@ bool rust_regex_certainly_rejected(const std::string& p) {
     }
     return false;
 }
-bool rust_regex_would_compile(const std::string& p) { return !rust_regex_certainly_rejected(p); }
 
 const char* type_of(const JValue* v) {
     if (!v || !v->is_obj()) return nullptr;
@@ -112,21 +111,37 @@ bool parse_normalizer(const JValue* v, bool& nfc, std::string& err) {
 }
 
 // parsing.rs:93-190.  Collects ByteLevel stages; returns 0 ok, 1 = "None", 2 = unsupported
-int parse_pre(const JValue* v, std::vector<bool>& stages, std::string& err) {
+// One parsed pre-tokenizer stage: the ByteLevel stage (with its add_prefix_space) or a compiled Split stage.
+struct PreStage { bool bytelevel = false; bool add_prefix_space = false; SplitStage split; };
+
+// parsing.rs:93-190.  0 = parsed (stages appended), 1 = None (unknown type), 2 = unsupported (err set)
+int parse_pre(const JValue* v, std::vector<PreStage>& stages, std::string& err) {
     const char* t = type_of(v);
-    if (!t) { stages.push_back(false); return 0; }              // default ByteLevel{false} (:187-189)
+    if (!t) { PreStage b; b.bytelevel = true; stages.push_back(b); return 0; }   // default ByteLevel{false} (:187-189)
     std::string ty = t;
     if (ty == "ByteLevel") {
         const JValue* a = v->get("add_prefix_space");
-        stages.push_back(a && a->t == JValue::Bool ? a->b : false);   // use_regex / trim_offsets ignored (:99-107)
+        PreStage b;
+        b.bytelevel = true;
+        b.add_prefix_space = a && a->t == JValue::Bool ? a->b : false;    // use_regex / trim_offsets ignored (:99-107)
+        stages.push_back(b);
         return 0;
     }
-    if (ty == "Split") {
+    if (ty == "Split") {                                        // parsing.rs:145-167 -> SplitWithBehavior
         const JValue* pat = v->get("pattern");
         const JValue* rx = pat ? pat->get("Regex") : nullptr;
-        std::string p = (rx && rx->is_str()) ? rx->s : "";
-        if (rust_regex_would_compile(p)) { err = "Split pre-tokenizer with a compilable regex is outside the hot path"; return 2; }
-        return 0;                                               // passes text through
+        PreStage sp;
+        sp.split.pattern = (rx && rx->is_str()) ? rx->s : "";   // a {"String": ...} pattern reads as "" (:147-151)
+        if (rust_regex_certainly_rejected(sp.split.pattern)) return 0;    // Regex::new fails: text passes through (pretokenizers.rs:299-302)
+        const JValue* inv = v->get("invert");
+        sp.split.invert = inv && inv->t == JValue::Bool ? inv->b : false;
+        const JValue* bh = v->get("behavior");
+        const std::string b = bh && bh->is_str() ? bh->s : "Removed";
+        sp.split.behavior = b == "Isolated" ? SPLIT_ISOLATED : b == "MergedWithPrevious" ? SPLIT_MERGED_PREV : b == "MergedWithNext" ? SPLIT_MERGED_NEXT
+                            : b == "Contiguous" ? SPLIT_CONTIGUOUS : SPLIT_REMOVED;
+        if (compile_split_regex(sp.split.pattern, sp.split.dfa, err) != 0) return 2;
+        stages.push_back(sp);
+        return 0;
     }
     if (ty == "Sequence") {
         const JValue* seq = v->get("pretokenizers");
@@ -421,15 +436,22 @@ int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err) 
     // ---- components
     const JValue* nj = root.get("normalizer");
     if (!parse_normalizer(nj && nj->t != JValue::Null ? nj : nullptr, m.nfc, err)) return CTK_ERR_UNSUPPORTED;
-    std::vector<bool> stages;
+    std::vector<PreStage> stages;
     const JValue* pj = root.get("pre_tokenizer");
     int pr = parse_pre(pj && pj->t != JValue::Null ? pj : nullptr, stages, err);
     if (pr == 2) return CTK_ERR_UNSUPPORTED;
-    if (pr == 1 || stages.size() != 1) {
-        err = "pre_tokenizer must resolve to exactly one ByteLevel stage for the hot path";
+    // the hot path: any number of Split stages, then exactly one ByteLevel stage, nothing after it (a Split behind the
+    // ByteLevel stage would see byte-mapped text, a second ByteLevel stage would map twice)
+    if (pr == 1 || stages.empty() || !stages.back().bytelevel) {
+        err = "pre_tokenizer must resolve to Split stages followed by exactly one ByteLevel stage for the hot path";
         return CTK_ERR_UNSUPPORTED;
     }
-    m.add_prefix_space = stages[0];
+    m.split_stages.clear();
+    for (size_t k = 0; k + 1 < stages.size(); ++k) {
+        if (stages[k].bytelevel) { err = "pre_tokenizer must resolve to Split stages followed by exactly one ByteLevel stage for the hot path"; return CTK_ERR_UNSUPPORTED; }
+        m.split_stages.push_back(std::move(stages[k].split));
+    }
+    m.add_prefix_space = stages.back().add_prefix_space;
     const JValue* dj = root.get("decoder");
     const char* dt = type_of(dj && dj->t != JValue::Null ? dj : nullptr);
     if (dt && std::string(dt) != "ByteLevel") { err = std::string("decoder '") + dt + "' is outside the ByteLevel-BPE hot path"; return CTK_ERR_UNSUPPORTED; }

@@ -6,6 +6,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include "regex_dfa.hpp"
+
 namespace ctk {
 
 constexpr uint32_t kNoId = 0xFFFFFFFFu;
@@ -29,6 +31,7 @@ struct HostModel {
     std::vector<std::pair<std::string, uint32_t>> specials;// special_tokens map (mod.rs:290-291)
     bool nfc = true;                                       // parsing.rs:89
     bool add_prefix_space = false;                         // parsing.rs:99-107
+    std::vector<SplitStage> split_stages;                  // Split stages in front of the ByteLevel stage (parsing.rs:145-167), compiled at load
     uint32_t byte_init_id[256];                            // byte -> id of its mapped char, kNoId if absent (bpe.rs:94-97)
     // decode side (vocab.rs:47-51 + decoders.rs:94-116 folded per token at load)
     std::vector<uint8_t> dec_blob;

@@ -121,6 +121,8 @@ class COracle:
         text = np.ascontiguousarray(text, dtype=np.uint8)
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         n = len(offs) - 1
+        if any(s[0] == 'split' for s in self.twin.pre_stages):
+            return self._encode_packed_split(text, offs, threads)
         tp = text.ctypes.data if text.size else ctypes.addressof(ctypes.create_string_buffer(1))
         r = self.lib.orc_encode_batch(self.h, tp, offs.ctypes.data, n, threads or os.cpu_count() or 1)
         off = np.ctypeslib.as_array(ctypes.cast(self.lib.orc_result_off(r), ctypes.POINTER(ctypes.c_uint64)), (n + 1,)).copy()
@@ -128,6 +130,36 @@ class COracle:
         ids = np.ctypeslib.as_array(ctypes.cast(self.lib.orc_result_ids(r), ctypes.POINTER(ctypes.c_uint32)), (max(tot, 1),))[:tot].copy()
         self.lib.orc_result_free(r)
         return ids, off
+
+    def _encode_packed_split(self, text, offs, threads):
+        """Split stages (pretokenizers.rs:298-433 through the Sequence arm :114-124) run in Python on the normalised document
+        (mod.rs:553 normalises first); the pieces then go through the C core one by one -- the ByteLevel stage restarts its
+        pattern at every piece -- and their ids are concatenated per document (mod.rs:562-612)."""
+        import unicodedata
+        import py_regex
+        raw = text.tobytes()
+        pieces, first = [], [0]
+        for d in range(len(offs) - 1):
+            doc = raw[int(offs[d]):int(offs[d + 1])].decode('utf-8')
+            if self.twin.normalizer == 'nfc':
+                doc = unicodedata.normalize('NFC', doc)
+            words = [doc]
+            for kind, arg in self.twin.pre_stages:
+                if kind == 'split':
+                    words = [p for w in words for p in py_regex.split_with_behavior(arg[0], w, arg[1], arg[2])]
+            pieces += [w.encode('utf-8') for w in words]
+            first.append(len(pieces))
+        po = np.zeros(len(pieces) + 1, dtype=np.uint64)
+        if pieces:
+            po[1:] = np.cumsum([len(b) for b in pieces], dtype=np.uint64)
+        pt = np.frombuffer(b''.join(pieces), dtype=np.uint8)
+        tp = pt.ctypes.data if pt.size else ctypes.addressof(ctypes.create_string_buffer(1))
+        r = self.lib.orc_encode_batch(self.h, tp, po.ctypes.data, len(pieces), threads or os.cpu_count() or 1)
+        off = np.ctypeslib.as_array(ctypes.cast(self.lib.orc_result_off(r), ctypes.POINTER(ctypes.c_uint64)), (len(pieces) + 1,)).copy()
+        tot = int(off[-1])
+        ids = np.ctypeslib.as_array(ctypes.cast(self.lib.orc_result_ids(r), ctypes.POINTER(ctypes.c_uint32)), (max(tot, 1),))[:tot].copy()
+        self.lib.orc_result_free(r)
+        return ids, off[np.array(first, dtype=np.int64)]
 
     def decode_packed(self, ids: np.ndarray, offs: np.ndarray, skip_special_tokens=False,
                       clean_up_tokenization_spaces=True, threads=None):

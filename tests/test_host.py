@@ -72,15 +72,19 @@ def test_loader_rules(built_lib):
     assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Unknown'}))[0] == 3
     compilable = {'type': 'Sequence', 'pretokenizers': [{'type': 'Split', 'pattern': {'Regex': r'\d'}, 'behavior': 'Isolated'},
                                                         {'type': 'ByteLevel'}]}
-    assert _load_only(lib, dict(BASE, pre_tokenizer=compilable))[0] == 3
+    assert _load_only(lib, dict(BASE, pre_tokenizer=compilable))[0] == 0          # compiled to a DFA at load (regex_dfa.cpp)
+    assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Split', 'pattern': {'Regex': r'\d'}, 'behavior': 'Isolated'}))[0] == 3   # no ByteLevel stage
+    assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Sequence', 'pretokenizers': [{'type': 'ByteLevel'}, compilable['pretokenizers'][0]]}))[0] == 3
     # Rust `regex` certainly rejects look-around and back-references (-> the Split stage passes text through); an ESCAPED
-    # "(?=" or one inside a character class is no look-around: such a pattern compiles, the Split would apply -> unsupported (3)
+    # "(?=" or one inside a character class is no look-around: such a pattern compiles and the Split applies -- compiled when
+    # it lies in the supported subset (0), else unsupported (3), never a silent pass-through
     import py_oracle
-    for rx, want in ((r"\s+(?!\S)", 0), (r"(?<=a)b", 0), (r"(a)\1", 0), (r"(?<!x)y", 0), (r"a(?=b)", 0),
-                     (r"\(\?=x\)", 3), (r"[(?=]+", 3), (r"[\1]", 3), (r"\\(?:a|b)", 3), (r"[^\]](?i:x)", 3), (r"[]](?=x)", 0), (r"\\(?=x)", 0)):
+    for rx, want, rejected in ((r"\s+(?!\S)", 0, True), (r"(?<=a)b", 0, True), (r"(a)\1", 0, True), (r"(?<!x)y", 0, True), (r"a(?=b)", 0, True),
+                               (r"\(\?=x\)", 0, False), (r"[(?=]+", 0, False), (r"[\1]", 3, False), (r"\\(?:a|b)", 0, False), (r"[^\]](?i:x)", 3, False),
+                               (r"[]](?=x)", 0, True), (r"\\(?=x)", 0, True), (r"(?i)x", 3, False), (r"x*", 3, False)):
         pt = {'type': 'Sequence', 'pretokenizers': [{'type': 'Split', 'pattern': {'Regex': rx}, 'behavior': 'Isolated'}, {'type': 'ByteLevel'}]}
         assert _load_only(lib, dict(BASE, pre_tokenizer=pt))[0] == want, rx
-        assert py_oracle._rust_regex_certainly_rejected(rx) == (want == 0), rx
+        assert py_oracle._rust_regex_certainly_rejected(rx) == rejected, rx
     assert _load_only(lib, dict(BASE, decoder={'type': 'ByteLevel'}))[0] == 0
     assert _load_only(lib, dict(BASE, decoder={'type': 'WordPiece'}))[0] == 3
     # invalid data (2): not JSON, no model, vocab id not a u32, added token without `special` (mod.rs:107)
