@@ -783,6 +783,52 @@ def run_extras(args, tok, tok_path, torch, dev, ct, synth, h_np, offs, h_text, B
                                      'seconds': cpu_s_, 'gpu_wall_seconds': gpu_s_, 'gpu_device_ms_merge_loop': trn2.last_stats['ms_merges'],
                                      'equal': got_ == want_}
         out['train_bpe'] = train
+        # ---- train_new_from_iterator (mod.rs:1231-1322) on config 1's own shape: normaliser, pre-tokenizer and trainer on the device
+        try:
+            p1 = synth.tokenizer_config1()
+            tok1 = ct.Tokenizer.from_file(p1, device=tok.device)
+            t1, o1 = synth.gen_corpus('english', 1001, 12 << 20)
+            nd = min(2000, len(o1) - 1)
+            raw1 = t1[:int(o1[nd])].tobytes()
+            docs1 = [raw1[int(o1[i]):int(o1[i + 1])].decode() for i in range(nd)]
+            tok1.train_new_from_iterator(docs1[:20], 400)
+            t0 = time.perf_counter()
+            new1 = tok1.train_new_from_iterator(docs1, 32000)
+            wall1 = time.perf_counter() - t0
+            st1 = tok1.last_train_stats
+            got1 = new1.encode_batch(docs1[:50])
+            out['train_new_from_iterator'] = {
+                'workload': 'config 1: first %d docs (%.1f MiB) through the tokenizer\'s own NFC + ByteLevel pre-tokenizer on the device, then BpeTrainer to 32 000 entries' % (nd, len(raw1) / 2**20),
+                'wall_s': wall1, 'merges': int(st1['n_merges']), 'words': int(st1['n_words']), 'unique_words': int(st1['n_unique_words']),
+                'device_ms_word_histogram': st1['ms_words'], 'device_ms_merge_loop': st1['ms_merges'],
+                'us_per_merge': 1e3 * st1['ms_merges'] / max(1, int(st1['n_merges'])), 'new_vocab_size': new1.vocab_size,
+                'round_trip_exact_on_50_docs': new1.decode_batch_with_options(got1, False, False) == docs1[:50]}
+        except Exception as ex:
+            out['train_new_from_iterator'] = {'error': repr(ex)}
+    # ---- Split stages: the headline corpus through Sequence[Split(\p{N}{1,3}, Isolated), ByteLevel]
+    try:
+        import tempfile
+        with open(tok_path, encoding='utf-8') as f:
+            tjs = json.load(f)
+        tjs['pre_tokenizer'] = {'type': 'Sequence', 'pretokenizers': [{'type': 'Split', 'pattern': {'Regex': r'\p{N}{1,3}'}, 'behavior': 'Isolated', 'invert': False},
+                                                                      {'type': 'ByteLevel', 'add_prefix_space': False, 'use_regex': False}]}
+        toks = ct.Tokenizer.from_str(json.dumps(tjs), device=tok.device)
+        n_s = int(np.searchsorted(offs, 256 << 20, side='right')) - 1
+        s_off = offs[:n_s + 1].copy()
+        s_text = h_np[:int(s_off[-1])]
+        ms, Ts, kern, ids_s, ioff_s = device_encode_ms(toks, torch, s_text, s_off, dev=dev)
+        ent = {'workload': 'first %d docs (%.1f MiB) of the headline corpus, pre_tokenizer Sequence[Split(\\p{N}{1,3}, Isolated), ByteLevel]' % (n_s, int(s_off[-1]) / 2**20),
+               'device_ms': ms, 'MB_per_s': int(s_off[-1]) / (ms * 1e-3) / 1e6, 'tokens': int(Ts), 'kernels_ms': {k: v for k, v in kern.items() if v >= 0.01}}
+        if not args.no_cpu:
+            import c_oracle
+            orcs = c_oracle.COracle.from_str(json.dumps(tjs))
+            k = min(n_s, 60)
+            wi, wo = orcs.encode_packed(s_text[:int(s_off[k])], s_off[:k + 1])
+            ent['ids_equal_oracle'] = bool(np.array_equal(wo, ioff_s[:k + 1]) and np.array_equal(wi, ids_s[:int(ioff_s[k])]))
+            ent['parity_sample_docs'] = k
+        out['split_stage'] = ent
+    except Exception as ex:
+        out['split_stage'] = {'error': repr(ex)}
     return out
 
 

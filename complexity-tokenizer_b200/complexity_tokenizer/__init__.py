@@ -9,6 +9,7 @@ CPU fallback: importing works without a GPU, but constructing a Tokenizer raises
 a device is missing.
 """
 import ctypes
+import json
 import os
 
 import numpy as np
@@ -138,6 +139,7 @@ def _lib():
         'ctk_post_processor_items': (S, [P, ctypes.POINTER(ctypes.c_int64), S]),
         'ctk_pad_token': (ctypes.c_uint32, [P, ctypes.POINTER(P), ctypes.POINTER(S)]),
         'ctk_train_bpe': (I, [ctypes.POINTER(_TrainerConfig), I, P, P, S, ctypes.POINTER(P)]),
+        'ctk_train_new_from_texts': (I, [P, ctypes.POINTER(_TrainerConfig), P, P, S, ctypes.POINTER(P)]),
         'ctk_trained_symbols': (S, [P, ctypes.POINTER(P), ctypes.POINTER(P), ctypes.POINTER(P)]),
         'ctk_trained_merges': (S, [P, ctypes.POINTER(P)]),
         'ctk_trained_merge_counts': (P, [P]),
@@ -257,7 +259,9 @@ class Tokenizer:
             rc = lib.ctk_from_file(os.fsencode(path), dev, ctypes.byref(h))
         if rc != CTK_OK:
             _raise(rc)
-        return Tokenizer(h)
+        t = Tokenizer(h)
+        t._source, t._ctor = ('file', path), dict(device=device, devices=devices)
+        return t
 
     @staticmethod
     def from_str(json_text, device=None, devices=None):
@@ -273,9 +277,69 @@ class Tokenizer:
             rc = lib.ctk_from_json(ctypes.addressof(buf), len(data), dev, ctypes.byref(h))
         if rc != CTK_OK:
             _raise(rc)
-        return Tokenizer(h)
+        t = Tokenizer(h)
+        t._source, t._ctor = ('str', data), dict(device=device, devices=devices)
+        return t
 
     from_buffer = from_str
+
+    # ---- training with this tokenizer's configuration
+    def _config_json(self):
+        kind, v = self._source
+        if kind == 'file':
+            with open(v, 'rb') as f:
+                v = f.read()
+        return json.loads(v.decode('utf-8'))
+
+    def all_special_tokens(self):
+        """mod.rs:1042-1057: bos, eos, pad, unk, sep, cls, mask (vocab.rs:18-30 defaults, overridden by the special added tokens
+        in file order, mod.rs:284-303), then the rest of the special-token map -- in hash order in the reference, by content here."""
+        roles = {'unk': '<unk>', 'bos': '<s>', 'eos': '</s>', 'pad': '<pad>', 'sep': None, 'cls': None, 'mask': None}
+        special = {}
+        for t in self._config_json().get('added_tokens') or []:
+            if not t.get('special'):
+                continue
+            c = t['content']
+            special[c] = t['id']
+            lo = c.lower()
+            if 'unk' in lo:
+                roles['unk'] = c
+            elif lo == '<s>' or 'bos' in lo:
+                roles['bos'] = c
+            elif lo == '</s>' or 'eos' in lo:
+                roles['eos'] = c
+            elif 'pad' in lo:
+                roles['pad'] = c
+            elif 'sep' in lo:
+                roles['sep'] = c
+            elif 'cls' in lo:
+                roles['cls'] = c
+            elif 'mask' in lo:
+                roles['mask'] = c
+        out = [roles[k] for k in ('bos', 'eos', 'pad', 'unk', 'sep', 'cls', 'mask') if roles[k] is not None]
+        for c in sorted(special, key=lambda x: x.encode('utf-8')):
+            if c not in out:
+                out.append(c)
+        return out
+
+    def train_new_from_iterator(self, texts, vocab_size):
+        """HuggingFaceTokenizer::train_new_from_iterator (mod.rs:1231-1322): same normaliser / pre-tokenizer / decoder /
+        post-processor and special tokens, a new vocabulary trained on `texts`.  Normalisation, pre-tokenisation and training
+        all run on the device (ctk_train_new_from_texts); returns the new Tokenizer."""
+        specials = self.all_special_tokens()
+        trainer = BpeTrainer(vocab_size=vocab_size, min_frequency=2, special_tokens=specials, show_progress=True)    # mod.rs:1244-1252
+        buf, off = _pack_texts(list(texts))
+        vocab, merges = trainer.train_packed(buf, off, tokenizer=self)
+        self.last_train_stats = trainer.last_stats
+        tj = self._config_json()
+        tj.setdefault('model', {})
+        tj['model']['vocab'] = vocab
+        tj['model']['merges'] = [a + ' ' + b for a, b in merges]
+        tj['added_tokens'] = [dict(id=vocab[t], content=t, special=True, single_word=False, lstrip=False, rstrip=False, normalized=False)
+                              for t in dict.fromkeys(specials) if t in vocab]                                      # mod.rs:1283-1298
+        new = Tokenizer.from_str(json.dumps(tj, ensure_ascii=False), **self._ctor)
+        new._model_max_length, new._padding_side, new._truncation_side = self._model_max_length, self._padding_side, self._truncation_side
+        return new
 
     def __del__(self):
         h, self._h = getattr(self, '_h', None), None
@@ -715,7 +779,9 @@ class BpeTrainer:
         buf, off = _pack_texts(texts)
         return self.train_packed(buf, off)
 
-    def train_packed(self, buf, off):
+    def train_packed(self, buf, off, tokenizer=None):
+        """tokenizer: run the texts through that tokenizer's normaliser and pre-tokenizer on the device first
+        (train_new_from_iterator, mod.rs:1257-1270)"""
         lib = _lib()
         sp, sp_off = _pack_texts(self._special)
         keep = [np.ascontiguousarray(buf, dtype=np.uint8), np.ascontiguousarray(off, dtype=np.uint64), sp, sp_off]
@@ -734,7 +800,10 @@ class BpeTrainer:
                 setattr(cfg, name, b.ctypes.data)
                 setattr(cfg, ln, len(b) - 1)
         h = ctypes.c_void_p()
-        rc = lib.ctk_train_bpe(ctypes.byref(cfg), self._device, keep[0].ctypes.data, keep[1].ctypes.data, len(keep[1]) - 1, ctypes.byref(h))
+        if tokenizer is not None:
+            rc = lib.ctk_train_new_from_texts(tokenizer._h, ctypes.byref(cfg), keep[0].ctypes.data, keep[1].ctypes.data, len(keep[1]) - 1, ctypes.byref(h))
+        else:
+            rc = lib.ctk_train_bpe(ctypes.byref(cfg), self._device, keep[0].ctypes.data, keep[1].ctypes.data, len(keep[1]) - 1, ctypes.byref(h))
         if rc != CTK_OK:
             _raise(rc)
         try:

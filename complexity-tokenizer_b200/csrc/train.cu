@@ -712,7 +712,7 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         uint8_t* d_text; uint64_t* d_off; uint32_t* d_brk; uint32_t* d_starts; uint32_t* d_num;
         TCK(db.get(&d_text, n + 64)); TCK(db.get(&d_off, n_texts + 1)); TCK(db.get(&d_brk, (n >> 5) + 2));
         TCK(db.get(&d_num, 4));
-        TCK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st));
+        TCK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyDefault, st));                // host or device text (ctk_train_new_from_texts hands over device text)
         if (n_texts) TCK(cudaMemcpyAsync(d_off, off, (n_texts + 1) * 8, cudaMemcpyHostToDevice, st));
         TCK(cudaEventRecord(ev[0], st));
         PhaseTrace tr; tr.mark("alloc + copy in", st);
@@ -1054,6 +1054,103 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
 
 }  // namespace ctk
 
+// ---- train_new_from_iterator (src/huggingface/mod.rs:1231-1275): the texts go through THIS tokenizer's normaliser and
+// pre-tokenizer, and the trainer sees the pre-tokens -- for a ByteLevel pipeline: byte-mapped strings without any white space,
+// so each pre-token is exactly one of the trainer's words (bpe_trainer.rs:248 splits on white space).  Here the pre-tokens
+// never visit the host: the encode path's start bitmap says where they begin, one kernel writes their byte-mapped characters
+// (pretokenizers.rs:130-153) with a U+0020 in front of each, and stage W above takes that text where it lies.
+namespace ctk {
+namespace {
+// thread per 32 bytes (one bitmap word): bytes of output this group produces
+__global__ void k_mapped_len(const uint8_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ start_bits, const uint16_t* __restrict__ map2,
+                             uint64_t n_groups, uint32_t* __restrict__ glen) {
+    const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g > n_groups) return;
+    if (g == n_groups) { glen[g] = 0; return; }
+    const uint32_t sb = start_bits[g];
+    uint32_t len = __popc(sb);
+    for (int k = 0; k < 32; ++k) {
+        const uint64_t i = g * 32 + k;
+        if (i < n) len += (map2[text[i]] >> 8) ? 2u : 1u;
+    }
+    glen[g] = len;
+}
+__global__ void k_mapped_write(const uint8_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ start_bits, const uint16_t* __restrict__ map2,
+                               uint64_t n_groups, const uint64_t* __restrict__ gpos, uint8_t* __restrict__ out) {
+    const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint32_t sb = start_bits[g];
+    uint64_t o = gpos[g];
+    for (int k = 0; k < 32; ++k) {
+        const uint64_t i = g * 32 + k;
+        if (i >= n) break;
+        if ((sb >> k) & 1u) out[o++] = ' ';
+        const uint32_t m = map2[text[i]];
+        out[o++] = (uint8_t)m;
+        if (m >> 8) out[o++] = (uint8_t)(m >> 8);
+    }
+}
+struct U32To64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return v; } };
+}  // namespace
+
+// normalise + pre-tokenise on the device -> one text of byte-mapped pre-tokens separated by spaces (device memory of eng.ws)
+static int pretokens_as_text(Engine& eng, const uint8_t* h_text, const uint64_t* h_off, size_t n_texts, const uint8_t** d_out, uint64_t* out_bytes) {
+#define CKE(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
+    cudaStream_t st = eng.st_comp;
+    const uint64_t n = n_texts ? h_off[n_texts] : 0;
+    *d_out = nullptr; *out_bytes = 0;
+    if (n == 0) return CTK_OK;
+    if (n >= 0x7FFFFFF0ull) return eng.fail(CTK_ERR_UNSUPPORTED, "train_new_from_iterator: one call takes less than 2 GiB of text");
+    Workspace& ws = eng.ws;
+    uint8_t* d_text; uint64_t* d_off;
+    CKE(ws.get(64, n + 128, (void**)&d_text));
+    CKE(ws.get(65, (n_texts + 2) * 8, (void**)&d_off));
+    CKE(cudaMemcpyAsync(d_text, h_text, n, cudaMemcpyHostToDevice, st));
+    CKE(cudaMemsetAsync(d_text + n, 0, 64, st));
+    CKE(cudaMemcpyAsync(d_off, h_off, (n_texts + 1) * 8, cudaMemcpyHostToDevice, st));
+    const uint8_t* t; const uint64_t* o; uint64_t b; size_t np = n_texts;
+    int rc = nfc_stage(eng, d_text, d_off, n_texts, n, &t, &o, &b, st);
+    if (rc != CTK_OK) return rc;
+    const uint64_t* first_piece;
+    rc = split_stages(eng, t, o, n_texts, b, &t, &o, &np, &b, &first_piece, st);
+    if (rc != CTK_OK) return rc;
+    rc = prefix_space_stage(eng, t, o, np, b, &t, &o, &b, st);
+    if (rc != CTK_OK) return rc;
+    if (b == 0) return CTK_OK;
+    const uint64_t n_groups = (b + 31) / 32;
+    const uint32_t n_blocks = (uint32_t)((n_groups + 255) / 256);
+    uint32_t *ds, *sb, *bc, *err, *glen; uint64_t* gpos; uint8_t* out; void* tmp;
+    CKE(ws.get(66, (n_groups + 2) * 4, (void**)&ds));
+    CKE(ws.get(67, (n_groups + 2) * 4, (void**)&sb));
+    CKE(ws.get(68, ((uint64_t)n_blocks + 1) * 4, (void**)&bc));
+    CKE(ws.get(69, 256, (void**)&err));
+    CKE(ws.get(70, (n_groups + 2) * 4, (void**)&glen));
+    CKE(ws.get(71, (n_groups + 2) * 8, (void**)&gpos));
+    CKE(cudaMemsetAsync(err, 0, 256, st));
+    rc = starts_bitmap(eng, t, o, np, b, ds, sb, bc, err, st);
+    if (rc != CTK_OK) return rc;
+    k_mapped_len<<<(unsigned)((n_groups + 1 + 255) / 256), 256, 0, st>>>(t, b, sb, eng.rich.byte_map2, n_groups, glen);
+    cub::TransformInputIterator<uint64_t, U32To64, const uint32_t*> it(glen, U32To64());
+    size_t tb = 0;
+    CKE(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, gpos, n_groups + 1, st));
+    CKE(ws.get(5, tb + 16, &tmp));
+    CKE(cub::DeviceScan::ExclusiveSum(tmp, tb, it, gpos, n_groups + 1, st));
+    CKE(eng.publish({{err, 1, 0}, {gpos + n_groups, 2, 2}}, st));
+    CKE(cudaStreamSynchronize(st));
+    if (eng.h_flags[0] & ERRF_OFFSETS) return eng.fail(CTK_ERR_ARG, "offsets must start at 0, be non-decreasing and end at the buffer length");
+    uint64_t total;
+    memcpy(&total, eng.h_flags + 2, 8);
+    CKE(ws.get(72, total + 128, (void**)&out));
+    k_mapped_write<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(t, b, sb, eng.rich.byte_map2, n_groups, gpos, out);
+    eng.launched(5);
+    CKE(cudaGetLastError());
+    CKE(cudaStreamSynchronize(st));
+    *d_out = out; *out_bytes = total;
+    return CTK_OK;
+#undef CKE
+}
+}  // namespace ctk
+
 extern "C" {
 
 struct ctk_trained { ctk::Trained t; };
@@ -1096,3 +1193,30 @@ void ctk_trained_stats(const ctk_trained* t, ctk_train_stats* s) {
 void ctk_trained_free(ctk_trained* t) { delete t; }
 
 }  // extern "C"
+
+extern "C" int ctk_train_new_from_texts(const ctk_tokenizer* tok, const ctk_bpe_trainer_config* cfg, const uint8_t* text, const uint64_t* text_off,
+                                        size_t n_texts, ctk_trained** out) {
+    if (!tok || !cfg || !out || (n_texts && (!text_off || (!text && text_off[n_texts])))) { ctk::set_last_error("null argument"); return CTK_ERR_ARG; }
+    if (cfg->n_special && (!cfg->special_tokens || !cfg->special_off)) { ctk::set_last_error("special tokens missing"); return CTK_ERR_ARG; }
+    *out = nullptr;
+    ctk::Engine* eng = const_cast<ctk::Engine*>(reinterpret_cast<const ctk::Engine*>(tok));
+    std::lock_guard<std::mutex> lk(eng->mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(eng->device);
+    if (e != cudaSuccess) return eng->cuda_fail(e, "cudaSetDevice");
+    struct DeviceGuard { int d; ~DeviceGuard() { cudaSetDevice(d); } } dguard{prev};
+    const uint8_t* d_words = nullptr;
+    uint64_t n_bytes = 0;
+    int rc = ctk::pretokens_as_text(*eng, text, text_off, n_texts, &d_words, &n_bytes);
+    if (rc != CTK_OK) return rc;
+    ctk_trained* res = new (std::nothrow) ctk_trained();
+    if (!res) { ctk::set_last_error("out of memory"); return CTK_ERR_CUDA; }
+    const uint64_t one_off[2] = {0, n_bytes};
+    try { rc = ctk::train_impl(*cfg, eng->device, d_words, one_off, n_bytes ? 1 : 0, res->t); }
+    catch (const std::bad_alloc&) { ctk::set_last_error("out of host memory"); rc = CTK_ERR_CUDA; }
+    if (rc != CTK_OK) { delete res; return rc; }
+    *out = res;
+    return CTK_OK;
+}
+

@@ -210,6 +210,13 @@ typedef struct ctk_train_stats {
 } ctk_train_stats;
 int ctk_train_bpe(const ctk_bpe_trainer_config* cfg, int device, const uint8_t* text, const uint64_t* text_off, size_t n_texts,
                   ctk_trained** out);
+/* Replaces the training half of HuggingFaceTokenizer::train_new_from_iterator (src/huggingface/mod.rs:1231-1275): the texts go
+ * through THIS tokenizer's normaliser and pre-tokenizer on the device (mod.rs:1257-1270) and the trainer runs on the pre-tokens
+ * (each byte-mapped pre-token is one word, bpe_trainer.rs:248) -- no pre-tokenisation on the CPU.  The caller passes the
+ * trainer configuration mod.rs:1244-1252 builds (vocab_size, min_frequency 2, special_tokens = all_special_tokens()) and
+ * assembles the new tokenizer from the result (mod.rs:1276-1322).  Texts are host memory, packed as everywhere else. */
+int ctk_train_new_from_texts(const ctk_tokenizer* tok, const ctk_bpe_trainer_config* cfg, const uint8_t* text, const uint64_t* text_off,
+                             size_t n_texts, ctk_trained** out);
 /* Every symbol string the training knows, by symbol index, and its id in the returned vocabulary map (-1: not in it).  Returns the count. */
 size_t ctk_trained_symbols(const ctk_trained* t, const uint8_t** bytes, const uint64_t** off, const int64_t** vocab_id);
 /* Merges in order, two symbol indices each.  Returns the count. */

@@ -112,3 +112,24 @@ def test_split_unsupported_and_encoding_outputs(built_lib, tok_paths):
         assert tok.encode("") == [] and tok.encode_batch([]) == []
     finally:
         os.unlink(path)
+
+
+def test_split_tokenizer_train_new_from_iterator(built_lib, tok_paths):
+    """train_new_from_iterator (mod.rs:1231-1275) with a Split stage in the pipeline: the trainer's words are the pre-tokens of the pieces"""
+    import complexity_tokenizer as ct
+    import py_oracle
+    import synth
+    path = _make(tok_paths, 'config1', [(r'\p{N}{1,3}', 'Isolated', False)], False)
+    try:
+        tok = ct.Tokenizer.from_file(path)
+        orc = py_oracle.OracleTokenizer.from_file(path)
+        text, offs = synth.gen_corpus('english', 99, 256 << 10)
+        raw = text.tobytes()
+        docs = [raw[int(offs[i]):int(offs[i + 1])].decode('utf-8') for i in range(40)] + ["2024 12345 7 1000000 3.14159"] * 3
+        new = tok.train_new_from_iterator(docs, 450)
+        want_vocab, want_merges = orc.train_new_from_iterator(docs, 450)
+        tj = new._config_json()
+        assert tj['model']['vocab'] == want_vocab and tj['model']['merges'] == [a + ' ' + b for a, b in want_merges]
+        assert new.encode_batch(docs[-2:]) == py_oracle.OracleTokenizer(tj).encode_batch(docs[-2:])
+    finally:
+        os.unlink(path)

@@ -176,3 +176,34 @@ def test_word_table_growth(built_lib, monkeypatch):
     texts = [" ".join(words[i:i + 100]) for i in range(0, len(words), 100)]
     _, stats = both(texts, vocab_size=4 + 10 + 8, min_frequency=1)
     assert stats['n_unique_words'] == len(words) > 65536           # more than the first table holds
+
+
+def test_train_new_from_iterator_on_device(built_lib, tok_paths):
+    """mod.rs:1231-1322: normaliser + pre-tokenizer + trainer all on the device == the restated reference (oracle pre-tokens ->
+    oracle/py_trainer.py); the new tokenizer keeps the pipeline and the special tokens and encodes like the oracle built from
+    the same result"""
+    import json
+    import complexity_tokenizer as ct
+    import py_oracle
+    import synth
+    for cfg, kind, n_docs, vs in (('config1', 'english', 60, 600), ('config3', 'mixed', 40, 700), ('config2', 'ascii', 30, 500)):
+        tok = ct.Tokenizer.from_file(tok_paths[cfg])
+        orc = py_oracle.OracleTokenizer.from_file(tok_paths[cfg])
+        text, offs = synth.gen_corpus(kind, 4242, 1 << 20)
+        raw = text.tobytes()
+        docs = [raw[int(offs[i]):int(offs[i + 1])].decode('utf-8') for i in range(n_docs)]
+        assert tok.all_special_tokens() == orc.all_special_tokens()
+        new = tok.train_new_from_iterator(docs, vs)
+        want_vocab, want_merges = orc.train_new_from_iterator(docs, vs)
+        tj = new._config_json()
+        assert tj['model']['vocab'] == want_vocab
+        assert tj['model']['merges'] == [a + ' ' + b for a, b in want_merges]
+        assert len(want_merges) > 100
+        orc_new = py_oracle.OracleTokenizer(tj)
+        assert new.encode_batch(docs[:10]) == orc_new.encode_batch(docs[:10])
+        assert new.decode_batch_with_options(new.encode_batch(docs[:5]), False, False) == [unicodedata_nfc(d, orc) for d in docs[:5]]
+
+
+def unicodedata_nfc(d, orc):
+    import unicodedata
+    return unicodedata.normalize('NFC', d) if orc.normalizer == 'nfc' else d
