@@ -493,12 +493,13 @@ int ctk_debug_starts_window_host(const uint8_t* text, uint64_t n, const uint64_t
 // automaton on the host with the same split_walk() the device kernels run.  pieces = (start, end) pairs.
 // Returns 0, CTK_ERR_UNSUPPORTED (pattern outside the subset), or -1 when the `regex` crate would reject the pattern.
 namespace { struct HostPieces {
-    uint64_t *cuts, *spans; size_t nc = 0, ns = 0;
+    uint64_t *cuts, *spans; size_t nc = 0, ns = 0; bool any = false;
     CTK_HD void boundary(uint64_t p) { if (nc == 0 || cuts[nc - 1] != p) cuts[nc++] = p; }
-    CTK_HD void span(uint64_t a, uint64_t b) { spans[ns++] = a; spans[ns++] = b; }
+    CTK_HD void span(uint64_t a, uint64_t b, bool starts_piece) { if (starts_piece || ns == 0) { spans[ns++] = a; spans[ns++] = b; } else spans[ns - 1] = b; }
+    CTK_HD void matched() { any = true; }
 }; }
 int ctk_debug_split_pieces(const char* pattern, int behavior, int invert, const uint8_t* text, uint64_t n, uint64_t* pieces, size_t cap_pairs, size_t* n_pairs,
-                           uint32_t* n_states, uint32_t* n_classes) {
+                           uint32_t* n_states, uint32_t* n_classes, int segment) {
     std::string json = std::string("{\"model\":{\"vocab\":{},\"merges\":[]},\"pre_tokenizer\":{\"type\":\"Sequence\",\"pretokenizers\":[{\"type\":\"Split\",\"pattern\":{\"Regex\":");
     json += '"';
     for (const char* c = pattern; *c; ++c) {
@@ -515,11 +516,28 @@ int ctk_debug_split_pieces(const char* pattern, int behavior, int invert, const 
     const SplitDfa& d = m.split_stages[0].dfa;
     if (n_states) *n_states = d.n_states;
     if (n_classes) *n_classes = d.n_classes;
-    SplitTables t{d.trans.data(), d.ascii_class.data(), d.stage1.data(), d.blocks.data(), d.n_classes, d.start, behavior, invert};
+    SplitTables t{d.trans.data(), d.ascii_class.data(), d.stage1.data(), d.blocks.data(), d.n_classes, d.start, behavior, invert,
+                  d.trans_ascii.empty() ? nullptr : d.trans_ascii.data()};
+    PtrReader rd{text};
     std::vector<uint64_t> cuts(n + 2), spans(2 * n + 4);
     HostPieces hp;
     hp.cuts = cuts.data(); hp.spans = spans.data();
-    split_walk(t, text, 0, n, hp);
+    // the text is walked in the segments the device kernel would use when `segment` > 0 (safe starts after neutral bytes)
+    {
+        const uint32_t* nm = d.neutral;
+        uint64_t seg_lo = 0;
+        while (seg_lo < n) {
+            uint64_t seg_hi = n;
+            if (segment > 0) {
+                const uint64_t x = (seg_lo / (uint64_t)segment + 1) * (uint64_t)segment;
+                for (uint64_t p = x ? x - 1 : 0; p + 1 < n && x < n; ++p)
+                    if (text[p] < 128 && ((nm[text[p] >> 5] >> (text[p] & 31)) & 1u)) { seg_hi = p + 1; break; }
+            }
+            split_walk<uint64_t>(t, rd, (uint64_t)0, n, seg_lo, seg_hi, hp);
+            seg_lo = seg_hi;
+        }
+        if (behavior == 0 && !invert && !hp.any && n) hp.span(0, n, true);       // pretokenizers.rs:305-307
+    }
     std::vector<uint64_t> out;
     if (behavior == 0) out.assign(spans.begin(), spans.begin() + hp.ns);
     else if (n) {

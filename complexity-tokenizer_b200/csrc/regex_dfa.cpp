@@ -496,6 +496,18 @@ int compile_split_regex(const std::string& pattern, SplitDfa& out, std::string& 
         std::vector<uint8_t> flat(MAXCP + 1);
         for (size_t k = 0; k < n_iv; ++k) std::fill(flat.begin() + cuts[k], flat.begin() + cuts[k + 1], (uint8_t)iv_class[k]);
         out.ascii_class.assign(flat.begin(), flat.begin() + 128);
+        out.neutral[0] = out.neutral[1] = out.neutral[2] = out.neutral[3] = 0;
+        for (uint32_t c = 0; c < 128; ++c) {                       // neutral: in no set at all (the all-zero membership signature)
+            bool in_any = false;
+            for (uint8_t v : class_sig[out.ascii_class[c]]) in_any = in_any || v;
+            if (!in_any) out.neutral[c >> 5] |= 1u << (c & 31);
+        }
+        out.trans_ascii.clear();
+        if (out.n_states <= 512) {
+            out.trans_ascii.resize((size_t)out.n_states * 128);
+            for (uint32_t st = 0; st < out.n_states; ++st)
+                for (uint32_t c = 0; c < 128; ++c) out.trans_ascii[st * 128 + c] = out.trans[st * n_cls + out.ascii_class[c]];
+        }
         out.stage1.assign(0x1100, 0);
         out.blocks.clear();
         std::map<std::vector<uint8_t>, uint16_t> block_id;

@@ -28,6 +28,8 @@ struct SplitDfa {
     std::vector<uint8_t> ascii_class;                     // [128]
     std::vector<uint16_t> stage1;                         // [0x1100] cp >> 8 -> block
     std::vector<uint8_t> blocks;                          // [n_blocks * 256] class of every code point of the block
+    uint32_t neutral[4] = {0, 0, 0, 0};                   // bit per ASCII byte that belongs to NONE of the pattern's sets: no match can contain it
+    std::vector<uint16_t> trans_ascii;                    // [n_states * 128] trans[state][ascii_class[byte]] (empty if n_states > 512)
 };
 
 struct SplitStage {

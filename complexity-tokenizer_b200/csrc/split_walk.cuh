@@ -1,5 +1,5 @@
 // The walk of one text through a compiled Split pattern (regex_dfa.hpp): find_iter + the five behaviours of
-// regex_split_with_behavior (reference src/pretokenizers.rs:298-433), written once for the device kernels (split.cu) and for
+// regex_split_with_behavior (reference src/pretokenizers.rs:298-433), written once for the device kernel (split.cu) and for
 // the host-side test hook ctk_debug_split_pieces (api.cu), which lets the CPU test-suite exercise the compiler + walk
 // without a GPU.  The product path is the device one.
 //
@@ -24,18 +24,25 @@ struct SplitTables {
     const uint8_t* blocks;          // [n_blocks * 256]
     uint32_t n_classes, start;
     int behavior, invert;
+    const uint16_t* trans_ascii;    // [n_states * 128] the same transitions indexed by an ASCII byte directly; may be NULL
 };
 
-// code point at t[i] (i < end) and its length; ill-formed input (cannot come from a Rust &str) degrades to single bytes
-CTK_HD uint32_t split_decode(const uint8_t* t, uint64_t i, uint64_t end, uint32_t& len) {
-    const uint32_t c = t[i];
+// plain memory reader (host hook); the device kernel reads through a register window (split.cu)
+struct PtrReader {
+    const uint8_t* t;
+    CTK_HD uint32_t byte(uint64_t i) { return t[i]; }
+};
+
+// code point at position i (i < end) and its length; ill-formed input (cannot come from a Rust &str) degrades to single bytes
+template <class Pos, class Reader>
+CTK_HD uint32_t split_decode(Reader& r, uint32_t c, Pos i, Pos end, uint32_t& len) {
     if (c < 0xC0u) { len = 1; return c; }
     const uint32_t want = c < 0xE0u ? 2u : (c < 0xF0u ? 3u : 4u);
     if (i + want > end) { len = 1; return c; }
     len = want;
-    if (want == 2) return ((c & 0x1Fu) << 6) | (t[i + 1] & 63u);
-    if (want == 3) return ((c & 0x0Fu) << 12) | ((t[i + 1] & 63u) << 6) | (t[i + 2] & 63u);
-    return ((c & 7u) << 18) | ((t[i + 1] & 63u) << 12) | ((t[i + 2] & 63u) << 6) | (t[i + 3] & 63u);
+    if (want == 2) return ((c & 0x1Fu) << 6) | (r.byte(i + 1) & 63u);
+    if (want == 3) return ((c & 0x0Fu) << 12) | ((r.byte(i + 1) & 63u) << 6) | (r.byte(i + 2) & 63u);
+    return ((c & 7u) << 18) | ((r.byte(i + 1) & 63u) << 12) | ((r.byte(i + 2) & 63u) << 6) | (r.byte(i + 3) & 63u);
 }
 
 CTK_HD uint32_t split_class(const SplitTables& s, uint32_t cp) {
@@ -45,36 +52,51 @@ CTK_HD uint32_t split_class(const SplitTables& s, uint32_t cp) {
 }
 
 // Emit must provide: void boundary(uint64_t pos)  (strictly inside the text; repeats allowed)
-//                    void span(uint64_t a, uint64_t b)  (Removed only; a < b)
-template <class Emit>
-CTK_HD void split_walk(const SplitTables& s, const uint8_t* t, uint64_t lo, uint64_t hi, Emit& em) {
-    uint64_t pos = lo, last_end = lo;
+//                    void span(uint64_t a, uint64_t b, bool starts_piece)  (Removed only; a < b)
+//                    void matched()  (the text has at least one match: see the no-match rule above)
+//
+// A text may be walked in SEGMENTS by different threads: [seg_lo, seg_hi) inside the text [lo, hi), where every segment
+// border inside the text is a SAFE START -- the position right after a byte that no match can contain (a "neutral" byte:
+// one that belongs to none of the pattern's sets), so that no match spans the border and the scan is fresh there.  The
+// byte before such a border is a gap byte: with it as the "previous end" the behaviours that look back (MergedWithPrevious,
+// Contiguous, inverted Removed) take the same decisions a single walk of the whole text takes.
+// Pos: the integer type of text positions (the device walks buffers below 4 GiB with 32-bit positions: half the instructions).
+template <class Pos, class Reader, class Emit>
+CTK_HD void split_walk(const SplitTables& s, Reader& rd, Pos lo, Pos hi, Pos seg_lo, Pos seg_hi, Emit& em) {
+    const bool continuing = seg_lo > lo;                 // the byte at seg_lo - 1 is a gap byte of this text
+    Pos last_end = continuing ? seg_lo - 1 : lo;
     bool any = false;
-    while (pos < hi) {
-        // the leftmost match at or after pos: try every character position in turn (the automaton is anchored)
-        uint64_t a = pos, b = 0;
-        for (; a < hi;) {
-            uint32_t st = s.start, len;
-            uint64_t q = a;
-            uint32_t first_len = 1;
-            while (q < hi) {
-                const uint32_t cp = split_decode(t, q, hi, len);
-                if (q == a) first_len = len;
-                const uint32_t nx = s.trans[st * s.n_classes + split_class(s, cp)];
-                st = nx & 0x7FFFu;
-                if (st == 0) break;
-                q += len;
-                if (nx & 0x8000u) b = q;
+    // ONE flat loop, one automaton step per iteration: find_iter tries an anchored match at every character position in
+    // turn (`a`), `q` runs ahead of it while the automaton lives, `b` is the last accepting position seen.  (Nested loops --
+    // positions, then steps -- split a warp into lane groups that never meet again: 5 of 32 lanes active, measured.)
+    Pos a = seg_lo, q = seg_lo, b = 0;
+    uint32_t st = s.start, first_len = 1;
+    const bool ascii_table = s.trans_ascii != nullptr;
+    while (a < seg_hi) {
+        uint32_t nx = 0, len = 1;
+        if (q < seg_hi) {
+            const uint32_t c = rd.byte(q);
+            if (c < 128u && ascii_table) nx = s.trans_ascii[st * 128u + c];
+            else {
+                const uint32_t cp = split_decode(rd, c, q, seg_hi, len);
+                nx = s.trans[st * s.n_classes + split_class(s, cp)];
             }
-            if (b) break;
-            a += first_len;
+            if (q == a) first_len = len;
         }
-        if (!b) break;
+        if (nx & 0x7FFFu) {                                      // the automaton lives: one character consumed
+            st = nx & 0x7FFFu;
+            q += len;
+            if (nx & 0x8000u) b = q;
+            continue;
+        }
+        if (!b) { a += first_len; q = a; st = s.start; continue; }      // no match at a: the next character position
         // ---- one match [a, b)
         switch (s.behavior) {
             case 0:                                              // Removed
-                if (s.invert) { if (a > last_end) em.span(last_end, a); }
-                else em.span(a, b);
+                if (s.invert) {
+                    const Pos from = any || !continuing ? last_end : seg_lo;
+                    if (a > from) em.span(from, a, any || !continuing);       // (the first gap of a later segment continues the previous segment's)
+                } else em.span(a, b, true);
                 break;
             case 1:                                              // Isolated
                 if (a > lo) em.boundary(a);
@@ -90,14 +112,20 @@ CTK_HD void split_walk(const SplitTables& s, const uint8_t* t, uint64_t lo, uint
                 if (a > last_end) { if (any) em.boundary(last_end); em.boundary(a); }
                 break;
         }
+        if (!any) em.matched();
         any = true;
         last_end = b;
-        pos = b;
+        a = q = b;
+        b = 0;
+        st = s.start;
     }
     if (s.behavior == 0) {
-        if (!any) { if (hi > lo) em.span(lo, hi); }
-        else if (s.invert && last_end < hi) em.span(last_end, hi);
-    } else if ((s.behavior == 2 || s.behavior == 4) && any && last_end < hi) em.boundary(last_end);
+        if (s.invert) {
+            const Pos from = any || !continuing ? last_end : seg_lo;
+            if (from < seg_hi) em.span(from, seg_hi, any || !continuing);
+        }
+        // (not inverted and no match anywhere in the text: the whole text is kept -- decided per text by the caller)
+    } else if ((s.behavior == 2 || s.behavior == 4) && any && last_end < seg_hi) em.boundary(last_end);
 }
 
 }  // namespace ctk

@@ -105,14 +105,14 @@ def _rand_pattern(rng, depth=0):
     return node
 
 
-def _host_pieces(lib, pattern, behavior, invert, text):
+def _host_pieces(lib, pattern, behavior, invert, text, segment=0):
     raw = text.encode('utf-8')
     cap = len(raw) + 4
     buf = (ctypes.c_uint64 * (2 * cap))()
     n = ctypes.c_size_t(0)
     ns, nc = ctypes.c_uint32(0), ctypes.c_uint32(0)
     tb = (ctypes.c_uint8 * max(1, len(raw))).from_buffer_copy(raw or b'\0')
-    rc = lib.ctk_debug_split_pieces(pattern.encode('utf-8'), behavior, int(invert), tb, len(raw), buf, cap, ctypes.byref(n), ctypes.byref(ns), ctypes.byref(nc))
+    rc = lib.ctk_debug_split_pieces(pattern.encode('utf-8'), behavior, int(invert), tb, len(raw), buf, cap, ctypes.byref(n), ctypes.byref(ns), ctypes.byref(nc), segment)
     if rc != 0:
         return rc, None
     return 0, [raw[buf[2 * k]:buf[2 * k + 1]].decode('utf-8') for k in range(n.value)]
@@ -124,7 +124,7 @@ def lib(built_lib):
     lb = ct._lib()
     lb.ctk_debug_split_pieces.restype = ctypes.c_int
     lb.ctk_debug_split_pieces.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
-                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     return lb
 
 
@@ -143,10 +143,11 @@ def test_host_dfa_against_oracle_all_behaviours(lib):
         for bi, beh in enumerate(py_regex.BEHAVIORS):
             for inv in ((False, True) if bi == 0 else (False,)):
                 for t in texts:
-                    rc, got = _host_pieces(lib, p, bi, inv, t)
-                    assert rc == 0, (p, rc)
                     want = [w for w in py_regex.split_with_behavior(node, t, beh, inv) if w]       # (an empty text stays [""] in the reference: no piece)
-                    assert got == want, (p, beh, inv, t)
+                    for seg in (0, 1, 5):                      # one walk / walked in segments cut at safe starts, as the device kernel does
+                        rc, got = _host_pieces(lib, p, bi, inv, t, seg)
+                        assert rc == 0, (p, rc)
+                        assert got == want, (p, beh, inv, t, seg)
                     n_ok += 1
     assert n_ok > 8000
 
