@@ -121,3 +121,19 @@ def test_golden_hf_vectors_on_the_gpu(built_lib):
     # decode of the golden ids gives the NFC text back (ByteLevel round trip, decoders.rs:94-119)
     back = tok.decode_batch_with_options(g['ids'], False, False)
     assert back == [unicodedata.normalize('NFC', t) for t in g['texts']]
+
+
+def test_golden_hf_wide_vectors_on_the_gpu(built_lib):
+    """tests/golden/hf_crosscheck_wide.json straight against the CUDA path: 7 816 texts over 13 pipelines (three tokenizers, NFC,
+    "normalizer": null, add_prefix_space, Split stages of every behaviour), ids from HuggingFace tokenizers"""
+    import json
+    import complexity_tokenizer as ct
+    from test_oracle_known_answers import _wide_cases
+    n = 0
+    for name, tj, texts, ids in _wide_cases():
+        tok = ct.Tokenizer.from_str(json.dumps(tj, ensure_ascii=False))
+        got = tok.encode_batch(texts)
+        bad = [i for i, (a, b) in enumerate(zip(got, ids)) if a != b]
+        assert not bad, (name, bad[:5], texts[bad[0]][:60])
+        n += len(texts)
+    assert n >= 7000

@@ -143,6 +143,31 @@ def test_golden_hf_crosscheck_twin_and_core():
     assert core.decode_batch(g['ids']) == twin.decode_batch(g['ids'])
 
 
+def _wide_cases():
+    with open(os.path.join(HERE, 'golden', 'hf_crosscheck_wide.json'), encoding='utf-8') as f:
+        g = json.load(f)
+    for c in g['cases']:
+        tj = json.loads(json.dumps(g['tokenizers'][c['tokenizer']]))
+        tj['normalizer'] = c['normalizer']
+        tj['pre_tokenizer'] = c['pre_tokenizer']
+        yield c['name'], tj, c['texts'], c['ids']
+
+
+def test_golden_hf_wide_twin_and_core():
+    """tests/golden/hf_crosscheck_wide.json (tools/make_golden_wide.py): 7 816 texts over 13 pipelines -- three tokenizers, NFC,
+    "normalizer": null, add_prefix_space, and Split stages of every behaviour -- ids from HuggingFace tokenizers 0.22.2 set up to
+    coincide with the reference; the Python twin and the C core must reproduce every one."""
+    import c_oracle
+    n = 0
+    for name, tj, texts, ids in _wide_cases():
+        twin = OracleTokenizer(tj)
+        core = c_oracle.COracle(twin)
+        assert core.encode_batch(texts) == ids, name
+        assert twin.encode_batch(texts[::9]) == ids[::9], name
+        n += len(texts)
+    assert n >= 7000
+
+
 def test_lossy_decode_matches_python_replace():
     """String::from_utf8_lossy (decoders.rs:118): maximal-subpart replacement == bytes.decode('utf-8','replace')"""
     import c_oracle
