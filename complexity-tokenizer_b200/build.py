@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'complexity_tokenizer', 'libctk.so')
-SOURCES = ['api.cu', 'host_api.cu', 'encode_fused.cu', 'encode_general.cu', 'decode.cu', 'decode_clean.cu', 'nfc.cu', 'encoding.cu', 'train.cu', 'split.cu', 'loader.cpp', 'regex_dfa.cpp']
+SOURCES = ['api.cu', 'host_api.cu', 'encode_fused.cu', 'encode_general.cu', 'decode.cu', 'decode_clean.cu', 'nfc.cu', 'encoding.cu', 'train.cu', 'split.cu', 'metaspace.cu', 'loader.cpp', 'regex_dfa.cpp']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
          '-Xcompiler', '-fPIC,-Wall,-Wno-unused-function', '-Xptxas', '-v']

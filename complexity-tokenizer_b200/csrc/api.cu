@@ -169,9 +169,25 @@ static int upload(Engine& eng) {
 static int encode_normalised(Engine& eng, const uint8_t* t, const uint64_t* o, size_t n, uint64_t b, uint32_t* d_ids, uint64_t ids_cap,
                              uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st, bool check_nfc) {
     const uint64_t* first_piece = nullptr;
+    const uint64_t* const text_off = o;                      // offsets of the normalised texts, before any Split stage
     size_t n_pieces = n;
     int rc = split_stages(eng, t, o, n, b, &t, &o, &n_pieces, &b, &first_piece, st);
     if (rc != CTK_OK) return rc;
+    if (eng.model.metaspace) {                               // pretokenizers.rs:188-200: the last stage is Metaspace, symbols are characters
+        if (!first_piece) return encode_metaspace(eng, t, o, n, b, d_ids, ids_cap, d_ids_off, n_ids_host, st);
+        uint64_t* piece_ids_off;
+        cudaError_t e = eng.ws.get(59, (n_pieces + 2) * 8, (void**)&piece_ids_off);
+        if (e != cudaSuccess) return eng.cuda_fail(e, "workspace");
+        uint64_t total = 0;
+        rc = encode_metaspace(eng, t, o, n_pieces, b, d_ids, ids_cap, piece_ids_off, &total, st);
+        if (rc != CTK_OK) return rc;
+        rc = split_fold_ids(eng, first_piece, piece_ids_off, n, d_ids_off, st);
+        if (rc != CTK_OK) return rc;
+        if (n_ids_host) *n_ids_host = total;
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return eng.cuda_fail(e, "split fold");
+        return metaspace_empty_texts(eng, text_off, n, d_ids, ids_cap, d_ids_off, n_ids_host, st);
+    }
     rc = prefix_space_stage(eng, t, o, n_pieces, b, &t, &o, &b, st);
     if (rc != CTK_OK) return rc;
     if (!first_piece) {
@@ -201,7 +217,7 @@ int encode_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, siz
     const uint8_t* t2; const uint64_t* o2; uint64_t b2;
     int rc;
     const bool sync_call = n_ids_host != nullptr || !eng.split_dev.empty();     // (Split stages synchronise anyway)
-    if (eng.model.nfc && eng.nfc_optimistic && sync_call && !eng.use_general && !getenv("CTK_NO_NFC_OPTIMISM")) {
+    if (eng.model.nfc && eng.nfc_optimistic && sync_call && !eng.use_general && !eng.model.metaspace && !getenv("CTK_NO_NFC_OPTIMISM")) {
         const bool keep = eng.keep_cache_once;
         uint64_t dummy;
         rc = encode_normalised(eng, d_text, d_off, n, n_bytes, d_ids, ids_cap, d_ids_off, n_ids_host ? n_ids_host : &dummy, st, true);
@@ -238,6 +254,7 @@ static int create(const uint8_t* json, size_t len, int device, ctk_tokenizer** o
     eng->numa_node = device_numa_node(device);
     rc = upload(*eng);
     if (rc == CTK_OK) rc = split_upload(*eng);
+    if (rc == CTK_OK) rc = metaspace_upload(*eng);
     if (rc != CTK_OK) { delete eng; return rc; }
     *out = reinterpret_cast<ctk_tokenizer*>(eng);
     return CTK_OK;

@@ -406,6 +406,24 @@ __global__ void k_dec_copy_out(const uint8_t* __restrict__ bufA, const uint8_t* 
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return eng.cuda_fail(e_, #x); } while (0)
 
+// Metaspace decoder (decoders.rs:121-131): after join + replacement -> ' ' (folded into the per-token blob at load), ONE leading
+// space of every text is dropped when add_prefix_space is set.
+__global__ void k_strip_len(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ off, uint64_t n, uint64_t* __restrict__ new_len) {
+    const uint64_t d = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (d > n) return;
+    if (d == n) { new_len[d] = 0; return; }
+    const uint64_t lo = off[d], hi = off[d + 1];
+    new_len[d] = (hi - lo) - ((hi > lo && raw[lo] == 0x20) ? 1 : 0);
+}
+__global__ void __launch_bounds__(256) k_strip_copy(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ off, uint64_t n,
+                                                    const uint64_t* __restrict__ new_off, uint8_t* __restrict__ out) {
+    const uint64_t d = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (d >= n) return;
+    const int lane = threadIdx.x & 31;
+    const uint64_t len = new_off[d + 1] - new_off[d], src = off[d + 1] - len;
+    for (uint64_t i = lane; i < len; i += 32) out[new_off[d] + i] = raw[src + i];
+}
+
 int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off, size_t n_docs, uint64_t T,
                   int skip_special, int cleanup, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off,
                   uint64_t* n_bytes_host, cudaStream_t st) {
@@ -456,7 +474,8 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
     CK(cudaStreamSynchronize(st));
     memcpy(&raw_total, eng.h_flags + 12, 8);
     // Without clean-up the gathered bytes are the result (if they are valid UTF-8): write them where they belong.
-    const bool direct = !cleanup && d_out && raw_total <= out_cap && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;
+    const bool strip = eng.model.dec_metaspace && eng.model.dec_meta_strip;
+    const bool direct = !cleanup && !strip && d_out && raw_total <= out_cap && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;
     uint8_t* raw;
     if (direct) raw = d_out;
     else CK(ws.get(13, raw_total + 16, (void**)&raw));
@@ -482,6 +501,23 @@ int decode_device(Engine& eng, const uint32_t* d_ids, const uint64_t* d_ids_off,
         eng.launched(1);
     } else CK(cudaMemsetAsync(raw_off, 0, (n_docs + 1) * 8, st));
     eng.mark("k_dec_write", st);
+    if (strip && n_docs) {                                               // (raw, raw_off) -> the same texts without their one leading space
+        uint64_t *s_len, *s_off; uint8_t* s_raw;
+        CK(ws.get(80, (n_docs + 2) * 8, (void**)&s_len));
+        CK(ws.get(81, (n_docs + 2) * 8, (void**)&s_off));
+        CK(ws.get(82, raw_total + 16, (void**)&s_raw));
+        k_strip_len<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(raw, raw_off, n_docs, s_len);
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, s_len, s_off, n_docs + 1, st));
+        CK(ws.get(5, cub_bytes + 16, &cub_tmp));
+        CK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, s_len, s_off, n_docs + 1, st));
+        k_strip_copy<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, st>>>(raw, raw_off, n_docs, s_off, s_raw);
+        eng.launched(3);
+        CK(eng.publish({{s_off + n_docs, 2, 12}}, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(&raw_total, eng.h_flags + 12, 8);
+        raw = s_raw; raw_off = s_off;
+        eng.mark("k_strip", st);
+    }
     // Is the gathered byte string already valid UTF-8?  Then String::from_utf8_lossy is the identity.  Pure ASCII is
     // (k_dec_write looked at every byte on its way out); anything else is checked sequence by sequence.
     bool invalid = false, has_high = false;

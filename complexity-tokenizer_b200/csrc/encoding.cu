@@ -440,6 +440,7 @@ int encode_rich_device(Engine& eng, const uint8_t* d_text, const uint64_t* d_off
     if (opt.pair && (n_texts & 1)) return eng.fail(CTK_ERR_ARG, "pair mode needs an even number of texts (text, text_pair, text, ...)");
     if (n_bytes >= 0xFFFFFFF0ull) return eng.fail(CTK_ERR_ARG, "one call handles less than 4 GiB of text");
     const HostModel& m = eng.model;
+    if (eng.model.metaspace) return eng.fail(CTK_ERR_UNSUPPORTED, "Encoding outputs are not built for Metaspace pipelines; encode / encode_batch / decode are");
     if (!eng.split_dev.empty()) return eng.fail(CTK_ERR_UNSUPPORTED, "Encoding outputs (offsets, word ids, padded rows) are not built for tokenizers with Split stages; encode / encode_batch are");
     RowArgs ra{};
     ra.mark = opt.add_special_tokens ? 1 : 0;

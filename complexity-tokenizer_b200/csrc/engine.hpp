@@ -27,7 +27,7 @@ extern std::atomic<uint64_t> g_kernel_launches;
 // Grow-only device scratch, one buffer per slot.  Growing frees the old buffer (cudaFree
 // synchronises the device, so nothing in flight can still be using it).
 struct Workspace {
-    static constexpr int kSlots = 80;
+    static constexpr int kSlots = 96;
     void* p[kSlots] = {};
     size_t cap[kSlots] = {};
     cudaError_t get(int slot, size_t bytes, void** out) {
@@ -85,6 +85,8 @@ struct Engine {
     void* d_table_mem[32] = {};
     std::vector<SplitTables> split_dev;  // device tables of model.split_stages (split.cu)
     std::vector<void*> split_mem;
+    const void* meta_char_tab = nullptr; // Metaspace pipelines: code point -> id of the single-character vocabulary entries (metaspace.cu)
+    uint32_t meta_char_mask = 0;
     Workspace ws;
     std::mutex mu;                      // serialises device work issued through this tokenizer
     bool cache_persistent = false;
@@ -162,7 +164,12 @@ int nfc_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t 
               const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st);
 int prefix_space_stage(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                        const uint8_t** o_text, const uint64_t** o_off, uint64_t* o_bytes, cudaStream_t st);
+int metaspace_empty_texts(Engine& eng, const uint64_t* d_text_off, size_t n, uint32_t* d_ids, uint64_t ids_cap, uint64_t* d_ids_off, uint64_t* n_ids_host,
+                          cudaStream_t st);
 int split_upload(Engine& eng);
+int metaspace_upload(Engine& eng);
+int encode_metaspace(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n, uint64_t n_bytes, uint32_t* d_ids, uint64_t ids_cap,
+                     uint64_t* d_ids_off, uint64_t* n_ids_host, cudaStream_t st);
 int split_stages(Engine& eng, const uint8_t* d_text, const uint64_t* d_off, size_t n_docs, uint64_t n_bytes,
                  const uint8_t** o_text, const uint64_t** o_off, size_t* o_n, uint64_t* o_bytes, const uint64_t** first_piece, cudaStream_t st);
 int split_fold_ids(Engine& eng, const uint64_t* first_piece, const uint64_t* piece_ids_off, size_t n_docs, uint64_t* d_ids_off, cudaStream_t st);

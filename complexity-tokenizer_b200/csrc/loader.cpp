@@ -112,7 +112,7 @@ bool parse_normalizer(const JValue* v, bool& nfc, std::string& err) {
 
 // parsing.rs:93-190.  Collects ByteLevel stages; returns 0 ok, 1 = "None", 2 = unsupported
 // One parsed pre-tokenizer stage: the ByteLevel stage (with its add_prefix_space) or a compiled Split stage.
-struct PreStage { bool bytelevel = false; bool add_prefix_space = false; SplitStage split; };
+struct PreStage { bool bytelevel = false; bool metaspace = false; bool add_prefix_space = false; uint32_t replacement = 0x2581; SplitStage split; };
 
 // parsing.rs:93-190.  0 = parsed (stages appended), 1 = None (unknown type), 2 = unsupported (err set)
 int parse_pre(const JValue* v, std::vector<PreStage>& stages, std::string& err) {
@@ -125,6 +125,16 @@ int parse_pre(const JValue* v, std::vector<PreStage>& stages, std::string& err) 
         b.bytelevel = true;
         b.add_prefix_space = a && a->t == JValue::Bool ? a->b : false;    // use_regex / trim_offsets ignored (:99-107)
         stages.push_back(b);
+        return 0;
+    }
+    if (ty == "Metaspace") {                                    // parsing.rs:108-123
+        PreStage ms;
+        ms.metaspace = true;
+        const JValue* r = v->get("replacement");
+        if (r && r->is_str() && !r->s.empty()) { size_t i = 0; ms.replacement = next_cp(r->s, i); }
+        const JValue* a = v->get("add_prefix_space");
+        ms.add_prefix_space = a && a->t == JValue::Bool ? a->b : true;
+        stages.push_back(ms);
         return 0;
     }
     if (ty == "Split") {                                        // parsing.rs:145-167 -> SplitWithBehavior
@@ -154,7 +164,7 @@ int parse_pre(const JValue* v, std::vector<PreStage>& stages, std::string& err) 
         }
         return any ? 0 : 1;
     }
-    static const char* out_of_scope[] = {"Metaspace", "Whitespace", "WhitespaceSplit", "Punctuation", "BertPreTokenizer",
+    static const char* out_of_scope[] = {"Whitespace", "WhitespaceSplit", "Punctuation", "BertPreTokenizer",
                                          "CharDelimiterSplit", "UnicodeScripts", "Digits"};
     for (const char* o : out_of_scope)
         if (ty == o) { err = "pre_tokenizer '" + ty + "' is outside the ByteLevel-BPE hot path"; return 2; }
@@ -442,19 +452,34 @@ int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err) 
     if (pr == 2) return CTK_ERR_UNSUPPORTED;
     // the hot path: any number of Split stages, then exactly one ByteLevel stage, nothing after it (a Split behind the
     // ByteLevel stage would see byte-mapped text, a second ByteLevel stage would map twice)
-    if (pr == 1 || stages.empty() || !stages.back().bytelevel) {
-        err = "pre_tokenizer must resolve to Split stages followed by exactly one ByteLevel stage for the hot path";
+    if (pr == 1 || stages.empty() || !(stages.back().bytelevel || stages.back().metaspace)) {
+        err = "pre_tokenizer must resolve to Split stages followed by exactly one ByteLevel (or Metaspace) stage for the hot path";
         return CTK_ERR_UNSUPPORTED;
     }
     m.split_stages.clear();
     for (size_t k = 0; k + 1 < stages.size(); ++k) {
-        if (stages[k].bytelevel) { err = "pre_tokenizer must resolve to Split stages followed by exactly one ByteLevel stage for the hot path"; return CTK_ERR_UNSUPPORTED; }
+        if (stages[k].bytelevel || stages[k].metaspace) { err = "pre_tokenizer must resolve to Split stages followed by exactly one ByteLevel stage for the hot path"; return CTK_ERR_UNSUPPORTED; }
         m.split_stages.push_back(std::move(stages[k].split));
     }
-    m.add_prefix_space = stages.back().add_prefix_space;
+    m.metaspace = stages.back().metaspace;
+    m.add_prefix_space = m.metaspace ? false : stages.back().add_prefix_space;
+    m.meta_replacement = stages.back().replacement;
+    m.meta_prefix = stages.back().add_prefix_space;
+    if (m.metaspace && (rust_is_whitespace(m.meta_replacement) || m.meta_replacement == 0)) {
+        err = "Metaspace replacement is a white-space character (words would contain the spaces they are split on)";
+        return CTK_ERR_UNSUPPORTED;
+    }
     const JValue* dj = root.get("decoder");
     const char* dt = type_of(dj && dj->t != JValue::Null ? dj : nullptr);
-    if (dt && std::string(dt) != "ByteLevel") { err = std::string("decoder '") + dt + "' is outside the ByteLevel-BPE hot path"; return CTK_ERR_UNSUPPORTED; }
+    m.dec_metaspace = false;
+    if (dt && std::string(dt) == "Metaspace") {                  // parsing.rs:279-293
+        m.dec_metaspace = true;
+        const JValue* r = dj->get("replacement");
+        m.dec_meta_replacement = 0x2581;
+        if (r && r->is_str() && !r->s.empty()) { size_t i = 0; m.dec_meta_replacement = next_cp(r->s, i); }
+        const JValue* a = dj->get("add_prefix_space");
+        m.dec_meta_strip = a && a->t == JValue::Bool ? a->b : true;
+    } else if (dt && std::string(dt) != "ByteLevel") { err = std::string("decoder '") + dt + "' is outside the hot path (ByteLevel and Metaspace are built)"; return CTK_ERR_UNSUPPORTED; }
 
     // ---- derived tables
     uint32_t b2c[256];
@@ -470,8 +495,33 @@ int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err) 
     m.any_added_may_match = false;
     for (auto& a : m.added) {
         if (a.content.empty()) { err = "empty added token (the reference loops forever on it)"; return CTK_ERR_UNSUPPORTED; }
-        analyse_added(a, c2b);
+        if (m.metaspace) {                                       // words are raw text without white space: any token without white space may occur
+            a.bytes.assign(a.content.begin(), a.content.end());
+            a.may_match = true;
+            for (size_t i = 0; i < a.content.size();) if (rust_is_whitespace(next_cp(a.content, i))) a.may_match = false;
+            if (a.may_match && a.single_word) {
+                err = "added token with single_word inside a Metaspace pipeline (needs char::is_alphanumeric of its neighbours)";
+                return CTK_ERR_UNSUPPORTED;
+            }
+        } else analyse_added(a, c2b);
         m.any_added_may_match = m.any_added_may_match || a.may_match;
+    }
+    m.char_ids.clear();
+    for (auto& kv : m.vocab) {                                   // single-character entries: the initial symbols of bpe.rs:94-97
+        if (kv.first.empty()) continue;
+        size_t i = 0;
+        const uint32_t cp = next_cp(kv.first, i);
+        if (i == kv.first.size()) m.char_ids.emplace_back(cp, kv.second);
+    }
+    std::sort(m.char_ids.begin(), m.char_ids.end());
+    m.meta_empty_ids.clear();
+    if (m.metaspace && m.meta_prefix) {                          // the word "<replacement>": an added token equal to it (mod.rs:566-594), else its vocabulary id, else nothing
+        std::string w;
+        put_utf8(w, m.meta_replacement);
+        const AddedTok* best = nullptr;
+        for (auto& a : m.added) if (a.may_match && a.content == w) best = &a;
+        if (best) m.meta_empty_ids.push_back(best->id);
+        else { auto it = m.vocab.find(w); if (it != m.vocab.end()) m.meta_empty_ids.push_back(it->second); }
     }
     // Vocab::new (vocab.rs:48-51): id -> token.  Two tokens with one id: the reference keeps an
     // arbitrary one (hash iteration order); we keep the lexicographically largest, deterministically.
@@ -491,7 +541,13 @@ int load_model(const uint8_t* json, size_t len, HostModel& m, std::string& err) 
         if (!m.id_present[id]) continue;
         const std::string& tok = m.id_to_token[id];
         size_t before = m.dec_blob.size();
-        for (size_t i = 0; i < tok.size();) {                   // decoders.rs:100-116
+        for (size_t i = 0; i < tok.size() && m.dec_metaspace;) {   // decoders.rs:121-124: join, then replacement -> ' '
+            const size_t i0 = i;
+            const uint32_t cp = next_cp(tok, i);
+            if (cp == m.dec_meta_replacement) m.dec_blob.push_back(0x20);
+            else m.dec_blob.insert(m.dec_blob.end(), tok.begin() + i0, tok.begin() + i);
+        }
+        for (size_t i = 0; i < tok.size() && !m.dec_metaspace;) {  // decoders.rs:100-116
             uint32_t cp = next_cp(tok, i);
             if (cp == 0x120) { m.dec_blob.push_back(0x20); continue; }
             auto it = c2b.find(cp);

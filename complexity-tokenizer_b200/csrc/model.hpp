@@ -31,6 +31,12 @@ struct HostModel {
     std::vector<std::pair<std::string, uint32_t>> specials;// special_tokens map (mod.rs:290-291)
     bool nfc = true;                                       // parsing.rs:89
     bool add_prefix_space = false;                         // parsing.rs:99-107
+    // Metaspace pipelines (pretokenizers.rs:188-200, decoders.rs:121-131): the LAST pre-tokenizer stage is Metaspace
+    // instead of ByteLevel (words are runs of non-white-space characters, BPE symbols are characters), and / or the decoder is
+    bool metaspace = false; uint32_t meta_replacement = 0x2581; bool meta_prefix = true;       // parsing.rs:108-123
+    bool dec_metaspace = false; uint32_t dec_meta_replacement = 0x2581; bool dec_meta_strip = true;   // parsing.rs:279-293
+    std::vector<uint32_t> meta_empty_ids;                  // ids of the word that consists of the replacement alone (what an EMPTY text encodes to when add_prefix_space is set)
+    std::vector<std::pair<uint32_t, uint32_t>> char_ids;   // (code point, id) of every single-character vocabulary entry (bpe.rs:94-97 on characters)
     std::vector<SplitStage> split_stages;                  // Split stages in front of the ByteLevel stage (parsing.rs:145-167), compiled at load
     uint32_t byte_init_id[256];                            // byte -> id of its mapped char, kNoId if absent (bpe.rs:94-97)
     // decode side (vocab.rs:47-51 + decoders.rs:94-116 folded per token at load)

@@ -1099,6 +1099,7 @@ static int pretokens_as_text(Engine& eng, const uint8_t* h_text, const uint64_t*
     cudaStream_t st = eng.st_comp;
     const uint64_t n = n_texts ? h_off[n_texts] : 0;
     *d_out = nullptr; *out_bytes = 0;
+    if (eng.model.metaspace) return eng.fail(CTK_ERR_UNSUPPORTED, "train_new_from_iterator is not built for Metaspace pipelines");
     if (n == 0) return CTK_OK;
     if (n >= 0x7FFFFFF0ull) return eng.fail(CTK_ERR_UNSUPPORTED, "train_new_from_iterator: one call takes less than 2 GiB of text");
     Workspace& ws = eng.ws;

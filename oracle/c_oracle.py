@@ -73,8 +73,8 @@ class COracle:
     def __init__(self, twin: OracleTokenizer):
         self.twin = twin
         self.lib = build_lib()
-        if len([s for s in twin.pre_stages if s[0] == 'bytelevel']) != 1:
-            raise ValueError('C core handles exactly one ByteLevel stage')
+        if len([s for s in twin.pre_stages if s[0] == 'bytelevel']) != 1 or twin.decoder != 'bytelevel':
+            raise ValueError('C core handles exactly one ByteLevel stage and the ByteLevel decoder (Metaspace: use the Python twin)')
         aps = [s for s in twin.pre_stages if s[0] == 'bytelevel'][0][1]
         pa = np.array([k[0] for k in twin.merge_ranks], dtype=np.uint32)
         pb = np.array([k[1] for k in twin.merge_ranks], dtype=np.uint32)

@@ -68,7 +68,9 @@ def test_loader_rules(built_lib):
     assert _load_only(lib, dict(BASE, pre_tokenizer=llama3))[0] == 0
     assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'ByteLevel', 'add_prefix_space': False, 'use_regex': True}))[0] == 0
     assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Whitespace'}))[0] == 3
-    assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Metaspace'}))[0] == 3
+    assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Metaspace'}))[0] == 0                  # built: csrc/metaspace.cu
+    assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Metaspace', 'replacement': ' '}))[0] == 3
+    assert _load_only(lib, dict(BASE, decoder={'type': 'Metaspace'}))[0] == 0
     assert _load_only(lib, dict(BASE, pre_tokenizer={'type': 'Unknown'}))[0] == 3
     compilable = {'type': 'Sequence', 'pretokenizers': [{'type': 'Split', 'pattern': {'Regex': r'\d'}, 'behavior': 'Isolated'},
                                                         {'type': 'ByteLevel'}]}
