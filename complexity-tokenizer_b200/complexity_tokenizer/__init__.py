@@ -569,11 +569,15 @@ class Tokenizer:
         max_len = self._model_max_length if max_length is None else int(max_length)
         if max_len < 0 or stride < 0:
             raise OverflowError("can't convert negative int to unsigned")
-        if truncation and stride > 0 and stride >= max_len:
-            raise ValueError('stride >= max_length: the reference loops forever (encoding.rs:190-193)')
         pad_mode = 0 if padding is None else 2 if padding == 'max_length' else 1
         pad_left = padding == 'left' or self._padding_side == 'left'
         buf, off = _pack_texts(flat)
+        if truncation and stride > 0 and stride >= max_len:
+            # the reference only loops forever for a row that IS longer than max_length (encoding.rs:190-193); shorter rows pass
+            probe = self._encode_rows(buf, off, pair=pairs is not None, add_special_tokens=add_special_tokens)
+            if bool((probe.row_full > max_len).any()):
+                raise ValueError('stride >= max_length: the reference loops forever (encoding.rs:190-193)')
+            truncation = False
         p = self._encode_rows(buf, off, pair=pairs is not None, add_special_tokens=add_special_tokens, truncation=truncation,
                               max_length=max_len, padding=pad_mode, pad_to=max_len, pad_left=pad_left,
                               overflow_mode='stride' if stride > 0 else 'single', stride=stride)
@@ -587,10 +591,14 @@ class Tokenizer:
 
     def encode_with_truncation(self, text, text_pair=None, max_length=512, stride=0):
         """mod.rs:349-357: truncate_with_stride whenever the row is longer than max_length (also for stride = 0)"""
-        if stride >= max_length > 0 or (max_length == 0):
-            raise ValueError('stride >= max_length: the reference loops forever (encoding.rs:190-193)')
         flat = [text] if text_pair is None else [text, text_pair]
         buf, off = _pack_texts(flat)
+        if stride >= max_length:
+            # the reference loops forever only when the row is longer than max_length (encoding.rs:190-193); otherwise nothing is cut
+            p = self._encode_rows(buf, off, pair=text_pair is not None)
+            if int(p.row_full[0]) > max_length:
+                raise ValueError('stride >= max_length: the reference loops forever (encoding.rs:190-193)')
+            return p.encoding(0)
         p = self._encode_rows(buf, off, pair=text_pair is not None, truncation=True, max_length=max_length,
                               overflow_mode='stride', stride=stride)
         return p.encoding(0)

@@ -534,7 +534,7 @@ int ctk_debug_split_pieces(const char* pattern, int behavior, int invert, const 
     if (n_states) *n_states = d.n_states;
     if (n_classes) *n_classes = d.n_classes;
     SplitTables t{d.trans.data(), d.ascii_class.data(), d.stage1.data(), d.blocks.data(), d.n_classes, d.start, behavior, invert,
-                  d.trans_ascii.empty() ? nullptr : d.trans_ascii.data()};
+                  d.trans_ascii.empty() ? nullptr : d.trans_ascii.data(), d.pair_impossible.data()};
     PtrReader rd{text};
     std::vector<uint64_t> cuts(n + 2), spans(2 * n + 4);
     HostPieces hp;
@@ -547,8 +547,12 @@ int ctk_debug_split_pieces(const char* pattern, int behavior, int invert, const 
             uint64_t seg_hi = n;
             if (segment > 0) {
                 const uint64_t x = (seg_lo / (uint64_t)segment + 1) * (uint64_t)segment;
-                for (uint64_t p = x ? x - 1 : 0; p + 1 < n && x < n; ++p)
+                const bool pairs = behavior == 1 || behavior == 3 || (behavior == 0 && !invert);       // no look-back: cut between impossible pairs
+                for (uint64_t p = x ? x - 1 : 0; p + 1 < n && x < n; ++p) {
                     if (text[p] < 128 && ((nm[text[p] >> 5] >> (text[p] & 31)) & 1u)) { seg_hi = p + 1; break; }
+                    if (pairs && p + 1 >= x && text[p] < 128 && text[p + 1] < 128 &&
+                        ((d.pair_impossible[text[p] * 4 + (text[p + 1] >> 5)] >> (text[p + 1] & 31)) & 1u)) { seg_hi = p + 1; break; }
+                }
             }
             split_walk<uint64_t>(t, rd, (uint64_t)0, n, seg_lo, seg_hi, hp);
             seg_lo = seg_hi;

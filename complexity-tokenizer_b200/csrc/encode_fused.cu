@@ -92,6 +92,7 @@ struct FusedParams {
 struct __align__(16) ChunkBuf { uint8_t pad0[16]; uint8_t chunk[CHUNK]; uint8_t pad1[16]; };
 struct __align__(16) WarpSmem {
     ChunkBuf buf[2];                                     // this slice's chunk and the next one's (in flight)
+    unsigned long long bar[2];                           // CTK_BULK_CHUNK: one mbarrier per buffer
     uint32_t ds[32];
     uint16_t list[SLICE + 40];                           // owned starts + a round of sentinels
     uint16_t l_at[MAXLONG + 2], l_k[MAXLONG + 2], l_pos[MAXLONG + 2], l_len[MAXLONG + 2];
@@ -197,6 +198,9 @@ namespace ctk {
 #ifndef CTK_COMPACT_UNROLL
 #define CTK_COMPACT_UNROLL 6   // measured: 4 -> 6: 3.50 -> 3.47 ms
 #endif
+#ifndef CTK_BULK_CHUNK
+#define CTK_BULK_CHUNK 0     // interior chunks by ONE 512-byte bulk async copy (TMA, cp.async.bulk + mbarrier) issued by one lane instead of 32 cp.async
+#endif
 #ifndef CTK_ASYNC_CHUNK
 #define CTK_ASYNC_CHUNK 1    // the next slice's chunk travels global -> shared with cp.async while this one is processed (no registers)
 #endif
@@ -215,6 +219,17 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t saddr, const void* g, 
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// ---- 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (the TMA engine moves the bytes)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{ .reg .pred p;\nW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra W; }" :: "r"(bar), "r"(parity) : "memory");
+}
 
 // RW = bytes per id in the slice runs: 2 when every id the tokenizer can emit is below 65 536 (half the scratch
 // traffic of this kernel and of k_compact), else 4.  In a cache slot ids then take 16 bits each (p.id_bits == 16).
@@ -252,6 +267,7 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
     uint32_t slice = blockIdx.x * FW + w;
     if (slice >= n_slices) return;
 
+    uint32_t bulk_pending = 0, bulk_phase = 0;                             // per buffer: a bulk copy is in flight / the parity to wait for (warp-uniform)
     // this lane's 16 bytes of a slice's chunk -> shared memory, zero beyond either end of the text
     auto fetch = [&](uint32_t sl, int b) {
         const uint32_t q = sl * SLICE - LCTX + 16 * lane;                 // (wraps for lane 0 of slice 0, which reads nothing)
@@ -261,6 +277,13 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
             const uint32_t mine = left > 16u * lane ? left - 16u * lane : 0u;
             sz = (sl == 0 && lane == 0) ? 0u : (mine < 16u ? mine : 16u);
         }
+#if CTK_BULK_CHUNK
+        if (!(sl == 0 || sl * SLICE + (CHUNK - LCTX) > nb32)) {           // interior chunk: 512 bytes, 16-byte aligned, whole
+            if (lane == 0) bulk_load(smem_u32(S.buf[b].chunk), text + (sl * SLICE - LCTX), CHUNK, smem_u32(&S.bar[b]));
+            bulk_pending |= 1u << b;
+            return;
+        }
+#endif
 #if CTK_ASYNC_CHUNK
         cp_async16_zfill(smem_u32(S.buf[b].chunk + 16 * lane), text + (sz ? q : 0), sz);
 #else
@@ -271,6 +294,12 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
 #endif
     };
     int buf = 0;
+#if CTK_BULK_CHUNK
+    if (lane == 0) { mbar_init(smem_u32(&S.bar[0]), 1); mbar_init(smem_u32(&S.bar[1]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+#endif
 #if CTK_ASYNC_CHUNK
     fetch(slice, 0);
 #endif
@@ -289,6 +318,13 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
         const uint32_t fd = fd_next;
 #if CTK_ASYNC_CHUNK
         cp_async_wait_all();
+#if CTK_BULK_CHUNK
+        if (bulk_pending & (1u << buf)) {
+            mbar_wait(smem_u32(&S.bar[buf]), (bulk_phase >> buf) & 1u);
+            bulk_phase ^= 1u << buf;
+            bulk_pending &= ~(1u << buf);
+        }
+#endif
         __syncwarp();                                                      // every lane's 16 bytes have landed; the previous slice's readers are done
         if (slice + stride < n_slices) { fetch(slice + stride, buf ^ 1); fd_next = __ldg(p.first_doc + slice + stride); }
 #else

@@ -502,6 +502,19 @@ int compile_split_regex(const std::string& pattern, SplitDfa& out, std::string& 
             for (uint8_t v : class_sig[out.ascii_class[c]]) in_any = in_any || v;
             if (!in_any) out.neutral[c >> 5] |= 1u << (c & 31);
         }
+        {   // class pairs that can be adjacent inside a match: some live state steps on c1 to a live state that steps on c2 to a live state
+            std::vector<uint8_t> possible(n_cls * n_cls, 0);
+            for (uint32_t st = 1; st < out.n_states; ++st)
+                for (size_t c1 = 0; c1 < n_cls; ++c1) {
+                    const uint32_t t = out.trans[st * n_cls + c1] & 0x7FFFu;
+                    if (!t) continue;
+                    for (size_t c2 = 0; c2 < n_cls; ++c2) if (out.trans[t * n_cls + c2] & 0x7FFFu) possible[c1 * n_cls + c2] = 1;
+                }
+            out.pair_impossible.assign(512, 0);
+            for (uint32_t b1 = 0; b1 < 128; ++b1)
+                for (uint32_t b2 = 0; b2 < 128; ++b2)
+                    if (!possible[out.ascii_class[b1] * n_cls + out.ascii_class[b2]]) out.pair_impossible[b1 * 4 + (b2 >> 5)] |= 1u << (b2 & 31);
+        }
         out.trans_ascii.clear();
         if (out.n_states <= 512) {
             out.trans_ascii.resize((size_t)out.n_states * 128);

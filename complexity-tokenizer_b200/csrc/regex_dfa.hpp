@@ -29,6 +29,8 @@ struct SplitDfa {
     std::vector<uint16_t> stage1;                         // [0x1100] cp >> 8 -> block
     std::vector<uint8_t> blocks;                          // [n_blocks * 256] class of every code point of the block
     uint32_t neutral[4] = {0, 0, 0, 0};                   // bit per ASCII byte that belongs to NONE of the pattern's sets: no match can contain it
+    // bit (c1 * 128 + c2): no match can contain the ASCII byte c1 immediately followed by c2 -- find_iter is fresh at such a c2
+    std::vector<uint32_t> pair_impossible;                // [512]
     std::vector<uint16_t> trans_ascii;                    // [n_states * 128] trans[state][ascii_class[byte]] (empty if n_states > 512)
 };
 

@@ -102,8 +102,19 @@ __device__ __forceinline__ bool neutral_byte(const uint4& m, uint32_t c) {
 }
 
 // The first safe start at or after x (x > 0), given the text d that contains position x - 1: the position after a neutral
-// byte, or the next text's start, whichever comes first.
-__device__ __forceinline__ uint64_t safe_start(const uint8_t* __restrict__ text, const uint4& neutral, uint64_t x, uint64_t next_text_start) {
+// byte -- or, for the behaviours that do not look back (pairs != NULL), the position between two bytes no match can contain
+// next to each other -- or the next text's start, whichever comes first.
+__device__ __forceinline__ uint64_t safe_start(const uint8_t* __restrict__ text, const uint4& neutral, const uint32_t* __restrict__ pairs, uint64_t x,
+                                               uint64_t next_text_start) {
+    if (pairs) {
+        uint32_t c1 = __ldg(text + x - 1);
+        for (uint64_t p = x; p < next_text_start; ++p) {
+            const uint32_t c2 = __ldg(text + p);
+            if (c1 < 128u && c2 < 128u && ((__ldg(pairs + c1 * 4 + (c2 >> 5)) >> (c2 & 31u)) & 1u)) return p;
+            c1 = c2;
+        }
+        return next_text_start;
+    }
     for (uint64_t p = x - 1; p + 1 < next_text_start; ++p)
         if (neutral_byte(neutral, __ldg(text + p))) return p + 1;
     return next_text_start;
@@ -139,14 +150,15 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split_mark(SplitTables g, uin
         if (__ldg(off + mid) <= probe) lo_i = mid; else hi_i = mid;
     }
     uint64_t d = lo_i;
-    uint64_t seg_lo = x ? safe_start(text, neutral, x, __ldg(off + d + 1)) : 0;
+    const uint32_t* pairs = (s.behavior == 1 || s.behavior == 3 || (s.behavior == 0 && !s.invert)) ? g.pair_impossible : nullptr;
+    uint64_t seg_lo = x ? safe_start(text, neutral, pairs, x, __ldg(off + d + 1)) : 0;
     if (seg_lo >= n_bytes) return;
     // the end: the same rule at x + SPLIT_CHUNK (the next thread computes the same number)
     uint64_t seg_end = n_bytes;
     if (x + SPLIT_CHUNK < n_bytes) {
         uint64_t de = d;
         while (__ldg(off + de + 1) <= x + SPLIT_CHUNK - 1) ++de;
-        seg_end = safe_start(text, neutral, x + SPLIT_CHUNK, __ldg(off + de + 1));
+        seg_end = safe_start(text, neutral, pairs, x + SPLIT_CHUNK, __ldg(off + de + 1));
     }
     if (seg_end <= seg_lo) return;                           // (no safe start inside this chunk: an earlier thread walks through it)
     while (__ldg(off + d + 1) <= seg_lo) ++d;                // the text that contains seg_lo
@@ -264,6 +276,7 @@ int split_upload(Engine& eng) {
         CKS(up(sg.dfa.stage1.data(), sg.dfa.stage1.size() * 2, (const void**)&t.stage1));
         CKS(up(sg.dfa.blocks.data(), sg.dfa.blocks.size(), (const void**)&t.blocks));
         if (!sg.dfa.trans_ascii.empty()) CKS(up(sg.dfa.trans_ascii.data(), sg.dfa.trans_ascii.size() * 2, (const void**)&t.trans_ascii));
+        if (!sg.dfa.pair_impossible.empty() && !getenv("CTK_SPLIT_NO_PAIRS")) CKS(up(sg.dfa.pair_impossible.data(), sg.dfa.pair_impossible.size() * 4, (const void**)&t.pair_impossible));
         t.n_classes = sg.dfa.n_classes; t.start = sg.dfa.start; t.behavior = sg.behavior; t.invert = sg.invert ? 1 : 0;
         eng.split_dev.push_back(t);
     }

@@ -25,6 +25,7 @@ struct SplitTables {
     uint32_t n_classes, start;
     int behavior, invert;
     const uint16_t* trans_ascii;    // [n_states * 128] the same transitions indexed by an ASCII byte directly; may be NULL
+    const uint32_t* pair_impossible;// [512] bit (c1 * 128 + c2): no match contains c1 c2 adjacent (regex_dfa.hpp)
 };
 
 // plain memory reader (host hook); the device kernel reads through a register window (split.cu)
@@ -59,7 +60,11 @@ CTK_HD uint32_t split_class(const SplitTables& s, uint32_t cp) {
 // border inside the text is a SAFE START -- the position right after a byte that no match can contain (a "neutral" byte:
 // one that belongs to none of the pattern's sets), so that no match spans the border and the scan is fresh there.  The
 // byte before such a border is a gap byte: with it as the "previous end" the behaviours that look back (MergedWithPrevious,
-// Contiguous, inverted Removed) take the same decisions a single walk of the whole text takes.
+// Contiguous, inverted Removed) take the same decisions a single walk of the whole text takes.  The behaviours that do NOT
+// look back (Isolated, MergedWithNext, Removed keeping the matches) may also be cut between two bytes that no match can
+// contain next to each other (pair_impossible): every attempt that starts before such a border dies at it, so the scan
+// arrives there fresh -- this is what lets a pattern that covers every character (the GPT-2 pattern itself) be walked in
+// parallel.
 // Pos: the integer type of text positions (the device walks buffers below 4 GiB with 32-bit positions: half the instructions).
 template <class Pos, class Reader, class Emit>
 CTK_HD void split_walk(const SplitTables& s, Reader& rd, Pos lo, Pos hi, Pos seg_lo, Pos seg_hi, Emit& em) {

@@ -139,6 +139,13 @@ def test_padding_variants_and_truncation_method(built_lib, small_tok_json):
     for ml, st in ((8, 0), (8, 3), (512, 0), (3, 2)):
         _same(tok.encode_with_truncation(long_text, None, ml, st), orc.encode_to_encoding(long_text, None, ml, st), repr((ml, st)))
         _same(tok.encode_with_truncation(long_text, "pair text", ml, st), orc.encode_to_encoding(long_text, "pair text", ml, st), repr((ml, st)))
+    # stride >= max_length only loops forever (encoding.rs:190-193) for a row that is longer than max_length: a short one passes
+    _same(tok.encode_with_truncation("a", None, 512, 600), orc.encode_to_encoding("a"), 'short row, degenerate stride')
+    assert tok("a", truncation=True, max_length=64, stride=64)[0].ids == tok("a")[0].ids
+    with pytest.raises(ValueError):
+        tok.encode_with_truncation(long_text, None, 4, 4)
+    with pytest.raises(ValueError):
+        tok(long_text, truncation=True, max_length=4, stride=9)
 
 
 def test_corpus_bit_exact(built_lib, tok_paths):
