@@ -41,7 +41,10 @@
 
 namespace ctk {
 
-constexpr int FW = 8;            // warps per CTA
+#ifndef CTK_FW
+#define CTK_FW 8
+#endif
+constexpr int FW = CTK_FW;       // warps per CTA (9 warps x 4 CTAs = 36 warps per SM at 56 registers was measured: see DESIGN 6.1)
 constexpr int SLICE = 448;       // bytes owned by a warp
 constexpr int CHUNK = 512;       // bytes a warp looks at
 constexpr int LCTX = 16;         // left context
@@ -242,7 +245,8 @@ __global__ void __launch_bounds__(FW * 32, CTK_LB) k_encode_slices(const FusedPa
     __shared__ uint4 s_kmask[17];                       // byte masks: keep the first n bytes of 16
     const int tid = threadIdx.x, lane = tid & 31;
     int w = tid >> 5;
-    s_byte_init[tid] = __ldg(p.t.byte_init + tid);
+    if (FW >= 8) { if (tid < 256) s_byte_init[tid] = __ldg(p.t.byte_init + tid); }
+    else for (int i = tid; i < 256; i += FW * 32) s_byte_init[i] = __ldg(p.t.byte_init + i);
     if (tid < 17) {
         uint32_t m[4];
         for (int j = 0; j < 4; ++j) { int b = tid - 4 * j; m[j] = b >= 4 ? 0xFFFFFFFFu : (b <= 0 ? 0u : ((1u << (8 * b)) - 1u)); }
