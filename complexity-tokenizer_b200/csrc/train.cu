@@ -350,7 +350,12 @@ struct TrainState {
 };
 
 struct __align__(16) TrainPair { unsigned long long key; uint32_t val, pad; };   // one 16-byte access reads key and count
-struct PairTable { TrainPair* e; uint32_t mask; };
+struct Best { uint32_t count, dirty; uint64_t key; };    // (dirty: only used by the per-segment cache)
+// The table is cut into segments of SEG slots; seg_best caches each segment's best pair and seg_dirty says whether a count of
+// the segment changed since it was computed (every change goes through pair_add).  A merge touches a handful of pairs, so the
+// best-pair step re-reads only the few segments that changed instead of the whole table.
+constexpr uint32_t SEG = 128;
+struct PairTable { TrainPair* e; uint32_t mask; Best* seg_best; };
 
 // count[(a, b)] += f (mod 2^32, like the reference's u32 sums; f may be "negative")
 __device__ __forceinline__ void pair_add(const PairTable& pt, TrainState* st, uint32_t a, uint32_t b, uint32_t f) {
@@ -362,7 +367,7 @@ __device__ __forceinline__ void pair_add(const PairTable& pt, TrainState* st, ui
             k = atomicCAS(&pt.e[slot].key, EMPTY64, key);
             if (k == EMPTY64) { atomicAdd(&st->fill, 1u); k = key; }
         }
-        if (k == key) { atomicAdd(&pt.e[slot].val, f); return; }
+        if (k == key) { atomicAdd(&pt.e[slot].val, f); pt.seg_best[slot / SEG].dirty = 1u; return; }
         slot = (slot + 1) & pt.mask;
     }
     st->overflow = 1;
@@ -383,6 +388,7 @@ struct Words {                           // every word keeps its slot range [wof
 __global__ void k_table_clear(PairTable pt) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= pt.mask) *reinterpret_cast<uint4*>(pt.e + i) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+    if (i <= pt.mask / SEG) pt.seg_best[i] = Best{0u, 0u, EMPTY64};
 }
 
 __global__ void __launch_bounds__(256) k_count_all(TrainState* st, Words W, PairTable pt) {
@@ -415,7 +421,17 @@ template <bool CG> __device__ __forceinline__ void detect_range(TrainState* st, 
     }
 }
 
+// Programmatic dependent launch: the three kernels of a merge are launched with programmatic stream serialisation, so a
+// kernel's CTAs are scheduled while the previous kernel drains and wait HERE until its memory is visible.  The chain of
+// three dependent launches per merge is launch-latency-bound (each kernel does microseconds of work); this removes most of
+// the gap between them.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(256) k_detect(TrainState* st, Words W) {
+    pdl_enter();
     if (st->done || st->pause) return;
     detect_range<false>(st, W, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
@@ -491,8 +507,49 @@ template <bool CG> __device__ __forceinline__ void apply_range(TrainState* st, c
 }
 
 __global__ void __launch_bounds__(128) k_apply(TrainState* st, Words W, PairTable pt) {
+    pdl_enter();
     if (st->done || st->pause) return;
     apply_range<false>(st, W, pt, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5);
+}
+
+// Detect and apply in ONE launch, a thread per word (words are short: 7.5 symbols on average for config 1): does the word
+// contain the pair?  Then its old pairs leave the table, the merge is applied left to right in place (bpe_trainer.rs:379-401),
+// and its new pairs enter -- the same u32 sums as the incremental update of k_apply, two launches per merge instead of three.
+// Chosen by the host when no word is longer than FUSED_MAX_WORD symbols (a thread walks its word alone).
+constexpr uint32_t FUSED_MAX_WORD = 256;
+__global__ void __launch_bounds__(256) k_word_merge(TrainState* st, Words W, PairTable pt) {
+    pdl_enter();
+    if (st->done || st->pause) return;
+    const uint32_t l = st->cur_l;
+    if (l == INVALID) return;
+    const uint32_t r = st->cur_r, m = st->cur_m;
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W.n_words) return;
+    const uint32_t len = W.wlen[w];
+    if (len < 2) return;
+    uint32_t* const s = W.sym + W.woff[w];
+    bool hit = false;
+    uint32_t prev = INVALID;
+    for (uint32_t c = 0; c < len && !hit; c += 8) {                  // eight loads in flight: the scan is a chain of L2 round trips otherwise
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = c + k < len ? s[c + k] : INVALID;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { hit = hit || (prev == l && v[k] == r); prev = v[k]; }
+    }
+    if (!hit) return;
+    const uint32_t f = W.wfreq[w];
+    prev = s[0];
+    for (uint32_t i = 1; i < len; ++i) { const uint32_t cur = s[i]; pair_add(pt, st, prev, cur, 0u - f); prev = cur; }
+    uint32_t out = 0;
+    for (uint32_t i = 0; i < len;) {
+        const uint32_t a = s[i];
+        if (i + 1 < len && a == l && s[i + 1] == r) { s[out++] = m; i += 2; }
+        else { s[out++] = a; ++i; }
+    }
+    W.wlen[w] = out;
+    prev = s[0];
+    for (uint32_t i = 1; i < out; ++i) { const uint32_t cur = s[i]; pair_add(pt, st, prev, cur, f); prev = cur; }
 }
 
 struct SymTab {                          // device copy of what the host knows about every symbol
@@ -501,25 +558,40 @@ struct SymTab {                          // device copy of what the host knows a
     uint64_t* map_key; uint64_t* map_h2; uint32_t* map_id; uint32_t map_mask;   // hash -> symbol
 };
 
-struct Best { uint32_t count; uint64_t key; };
 __device__ __forceinline__ bool better(const Best& a, const Best& b) { return a.count > b.count || (a.count == b.count && a.key < b.key); }
 
 // Best pair of the table (bpe_trainer.rs:152-155 with the tie rule of oracle/py_trainer.py); the last CTA decides.
 template <bool CG> __device__ __forceinline__ void best_phase(TrainState* st, const PairTable& pt, Best* block_best, const SymTab& sy, uint4* log) {
-    Best best{0u, EMPTY64};
+    Best best{0u, 0u, EMPTY64};
     const uint32_t cap = pt.mask + 1;
-#pragma unroll 4
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const uint4 e = ld<CG>(reinterpret_cast<const uint4*>(pt.e + i));
-        if (e.z == 0) continue;                                        // empty slot, or a pair that no longer occurs
-        Best b{e.z, ((uint64_t)e.y << 32) | e.x};
-        if (better(b, best)) best = b;
+    {   // a warp per segment: the cached best of a clean segment, a fresh scan of a dirty one (which also refreshes the cache)
+        const uint32_t n_seg = cap / SEG, lane = threadIdx.x & 31;
+        const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps_all = (gridDim.x * blockDim.x) >> 5;
+        for (uint32_t sg = warp; sg < n_seg; sg += n_warps_all) {
+            Best b{0u, 0u, EMPTY64};
+            const uint4 cached = ld<CG>(reinterpret_cast<const uint4*>(pt.seg_best + sg));      // {count, dirty, key lo, key hi}: one access
+            if (cached.y) {                                            // (warp-uniform)
+#pragma unroll
+                for (uint32_t q = 0; q < SEG / 32; ++q) {
+                    const uint4 e = ld<CG>(reinterpret_cast<const uint4*>(pt.e + sg * SEG + q * 32 + lane));
+                    if (e.z == 0) continue;                            // empty slot, or a pair that no longer occurs
+                    Best c{e.z, 0u, ((uint64_t)e.y << 32) | e.x};
+                    if (better(c, b)) b = c;
+                }
+                for (int d = 16; d > 0; d >>= 1) {
+                    Best o{__shfl_down_sync(0xFFFFFFFFu, b.count, d), 0u, __shfl_down_sync(0xFFFFFFFFu, b.key, d)};
+                    if (better(o, b)) b = o;
+                }
+                if (lane == 0) pt.seg_best[sg] = b;                    // (dirty = 0 again)
+            } else b = Best{cached.x, 0u, ((uint64_t)cached.w << 32) | cached.z};
+            if (lane == 0 && better(b, best)) best = b;
+        }
     }
     __shared__ Best sb[32];
     __shared__ bool s_last;
     const int n_warps = blockDim.x >> 5;
     for (int d = 16; d > 0; d >>= 1) {
-        Best o{__shfl_down_sync(0xFFFFFFFFu, best.count, d), __shfl_down_sync(0xFFFFFFFFu, best.key, d)};
+        Best o{__shfl_down_sync(0xFFFFFFFFu, best.count, d), 0u, __shfl_down_sync(0xFFFFFFFFu, best.key, d)};
         if (better(o, best)) best = o;
     }
     if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
@@ -533,14 +605,14 @@ template <bool CG> __device__ __forceinline__ void best_phase(TrainState* st, co
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    best = Best{0u, EMPTY64};
+    best = Best{0u, 0u, EMPTY64};
     for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
         const volatile Best* p = block_best + i;
-        Best c{p->count, p->key};
+        Best c{p->count, 0u, p->key};
         if (better(c, best)) best = c;
     }
     for (int d = 16; d > 0; d >>= 1) {
-        Best o{__shfl_down_sync(0xFFFFFFFFu, best.count, d), __shfl_down_sync(0xFFFFFFFFu, best.key, d)};
+        Best o{__shfl_down_sync(0xFFFFFFFFu, best.count, d), 0u, __shfl_down_sync(0xFFFFFFFFu, best.key, d)};
         if (better(o, best)) best = o;
     }
     __syncthreads();
@@ -579,6 +651,7 @@ template <bool CG> __device__ __forceinline__ void best_phase(TrainState* st, co
 }
 
 __global__ void __launch_bounds__(256) k_best_pair(TrainState* st, PairTable pt, Best* block_best, SymTab sy, uint4* log) {
+    pdl_enter();
     if (st->done || st->pause) return;
     best_phase<false>(st, pt, block_best, sy, log);
 }
@@ -967,8 +1040,10 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
         // (re)build the pair table from the words: a full recount into a fresh table of `pcap` slots
         auto rebuild = [&]() -> int {
             if (tab_mem) { cudaFree(tab_mem); tab_mem = nullptr; }
-            TCK(cudaMalloc(&tab_mem, pcap * sizeof(TrainPair)));
+            const size_t n_seg = pcap / SEG + 1;
+            TCK(cudaMalloc(&tab_mem, pcap * sizeof(TrainPair) + n_seg * sizeof(Best)));
             pt.e = (TrainPair*)tab_mem; pt.mask = pcap - 1;
+            pt.seg_best = reinterpret_cast<Best*>(pt.e + pcap);
             k_table_clear<<<(pcap + 255) / 256, 256, 0, st>>>(pt); ++launches;
             TCK(cudaMemsetAsync(&d_st->pause, 0, 12, st));               // pause, overflow, fill
             k_count_all<<<g_slots, 256, 0, st>>>(d_st, W, pt); ++launches;
@@ -995,6 +1070,9 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
             cudaGetLastError();
         }
         out.cluster = cluster;
+        uint32_t max_word = 0;
+        for (uint32_t i = 0; i < nw; ++i) max_word = std::max(max_word, ws[i].len);
+        const bool fused = !cluster && max_word <= FUSED_MAX_WORD && !getenv("CTK_TRAIN_THREE_KERNELS");
         for (;;) {
             const unsigned g_best = std::max(1u, std::min((unsigned)sms * 2, pcap / 1024u));   // few CTAs: one ticket atomic and one candidate each
             if (cluster) {
@@ -1004,12 +1082,26 @@ static int train_impl(const ctk_bpe_trainer_config& cfg, int device, const uint8
                 TCK(cudaLaunchKernelEx(&lc, k_train_cluster, d_st, W, pt, d_bb, sy, d_log, (int)BATCH));
                 launches += 1;
             } else {
+                static const bool pdl = !getenv("CTK_TRAIN_NO_PDL");
+                cudaLaunchAttribute pa[1];
+                pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                pa[0].val.programmaticStreamSerializationAllowed = 1;
+                auto cfg_of = [&](unsigned grid, unsigned block) {
+                    cudaLaunchConfig_t c{};
+                    c.gridDim = dim3(grid); c.blockDim = dim3(block); c.stream = st; c.attrs = pa; c.numAttrs = pdl ? 1 : 0;
+                    return c;
+                };
+                const cudaLaunchConfig_t c_detect = cfg_of(g_detect, 256), c_apply = cfg_of(g_apply, 128), c_best = cfg_of(g_best, 256),
+                                         c_fused = cfg_of((nw + 255) / 256, 256);
                 for (int it = 0; it < BATCH; ++it) {
-                    k_detect<<<g_detect, 256, 0, st>>>(d_st, W);
-                    k_apply<<<g_apply, 128, 0, st>>>(d_st, W, pt);
-                    k_best_pair<<<g_best, 256, 0, st>>>(d_st, pt, d_bb, sy, d_log);
+                    if (fused) TCK(cudaLaunchKernelEx(&c_fused, k_word_merge, d_st, W, pt));
+                    else {
+                        TCK(cudaLaunchKernelEx(&c_detect, k_detect, d_st, W));
+                        TCK(cudaLaunchKernelEx(&c_apply, k_apply, d_st, W, pt));
+                    }
+                    TCK(cudaLaunchKernelEx(&c_best, k_best_pair, d_st, pt, d_bb, sy, d_log));
                 }
-                launches += 3 * BATCH;
+                launches += (fused ? 2 : 3) * BATCH;
             }
             TCK(cudaMemcpyAsync(&back, d_st, sizeof back, cudaMemcpyDeviceToHost, st));
             TCK(cudaMemcpyAsync(log.data(), d_log, BATCH * sizeof(uint4), cudaMemcpyDeviceToHost, st));

@@ -146,6 +146,18 @@ def test_cluster_merge_loop(built_lib, monkeypatch, size):
     both(["a" * 1000, "ab" * 333 + "a", "<s> <s> x<s>y"], vocab_size=60, min_frequency=1, special_tokens=['<s>'])
 
 
+def test_three_kernel_merge_loop(built_lib, monkeypatch):
+    """Default: detect + apply fused, a thread per word (two launches per merge) when no word is longer than 256 symbols; the
+    three-kernel loop (warp per listed word) otherwise, or with CTK_TRAIN_THREE_KERNELS: both equal the oracle."""
+    texts = _english(9, 64 << 10)
+    both(texts, vocab_size=500, min_frequency=2)                                    # fused path (short words)
+    both(["a" * 1000, "ab" * 333 + "a", "<s> <s> x<s>y"], vocab_size=60, min_frequency=1, special_tokens=['<s>'])   # long words: three kernels
+    monkeypatch.setenv('CTK_TRAIN_THREE_KERNELS', '1')
+    both(texts, vocab_size=500, min_frequency=2)
+    monkeypatch.setenv('CTK_TRAIN_NO_PDL', '1')
+    both(texts[:40], vocab_size=300, min_frequency=2)
+
+
 def test_properties_at_scale(built_lib):
     """64 MiB (11 M words), where the oracle cannot go: size-independent properties of the reference's loop."""
     import complexity_tokenizer as ct
