@@ -67,39 +67,73 @@ def kernel_source_sha():
 
 
 class ClockSampler:
+    """SM clocks and throttle reasons DURING the timed region, for every GPU of the job, from ONE poller started by rank 0.
+    NVML (what nvidia-smi reads) is polled every ~5 ms by a separate process: the timed region of a default run lasts 20 ms,
+    far below nvidia-smi's own 100-200 ms loop (the recipe's command line is the fallback when NVML cannot be loaded)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, indices):
+        self.indices, self.rows, self.proc, self.nv, self.stop_flag = list(indices), [], None, None, False
+
+    POLLER = r"""
+import sys, time, pynvml as nv
+nv.nvmlInit()
+hs = [nv.nvmlDeviceGetHandleByIndex(int(i)) for i in sys.argv[1].split(',')]
+mx = nv.nvmlDeviceGetMaxClockInfo(hs[0], nv.NVML_CLOCK_SM)
+R = (nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown, nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap)
+print('ready', flush=True)
+while True:
+    for h in hs:
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM); bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h); pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        print('%.6f,%d,%d,%.1f,%s' % (time.time(), sm, mx, pw, ','.join('Active' if bits & m else 'Not Active' for m in R)), flush=True)
+    time.sleep(0.004)
+"""
 
     def start(self):
+        try:                                                   # a separate process: the poller must not share this rank's interpreter or CUDA context
+            self.proc = subprocess.Popen([sys.executable, '-c', self.POLLER, ','.join(str(i) for i in self.indices)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            if self.proc.stdout.readline().strip() == 'ready':
+                self.nv = True
+                threading.Thread(target=self._read, daemon=True).start()
+                return
+            self.proc.kill()
+        except Exception:
+            pass
+        self.nv = None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', ','.join(str(i) for i in self.indices), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+            f = [x.strip() for x in line.split(',')]
+            if self.nv:                                         # the poller stamps its own rows
+                self.rows.append((float(f[0]), f[1:]))
+            else:
+                self.rows.append((time.time(), f))
 
     def stop(self, t0, t1):
         if self.proc is None:
             return None
-        time.sleep(0.15)
+        time.sleep(0.15 if not self.nv else 0.03)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
         if not rows:
             return None
         try:
             sm = sorted(float(r[0]) for r in rows)
             reasons = []
             for name, col in (('hw_slowdown', 3), ('hw_thermal_slowdown', 4), ('sw_thermal_slowdown', 5), ('sw_power_cap', 6)):
-                if any(r[col].lower().startswith('active') for r in rows):
+                if any(str(r[col]).lower().startswith('active') for r in rows):
                     reasons.append(name)
-            return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][1]), 'reasons': reasons, 'samples': len(rows)}
+            return {'sm_mhz': sm[len(sm) // 2], 'sm_mhz_min': sm[0], 'sm_max_mhz': float(rows[0][1]), 'reasons': reasons, 'samples': len(rows),
+                    'power_w_max': max(float(r[2]) for r in rows), 'gpus': len(self.indices),
+                    'source': 'NVML polled every ~5 ms by a separate process, samples inside the timed region only' if self.nv else 'nvidia-smi -lms 100'}
         except Exception:
             return None
 
@@ -249,6 +283,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip configs / sweep / comparators / encodings / train (kernel experiments)')
+    ap.add_argument('--no-single', action='store_true', help='skip the single-process multi-device block (N > 1)')
     ap.add_argument('--no-encodings', action='store_true')
     ap.add_argument('--encodings-bytes', type=int, default=256 << 20)
     ap.add_argument('--no-train', action='store_true')
@@ -280,6 +315,11 @@ def main():
     placement = numa.bind_process_to_device(local) if world > 1 else numa.describe(local)
     cpu_group = None
     if world > 1:
+        # NCCL is plumbing here (barriers, the max over ranks): the data path has no collective.  At 8 GPUs NCCL would set up
+        # NVLS (NVLink SHARP multicast), and a communicator that holds NVLS resources makes k_encode_slices 11 % slower on every
+        # rank (3.86 vs 3.48 ms, measured: profiles/r2_v31_bench_n8.json vs r2_v33_nvls0.json; clocks, power and eight
+        # independent processes are unaffected).  Nothing here reduces through the switch, so NVLS stays off unless asked for.
+        os.environ.setdefault('NCCL_NVLS_ENABLE', '0')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
         cpu_group = dist.new_group(backend='gloo')          # for waits that must not keep a GPU busy (an NCCL barrier spins in a kernel)
     dev = torch.device('cuda', local)
@@ -313,8 +353,9 @@ def main():
 
     # ---- device-resident timed region: exactly K steps
     tok.profile_enable(True)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(range(world) if world > 1 else [local]) if rank == 0 else None     # rank 0 watches every GPU of the job
+    if sampler:
+        sampler.start()
     time.sleep(0.3)
     launches0 = ct._lib().ctk_kernel_launches()
     barrier()
@@ -327,7 +368,7 @@ def main():
     barrier()
     w1 = time.time()
     launches = ct._lib().ctk_kernel_launches() - launches0
-    clocks = sampler.stop(w0, w1)
+    clocks = sampler.stop(w0, w1) if sampler else None
     prof = tok.profile_report()
     tok.profile_enable(False)
     # the only cross-shard exchange of the path: per-shard (first_doc, n_docs, n_ids) -> global id offsets; nothing on the
@@ -336,7 +377,11 @@ def main():
     ms = e0.elapsed_time(e1)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(B), float(T), float(D)], dtype=torch.float64, device=dev)
+    per_rank_ms = None
     if world > 1:
+        allms = [torch.zeros_like(tms) for _ in range(world)]
+        dist.all_gather(allms, tms)
+        per_rank_ms = [float(x.item()) / args.steps for x in allms]
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
     ms = float(tms.item())
@@ -437,7 +482,7 @@ def main():
         barrier()
         torch.cuda.synchronize()
         dist.barrier(group=cpu_group)                       # from here the other ranks wait on the CPU: their GPUs are free for rank 0's process
-        if rank == 0:
+        if rank == 0 and not args.no_single:
             try:
                 # this rank was bound to GPU 0's node: let the library's per-device threads place themselves
                 numa.unbind_process()
@@ -532,11 +577,12 @@ def main():
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
-        'data': 'synthetic', 'tokens_per_s': T_all / (ms_per_step * 1e-3),
+        'data': 'synthetic', 'tokens_per_s': T_all / (ms_per_step * 1e-3), 'ms_per_step_per_rank': per_rank_ms,
         'config': {'workload': WORKLOAD, 'bytes_per_gpu': int(B), 'docs_per_gpu': int(D), 'tokens_per_gpu': int(T),
                    'lexicon_words': 50000, 'vocab': 50257, 'l2': 'inputs (1 GiB) larger than L2 (126 MB); no flush needed',
                    'pretoken_cache': 'cleared inside every step', 'parallelism': 'documents sharded over %d GPU(s), no collective on the data path' % world,
-                   'shard_metadata': 'exchanged once after the timed steps (24 bytes per rank)' if world > 1 else None},
+                   'shard_metadata': 'exchanged once after the timed steps (24 bytes per rank)' if world > 1 else None,
+                   'nccl': ('plumbing only (barrier, max over ranks); NCCL_NVLS_ENABLE=%s' % os.environ.get('NCCL_NVLS_ENABLE')) if world > 1 else None},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
         'decode_batch': decode, 'single_process': single}
     out.update(extras)
