@@ -641,10 +641,14 @@ def run_extras(args, tok, tok_path, torch, dev, ct, synth, h_np, offs, h_text, B
     configs['config1'] = one_config('config1', tok1, orc1, t1, o1, 6.0, 10, '10K synthetic English texts (12 MB), 32K byte-level BPE vocabulary')
     docs1 = [bytes(t1[int(o1[i]):int(o1[i + 1])]).decode() for i in range(len(o1) - 1)]
     tok1.encode_batch(docs1[:100])
-    t0 = time.perf_counter()
-    lst = tok1.encode_batch(docs1)
-    configs['config1']['list_api'] = {'api': 'Tokenizer.encode_batch(list[str]) -> list[list[int]] (the literal drop-in call)', 'ms': (time.perf_counter() - t0) * 1e3,
-                                      'MB_per_s': t1.size / (time.perf_counter() - t0) / 1e6, 'ids': int(sum(map(len, lst)))}
+    best_l = None
+    for _ in range(3):                                      # best of 3: one shot once measured 328 ms against 91-100 ms (allocator / GC noise of 3.4 M Python ints)
+        t0 = time.perf_counter()
+        lst = tok1.encode_batch(docs1)
+        dt_l = time.perf_counter() - t0
+        best_l = dt_l if best_l is None else min(best_l, dt_l)
+    configs['config1']['list_api'] = {'api': 'Tokenizer.encode_batch(list[str]) -> list[list[int]] (the literal drop-in call), best of 3', 'ms': best_l * 1e3,
+                                      'MB_per_s': t1.size / best_l / 1e6, 'ids': int(sum(map(len, lst)))}
     rng = np.random.default_rng(7)
     words = [bytes(rng.integers(97, 123, size=int(k), dtype=np.uint8)).decode() for k in rng.integers(4, 13, size=10000)]
     tok1.encode_batch(words[:10])

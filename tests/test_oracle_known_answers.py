@@ -180,3 +180,19 @@ def test_lossy_decode_matches_python_replace():
     batch = [[pool[int(k)] for k in rng.integers(0, len(pool), size=int(rng.integers(0, 12)))] for _ in range(3000)]
     got = core.decode_batch(batch, False, False)
     assert got == [bytes(b).decode('utf-8', 'replace') for b in batch]
+
+
+def test_metaspace_known_answers():
+    """the reference's own tests for the Metaspace pre-tokenizer (pretokenizers.rs:633-640) and decoder (decoders.rs:255-262)"""
+    vocab = {'<unk>': 0, '\u2581': 1, 'H': 2, 'e': 3, 'l': 4, 'o': 5, 'w': 6, 'r': 7, 'd': 8, 'h': 9, '\u2581Hello': 10, '\u2581world': 11}
+    tj = {'model': {'type': 'BPE', 'vocab': vocab, 'merges': []}, 'pre_tokenizer': {'type': 'Metaspace', 'replacement': '\u2581', 'add_prefix_space': True},
+          'decoder': {'type': 'Metaspace', 'replacement': '\u2581', 'add_prefix_space': True}, 'added_tokens': []}
+    t = OracleTokenizer(tj)
+    words = t.pre_tokenize('hello world')
+    assert words[0].startswith('\u2581') and words == ['\u2581hello\u2581world']       # U+0020 is replaced before the split: one word
+    assert t.pre_tokenize('a\tb  c\n') == ['\u2581a', 'b\u2581\u2581c']
+    assert t.decode([10, 11], False, False) == 'Hello world'
+    assert t.decode([11], False, False) == 'world' and t.decode([], False, False) == ''
+    assert t.encode('') == [1]                                                          # the prefix alone is a word
+    tj['pre_tokenizer'] = {'type': 'Metaspace'}                                         # defaults: parsing.rs:108-123
+    assert OracleTokenizer(tj).pre_stages == [('metaspace', ('\u2581', True))]
