@@ -94,13 +94,18 @@ while True:
         try:                                                   # a separate process: the poller must not share this rank's interpreter or CUDA context
             self.proc = subprocess.Popen([sys.executable, '-c', self.POLLER, ','.join(str(i) for i in self.indices)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            if self.proc.stdout.readline().strip() == 'ready':
-                self.nv = True
-                threading.Thread(target=self._read, daemon=True).start()
-                return
+            self.nv = True
+            self.ready = threading.Event()
+            threading.Thread(target=self._read, daemon=True).start()
+            for _ in range(80):                                 # (a poller that never reports must not hang the bench)
+                if self.ready.wait(0.1):
+                    return
+                if self.proc.poll() is not None:
+                    break
             self.proc.kill()
         except Exception:
             pass
+        self.rows = []
         self.nv = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', ','.join(str(i) for i in self.indices), '--query-gpu=' + self.Q,
@@ -113,6 +118,11 @@ while True:
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(',')]
             if self.nv:                                         # the poller stamps its own rows
+                if f[0] == 'ready':
+                    self.ready.set()
+                    continue
+                if len(f) < 8:
+                    continue
                 self.rows.append((float(f[0]), f[1:]))
             else:
                 self.rows.append((time.time(), f))
