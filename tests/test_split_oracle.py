@@ -208,3 +208,60 @@ def test_split_tokenizer_oracle_end_to_end():
     with pytest.raises(py_oracle.Unsupported):
         py_oracle.OracleTokenizer(tj)                          # no ByteLevel stage: outside the hot path
     assert json.dumps(tj)
+
+
+def _rich_pattern(rng, depth=0):
+    """a wider slice of the supported syntax than _rand_pattern: bracket classes with ranges / negation / escapes / nesting,
+    negated properties, hex escapes, counted repetitions with zero lower bounds, named and capturing groups"""
+    def klass():
+        items = rng.sample(['a-c', 'x', '0-9', r'\d', r'\s', r'\p{L}', r'\p{Lu}', 'é', '中-和', r'\-', r'\]', '_', r'\x41', r'\u{3042}', '[b-d]', r'\P{N}'], rng.randint(1, 3))
+        return '[' + ('^' if rng.random() < 0.3 else '') + ''.join(items) + ']'
+    atoms = ['a', 'b', '1', ' ', '_', 'é', '中', r'\.', r'\p{L}', r'\P{L}', r'\pN', r'\s', r'\S', r'\w', r'\W', r'\d', r'\D', '.', r'\x62', r'\n']
+    r = rng.random()
+    if depth > 2 or r < 0.3:
+        node = klass() if rng.random() < 0.4 else rng.choice(atoms)
+    elif r < 0.55:
+        node = ''.join(_rich_pattern(rng, depth + 1) for _ in range(rng.randint(2, 3)))
+    elif r < 0.75:
+        node = rng.choice(['(?:', '(', '(?P<n%d>' % rng.randint(0, 9)]) + '|'.join(_rich_pattern(rng, depth + 1) for _ in range(rng.randint(2, 3))) + ')'
+    else:
+        node = '(?:' + _rich_pattern(rng, depth + 1) + ')'
+    if rng.random() < 0.4:
+        node = '(?:' + node + ')' + rng.choice(['?', '*', '+', '{0,2}', '{1,3}', '{2,}', '{3}', '+?', '*?', '??', '{0,2}?', '{1,}?'])
+    return node
+
+
+def test_rich_patterns_oracle_against_host_dfa(lib):
+    """400 random patterns of the wider grammar: the oracle's backtracking matcher and the product's DFA + walk (also cut at
+    every safe start) produce the same pieces for every behaviour; where the `regex` module reads the pattern the same way, it agrees too"""
+    rng = random.Random(2024)
+    done = tries = agree_module = 0
+    while done < 400 and tries < 6000:
+        tries += 1
+        p = _rich_pattern(rng)
+        try:
+            node = py_regex.compile_pattern(p)
+        except py_regex.Unsupported:
+            rc, _ = _host_pieces(lib, p, 1, False, 'abc')
+            assert rc == 3, p
+            continue
+        rc, _ = _host_pieces(lib, p, 1, False, 'abc')
+        if rc == 3:                                            # the product bounds its automaton (states, table size); the oracle has no such bound
+            msg = ctypes.cast(lib.ctk_last_error(), ctypes.c_char_p).value or b''
+            assert b'too many' in msg or b'too large' in msg, (p, msg)
+            continue
+        done += 1
+        bi = rng.randrange(5)
+        inv = bi == 0 and rng.random() < 0.5
+        for t in _texts(rng, 8, 0, 40):
+            want = [w for w in py_regex.split_with_behavior(node, t, py_regex.BEHAVIORS[bi], inv) if w]
+            for seg in (0, 1):
+                rc, got = _host_pieces(lib, p, bi, inv, t, seg)
+                assert rc == 0, (p, rc)
+                assert got == want, (p, py_regex.BEHAVIORS[bi], inv, t, seg)
+            try:
+                if '(?P<' not in p and py_regex.find_iter(node, t) == _module_spans(p, t):
+                    agree_module += 1
+            except Exception:
+                pass
+    assert done == 400 and agree_module > 2000
